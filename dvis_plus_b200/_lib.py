@@ -1,0 +1,55 @@
+"""ctypes binding of libdvis_b200.so (interface: include/dvis_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised
+so a caller can never silently end up on a slow / different code path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdvis_b200.so")
+
+DVIS_F32, DVIS_F64, DVIS_BF16 = 0, 1, 2
+ABI_VERSION = 1
+
+_vp, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+# name -> argtypes; mirrors include/dvis_b200.h one to one (tests/test_abi.py cross-checks against the header)
+SIGNATURES = {
+    "dvis_msda_forward": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "dvis_msda_fused_forward": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp,
+                                _i, _vp],
+}
+
+_lib = None
+launch_count = 0  # number of C-ABI calls that launched device work (bench.py reports it as gpu_launches)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m dvis_plus_b200.csrc.build` "
+                "(there is no CPU or PyTorch fallback for the dvis_plus_b200 kernels)")
+        l = ctypes.CDLL(LIB_PATH)
+        l.dvis_abi_version.restype = _i
+        l.dvis_last_error.restype = ctypes.c_char_p
+        if l.dvis_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libdvis_b200 ABI {l.dvis_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = _i
+        _lib = l
+    return _lib
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point; raise RuntimeError (like the reference's c10::Error) on a non-zero status."""
+    global launch_count
+    l = lib()
+    rc = getattr(l, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {l.dvis_last_error().decode()}")
+    launch_count += 1

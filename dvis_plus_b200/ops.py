@@ -1,0 +1,103 @@
+"""Torch-tensor front ends of the C ABI (include/dvis_b200.h).
+
+`ms_deform_attn_forward` / `ms_deform_attn_backward` have the exact signatures of the reference's compiled
+module `MultiScaleDeformableAttention` (OPS/src/vision.cpp:18-21), including its argument checks
+(OPS/src/cuda/ms_deform_attn_cuda.cu:33-57): `install_as_reference_extension()` registers this module under
+that name so `OPS/functions/ms_deform_attn_func.py:22` imports it unchanged.
+"""
+import sys
+import types
+
+import torch
+
+from . import _lib
+from ._lib import DVIS_BF16, DVIS_F32, DVIS_F64
+
+_DTYPE = {torch.float32: DVIS_F32, torch.float64: DVIS_F64, torch.bfloat16: DVIS_BF16}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_cuda_contig(**tensors):
+    for name, t in tensors.items():
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_cuda:
+            # the reference dispatcher raises exactly this for CPU tensors (OPS/src/ms_deform_attn.h:43)
+            raise RuntimeError("Not implemented on the CPU" if name == "value" else f"{name} must be a CUDA tensor")
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
+                           item_order=None):
+    """value (N,S,M,D); spatial_shapes (L,2) int64 cuda; level_start_index (L,) int64 cuda;
+    sampling_loc (N,Lq,M,L,P,2); attn_weight (N,Lq,M,L,P) -> (N, Lq, M*D).  fp32 or fp64."""
+    _check_cuda_contig(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                       sampling_loc=sampling_loc, attn_weight=attn_weight)
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    step = min(N, int(im2col_step))
+    if N % step != 0:
+        raise RuntimeError(f"batch({N}) must divide im2col_step({step})")
+    if value.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError(f'"ms_deform_attn_forward_cuda" not implemented for \'{value.dtype}\'')
+    if sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
+        raise RuntimeError("value, sampling_loc and attn_weight must have the same dtype")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64")
+    if sampling_loc.shape != (N, Lq, M, L, P, 2) or attn_weight.shape != (N, Lq, M, L, P):
+        raise RuntimeError("sampling_loc / attn_weight shapes do not match value / spatial_shapes")
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    if out.numel() == 0:
+        return out
+    order_ptr = None
+    if item_order is not None:
+        assert item_order.dtype == torch.int32 and item_order.is_cuda and item_order.numel() == Lq * M
+        order_ptr = item_order.data_ptr()
+    with torch.cuda.device(value.device):
+        _lib.call("dvis_msda_forward", value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                  sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P, _DTYPE[value.dtype],
+                  order_ptr, out.data_ptr(), _stream())
+    return out
+
+
+def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits, reference_points, num_heads,
+                       num_levels, num_points, item_order=None, out_dtype=None):
+    """Fused softmax + location arithmetic + gather (dvis_msda_fused_forward).
+
+    value (N,S,M,D) f32|bf16; offsets (N,Lq,M*L*P*2) and logits (N,Lq,M*L*P) f32 -- possibly column slices of one
+    (N,Lq,M*L*P*3) tensor (last dim contiguous); reference_points (N,Lq,L,2|4) f32.
+    """
+    N, S, M, D = value.shape
+    Lq = offsets.shape[1]
+    assert value.is_contiguous() and reference_points.is_contiguous()
+    assert offsets.dtype == torch.float32 and logits.dtype == torch.float32 and reference_points.dtype == torch.float32
+    assert offsets.stride(-1) == 1 and logits.stride(-1) == 1
+    assert offsets.stride(0) == offsets.stride(1) * Lq and logits.stride(0) == logits.stride(1) * Lq
+    out_dtype = out_dtype or value.dtype
+    out = torch.empty((N, Lq, M * D), dtype=out_dtype, device=value.device)
+    order_ptr = item_order.data_ptr() if item_order is not None else None
+    with torch.cuda.device(value.device):
+        _lib.call("dvis_msda_fused_forward", value.data_ptr(), _DTYPE[value.dtype], spatial_shapes.data_ptr(),
+                  level_start_index.data_ptr(), offsets.data_ptr(), offsets.stride(1), logits.data_ptr(),
+                  logits.stride(1), reference_points.data_ptr(), reference_points.shape[-1], N, S, M, D, num_levels,
+                  Lq, num_points, order_ptr, out.data_ptr(), _DTYPE[out_dtype], _stream())
+    return out
+
+
+def install_as_reference_extension():
+    """Register this module's op functions as the importable module `MultiScaleDeformableAttention`
+    (OPS/setup.py:60) so the reference's `import MultiScaleDeformableAttention as MSDA` binds to them."""
+    m = types.ModuleType("MultiScaleDeformableAttention")
+    m.ms_deform_attn_forward = lambda v, s, l, loc, a, step: ms_deform_attn_forward(v, s, l, loc, a, step)
+    m.ms_deform_attn_backward = ms_deform_attn_backward
+    m.__doc__ = "dvis_plus_b200 drop-in for the reference's MultiScaleDeformableAttention extension"
+    sys.modules["MultiScaleDeformableAttention"] = m
+    return m
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step):
+    raise RuntimeError("ms_deform_attn_backward: not built yet")

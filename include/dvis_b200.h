@@ -1,0 +1,77 @@
+/*
+ * dvis_b200.h -- C ABI of the B200-native DVIS++ hot path (libdvis_b200.so, sm_100a).
+ *
+ * Plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in `_host`.
+ * Every entry point launches asynchronously on `stream` (a cudaStream_t passed as void*), never
+ * synchronises, never allocates, never mutates its inputs, and returns DVIS_OK or a DVIS_ERR_* code
+ * (message via dvis_last_error()).  There is no CPU fallback anywhere behind this interface.
+ *
+ * Citations: OPS = DVIS_Plus/mask2former/modeling/pixel_decoder/ops, P = DVIS_Plus (reference @ c0eb2495).
+ */
+#ifndef DVIS_B200_H_
+#define DVIS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVIS_B200_ABI_VERSION 1
+
+enum {
+  DVIS_OK = 0,
+  DVIS_ERR_INVALID = 1,      /* bad argument (null pointer, non-positive size, misalignment) */
+  DVIS_ERR_UNSUPPORTED = 2,  /* dtype / shape combination this build has no kernel for */
+  DVIS_ERR_CUDA = 3          /* launch or driver error */
+};
+
+/* element types */
+enum { DVIS_F32 = 0, DVIS_F64 = 1, DVIS_BF16 = 2 };
+
+int dvis_abi_version(void);
+/* thread-local, valid until the next failing call on this thread */
+const char *dvis_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention, forward.
+ * Replaces MSDA.ms_deform_attn_forward (OPS/src/vision.cpp:19 -> OPS/src/ms_deform_attn.h:25-44 ->
+ * OPS/src/cuda/ms_deform_attn_cuda.cu:25-85 -> ms_deformable_im2col_cuda, ms_deform_im2col_cuda.cuh:928-959).
+ * The seven ints are the reference launcher's (cuh:936-942).
+ *   value            (batch, spatial_size, num_heads, channels)        dtype
+ *   spatial_shapes   (num_levels, 2) int64 (H_l, W_l)                  -- on device, like the reference (cu:72)
+ *   level_start      (num_levels,)   int64                             -- on device (cu:73)
+ *   sampling_loc     (batch, num_query, num_heads, num_levels, num_point, 2)  dtype, (x, y) in [0,1]
+ *   attn_weight      (batch, num_query, num_heads, num_levels, num_point)     dtype
+ *   out              (batch, num_query, num_heads*channels)            dtype; fully overwritten (no memset needed)
+ *   item_order       optional (num_query*num_heads,) int32 permutation of q*num_heads+m giving the order in
+ *                    which (query, head) items are walked -- a locality schedule only; may be NULL.
+ * dtype: DVIS_F32 or DVIS_F64 (the reference dispatches float/double only, cu:69).
+ * Unlike the reference there is no im2col_step chunking: one launch covers the whole batch.
+ */
+int dvis_msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                      const void *sampling_loc, const void *attn_weight, int batch, int spatial_size,
+                      int num_heads, int channels, int num_levels, int num_query, int num_point, int dtype,
+                      const int32_t *item_order, void *out, void *stream);
+
+/* Fused variant used by the module-level drop-in (MSDeformAttn.forward, OPS/modules/ms_deform_attn.py:98-118):
+ * takes the raw outputs of the sampling_offsets / attention_weights linears and the reference points and does
+ * softmax over L*P (py:104), location = ref + offset / (W_l, H_l) (py:106-109, 2-d reference points) or the
+ * box form (py:110-112, 4-d), bilinear gather and the weighted reduction in one pass.
+ *   offsets   (batch, num_query, num_heads, num_levels, num_point, 2) f32, row stride `offsets_stride` elements
+ *   logits    (batch, num_query, num_heads, num_levels*num_point)     f32, row stride `logits_stride` elements
+ *             (strides let both live in one fused linear output of width M*L*P*3)
+ *   ref       (batch, num_query, num_levels, ref_dim) f32, ref_dim = 2 or 4
+ *   value     f32 or bf16 (value_dtype); out f32 or bf16 (out_dtype)
+ */
+int dvis_msda_fused_forward(const void *value, int value_dtype, const int64_t *spatial_shapes,
+                            const int64_t *level_start, const float *offsets, int64_t offsets_stride,
+                            const float *logits, int64_t logits_stride, const float *ref, int ref_dim,
+                            int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                            int num_query, int num_point, const int32_t *item_order, void *out, int out_dtype,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVIS_B200_H_ */
