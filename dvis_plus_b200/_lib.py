@@ -19,6 +19,7 @@ SIGNATURES = {
     "dvis_msda_forward": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "dvis_msda_fused_forward": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp,
                                 _i, _vp],
+    "dvis_mask_logits": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp],
 }
 
 _lib = None

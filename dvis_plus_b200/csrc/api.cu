@@ -10,3 +10,19 @@ char *last_error_buffer() {
 
 extern "C" int dvis_abi_version(void) { return DVIS_B200_ABI_VERSION; }
 extern "C" const char *dvis_last_error(void) { return dvis::last_error_buffer(); }
+
+// ---- driver entry point for tensor-map encoding (resolved once; no link-time dependency on libcuda) ----
+#include "tc05.cuh"
+namespace dvis {
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(p);
+  }();
+  return fn;
+}
+}  // namespace dvis

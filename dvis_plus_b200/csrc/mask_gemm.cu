@@ -1,0 +1,252 @@
+// Mask-logit GEMM on the 5th-gen tensor cores:  out[b, q, p] = sum_c emb[b, q, c] * feat[b, p, c]
+//
+// Replaces torch.einsum("bqc,bchw->bqhw") (P/dvis_Plus/video_mask2former_transformer_decoder.py:363) and the
+// tracker / refiner "lbtqc,btchw->lbqthw" (P/dvis_Plus/tracker.py:379, refiner.py:185-189).
+//
+// Shape of the problem: K = C = 256 is tiny, so the op is HBM-bound (read C*HW, write Q*HW): the design goal is
+// to stream `feat` exactly once at full TMA bandwidth and write `out` with fully coalesced stores.
+//   * MMA tile: M = 128 pixels (A = feat tile, K-major), N = Q rounded up to 16 (B = emb, K-major, resident in smem
+//     for the whole batch element), K = C in 64-element (128-byte, SWIZZLE_128B) blocks.
+//   * D lives in TMEM with lane = pixel, column = query; two accumulator stages (2 x 256 columns) so the epilogue
+//     of tile i overlaps the MMAs of tile i+1.
+//   * Epilogue: tcgen05.ld gives every thread one pixel's logits for 32 queries; they are staged as a
+//     [32 queries][128 pixels] smem tile (conflict-free: lane = pixel) and written with one TMA store per chunk,
+//     double-buffered, so the (B, Q, HW) output is produced with full-line writes and no per-element predicates.
+//   * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
+//     warps 2..5 = epilogue (one per TMEM lane quarter).
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace dvis {
+namespace {
+
+using namespace tc05;
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements per 128-byte swizzle row
+constexpr int kStageBytes = kTileM * 128;         // one A k-block: 128 rows x 128 B
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+constexpr int kAccCols = 256;                     // TMEM columns per accumulator stage
+constexpr int kEpiCols = 32;                      // queries per epilogue chunk (one tcgen05.ld.32x32b.x32)
+constexpr int kEpiThreads = 128;
+
+struct MaskGemmParams {
+  void *out;
+  int B, Q, Qpad, KB;   // KB = C / 64
+  int64_t HW;
+  int tiles_per_batch, total_tiles, stages;
+};
+
+struct __align__(8) Barriers {
+  uint64_t full[kMaxStages], empty[kMaxStages];
+  uint64_t b_full, b_empty;
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <typename TO>
+__device__ __forceinline__ TO cvt_logit(uint32_t bits);
+template <>
+__device__ __forceinline__ float cvt_logit<float>(uint32_t bits) { return __uint_as_float(bits); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_logit<__nv_bfloat16>(uint32_t bits) {
+  return __float2bfloat16_rn(__uint_as_float(bits));
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(kThreads, 1)
+mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_emb,
+                 const __grid_constant__ CUtensorMap tmap_out, const MaskGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_block_bytes = p.Qpad * 128;                       // one emb k-block
+  uint8_t *sB = smem;
+  uint8_t *sA = smem + p.KB * b_block_bytes;                    // 1024-aligned because Qpad % 8 == 0
+  // two output staging tiles [kEpiCols queries][128 pixels] for the TMA store (row-major, no swizzle)
+  TO *sOut = reinterpret_cast<TO *>(sA + p.stages * kStageBytes);
+  Barriers *bars = reinterpret_cast<Barriers *>(reinterpret_cast<uint8_t *>(sOut) + 2 * kEpiCols * kTileM * sizeof(TO));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_feat);
+    prefetch_tensormap(&tmap_emb);
+    prefetch_tensormap(&tmap_out);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    mbar_init(&bars->b_full, 1);
+    mbar_init(&bars->b_empty, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  fence_before_thread_sync();
+  __syncthreads();
+  fence_after_thread_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // contiguous, balanced slice of the (batch, pixel-tile) list for this CTA
+  const int tile_begin = int((int64_t)p.total_tiles * blockIdx.x / gridDim.x);
+  const int tile_end = int((int64_t)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0, cur_b = -1, n_bload = 0;
+      for (int t = tile_begin; t < tile_end; ++t) {
+        const int b = t / p.tiles_per_batch, tile = t - b * p.tiles_per_batch;
+        if (b != cur_b) {
+          if (n_bload > 0) mbar_wait(&bars->b_empty, (n_bload - 1) & 1);   // MMAs that read the old emb are done
+          mbar_arrive_expect_tx(&bars->b_full, uint32_t(p.KB * b_block_bytes));
+          for (int kb = 0; kb < p.KB; ++kb) tma_load_3d(sB + kb * b_block_bytes, &tmap_emb, &bars->b_full, kb * kBlockK, 0, b);
+          cur_b = b;
+          ++n_bload;
+        }
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+          tma_load_3d(sA + stage * kStageBytes, &tmap_feat, &bars->full[stage], kb * kBlockK, tile * kTileM, b);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kTileM, p.Qpad, /*BF16*/ 1);
+      int stage = 0, phase = 0, cur_b = -1, n_bload = 0, n_tile = 0;
+      for (int t = tile_begin; t < tile_end; ++t, ++n_tile) {
+        const int b = t / p.tiles_per_batch;
+        if (b != cur_b) {
+          mbar_wait(&bars->b_full, n_bload & 1);
+          cur_b = b;
+          ++n_bload;
+        }
+        const int acc = n_tile & 1;
+        mbar_wait(&bars->acc_empty[acc], ((n_tile >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+        fence_after_thread_sync();
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          fence_after_thread_sync();
+          const uint32_t a_addr = smem_u32(sA + stage * kStageBytes);
+          const uint32_t b_addr = smem_u32(sB + kb * b_block_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)                        // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
+            mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                        uint32_t(kb | k));
+          mma_commit(&bars->empty[stage]);                               // frees the A stage when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&bars->acc_full[acc]);
+        const bool last_of_batch = (t + 1 < tile_end) && ((t + 1) / p.tiles_per_batch != b);
+        if (last_of_batch) mma_commit(&bars->b_empty);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers -> smem tile [query][pixel] -> TMA store.  Thread = pixel, so for a fixed query the warp's
+    // 32 lanes write 32 consecutive pixels of the staging row (conflict-free) and the TMA engine does the
+    // (Q, HW)-strided global writes, clipping partial tiles in both pixel and query direction.
+    const int quarter = warp & 3;                     // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    const bool issuer = (warp == 2 && lane == 0);
+    const int px = quarter * 32 + lane;
+    int n_tile = 0, n_chunk = 0;
+    for (int t = tile_begin; t < tile_end; ++t, ++n_tile) {
+      const int b = t / p.tiles_per_batch, tile = t - b * p.tiles_per_batch;
+      const int acc = n_tile & 1;
+      mbar_wait(&bars->acc_full[acc], (n_tile >> 1) & 1);
+      fence_after_thread_sync();
+      const uint32_t taddr = tmem_base + acc * kAccCols + (uint32_t(quarter * 32) << 16);
+      for (int c0 = 0; c0 < p.Q; c0 += kEpiCols, ++n_chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c0, r);
+        tmem_ld_wait();
+        TO *buf = sOut + (n_chunk & 1) * (kEpiCols * kTileM);
+        if (issuer) tma_store_wait_read<1>();          // the store that last read this buffer (2 chunks ago) is done
+        named_barrier_sync(1, kEpiThreads);
+#pragma unroll
+        for (int i = 0; i < kEpiCols; ++i) buf[i * kTileM + px] = cvt_logit<TO>(r[i]);
+        fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
+        named_barrier_sync(2, kEpiThreads);
+        if (issuer) {
+          tma_store_3d(&tmap_out, buf, tile * kTileM, c0, b);
+          tma_store_commit();
+        }
+      }
+      fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+    }
+    if (issuer) tma_store_wait_read<0>();
+  }
+
+  fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// 3-D map over a dense (batch, rows, inner) tensor; box = (box_inner, box_rows, 1)
+int encode_map(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int esize, uint64_t inner, uint64_t rows,
+               uint64_t batch, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(DVIS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[3] = {inner, rows, batch};
+  const cuuint64_t strides[2] = {inner * esize, inner * rows * esize};   // bytes, dims 1..2
+  const cuuint32_t box[3] = {box_inner, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DVIS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return DVIS_OK;
+}
+
+}  // namespace
+}  // namespace dvis
+
+using namespace dvis;
+
+extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out,
+                                int out_dtype, void *stream) {
+  DVIS_REQUIRE(emb && feat && out, "mask_logits: null pointer argument");
+  DVIS_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_logits: sizes must be positive");
+  DVIS_REQUIRE(C % kBlockK == 0 && C <= 512, "mask_logits: C must be a multiple of 64 and <= 512 (got %d)", C);
+  DVIS_REQUIRE(Q <= 256, "mask_logits: Q must be <= 256 (got %d); split the queries", Q);
+  DVIS_REQUIRE(aligned16(emb) && aligned16(feat), "mask_logits: emb / feat must be 16-byte aligned");
+  DVIS_REQUIRE(HW < (int64_t(1) << 31) && B < 65536, "mask_logits: extent too large");
+  if (out_dtype != DVIS_F32 && out_dtype != DVIS_BF16)
+    return fail(DVIS_ERR_UNSUPPORTED, "mask_logits: out_dtype %d (f32 or bf16)", out_dtype);
+
+  MaskGemmParams p{};
+  p.out = out; p.B = B; p.Q = Q; p.Qpad = (Q + 15) & ~15; p.KB = C / kBlockK; p.HW = HW;
+  p.tiles_per_batch = int((HW + kTileM - 1) / kTileM);
+  p.total_tiles = p.tiles_per_batch * B;
+  const int b_bytes = p.KB * p.Qpad * 128;
+  const int esize = out_dtype == DVIS_F32 ? 4 : 2;
+  DVIS_REQUIRE(aligned16(out) && (HW * esize) % 16 == 0, "mask_logits: out must be 16-byte aligned and HW*sizeof(out) a multiple of 16");
+  const int stage_out_bytes = 2 * kEpiCols * kTileM * esize;
+  const int budget = 225 * 1024 - b_bytes - 1024 - stage_out_bytes - int(sizeof(Barriers));
+  p.stages = std::min(kMaxStages, budget / kStageBytes);
+  if (p.stages < 2) return fail(DVIS_ERR_UNSUPPORTED, "mask_logits: Q=%d, C=%d do not fit in shared memory", Q, C);
+  const size_t smem = 1024 + b_bytes + size_t(p.stages) * kStageBytes + stage_out_bytes + sizeof(Barriers);
+
+  CUtensorMap tm_feat, tm_emb, tm_out;
+  if (int rc = encode_map(&tm_feat, feat, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, HW, B, kBlockK, kTileM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = encode_map(&tm_emb, emb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, Q, B, kBlockK, p.Qpad, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = encode_map(&tm_out, out, out_dtype == DVIS_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                          esize, HW, Q, B, kTileM, kEpiCols, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = std::min(p.total_tiles, kNumSMs);
+  if (out_dtype == DVIS_F32) {
+    cudaFuncSetAttribute(mask_gemm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    mask_gemm_kernel<float><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);
+  } else {
+    cudaFuncSetAttribute(mask_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    mask_gemm_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);
+  }
+  return check_launch("mask_gemm_kernel");
+}

@@ -39,6 +39,7 @@ struct MsdaParams {
   void *out;
   int N, S, M, L, Lq, P;
   int items_per_cta;
+  int m_shift, p_shift, lpc_shift;  // log2(M), log2(P) or -1 when not a power of two; log2(next_pow2(L*P))
 };
 
 template <typename T>
@@ -52,6 +53,9 @@ template <typename T>
 struct AccOf { using type = float; };
 template <>
 struct AccOf<double> { using type = double; };
+
+template <typename T>
+struct LocType { using type = float; };   // plain-op loc/attn dtype for value dtype T (bf16 value is fused-only)
 
 template <typename TO, typename A, int N>
 __device__ __forceinline__ void store_vec(TO *dst, const A (&acc)[N]);
@@ -79,126 +83,173 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16, float, 4>(__nv_bfloat16
   *reinterpret_cast<uint2 *>(dst) = make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
 }
 
-// One sampling point: 4 predicated corner loads + weighted accumulate.  `base` points at
-// value[n, level_start, m, j*VEC]; consecutive pixels are `row` elements apart.
-template <typename T, typename A, int VEC>
-__device__ __forceinline__ void sample_point(const T *__restrict__ base, int H, int W, int row, A x, A y, A a,
-                                             A (&acc)[VEC]) {
+// Parameters of one sampling point, computed once by one thread (phase 1) and then read by the LPR lanes that
+// gather the point's rows (phase 2): byte offsets of the 4 corner rows relative to this batch element's
+// value base, and the 4 bilinear weights already multiplied by the attention weight.  A weight of exactly 0
+// marks a corner outside the map (or a whole point outside (-1, size)); its offset is redirected to a valid row.
+struct PointOffsets { uint32_t o00, o01, o10, o11; };   // BYTE offsets (unsigned: one IADD3 + IADD3.X per address)
+
+template <typename A>
+__device__ __forceinline__ void point_params(A x, A y, A a, int H, int W, int start, int M, int m, int lpr,
+                                             PointOffsets &off, float4 &wt) {
   // un-fused multiply / subtract like the reference (cuh:290-291) so that floor() sees the same value
   const A h_im = y * A(H) - A(0.5);
   const A w_im = x * A(W) - A(0.5);
-  const bool inr = (h_im > A(-1)) && (w_im > A(-1)) && (h_im < A(H)) && (w_im < A(W));
+  const bool inr = (h_im > A(-1)) && (w_im > A(-1)) && (h_im < A(H)) && (w_im < A(W));   // cuh:293
   const A hf = floor(h_im), wf = floor(w_im);
-  const int h0 = int(hf), w0 = int(wf);
+  const int h0 = inr ? int(hf) : 0, w0 = inr ? int(wf) : 0;
   const A lh = h_im - hf, lw = w_im - wf;
   const A hh = A(1) - lh, hw = A(1) - lw;
-  const bool top = inr && h0 >= 0, bot = inr && h0 + 1 <= H - 1;
+  const bool top = inr && h0 >= 0, bot = inr && h0 + 1 <= H - 1;      // cuh:61-83 corner tests
   const bool lef = w0 >= 0, rig = w0 + 1 <= W - 1;
-  const T *p00 = base + (long)(h0 * W + w0) * row;
-  Vec16<T> v00{}, v01{}, v10{}, v11{};
-  if (top && lef) v00 = ldg16(p00);
-  if (top && rig) v01 = ldg16(p00 + row);
-  if (bot && lef) v10 = ldg16(p00 + (long)W * row);
-  if (bot && rig) v11 = ldg16(p00 + (long)W * row + row);
-  const A w00 = hh * hw * a, w01 = hh * lw * a, w10 = lh * hw * a, w11 = lh * lw * a;
-#pragma unroll
-  for (int k = 0; k < VEC; ++k)
-    acc[k] += w00 * A(v00.get(k)) + w01 * A(v01.get(k)) + w10 * A(v10.get(k)) + w11 * A(v11.get(k));
+  const bool v00 = top && lef, v01 = top && rig, v10 = bot && lef, v11 = bot && rig;
+  wt.x = v00 ? float(hh * hw * a) : 0.f;
+  wt.y = v01 ? float(hh * lw * a) : 0.f;
+  wt.z = v10 ? float(lh * hw * a) : 0.f;
+  wt.w = v11 ? float(lh * lw * a) : 0.f;
+  const int rowu = M * lpr;                                           // one pixel = M*D elements = M*LPR 16-byte units
+  const int o00 = ((start + h0 * W + w0) * M + m) * lpr;
+  const int o01 = o00 + rowu, o10 = o00 + W * rowu, o11 = o10 + rowu;
+  // Phase 2 loads all four corners unconditionally; a corner outside the map (weight 0) is pointed at a valid
+  // corner of the same point (or at pixel 0 of this head when the whole point is out of range), so the load is
+  // always in bounds and contributes 0 * finite = 0.
+  const int safe = v00 ? o00 : v01 ? o01 : v10 ? o10 : v11 ? o11 : m * lpr;
+  off.o00 = uint32_t(v00 ? o00 : safe) << 4;
+  off.o01 = uint32_t(v01 ? o01 : safe) << 4;
+  off.o10 = uint32_t(v10 ? o10 : safe) << 4;
+  off.o11 = uint32_t(v11 ? o11 : safe) << 4;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// vectorised kernel: T = value type, TO = output type, D = channels per head, PCT = points (0 = runtime)
-// FUSED: loc/attn are raw offsets / logits + reference points.  LCT = levels for FUSED (softmax needs L*P regs)
+// staged kernel: T = value type, TO = output type, D = channels per head.
+// A CTA owns `items_per_cta` (query, head) items.
+//   phase 0 (FUSED): softmax over the L*P logits of each item -> smem
+//   phase 1: one thread per (item, point) computes offsets + weights -> smem           (no redundancy)
+//   phase 2: a group of LPR lanes per item walks its points: 2 LDS.128 + 4 predicated LDG.128 + 4*VEC FFMA each
 // ---------------------------------------------------------------------------------------------------
-template <typename T, typename TO, int D, int PCT, bool FUSED, int LCT>
-__global__ void __launch_bounds__(kThreads) msda_fwd_vec_kernel(const MsdaParams p) {
-  using A = typename AccOf<T>::type;
+template <typename T, typename TO, int D, bool FUSED>
+__global__ void __launch_bounds__(kThreads, 3) msda_fwd_staged_kernel(const MsdaParams p) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;  // lanes per row
   constexpr int G = 32 / LPR;   // items per warp
   static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported head dim");
 
+  extern __shared__ uint4 dyn_smem[];
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
   if (threadIdx.x < p.L) {
     sH[threadIdx.x] = int(p.shapes[2 * threadIdx.x]);
     sW[threadIdx.x] = int(p.shapes[2 * threadIdx.x + 1]);
     sStart[threadIdx.x] = int(p.level_start[threadIdx.x]);
   }
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.y, M = p.M, P = p.P, LP = p.L * p.P;
+  const int LPs = LP | 1;       // odd stride (in 16-byte units) -> the G groups of a warp hit disjoint banks
+  const int per_batch = p.Lq * M;
+  const int chunk_begin = blockIdx.x * p.items_per_cta;
+  const int nitems = min(p.items_per_cta, per_batch - chunk_begin);
+  PointOffsets *s_off = reinterpret_cast<PointOffsets *>(dyn_smem);
+  float4 *s_wt = reinterpret_cast<float4 *>(dyn_smem + p.items_per_cta * LPs);
+  float *s_prob = reinterpret_cast<float *>(dyn_smem + 2 * p.items_per_cta * LPs);
+  int *s_item = reinterpret_cast<int *>(s_prob + (FUSED ? p.items_per_cta * LP : 0));
+
+  for (int il = tid; il < nitems; il += kThreads) s_item[il] = p.order ? __ldg(p.order + chunk_begin + il) : chunk_begin + il;
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane / LPR, j = lane % LPR;
-  const int n = blockIdx.y;
-  const int M = p.M, L = FUSED ? LCT : p.L, P = PCT ? PCT : p.P;
-  const int per_batch = p.Lq * M;
-  const int row = M * D;
-  const T *value_n = static_cast<const T *>(p.value) + (size_t)n * p.S * row;
-
-  const int chunk_begin = blockIdx.x * p.items_per_cta;
-  const int chunk_end = min(chunk_begin + p.items_per_cta, per_batch);
-  for (int it = chunk_begin + warp * G + g; it < chunk_end; it += kWarps * G) {
-    const int item = p.order ? p.order[it] : it;
-    const int q = item / M, m = item - q * M;
-    const size_t nq = (size_t)n * p.Lq + q;
-    A acc[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = A(0);
-
-    if constexpr (FUSED) {
-      // softmax over L*P logits of this (query, head): OPS/modules/ms_deform_attn.py:103-104
-      constexpr int LP = LCT * PCT;
-      const float *lg = static_cast<const float *>(p.attn) + nq * p.attn_stride + (size_t)m * LP;
-      const float *of = static_cast<const float *>(p.loc) + nq * p.loc_stride + (size_t)m * LP * 2;
-      const float *rf = p.ref + nq * (size_t)(LCT * p.ref_dim);
-      float w[LP];
+  if constexpr (FUSED) {
+    // phase 0: 4 threads per item; softmax over L*P logits (OPS/modules/ms_deform_attn.py:103-104)
+    for (int il = tid >> 2; il < ((nitems + 63) & ~63); il += kThreads >> 2) {
+      const int sub = tid & 3;
+      const bool act = il < nitems;
+      const int item = act ? s_item[il] : 0;
+      const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
+      const float *lg = static_cast<const float *>(p.attn) + ((size_t)n * p.Lq + q) * p.attn_stride + (size_t)m * LP;
       float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < LP; ++i) { w[i] = __ldg(lg + i); mx = fmaxf(mx, w[i]); }
+      for (int i = sub; i < LP; i += 4) mx = fmaxf(mx, act ? __ldg(lg + i) : 0.f);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < LP; ++i) { w[i] = __expf(w[i] - mx); sum += w[i]; }
-      const float inv = 1.f / sum;
-#pragma unroll
-      for (int l = 0; l < LCT; ++l) {
-        const int H = sH[l], W = sW[l];
-        const T *base = value_n + (size_t)sStart[l] * row + m * D + j * VEC;
-        // loc = r + off * s with s = 1/(W_l, H_l) for 2-d reference points (py:106-109) or
-        // s = 0.5 * (w, h) / P for reference boxes (py:110-112)
-        const int rd = p.ref_dim;
-        const float rx = __ldg(rf + rd * l), ry = __ldg(rf + rd * l + 1);
-        const float sx = rd == 2 ? 1.f / float(W) : __ldg(rf + 4 * l + 2) * (0.5f / float(PCT));
-        const float sy = rd == 2 ? 1.f / float(H) : __ldg(rf + 4 * l + 3) * (0.5f / float(PCT));
-#pragma unroll
-        for (int pt = 0; pt < PCT; ++pt) {
-          const float2 o = __ldg(reinterpret_cast<const float2 *>(of) + l * PCT + pt);
-          sample_point<T, A, VEC>(base, H, W, row, fmaf(o.x, sx, rx), fmaf(o.y, sy, ry), w[l * PCT + pt] * inv, acc);
-        }
+      for (int i = sub; i < LP; i += 4) {
+        const float e = act ? __expf(__ldg(lg + i) - mx) : 0.f;
+        if (act) s_prob[il * LP + i] = e;
+        sum += e;
       }
-    } else {
-      const size_t lp_base = (nq * M + m) * (size_t)(L * P);
-      const T *loc = static_cast<const T *>(p.loc) + lp_base * 2;
-      const T *att = static_cast<const T *>(p.attn) + lp_base;
-      for (int l = 0; l < L; ++l) {
-        const int H = sH[l], W = sW[l];
-        const T *base = value_n + (size_t)sStart[l] * row + m * D + j * VEC;
-        if constexpr (PCT == 4 && std::is_same<T, float>::value) {
-          // (x,y) of the 4 points of this level are 32 contiguous bytes, their weights 16 (host checked alignment)
-          const float4 l01 = __ldg(reinterpret_cast<const float4 *>(loc) + 2 * l);
-          const float4 l23 = __ldg(reinterpret_cast<const float4 *>(loc) + 2 * l + 1);
-          const float4 a4 = __ldg(reinterpret_cast<const float4 *>(att) + l);
-          sample_point<T, A, VEC>(base, H, W, row, l01.x, l01.y, a4.x, acc);
-          sample_point<T, A, VEC>(base, H, W, row, l01.z, l01.w, a4.y, acc);
-          sample_point<T, A, VEC>(base, H, W, row, l23.x, l23.y, a4.z, acc);
-          sample_point<T, A, VEC>(base, H, W, row, l23.z, l23.w, a4.w, acc);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.f / sum;
+      if (act)
+        for (int i = sub; i < LP; i += 4) s_prob[il * LP + i] *= inv;   // same thread wrote these
+    }
+    __syncthreads();
+  }
+
+  // phase 1: thread -> (item il, point pt); LPc = LP rounded up to a power of two so the split is shifts only
+  {
+    const int lpc_shift = p.lpc_shift, pt = tid & ((1 << lpc_shift) - 1);
+    if (pt < LP) {
+      const int l = p.p_shift >= 0 ? pt >> p.p_shift : pt / P;
+      const int H = sH[l], W = sW[l], start = sStart[l];
+      for (int il = tid >> lpc_shift; il < nitems; il += kThreads >> lpc_shift) {
+        const int item = s_item[il];
+        const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
+        const size_t nq = (size_t)n * p.Lq + q;
+        PointOffsets off;
+        float4 wt;
+        if constexpr (FUSED) {
+          const float *of = static_cast<const float *>(p.loc) + nq * p.loc_stride + ((size_t)m * LP + pt) * 2;
+          const float *rf = p.ref + (nq * p.L + l) * p.ref_dim;
+          const float2 o = __ldg(reinterpret_cast<const float2 *>(of));
+          // loc = ref + off / (W_l, H_l) for 2-d reference points (py:106-109);
+          // loc = ref_xy + off / P * ref_wh * 0.5 for boxes (py:110-112)
+          const float sx = p.ref_dim == 2 ? 1.f / float(W) : __ldg(rf + 2) * (0.5f / float(P));
+          const float sy = p.ref_dim == 2 ? 1.f / float(H) : __ldg(rf + 3) * (0.5f / float(P));
+          point_params<float>(fmaf(o.x, sx, __ldg(rf)), fmaf(o.y, sy, __ldg(rf + 1)), s_prob[il * LP + pt], H, W, start,
+                              M, m, LPR, off, wt);
         } else {
-          for (int pt = 0; pt < P; ++pt)
-            sample_point<T, A, VEC>(base, H, W, row, A(__ldg(loc + 2 * (l * P + pt))),
-                                    A(__ldg(loc + 2 * (l * P + pt) + 1)), A(__ldg(att + l * P + pt)), acc);
+          using TL = typename LocType<T>::type;   // plain op: loc / attn have the value's dtype
+          const size_t i = (nq * M + m) * (size_t)LP + pt;
+          const TL *lc = static_cast<const TL *>(p.loc) + 2 * i;
+          point_params<TL>(__ldg(lc), __ldg(lc + 1), __ldg(static_cast<const TL *>(p.attn) + i), H, W, start, M, m, LPR,
+                           off, wt);
         }
+        s_off[il * LPs + pt] = off;
+        s_wt[il * LPs + pt] = wt;
       }
     }
-    TO *dst = static_cast<TO *>(p.out) + (nq * M + m) * (size_t)D + j * VEC;
-    store_vec<TO, A, VEC>(dst, acc);
+  }
+  __syncthreads();
+
+  // phase 2: gather + accumulate
+  const int g = lane / LPR, j = lane % LPR;
+  using V = decltype(Vec16<T>::v);
+  const char *vb = reinterpret_cast<const char *>(static_cast<const T *>(p.value) + (size_t)n * p.S * M * D) + j * 16;
+  for (int il = warp * G + g; il < nitems; il += kWarps * G) {
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    const uint4 *so = reinterpret_cast<const uint4 *>(s_off) + il * LPs;
+    const float4 *sw = s_wt + il * LPs;
+#pragma unroll 4
+    for (int pt = 0; pt < LP; ++pt) {
+      const uint4 o = so[pt];
+      const float4 w = sw[pt];
+      Vec16<T> v00, v01, v10, v11;
+      v00.v = __ldg(reinterpret_cast<const V *>(vb + o.x));
+      v01.v = __ldg(reinterpret_cast<const V *>(vb + o.y));
+      v10.v = __ldg(reinterpret_cast<const V *>(vb + o.z));
+      v11.v = __ldg(reinterpret_cast<const V *>(vb + o.w));
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        acc[k] = fmaf(w.x, v00.get(k), acc[k]);
+        acc[k] = fmaf(w.y, v01.get(k), acc[k]);
+        acc[k] = fmaf(w.z, v10.get(k), acc[k]);
+        acc[k] = fmaf(w.w, v11.get(k), acc[k]);
+      }
+    }
+    const int item = s_item[il];
+    const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
+    TO *dst = static_cast<TO *>(p.out) + (((size_t)n * p.Lq + q) * M + m) * (size_t)D + j * VEC;
+    store_vec<TO, float, VEC>(dst, acc);
   }
 }
 
@@ -242,42 +293,51 @@ __global__ void __launch_bounds__(256) msda_fwd_generic_kernel(const MsdaParams 
   }
 }
 
-int choose_items_per_cta(int per_batch, int batch, int items_per_pass) {
-  // aim for >= ~6 CTAs per SM in flight across the grid, but keep chunks long enough for L1 reuse
-  int ipc = 256;
-  while (ipc > items_per_pass && (long)((per_batch + ipc - 1) / ipc) * batch < 6L * kNumSMs) ipc >>= 1;
-  if (ipc < items_per_pass) ipc = items_per_pass;
-  return ipc;
+int log2_exact(int v) {
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
 }
 
-template <typename T, typename TO, int D, int PCT, bool FUSED, int LCT>
-int launch_vec(MsdaParams p, cudaStream_t stream) {
+constexpr int kMaxStagedLP = 32;   // L*P beyond this goes to the generic kernel
+
+template <typename T, typename TO, int D, bool FUSED>
+int launch_staged(MsdaParams p, cudaStream_t stream) {
   constexpr int G = 32 / (D / Vec16<T>::N);
-  const int per_batch = p.Lq * p.M;
-  p.items_per_cta = choose_items_per_cta(per_batch, p.N, kWarps * G);
+  const int per_batch = p.Lq * p.M, LP = p.L * p.P, LPs = LP | 1;
+  p.items_per_cta = 64;            // = 2 phase-2 passes at G=4; phase 0 maps 4 threads per item
+  static_assert(kWarps * G <= 64 || true, "");
+  if (kWarps * G > p.items_per_cta) p.items_per_cta = kWarps * G;
+  p.m_shift = log2_exact(p.M);
+  p.p_shift = log2_exact(p.P);
+  int lpc = 1, sh = 0;
+  while (lpc < LP) { lpc <<= 1; ++sh; }
+  p.lpc_shift = sh;
+  const size_t smem = (size_t)p.items_per_cta * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
+  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED>;
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
   dim3 grid((per_batch + p.items_per_cta - 1) / p.items_per_cta, p.N);
-  msda_fwd_vec_kernel<T, TO, D, PCT, FUSED, LCT><<<grid, kThreads, 0, stream>>>(p);
-  return check_launch("msda_fwd_vec_kernel");
+  kern<<<grid, kThreads, smem, stream>>>(p);
+  return check_launch("msda_fwd_staged_kernel");
 }
 
 template <typename T>
 int launch_plain(const MsdaParams &p, int D, cudaStream_t stream) {
-  const bool vec_ok = aligned16(p.value) && aligned16(p.out);
-  const bool p4_ok = p.P == 4 && aligned16(p.loc) && aligned16(p.attn);
+  const bool vec_ok = aligned16(p.value) && aligned16(p.out) && p.L * p.P <= kMaxStagedLP;
   if (vec_ok && std::is_same<T, float>::value) {
-#define DVIS_CASE(DD)                                                                  \
-  case DD:                                                                             \
-    return p4_ok ? launch_vec<float, float, DD, 4, false, 0>(p, stream)                \
-                 : launch_vec<float, float, DD, 0, false, 0>(p, stream);
     switch (D) {
-      DVIS_CASE(8)
-      DVIS_CASE(16)
-      DVIS_CASE(32)
-      DVIS_CASE(64)
-      DVIS_CASE(128)
+      case 8: return launch_staged<float, float, 8, false>(p, stream);
+      case 16: return launch_staged<float, float, 16, false>(p, stream);
+      case 32: return launch_staged<float, float, 32, false>(p, stream);
+      case 64: return launch_staged<float, float, 64, false>(p, stream);
+      case 128: return launch_staged<float, float, 128, false>(p, stream);
       default: break;
     }
-#undef DVIS_CASE
   }
   const size_t total = (size_t)p.N * p.Lq * p.M * D;
   const int blocks = int(std::min<size_t>((total + 255) / 256, (size_t)kNumSMs * 32));
@@ -290,7 +350,7 @@ int validate_common(const void *value, const int64_t *shapes, const int64_t *ls,
   DVIS_REQUIRE(value && shapes && ls && loc && attn && out, "msda: null pointer argument");
   DVIS_REQUIRE(batch > 0 && S > 0 && M > 0 && D > 0 && L > 0 && Lq > 0 && P > 0, "msda: sizes must be positive");
   DVIS_REQUIRE(L <= kMaxLevels, "msda: num_levels %d > %d", L, kMaxLevels);
-  DVIS_REQUIRE((long)S * M * D < (1L << 31), "msda: spatial_size*heads*channels must fit in int32");
+  DVIS_REQUIRE((long)S * M * D < (1L << 29), "msda: spatial_size*heads*channels must be < 2^29 elements");
   DVIS_REQUIRE((long)Lq * M < (1L << 31) && batch < 65536, "msda: query/batch extent too large");
   return DVIS_OK;
 }
@@ -336,30 +396,21 @@ extern "C" int dvis_msda_fused_forward(const void *value, int value_dtype, const
   p.order = item_order; p.out = out;
   p.N = batch; p.S = spatial_size; p.M = num_heads; p.L = num_levels; p.Lq = num_query; p.P = num_point;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (num_point != 4)
-    return fail(DVIS_ERR_UNSUPPORTED, "msda_fused: num_point %d (only 4 is built; use dvis_msda_forward)", num_point);
-#define DVIS_FUSED(TV, TOUT, DD, LL) return launch_vec<TV, TOUT, DD, 4, true, LL>(p, s)
-#define DVIS_FUSED_L(TV, TOUT, DD)                    \
-  switch (num_levels) {                               \
-    case 1: DVIS_FUSED(TV, TOUT, DD, 1);              \
-    case 3: DVIS_FUSED(TV, TOUT, DD, 3);              \
-    case 4: DVIS_FUSED(TV, TOUT, DD, 4);              \
-    default: break;                                   \
-  }
-#define DVIS_FUSED_D(TV, TOUT)                        \
-  switch (channels) {                                 \
-    case 32: DVIS_FUSED_L(TV, TOUT, 32) break;        \
-    case 64: DVIS_FUSED_L(TV, TOUT, 64) break;        \
-    default: break;                                   \
+  if (num_levels * num_point > kMaxStagedLP)
+    return fail(DVIS_ERR_UNSUPPORTED, "msda_fused: num_levels*num_point %d > %d", num_levels * num_point, kMaxStagedLP);
+#define DVIS_FUSED_D(TV, TOUT)                                              \
+  switch (channels) {                                                       \
+    case 16: return launch_staged<TV, TOUT, 16, true>(p, s);                \
+    case 32: return launch_staged<TV, TOUT, 32, true>(p, s);                \
+    case 64: return launch_staged<TV, TOUT, 64, true>(p, s);                \
+    default: break;                                                         \
   }
   if (value_dtype == DVIS_F32 && out_dtype == DVIS_F32) { DVIS_FUSED_D(float, float) }
   else if (value_dtype == DVIS_BF16 && out_dtype == DVIS_BF16) { DVIS_FUSED_D(__nv_bfloat16, __nv_bfloat16) }
   else if (value_dtype == DVIS_BF16 && out_dtype == DVIS_F32) { DVIS_FUSED_D(__nv_bfloat16, float) }
   else if (value_dtype == DVIS_F32 && out_dtype == DVIS_BF16) { DVIS_FUSED_D(float, __nv_bfloat16) }
 #undef DVIS_FUSED_D
-#undef DVIS_FUSED_L
-#undef DVIS_FUSED
   return fail(DVIS_ERR_UNSUPPORTED,
-              "msda_fused: no kernel for value_dtype=%d out_dtype=%d channels=%d levels=%d (built: f32/bf16, D in {32,64}, L in {1,3,4})",
-              value_dtype, out_dtype, channels, num_levels);
+              "msda_fused: no kernel for value_dtype=%d out_dtype=%d channels=%d (built: f32/bf16 value and output, channels in {16,32,64})",
+              value_dtype, out_dtype, channels);
 }

@@ -101,3 +101,38 @@ def install_as_reference_extension():
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                             im2col_step):
     raise RuntimeError("ms_deform_attn_backward: not built yet")
+
+
+def mask_logits(mask_embed, mask_features, out_dtype=torch.float32):
+    """out[b,q,h,w] = sum_c mask_embed[b,q,c] * mask_features[b,c,h,w] on the tcgen05 tensor path (dvis_mask_logits).
+
+    mask_embed (B,Q,C) any float dtype (cast to bf16; Q*C elements -- negligible); mask_features (B,C,H,W) bf16 in
+    torch.channels_last memory format (that is what the pixel decoder drop-in emits); any other layout / dtype is
+    converted once here.  Q > 256 is processed in slices of 256 queries.
+    Replaces torch.einsum("bqc,bchw->bqhw") (P/dvis_Plus/video_mask2former_transformer_decoder.py:363).
+    """
+    B, Q, C = mask_embed.shape
+    Bf, Cf, H, W = mask_features.shape
+    if Bf != B or Cf != C:
+        raise RuntimeError(f"mask_logits: shape mismatch {tuple(mask_embed.shape)} vs {tuple(mask_features.shape)}")
+    if not mask_features.is_cuda:
+        raise RuntimeError("mask_logits: CUDA tensors required (there is no CPU path)")
+    feat = mask_features
+    if feat.dtype != torch.bfloat16 or not feat.is_contiguous(memory_format=torch.channels_last):
+        feat = feat.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    emb = mask_embed.to(torch.bfloat16).contiguous()
+    out = torch.empty((B, Q, H, W), dtype=out_dtype, device=feat.device)
+    with torch.cuda.device(feat.device):
+        for q0 in range(0, Q, 256):
+            q1 = min(Q, q0 + 256)
+            if q0 == 0 and q1 == Q:
+                e, o = emb, out
+                _lib.call("dvis_mask_logits", e.data_ptr(), feat.data_ptr(), B, Q, C, H * W, o.data_ptr(),
+                          _DTYPE[out_dtype], _stream())
+            else:
+                # a query slice of a (B,Q,HW) output is not one dense block: run per batch element
+                for b in range(B):
+                    e = emb[b, q0:q1].contiguous()
+                    _lib.call("dvis_mask_logits", e.data_ptr(), feat[b].data_ptr(), 1, q1 - q0, C, H * W,
+                              out[b, q0:q1].data_ptr(), _DTYPE[out_dtype], _stream())
+    return out

@@ -71,6 +71,18 @@ int dvis_msda_fused_forward(const void *value, int value_dtype, const int64_t *s
                             int num_query, int num_point, const int32_t *item_order, void *out, int out_dtype,
                             void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Mask logits:  out[b, q, p] = sum_c emb[b, q, c] * feat[b, p, c]      (tcgen05 / TMEM GEMM, TMA-fed)
+ * Replaces torch.einsum("bqc,bchw->bqhw") of the mask head (P/dvis_Plus/video_mask2former_transformer_decoder.py:363)
+ * and "lbtqc,btchw->lbqthw" of tracker / refiner (P/dvis_Plus/tracker.py:379, refiner.py:185-189).
+ *   emb   (B, Q, C)    bf16, row-major
+ *   feat  (B, HW, C)   bf16, channels-last pixel features (an NCHW tensor in torch.channels_last memory format)
+ *   out   (B, Q, HW)   out_dtype (DVIS_F32 or DVIS_BF16), row stride HW; fully overwritten
+ * Constraints: C % 64 == 0, C <= 512, Q <= 256 (split larger query sets), 16-byte aligned emb / feat.
+ */
+int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out,
+                     int out_dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
