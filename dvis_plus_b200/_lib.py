@@ -17,9 +17,10 @@ _vp, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_floa
 # name -> argtypes; mirrors include/dvis_b200.h one to one (tests/test_abi.py cross-checks against the header)
 SIGNATURES = {
     "dvis_msda_forward": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
-    "dvis_msda_fused_forward": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp,
-                                _i, _vp],
+    "dvis_msda_fused_forward": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp,
+                                _vp, _i, _vp],
     "dvis_mask_logits": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp],
+    "dvis_add_layernorm": [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _i64, _i, _f, _vp, _vp, _vp, _i, _vp],
 }
 
 _lib = None

@@ -56,7 +56,8 @@ __device__ __forceinline__ __nv_bfloat16 cvt_logit<__nv_bfloat16>(uint32_t bits)
   return __float2bfloat16_rn(__uint_as_float(bits));
 }
 
-template <typename TO>
+// kTmaStore = false: direct (still coalesced) global stores for outputs whose row pitch is not a multiple of 16 bytes
+template <typename TO, bool kTmaStore>
 __global__ void __launch_bounds__(kThreads, 1)
 mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_emb,
                  const __grid_constant__ CUtensorMap tmap_out, const MaskGemmParams p) {
@@ -164,23 +165,32 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
         uint32_t r[32];
         tmem_ld_32x32(taddr + c0, r);
         tmem_ld_wait();
-        TO *buf = sOut + (n_chunk & 1) * (kEpiCols * kTileM);
-        if (issuer) tma_store_wait_read<1>();          // the store that last read this buffer (2 chunks ago) is done
-        named_barrier_sync(1, kEpiThreads);
+        if constexpr (kTmaStore) {
+          TO *buf = sOut + (n_chunk & 1) * (kEpiCols * kTileM);
+          if (issuer) tma_store_wait_read<1>();          // the store that last read this buffer (2 chunks ago) is done
+          named_barrier_sync(1, kEpiThreads);
 #pragma unroll
-        for (int i = 0; i < kEpiCols; ++i) buf[i * kTileM + px] = cvt_logit<TO>(r[i]);
-        fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
-        named_barrier_sync(2, kEpiThreads);
-        if (issuer) {
-          tma_store_3d(&tmap_out, buf, tile * kTileM, c0, b);
-          tma_store_commit();
+          for (int i = 0; i < kEpiCols; ++i) buf[i * kTileM + px] = cvt_logit<TO>(r[i]);
+          fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
+          named_barrier_sync(2, kEpiThreads);
+          if (issuer) {
+            tma_store_3d(&tmap_out, buf, tile * kTileM, c0, b);
+            tma_store_commit();
+          }
+        } else {
+          const int64_t pix = (int64_t)tile * kTileM + px;
+          if (pix < p.HW) {
+            TO *dst = static_cast<TO *>(p.out) + ((int64_t)b * p.Q + c0) * p.HW + pix;
+            const int nq = min(kEpiCols, p.Q - c0);
+            for (int i = 0; i < nq; ++i) dst[(int64_t)i * p.HW] = cvt_logit<TO>(r[i]);
+          }
         }
       }
       fence_before_thread_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
     }
-    if (issuer) tma_store_wait_read<0>();
+    if (kTmaStore && issuer) tma_store_wait_read<0>();
   }
 
   fence_before_thread_sync();
@@ -226,7 +236,7 @@ extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q,
   p.total_tiles = p.tiles_per_batch * B;
   const int b_bytes = p.KB * p.Qpad * 128;
   const int esize = out_dtype == DVIS_F32 ? 4 : 2;
-  DVIS_REQUIRE(aligned16(out) && (HW * esize) % 16 == 0, "mask_logits: out must be 16-byte aligned and HW*sizeof(out) a multiple of 16");
+  const bool tma_store = aligned16(out) && (HW * esize) % 16 == 0;   // TMA needs a 16-byte row pitch
   const int stage_out_bytes = 2 * kEpiCols * kTileM * esize;
   const int budget = 225 * 1024 - b_bytes - 1024 - stage_out_bytes - int(sizeof(Barriers));
   p.stages = std::min(kMaxStages, budget / kStageBytes);
@@ -236,17 +246,22 @@ extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q,
   CUtensorMap tm_feat, tm_emb, tm_out;
   if (int rc = encode_map(&tm_feat, feat, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, HW, B, kBlockK, kTileM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = encode_map(&tm_emb, emb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, Q, B, kBlockK, p.Qpad, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  if (int rc = encode_map(&tm_out, out, out_dtype == DVIS_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                          esize, HW, Q, B, kTileM, kEpiCols, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  if (tma_store) {
+    if (int rc = encode_map(&tm_out, out, out_dtype == DVIS_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                            esize, HW, Q, B, kTileM, kEpiCols, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  } else {
+    tm_out = tm_emb;   // unused by the direct-store variant; any valid map
+  }
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = std::min(p.total_tiles, kNumSMs);
-  if (out_dtype == DVIS_F32) {
-    cudaFuncSetAttribute(mask_gemm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    mask_gemm_kernel<float><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);
-  } else {
-    cudaFuncSetAttribute(mask_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    mask_gemm_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);
-  }
+#define DVIS_LAUNCH(TO, TMA)                                                                                   \
+  do {                                                                                                         \
+    cudaFuncSetAttribute(mask_gemm_kernel<TO, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));    \
+    mask_gemm_kernel<TO, TMA><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);                         \
+  } while (0)
+  if (out_dtype == DVIS_F32) { if (tma_store) DVIS_LAUNCH(float, true); else DVIS_LAUNCH(float, false); }
+  else { if (tma_store) DVIS_LAUNCH(__nv_bfloat16, true); else DVIS_LAUNCH(__nv_bfloat16, false); }
+#undef DVIS_LAUNCH
   return check_launch("mask_gemm_kernel");
 }

@@ -127,7 +127,17 @@ __device__ __forceinline__ void point_params(A x, A y, A a, int H, int W, int st
 //   phase 1: one thread per (item, point) computes offsets + weights -> smem           (no redundancy)
 //   phase 2: a group of LPR lanes per item walks its points: 2 LDS.128 + 4 predicated LDG.128 + 4*VEC FFMA each
 // ---------------------------------------------------------------------------------------------------
-template <typename T, typename TO, int D, bool FUSED>
+template <typename TP>
+__device__ __forceinline__ float ldp(const TP *p);
+template <>
+__device__ __forceinline__ float ldp<float>(const float *p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ldp<__nv_bfloat16>(const __nv_bfloat16 *p) {
+  return __bfloat162float(__ldg(p));
+}
+
+// TP: dtype of the FUSED path's offsets / logits (float or bf16); unused for the plain op
+template <typename T, typename TO, int D, bool FUSED, typename TP = float>
 __global__ void __launch_bounds__(kThreads, 3) msda_fwd_staged_kernel(const MsdaParams p) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;  // lanes per row
@@ -163,14 +173,14 @@ __global__ void __launch_bounds__(kThreads, 3) msda_fwd_staged_kernel(const Msda
       const bool act = il < nitems;
       const int item = act ? s_item[il] : 0;
       const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
-      const float *lg = static_cast<const float *>(p.attn) + ((size_t)n * p.Lq + q) * p.attn_stride + (size_t)m * LP;
+      const TP *lg = static_cast<const TP *>(p.attn) + ((size_t)n * p.Lq + q) * p.attn_stride + (size_t)m * LP;
       float mx = -INFINITY;
-      for (int i = sub; i < LP; i += 4) mx = fmaxf(mx, act ? __ldg(lg + i) : 0.f);
+      for (int i = sub; i < LP; i += 4) mx = fmaxf(mx, act ? ldp<TP>(lg + i) : 0.f);
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       float sum = 0.f;
       for (int i = sub; i < LP; i += 4) {
-        const float e = act ? __expf(__ldg(lg + i) - mx) : 0.f;
+        const float e = act ? __expf(ldp<TP>(lg + i) - mx) : 0.f;
         if (act) s_prob[il * LP + i] = e;
         sum += e;
       }
@@ -196,9 +206,9 @@ __global__ void __launch_bounds__(kThreads, 3) msda_fwd_staged_kernel(const Msda
         PointOffsets off;
         float4 wt;
         if constexpr (FUSED) {
-          const float *of = static_cast<const float *>(p.loc) + nq * p.loc_stride + ((size_t)m * LP + pt) * 2;
+          const TP *of = static_cast<const TP *>(p.loc) + nq * p.loc_stride + ((size_t)m * LP + pt) * 2;
           const float *rf = p.ref + (nq * p.L + l) * p.ref_dim;
-          const float2 o = __ldg(reinterpret_cast<const float2 *>(of));
+          const float2 o = make_float2(ldp<TP>(of), ldp<TP>(of + 1));
           // loc = ref + off / (W_l, H_l) for 2-d reference points (py:106-109);
           // loc = ref_xy + off / P * ref_wh * 0.5 for boxes (py:110-112)
           const float sx = p.ref_dim == 2 ? 1.f / float(W) : __ldg(rf + 2) * (0.5f / float(P));
@@ -302,7 +312,7 @@ int log2_exact(int v) {
 
 constexpr int kMaxStagedLP = 32;   // L*P beyond this goes to the generic kernel
 
-template <typename T, typename TO, int D, bool FUSED>
+template <typename T, typename TO, int D, bool FUSED, typename TP = float>
 int launch_staged(MsdaParams p, cudaStream_t stream) {
   constexpr int G = 32 / (D / Vec16<T>::N);
   const int per_batch = p.Lq * p.M, LP = p.L * p.P, LPs = LP | 1;
@@ -315,7 +325,7 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
   while (lpc < LP) { lpc <<= 1; ++sh; }
   p.lpc_shift = sh;
   const size_t smem = (size_t)p.items_per_cta * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
-  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED>;
+  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -378,8 +388,8 @@ extern "C" int dvis_msda_forward(const void *value, const int64_t *spatial_shape
 }
 
 extern "C" int dvis_msda_fused_forward(const void *value, int value_dtype, const int64_t *spatial_shapes,
-                                       const int64_t *level_start, const float *offsets, int64_t offsets_stride,
-                                       const float *logits, int64_t logits_stride, const float *ref, int ref_dim,
+                                       const int64_t *level_start, const void *offsets, int64_t offsets_stride,
+                                       const void *logits, int64_t logits_stride, int param_dtype, const float *ref, int ref_dim,
                                        int batch, int spatial_size, int num_heads, int channels, int num_levels,
                                        int num_query, int num_point, const int32_t *item_order, void *out,
                                        int out_dtype, void *stream) {
@@ -387,9 +397,8 @@ extern "C" int dvis_msda_fused_forward(const void *value, int value_dtype, const
                                channels, num_levels, num_query, num_point))
     return rc;
   DVIS_REQUIRE(ref && (ref_dim == 2 || ref_dim == 4), "msda_fused: reference points must be 2-d or 4-d");
-  DVIS_REQUIRE(aligned16(value) && aligned16(out) && (reinterpret_cast<uintptr_t>(offsets) & 7u) == 0 &&
-                   offsets_stride % 2 == 0,
-               "msda_fused: value/out must be 16-byte aligned, offsets 8-byte aligned");
+  DVIS_REQUIRE(aligned16(value) && aligned16(out), "msda_fused: value/out must be 16-byte aligned");
+  DVIS_REQUIRE(param_dtype == DVIS_F32 || param_dtype == DVIS_BF16, "msda_fused: offsets/logits must be f32 or bf16");
   MsdaParams p{};
   p.value = value; p.shapes = spatial_shapes; p.level_start = level_start; p.loc = offsets; p.attn = logits;
   p.ref = ref; p.ref_dim = ref_dim; p.loc_stride = offsets_stride; p.attn_stride = logits_stride;
@@ -398,12 +407,15 @@ extern "C" int dvis_msda_fused_forward(const void *value, int value_dtype, const
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (num_levels * num_point > kMaxStagedLP)
     return fail(DVIS_ERR_UNSUPPORTED, "msda_fused: num_levels*num_point %d > %d", num_levels * num_point, kMaxStagedLP);
-#define DVIS_FUSED_D(TV, TOUT)                                              \
-  switch (channels) {                                                       \
-    case 16: return launch_staged<TV, TOUT, 16, true>(p, s);                \
-    case 32: return launch_staged<TV, TOUT, 32, true>(p, s);                \
-    case 64: return launch_staged<TV, TOUT, 64, true>(p, s);                \
-    default: break;                                                         \
+#define DVIS_FUSED_D(TV, TOUT)                                                                          \
+  switch (channels) {                                                                                   \
+    case 16: return param_dtype == DVIS_F32 ? launch_staged<TV, TOUT, 16, true, float>(p, s)            \
+                                            : launch_staged<TV, TOUT, 16, true, __nv_bfloat16>(p, s);   \
+    case 32: return param_dtype == DVIS_F32 ? launch_staged<TV, TOUT, 32, true, float>(p, s)            \
+                                            : launch_staged<TV, TOUT, 32, true, __nv_bfloat16>(p, s);   \
+    case 64: return param_dtype == DVIS_F32 ? launch_staged<TV, TOUT, 64, true, float>(p, s)            \
+                                            : launch_staged<TV, TOUT, 64, true, __nv_bfloat16>(p, s);   \
+    default: break;                                                                                     \
   }
   if (value_dtype == DVIS_F32 && out_dtype == DVIS_F32) { DVIS_FUSED_D(float, float) }
   else if (value_dtype == DVIS_BF16 && out_dtype == DVIS_BF16) { DVIS_FUSED_D(__nv_bfloat16, __nv_bfloat16) }

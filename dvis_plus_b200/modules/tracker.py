@@ -1,0 +1,208 @@
+"""Drop-in for ReferringTracker_noiser and Noiser (P/dvis_Plus/tracker.py:94-380, P/dvis_Plus/noiser.py).
+
+Same constructor keywords, parameter names, recurrent state (`last_outputs`, `last_frame_embeds`,
+`last_reference`, `_clear_memory`) and output dictionary.  Inference-path differences:
+  * the 1x1 `mask_feature_proj` conv over all (T, C, H, W) mask features (py:199) is folded into the query side:
+        einsum(me, W F + b) = einsum(W^T me, F) + me . b
+    so the projected feature maps are never materialised (saves one read + one write of T*C*H*W per window);
+  * the mask einsum (py:379) runs on the tcgen05 mask GEMM;
+  * `with_masks=False` skips mask prediction altogether -- the offline meta-architecture deletes the tracker's
+    masks right after the call (P/dvis_Plus/meta_architecture.py:1486).
+"""
+import random
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from .blocks import MLP, FFNLayer, ReferringCrossAttentionLayer, SelfAttentionLayer, _fast_path, linear
+from .pixel_decoder import _c2_xavier_fill
+
+
+class Noiser:
+    """P/dvis_Plus/noiser.py: Hungarian matching of the current frame's queries to the previous frame's (the noise
+    branches only fire in training)."""
+
+    def __init__(self, noise_ratio=0.8, mode="wa"):
+        assert mode in ["none", "rs", "wa", "cc"]
+        self.mode = mode
+        self.noise_ratio = noise_ratio
+
+    def _rs_noise_forward(self, cur_embeds):
+        indices = list(range(cur_embeds.shape[0]))
+        np.random.shuffle(indices)
+        return indices, cur_embeds[indices]
+
+    def _wa_noise_forward(self, cur_embeds):
+        indices = list(range(cur_embeds.shape[0]))
+        np.random.shuffle(indices)
+        noise_init = cur_embeds[indices]
+        weight_ratio = torch.rand(cur_embeds.shape[0], 1, 1)
+        noise_init = cur_embeds * weight_ratio.to(cur_embeds) + noise_init * (1.0 - weight_ratio.to(cur_embeds))
+        ret = torch.arange(cur_embeds.shape[0], dtype=torch.int64).numpy()
+        sel = (weight_ratio[:, 0, 0] < 0.5).to(torch.bool).numpy()
+        ret[sel] = np.array(indices)[sel]
+        return list(ret), noise_init
+
+    def _cc_noise_forward(self, cur_embeds):
+        C = cur_embeds.shape[-1]
+        indices = torch.randint(0, C, (cur_embeds.shape[0],)).unsqueeze(-1).unsqueeze(-1)
+        weight = torch.arange(C, dtype=torch.int64).unsqueeze(0).unsqueeze(0)
+        weight = (weight < indices).to(torch.float32).to(cur_embeds)
+        indices_, cur_embeds_ = self._rs_noise_forward(cur_embeds)
+        ret_embeds = cur_embeds * weight + cur_embeds_ * (1 - weight)
+        ret = torch.arange(cur_embeds.shape[0], dtype=torch.int64).numpy()
+        sel = (indices[:, 0, 0] < C // 2).to(torch.bool).numpy()
+        ret[sel] = np.array(indices_)[sel]
+        return list(ret), ret_embeds
+
+    def match_embds(self, ref_embds, cur_embds):
+        """noiser.py:43-56: cosine cost, scipy.optimize.linear_sum_assignment on the host."""
+        from scipy.optimize import linear_sum_assignment
+        ref_embds, cur_embds = ref_embds.detach()[:, 0, :].float(), cur_embds.detach()[:, 0, :].float()
+        ref_embds = ref_embds / (ref_embds.norm(dim=1)[:, None] + 1e-6)
+        cur_embds = cur_embds / (cur_embds.norm(dim=1)[:, None] + 1e-6)
+        C = 1 - torch.mm(cur_embds, ref_embds.transpose(0, 1))
+        C = C.cpu()
+        C = torch.where(torch.isnan(C), torch.full_like(C, 0), C)
+        return linear_sum_assignment(C.transpose(0, 1))[1]
+
+    def __call__(self, ref_embeds, cur_embeds, cur_embeds_no_norm=None, activate=False, cur_classes=None):
+        if cur_embeds_no_norm is None:
+            cur_embeds_no_norm = cur_embeds
+        matched_indices = self.match_embds(ref_embeds, cur_embeds)
+        if activate and random.random() < self.noise_ratio:
+            if self.mode == "rs":
+                return self._rs_noise_forward(cur_embeds_no_norm)
+            if self.mode == "wa":
+                return self._wa_noise_forward(cur_embeds_no_norm)
+            if self.mode == "cc":
+                return self._cc_noise_forward(cur_embeds_no_norm)
+        return matched_indices, cur_embeds_no_norm[matched_indices]
+
+
+class ReferringTracker_noiser(nn.Module):
+    def __init__(self, hidden_channel=256, feedforward_channel=2048, num_head=8, decoder_layer_num=6, mask_dim=256,
+                 class_num=25, noise_mode="hard", noise_ratio=0.5):
+        super().__init__()
+        self.num_heads = num_head
+        self.num_layers = decoder_layer_num
+        self.transformer_self_attention_layers = nn.ModuleList()
+        self.transformer_cross_attention_layers = nn.ModuleList()
+        self.transformer_ffn_layers = nn.ModuleList()
+        for _ in range(self.num_layers):
+            self.transformer_self_attention_layers.append(SelfAttentionLayer(hidden_channel, num_head, 0.0))
+            self.transformer_cross_attention_layers.append(ReferringCrossAttentionLayer(hidden_channel, num_head, 0.0))
+            self.transformer_ffn_layers.append(FFNLayer(hidden_channel, feedforward_channel, 0.0))
+        self.use_memory = False
+        self.decoder_norm = nn.LayerNorm(hidden_channel)
+        self.class_embed = nn.Linear(2 * hidden_channel, class_num + 1)
+        self.mask_embed = MLP(hidden_channel, hidden_channel, mask_dim, 3)
+        self.ref_proj = MLP(hidden_channel, hidden_channel, hidden_channel, 3)
+        for layer in self.ref_proj.layers:
+            _c2_xavier_fill(layer)
+        self.mask_feature_proj = nn.Conv2d(mask_dim, mask_dim, kernel_size=1, stride=1, padding=0)
+        self.last_outputs = None
+        self.last_frame_embeds = None
+        self.last_reference = None
+        # the reference passes noise_mode='hard' by default, which its Noiser asserts against; DVIS configs set it
+        self.noiser = Noiser(noise_ratio=noise_ratio, mode=noise_mode if noise_mode != "hard" else "none")
+
+    def _clear_memory(self):
+        self.last_outputs = None
+        self.last_reference = None
+
+    def _layer_stack(self, identity, tgt_fn, frame_key, memory):
+        """6 x (referring cross-attn -> self-attn -> FFN); tgt_fn(j, ms_output) gives the query of layer j (py:236-329)."""
+        ms_output = [identity]
+        for j in range(self.num_layers):
+            output = self.transformer_cross_attention_layers[j](ms_output[-1], tgt_fn(j, ms_output), frame_key, memory,
+                                                                memory_mask=None, memory_key_padding_mask=None,
+                                                                pos=None, query_pos=None)
+            output = self.transformer_self_attention_layers[j](output, tgt_mask=None, tgt_key_padding_mask=None, query_pos=None)
+            output = self.transformer_ffn_layers[j](output)
+            ms_output.append(output)
+        return ms_output
+
+    def forward(self, frame_embeds, mask_features, resume=False, return_indices=False, frame_classes=None,
+                frame_embeds_no_norm=None, with_masks=True):
+        """frame_embeds (b, c, t, q); mask_features (b, t, c, h, w) (may be None when with_masks=False)."""
+        frame_embeds = frame_embeds.permute(2, 3, 0, 1).float()                  # t, q, b, c
+        if frame_embeds_no_norm is not None:
+            frame_embeds_no_norm = frame_embeds_no_norm.permute(2, 3, 0, 1).float()
+        n_frame = frame_embeds.shape[0]
+        outputs, ret_indices, all_refs = [], [], []
+        for i in range(n_frame):
+            cur = frame_embeds[i]
+            cur_nn = frame_embeds_no_norm[i] if frame_embeds_no_norm is not None else cur
+            cur_cls = None if frame_classes is None else frame_classes[i]
+            frame_key = cur_nn
+            if i == 0 and resume is False:
+                self._clear_memory()
+                indices, noised_init = self.noiser(cur, cur, cur_embeds_no_norm=cur_nn, activate=False, cur_classes=cur_cls)
+                self.last_frame_embeds = cur[indices]
+                ret_indices.append(indices)
+                ms_output = self._layer_stack(
+                    noised_init, lambda j, ms: self.ref_proj(frame_key if j == 0 else ms[-1]).float(), frame_key, cur_nn)
+                ms_output[0] = cur_nn[indices]
+                self.last_reference = self.ref_proj(frame_key).float()
+            else:
+                reference = self.ref_proj(self.last_outputs[-1]).float()
+                self.last_reference = reference
+                indices, noised_init = self.noiser(self.last_frame_embeds, cur, cur_embeds_no_norm=cur_nn,
+                                                   activate=self.training, cur_classes=cur_cls)
+                self.last_frame_embeds = cur[indices]
+                ret_indices.append(indices)
+                ms_output = self._layer_stack(noised_init, lambda j, ms: reference, frame_key, cur_nn)
+                ms_output[0] = cur_nn[indices]
+            all_refs.append(self.last_reference)
+            ms_output = torch.stack([m.float() for m in ms_output], dim=0)      # (1 + layers, q, b, c)
+            self.last_outputs = ms_output
+            outputs.append(ms_output[1:])
+        outputs = torch.stack(outputs, dim=0)                                    # (t, l, q, b, c)
+        all_refs = torch.stack(all_refs, dim=0)                                  # (t, q, b, c)
+        if not self.training:
+            outputs = outputs[:, -1:]
+        outputs_class, outputs_masks = self.prediction(outputs, mask_features, all_refs, with_masks=with_masks)
+        out = {
+            "pred_logits": outputs_class[-1].transpose(1, 2),                    # (b, t, q, c)
+            "pred_masks": None if outputs_masks is None else outputs_masks[-1],   # (b, q, t, h, w)
+            "aux_outputs": self._set_aux_loss(outputs_class, outputs_masks),
+            "pred_embds": outputs[:, -1].permute(2, 3, 0, 1),                    # (b, c, t, q)
+            "pred_references": all_refs.permute(2, 3, 0, 1),
+        }
+        return (out, ret_indices) if return_indices else out
+
+    @torch.jit.unused
+    def _set_aux_loss(self, outputs_class, outputs_seg_masks):
+        if outputs_seg_masks is None:
+            return [{"pred_logits": a.transpose(1, 2)} for a in outputs_class[:-1]]
+        return [{"pred_logits": a.transpose(1, 2), "pred_masks": b} for a, b in zip(outputs_class[:-1], outputs_seg_masks[:-1])]
+
+    def prediction(self, outputs, mask_features, references, with_masks=True):
+        """py:368-380.  outputs (t,l,q,b,c); mask_features (b,t,c,h,w) *un-projected*; references (t,q,b,c)."""
+        decoder_output = self.decoder_norm(outputs.float()).permute(1, 3, 0, 2, 4)          # (l, b, t, q, c)
+        references = references.unsqueeze(1).repeat(1, decoder_output.size(0), 1, 1, 1).permute(1, 3, 0, 2, 4)
+        outputs_class = linear(self.class_embed, torch.cat([references, decoder_output], dim=-1)).float().transpose(2, 3)
+        if not with_masks:
+            return outputs_class, None
+        mask_embed = self.mask_embed(decoder_output).float()                               # (l, b, t, q, c)
+        W = self.mask_feature_proj.weight.flatten(1).float()                               # (c_out, c_in)
+        bias = self.mask_feature_proj.bias.float()
+        if _fast_path(mask_features):
+            # fold the 1x1 conv into the embeddings: me' = me @ W  (c_in), offset = me . b
+            l, b, t, q, c = mask_embed.shape
+            me_f = torch.matmul(mask_embed, W)
+            offs = torch.matmul(mask_embed, bias)                                          # (l, b, t, q)
+            masks = []
+            for li in range(l):
+                feats = mask_features.flatten(0, 1)                                        # (b*t, c, h, w)
+                m = ops.mask_logits(me_f[li].flatten(0, 1), feats, torch.float32)          # (b*t, q, h, w)
+                m = m.reshape(b, t, q, *m.shape[-2:]) + offs[li][..., None, None]
+                masks.append(m.permute(0, 2, 1, 3, 4))
+            return outputs_class, torch.stack(masks, 0)
+        shape = mask_features.shape
+        mf = F.conv2d(mask_features.flatten(0, 1).float(), self.mask_feature_proj.weight, self.mask_feature_proj.bias).reshape(shape)
+        return outputs_class, torch.einsum("lbtqc,btchw->lbqthw", mask_embed, mf)

@@ -67,13 +67,14 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
                        num_levels, num_points, item_order=None, out_dtype=None):
     """Fused softmax + location arithmetic + gather (dvis_msda_fused_forward).
 
-    value (N,S,M,D) f32|bf16; offsets (N,Lq,M*L*P*2) and logits (N,Lq,M*L*P) f32 -- possibly column slices of one
+    value (N,S,M,D) f32|bf16; offsets (N,Lq,M*L*P*2) and logits (N,Lq,M*L*P) f32|bf16 -- possibly column slices of one
     (N,Lq,M*L*P*3) tensor (last dim contiguous); reference_points (N,Lq,L,2|4) f32.
     """
     N, S, M, D = value.shape
     Lq = offsets.shape[1]
     assert value.is_contiguous() and reference_points.is_contiguous()
-    assert offsets.dtype == torch.float32 and logits.dtype == torch.float32 and reference_points.dtype == torch.float32
+    assert offsets.dtype == logits.dtype and offsets.dtype in (torch.float32, torch.bfloat16)
+    assert reference_points.dtype == torch.float32
     assert offsets.stride(-1) == 1 and logits.stride(-1) == 1
     assert offsets.stride(0) == offsets.stride(1) * Lq and logits.stride(0) == logits.stride(1) * Lq
     out_dtype = out_dtype or value.dtype
@@ -82,7 +83,8 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     with torch.cuda.device(value.device):
         _lib.call("dvis_msda_fused_forward", value.data_ptr(), _DTYPE[value.dtype], spatial_shapes.data_ptr(),
                   level_start_index.data_ptr(), offsets.data_ptr(), offsets.stride(1), logits.data_ptr(),
-                  logits.stride(1), reference_points.data_ptr(), reference_points.shape[-1], N, S, M, D, num_levels,
+                  logits.stride(1), _DTYPE[offsets.dtype], reference_points.data_ptr(), reference_points.shape[-1],
+                  N, S, M, D, num_levels,
                   Lq, num_points, order_ptr, out.data_ptr(), _DTYPE[out_dtype], _stream())
     return out
 
@@ -136,3 +138,32 @@ def mask_logits(mask_embed, mask_features, out_dtype=torch.float32):
                     _lib.call("dvis_mask_logits", e.data_ptr(), feat[b].data_ptr(), 1, q1 - q0, C, H * W,
                               out[b, q0:q1].data_ptr(), _DTYPE[out_dtype], _stream())
     return out
+
+
+def add_layernorm(x, residual, weight, bias, eps=1e-5, *, want_f32=True, lp_dtype=None, pos=None):
+    """LayerNorm(x + residual) in one pass (dvis_add_layernorm).
+
+    x, residual: (..., C) f32|bf16 contiguous (residual may be None).  Returns (y_f32 | None, y_lp | None, y_lp_pos | None)
+    where y_lp is a copy in `lp_dtype` and y_lp_pos = y + pos (pos: (rows_p, C) f32 broadcast over leading rows).
+    """
+    C = x.shape[-1]
+    rows = x.numel() // C
+    assert x.is_cuda and x.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.shape == x.shape))
+    w = weight if weight.dtype == torch.float32 else weight.float()
+    b = bias if bias.dtype == torch.float32 else bias.float()
+    out_f32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_f32 else None
+    out_lp = torch.empty(x.shape, dtype=lp_dtype, device=x.device) if lp_dtype is not None else None
+    out_lp_pos = None
+    pos_rows = 0
+    if pos is not None:
+        assert lp_dtype is not None and pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape[-1] == C
+        pos_rows = pos.numel() // C
+        assert rows % pos_rows == 0
+        out_lp_pos = torch.empty(x.shape, dtype=lp_dtype, device=x.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(x.device):
+        _lib.call("dvis_add_layernorm", x.data_ptr(), _DTYPE[x.dtype], ptr(residual),
+                  _DTYPE[residual.dtype] if residual is not None else DVIS_F32, w.data_ptr(), b.data_ptr(), ptr(pos),
+                  pos_rows, rows, C, float(eps), ptr(out_f32), ptr(out_lp), ptr(out_lp_pos),
+                  _DTYPE[lp_dtype] if lp_dtype is not None else DVIS_F32, _stream())
+    return out_f32, out_lp, out_lp_pos

@@ -58,15 +58,16 @@ int dvis_msda_forward(const void *value, const int64_t *spatial_shapes, const in
  * takes the raw outputs of the sampling_offsets / attention_weights linears and the reference points and does
  * softmax over L*P (py:104), location = ref + offset / (W_l, H_l) (py:106-109, 2-d reference points) or the
  * box form (py:110-112, 4-d), bilinear gather and the weighted reduction in one pass.
- *   offsets   (batch, num_query, num_heads, num_levels, num_point, 2) f32, row stride `offsets_stride` elements
- *   logits    (batch, num_query, num_heads, num_levels*num_point)     f32, row stride `logits_stride` elements
- *             (strides let both live in one fused linear output of width M*L*P*3)
+ *   offsets   (batch, num_query, num_heads, num_levels, num_point, 2), row stride `offsets_stride` elements
+ *   logits    (batch, num_query, num_heads, num_levels*num_point),    row stride `logits_stride` elements
+ *             both of `param_dtype` (DVIS_F32 or DVIS_BF16); the strides let both live in one fused linear
+ *             output of width M*L*P*3
  *   ref       (batch, num_query, num_levels, ref_dim) f32, ref_dim = 2 or 4
  *   value     f32 or bf16 (value_dtype); out f32 or bf16 (out_dtype)
  */
 int dvis_msda_fused_forward(const void *value, int value_dtype, const int64_t *spatial_shapes,
-                            const int64_t *level_start, const float *offsets, int64_t offsets_stride,
-                            const float *logits, int64_t logits_stride, const float *ref, int ref_dim,
+                            const int64_t *level_start, const void *offsets, int64_t offsets_stride,
+                            const void *logits, int64_t logits_stride, int param_dtype, const float *ref, int ref_dim,
                             int batch, int spatial_size, int num_heads, int channels, int num_levels,
                             int num_query, int num_point, const int32_t *item_order, void *out, int out_dtype,
                             void *stream);
@@ -82,6 +83,22 @@ int dvis_msda_fused_forward(const void *value, int value_dtype, const int64_t *s
  */
 int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out,
                      int out_dtype, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * y = LayerNorm(x + residual) * gamma + beta over the last dim C, one pass.
+ * The post-norm residual blocks of the path: MSDeformAttnTransformerEncoderLayer.forward
+ * (P/mask2former/modeling/pixel_decoder/msdeformattn.py:118-119,125-126) and SelfAttentionLayer / CrossAttentionLayer /
+ * FFNLayer.forward_post (P/mask2former_video/modeling/transformer_decoder/video_mask2former_transformer_decoder.py:48-49,
+ * 109-110,165-166; P/dvis_Plus/tracker.py:50-51).
+ *   x (rows, C) x_dtype; residual (rows, C) residual_dtype or NULL; gamma, beta (C,) f32
+ *   outputs, each optional (NULL to skip): out_f32 (rows, C) f32; out_lp (rows, C) lp_dtype -- the copy the next
+ *   GEMM reads; out_lp_pos (rows, C) lp_dtype = y + pos[row % pos_rows] (with_pos_embed, msdeformattn.py:112-114),
+ *   pos (pos_rows, C) f32.
+ * dtypes: DVIS_F32 or DVIS_BF16.  C must be a multiple of 128 (built: 128..1024, 2048).
+ */
+int dvis_add_layernorm(const void *x, int x_dtype, const void *residual, int residual_dtype, const float *gamma,
+                       const float *beta, const float *pos, int64_t pos_rows, int64_t rows, int C, float eps,
+                       float *out_f32, void *out_lp, void *out_lp_pos, int lp_dtype, void *stream);
 
 #ifdef __cplusplus
 }
