@@ -17,6 +17,7 @@ _vp, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_floa
 # name -> argtypes; mirrors include/dvis_b200.h one to one (tests/test_abi.py cross-checks against the header)
 SIGNATURES = {
     "dvis_msda_forward": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "dvis_msda_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "dvis_msda_fused_forward": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp,
                                 _vp, _i, _vp],
     "dvis_mask_logits": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp],
@@ -47,11 +48,39 @@ def lib():
     return _lib
 
 
+_timing = None  # list of (name, start_event, end_event) while per-kernel timing is on (bench.py roofline)
+
+
+def start_timing():
+    global _timing
+    _timing = []
+
+
+def stop_timing():
+    """-> {entry point: (launches, total milliseconds)} measured with CUDA events on the launching stream."""
+    global _timing
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, s, e in _timing or []:
+        n, t = out.get(name, (0, 0.0))
+        out[name] = (n + 1, t + s.elapsed_time(e))
+    _timing = None
+    return out
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point; raise RuntimeError (like the reference's c10::Error) on a non-zero status."""
     global launch_count
     l = lib()
+    if _timing is not None:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
     rc = getattr(l, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {l.dvis_last_error().decode()}")
+    if _timing is not None:
+        e.record()
+        _timing.append((name, s, e))
     launch_count += 1

@@ -47,8 +47,8 @@ class TemporalRefiner(nn.Module):
         y = F.conv1d(F.pad(F.relu(y), (1, 1), mode="replicate"), c3.weight.to(dt), c3.bias.to(dt))
         return y
 
-    def forward(self, instance_embeds, frame_embeds, mask_features, with_masks=True):
-        """instance_embeds, frame_embeds (b, c, t, q); mask_features (b, t, c, h, w)."""
+    def refine(self, instance_embeds, frame_embeds):
+        """The 6 refinement layers (py:104-145).  (b, c, t, q) x2 -> stacked per-layer outputs (t, l, q, b, c), fp32."""
         n_batch, n_channel, n_frames, n_instance = instance_embeds.size()
         outputs = []
         output = instance_embeds.float()
@@ -66,7 +66,18 @@ class TemporalRefiner(nn.Module):
             output = self.transformer_ffn_layers[i](output)
             output = output.reshape(n_instance, n_batch, n_frames, n_channel).permute(1, 3, 2, 0)                 # (b, c, t, q)
             outputs.append(output)
-        outputs = torch.stack(outputs, dim=0).permute(3, 0, 4, 1, 2)                 # (l, b, c, t, q) -> (t, l, q, b, c)
+        return torch.stack(outputs, dim=0).permute(3, 0, 4, 1, 2)                    # (l, b, c, t, q) -> (t, l, q, b, c)
+
+    def predict_masks(self, outputs, mask_features):
+        """Masks of the last layer for a slice of frames: outputs (t', l, q, b, c) of `refine`, mask_features
+        (b, t', c, h, w) of the SAME frames -> (b, q, t', h, w).  Lets every rank of a frame-sharded clip finish only
+        its own frames against its local mask features."""
+        dec = self.decoder_norm(outputs[:, -1:]).permute(1, 3, 0, 2, 4)              # (1, b, t', q, c)
+        return self._masks(self.mask_embed(dec).float(), mask_features)[-1]
+
+    def forward(self, instance_embeds, frame_embeds, mask_features, with_masks=True):
+        """instance_embeds, frame_embeds (b, c, t, q); mask_features (b, t, c, h, w)."""
+        outputs = self.refine(instance_embeds, frame_embeds)
         outputs_class, outputs_masks = self.prediction(outputs, mask_features, with_masks=with_masks)
         outputs = self.decoder_norm(outputs)
         return {
@@ -82,12 +93,14 @@ class TemporalRefiner(nn.Module):
             return [{"pred_logits": a.transpose(1, 2)} for a in outputs_class[:-1]]
         return [{"pred_logits": a.transpose(1, 2), "pred_masks": b} for a, b in zip(outputs_class[:-1], outputs_seg_masks[:-1])]
 
+    mask_dtype = torch.float32   # dtype of the inference-path mask logits (torch.bfloat16 halves the write traffic)
+
     def _masks(self, mask_embed, mask_features):
         """einsum "lbtqc,btchw->lbqthw" (py:185-189,223)."""
         if _fast_path(mask_features):
             l, b, t, q, c = mask_embed.shape
             feats = mask_features.flatten(0, 1)
-            out = [ops.mask_logits(mask_embed[li].flatten(0, 1), feats, torch.float32)
+            out = [ops.mask_logits(mask_embed[li].flatten(0, 1), feats, self.mask_dtype)
                    .reshape(b, t, q, *mask_features.shape[-2:]).permute(0, 2, 1, 3, 4) for li in range(l)]
             return torch.stack(out, 0)
         return torch.einsum("lbtqc,btchw->lbqthw", mask_embed.float(), mask_features.float())

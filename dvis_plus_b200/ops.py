@@ -102,7 +102,26 @@ def install_as_reference_extension():
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                             im2col_step):
-    raise RuntimeError("ms_deform_attn_backward: not built yet")
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight]  (OPS/src/vision.cpp:20, ms_deform_attn_cuda.cu:88-158)."""
+    _check_cuda_contig(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                       sampling_loc=sampling_loc, attn_weight=attn_weight, grad_output=grad_output)
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    step = min(N, int(im2col_step))
+    if N % step != 0:
+        raise RuntimeError(f"batch({N}) must divide im2col_step({step})")
+    if value.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError(f'"ms_deform_attn_backward_cuda" not implemented for \'{value.dtype}\'')
+    grad_value = torch.zeros_like(value)
+    grad_loc = torch.zeros_like(sampling_loc)
+    grad_attn = torch.zeros_like(attn_weight)
+    if value.numel() and sampling_loc.numel():
+        with torch.cuda.device(value.device):
+            _lib.call("dvis_msda_backward", value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                      sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(), N, S, M, D, L, Lq, P,
+                      _DTYPE[value.dtype], grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(), _stream())
+    return [grad_value, grad_loc, grad_attn]
 
 
 def mask_logits(mask_embed, mask_features, out_dtype=torch.float32):

@@ -54,6 +54,16 @@ int dvis_msda_forward(const void *value, const int64_t *spatial_shapes, const in
                       int num_heads, int channels, int num_levels, int num_query, int num_point, int dtype,
                       const int32_t *item_order, void *out, void *stream);
 
+/* Multi-scale deformable attention, backward.
+ * Replaces MSDA.ms_deform_attn_backward (OPS/src/vision.cpp:20 -> ms_deform_attn_cuda.cu:88-158 ->
+ * ms_deformable_col2im_cuda, cuh:961-1331).  grad_value / grad_sampling_loc / grad_attn_weight must be
+ * zero-filled by the caller (the reference does at::zeros_like, cu:126-128). */
+int dvis_msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                       const void *sampling_loc, const void *attn_weight, const void *grad_out, int batch,
+                       int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                       int num_point, int dtype, void *grad_value, void *grad_sampling_loc,
+                       void *grad_attn_weight, void *stream);
+
 /* Fused variant used by the module-level drop-in (MSDeformAttn.forward, OPS/modules/ms_deform_attn.py:98-118):
  * takes the raw outputs of the sampling_offsets / attention_weights linears and the reference points and does
  * softmax over L*P (py:104), location = ref + offset / (W_l, H_l) (py:106-109, 2-d reference points) or the
