@@ -52,6 +52,12 @@ class OfflineClipRunner:
         pred_masks (1, Q, t_local, H/4, W/4) for this rank's frames."""
         mask_features, _, multi_scale = self.pixel_decoder.forward_features(features)
         seg = self.predictor(multi_scale, mask_features)
+        return self.temporal_stage(seg, mask_features)
+
+    @torch.no_grad()
+    def temporal_stage(self, seg, mask_features):
+        """Exchange + tracker + refiner + final masks, given this rank's segmenter outputs (`seg`: the predictor's
+        dict for t_local frames) and its local mask features (t_local, C, H, W)."""
         C = seg["pred_embds"].shape[1]
         t_local = mask_features.shape[0]
         block = self.gather_queries(self.pack_queries(seg))

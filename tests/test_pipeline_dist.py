@@ -1,0 +1,81 @@
+"""Host-side logic of the frame-sharded clip pipeline on CPU with the gloo backend, world_size 2:
+the packed query all-gather keeps temporal order, tracker + refiner are identical on all ranks, each rank produces the
+masks of its own frames, and the sharded result equals the single-process result."""
+import os
+import socket
+import tempfile
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dvis_plus_b200 import modules as M
+from dvis_plus_b200.pipeline import OfflineClipRunner
+
+T, Q, C, K, H, W = 4, 10, 64, 5, 8, 12
+
+
+def _models():
+    torch.manual_seed(0)
+    trk = M.ReferringTracker_noiser(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2,
+                                    mask_dim=32, class_num=K, noise_mode="none").eval()
+    rfn = M.TemporalRefiner(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=32,
+                            class_num=K, windows=2).eval()
+    return trk, rfn
+
+
+def _seg_inputs():
+    g = torch.Generator().manual_seed(1)
+    return dict(pred_embds=torch.randn(1, C, T, Q, generator=g), pred_embds_without_norm=torch.randn(1, C, T, Q, generator=g),
+                pred_logits=torch.randn(1, T, Q, K + 1, generator=g)), torch.randn(T, 32, H, W, generator=g)
+
+
+def _slice(seg, mf, t0, t1):
+    return dict(pred_embds=seg["pred_embds"][:, :, t0:t1], pred_embds_without_norm=seg["pred_embds_without_norm"][:, :, t0:t1],
+                pred_logits=seg["pred_logits"][:, t0:t1]), mf[t0:t1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        trk, rfn = _models()
+        runner = OfflineClipRunner(None, None, trk, rfn)
+        assert runner.world == world and runner.rank == rank
+        seg, mf = _seg_inputs()
+        t = T // world
+        seg_r, mf_r = _slice(seg, mf, rank * t, (rank + 1) * t)
+        block = runner.gather_queries(runner.pack_queries(seg_r))
+        assert torch.equal(block, runner.pack_queries(seg))          # contiguous blocks -> temporal order preserved
+        out = runner.temporal_stage(seg_r, mf_r)
+        torch.save({k: v for k, v in out.items()}, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_sharded_pipeline_world2_matches_single_process():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(2, port, d), nprocs=2, join=True)
+        r0 = torch.load(os.path.join(d, "rank0.pt"))
+        r1 = torch.load(os.path.join(d, "rank1.pt"))
+    trk, rfn = _models()
+    single = OfflineClipRunner(None, None, trk, rfn)
+    assert single.world == 1
+    seg, mf = _seg_inputs()
+    ref = single.temporal_stage(seg, mf)
+    for k in ("pred_logits", "pred_embds", "online_pred_logits"):
+        assert torch.equal(r0[k], r1[k]), k                           # replicated stage is bit-identical across ranks
+        assert torch.allclose(r0[k], ref[k], atol=1e-6), k
+    masks = torch.cat([r0["pred_masks"], r1["pred_masks"]], dim=2)    # (1, Q, T, H, W): rank order == frame order
+    assert torch.allclose(masks, ref["pred_masks"], atol=1e-5)
+
+
+def test_pack_unpack_roundtrip():
+    seg, _ = _seg_inputs()
+    block = OfflineClipRunner.pack_queries(seg)
+    assert block.shape == (T, Q, 2 * C + K + 1)
+    e, n, l = OfflineClipRunner.unpack_queries(block, C)
+    assert torch.equal(e, seg["pred_embds"]) and torch.equal(n, seg["pred_embds_without_norm"]) and torch.equal(l, seg["pred_logits"])
