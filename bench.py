@@ -38,7 +38,9 @@ def synthetic_features(T, backbone="swinl", seed=0, dtype=torch.bfloat16, pin=Fa
     feats = {}
     for k, c in BACKBONE_CHANNELS[backbone].items():
         h, w = hw[0] // STRIDES[k], hw[1] // STRIDES[k]
-        t = torch.empty(T, c, h, w, dtype=dtype)
+        # channels_last memory (logical NCHW): what Swin / ViT backbones natively produce (token-major) before the
+        # reference permutes them (P/mask2former/modeling/backbone/swin.py); the pixel decoder accepts either layout
+        t = torch.empty(T, c, h, w, dtype=dtype).contiguous(memory_format=torch.channels_last)
         for i in range(T):
             t[i] = torch.randn(c, h, w, generator=g).to(dtype)
         feats[k] = t.pin_memory() if pin else t
@@ -208,7 +210,7 @@ def main():
     runner = build_models(dev, queries=Q)
     t_local = T // world
     host = synthetic_features(T, pin=False)
-    host = {k: v[rank * t_local:(rank + 1) * t_local].contiguous().pin_memory() for k, v in host.items()}
+    host = {k: v[rank * t_local:(rank + 1) * t_local].contiguous(memory_format=torch.channels_last).pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 

@@ -1,0 +1,170 @@
+// GroupNorm for channels-last (N, HW, C) maps, split into a statistics pass and a fused apply pass.
+//
+// The pixel decoder normalises every conv output with GroupNorm(32, C): input_proj (P/mask2former/modeling/
+// pixel_decoder/msdeformattn.py:213-226,321), FPN lateral and output convs (:262-286,346-351).  The reference runs them
+// on NCHW fp32 tensors through at::group_norm plus separate add / interpolate / relu / cast kernels; here the maps stay
+// channels-last (the layout the GEMMs and the tcgen05 mask GEMM want) and the apply pass fuses what follows the norm:
+//   y = GN(x) [+ bilinear_upsample(low-res map)] [ReLU]          (FPN top-down add, msdeformattn.py:349; F.relu :278)
+//   outputs (each optional): fp32, GEMM-dtype copy, GEMM-dtype (y + pos)   (encoder inputs: src, with_pos_embed(src, pos))
+// written with an arbitrary batch stride so each level lands directly in its slice of the (N, S, C) token buffer
+// (replaces flatten / transpose / cat, msdeformattn.py:70-80).
+#include "common.cuh"
+
+namespace dvis {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T *p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16 *p) {
+  const uint2 u = *reinterpret_cast<const uint2 *>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+template <typename T>
+__device__ __forceinline__ void st4(T *p, float4 v);
+template <>
+__device__ __forceinline__ void st4<float>(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p, float4 v) {
+  *reinterpret_cast<uint2 *>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+constexpr int kMaxGroups = 64;
+
+// ---- pass 1: per (n, group) sum and sum of squares, accumulated in double -----------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T *__restrict__ x, int64_t batch_stride, int HW, int C, int G,
+                                                       int pix_per_cta, double *__restrict__ sums) {
+  __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
+  const int n = blockIdx.y;
+  const int quads = C / 4, cpg = C / G;
+  const int cq = threadIdx.x % quads, pl = threadIdx.x / quads, prow = blockDim.x / quads;
+  if (threadIdx.x < G) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, HW);
+  const T *xn = x + (size_t)n * batch_stride + cq * 4;
+  float s = 0.f, q = 0.f;
+  if (pl < prow) {
+    for (int p = p0 + pl; p < p1; p += prow) {
+      const float4 v = ld4<T>(xn + (size_t)p * C);
+      s += v.x + v.y + v.z + v.w;
+      q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    const int g = (cq * 4) / cpg;
+    atomicAdd(&s_sum[g], s);
+    atomicAdd(&s_sq[g], q);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    atomicAdd(&sums[((size_t)n * G + threadIdx.x) * 2], double(s_sum[threadIdx.x]));
+    atomicAdd(&sums[((size_t)n * G + threadIdx.x) * 2 + 1], double(s_sq[threadIdx.x]));
+  }
+}
+
+struct GnApplyParams {
+  const void *x;
+  int64_t x_batch_stride;
+  const double *sums;
+  const float *gamma, *beta;
+  int N, HW, C, G;
+  float eps;
+  int relu;
+  const float *up;           // optional low-res fp32 map (N, uh, uw, C) added after bilinear upsampling to (H, W)
+  int64_t up_batch_stride;
+  int uh, uw, H, W;
+  const float *pos;          // optional (HW, C) fp32, for out_lp_pos
+  float *out_f32;
+  void *out_lp, *out_lp_pos;
+  int64_t out_batch_stride;  // elements between batch items of every output
+};
+
+template <typename T, typename TL>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+  const int quads = p.C / 4;
+  const int64_t total = (int64_t)p.N * p.HW * quads;
+  const float inv_cnt = 1.f / (float(p.HW) * float(p.C / p.G));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = int(i % quads);
+    const int64_t np = i / quads;
+    const int pix = int(np % p.HW), n = int(np / p.HW);
+    const int c = cq * 4, g = c / (p.C / p.G);
+    const double su = p.sums[((size_t)n * p.G + g) * 2], sq = p.sums[((size_t)n * p.G + g) * 2 + 1];
+    const float mean = float(su * inv_cnt);
+    const float var = fmaxf(float(sq * inv_cnt - (su * inv_cnt) * (su * inv_cnt)), 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    const float4 v = ld4<T>(static_cast<const T *>(p.x) + (size_t)n * p.x_batch_stride + (size_t)pix * p.C + c);
+    const float4 ga = *reinterpret_cast<const float4 *>(p.gamma + c), be = *reinterpret_cast<const float4 *>(p.beta + c);
+    float4 y = make_float4((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y,
+                           (v.z - mean) * rstd * ga.z + be.z, (v.w - mean) * rstd * ga.w + be.w);
+    if (p.up) {
+      // F.interpolate(mode="bilinear", align_corners=False): src = (dst + 0.5) * in/out - 0.5, clamped at 0
+      const int oy = pix / p.W, ox = pix - oy * p.W;
+      const float fy = fmaxf((oy + 0.5f) * (float(p.uh) / float(p.H)) - 0.5f, 0.f);
+      const float fx = fmaxf((ox + 0.5f) * (float(p.uw) / float(p.W)) - 0.5f, 0.f);
+      const int y0 = int(fy), x0 = int(fx);
+      const int y1 = min(y0 + 1, p.uh - 1), x1 = min(x0 + 1, p.uw - 1);
+      const float ly = fy - y0, lx = fx - x0;
+      const float *u = p.up + (size_t)n * p.up_batch_stride + c;
+      const float4 a = *reinterpret_cast<const float4 *>(u + ((size_t)y0 * p.uw + x0) * p.C);
+      const float4 b = *reinterpret_cast<const float4 *>(u + ((size_t)y0 * p.uw + x1) * p.C);
+      const float4 cc = *reinterpret_cast<const float4 *>(u + ((size_t)y1 * p.uw + x0) * p.C);
+      const float4 d = *reinterpret_cast<const float4 *>(u + ((size_t)y1 * p.uw + x1) * p.C);
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      y.x += w00 * a.x + w01 * b.x + w10 * cc.x + w11 * d.x;
+      y.y += w00 * a.y + w01 * b.y + w10 * cc.y + w11 * d.y;
+      y.z += w00 * a.z + w01 * b.z + w10 * cc.z + w11 * d.z;
+      y.w += w00 * a.w + w01 * b.w + w10 * cc.w + w11 * d.w;
+    }
+    if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+    const size_t o = (size_t)n * p.out_batch_stride + (size_t)pix * p.C + c;
+    if (p.out_f32) st4<float>(p.out_f32 + o, y);
+    if (p.out_lp) st4<TL>(static_cast<TL *>(p.out_lp) + o, y);
+    if (p.out_lp_pos) {
+      const float4 q = *reinterpret_cast<const float4 *>(p.pos + (size_t)pix * p.C + c);
+      st4<TL>(static_cast<TL *>(p.out_lp_pos) + o, make_float4(y.x + q.x, y.y + q.y, y.z + q.z, y.w + q.w));
+    }
+  }
+}
+
+}  // namespace
+}  // namespace dvis
+
+using namespace dvis;
+
+extern "C" int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_stride, int N, int HW, int C, int G,
+                                   const float *gamma, const float *beta, float eps, int relu, double *sums_workspace,
+                                   const float *up, int64_t up_batch_stride, int up_h, int up_w, int H, int W,
+                                   const float *pos, float *out_f32, void *out_lp, void *out_lp_pos, int lp_dtype,
+                                   int64_t out_batch_stride, void *stream) {
+  DVIS_REQUIRE(x && gamma && beta && sums_workspace, "groupnorm_nhwc: null pointer argument");
+  DVIS_REQUIRE(N > 0 && HW > 0 && C > 0 && G > 0 && C % G == 0, "groupnorm_nhwc: bad sizes");
+  DVIS_REQUIRE(C % 4 == 0 && (C / G) % 4 == 0 && C <= 1024 && G <= kMaxGroups,
+               "groupnorm_nhwc: need C %% 4 == 0, (C/G) %% 4 == 0, C <= 1024, G <= 64 (C=%d G=%d)", C, G);
+  DVIS_REQUIRE(out_f32 || out_lp || out_lp_pos, "groupnorm_nhwc: no output requested");
+  DVIS_REQUIRE(!out_lp_pos || pos, "groupnorm_nhwc: out_lp_pos needs pos");
+  DVIS_REQUIRE(!up || (up_h > 0 && up_w > 0 && H * W == HW), "groupnorm_nhwc: upsample-add needs H*W == HW");
+  if ((x_dtype != DVIS_F32 && x_dtype != DVIS_BF16) || (lp_dtype != DVIS_F32 && lp_dtype != DVIS_BF16))
+    return fail(DVIS_ERR_UNSUPPORTED, "groupnorm_nhwc: dtypes must be f32 or bf16");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(sums_workspace, 0, sizeof(double) * 2 * N * G, s);
+  const int pix_per_cta = 256;
+  dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
+  if (x_dtype == DVIS_F32)
+    gn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(x), x_batch_stride, HW, C, G, pix_per_cta, sums_workspace);
+  else
+    gn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(x), x_batch_stride, HW, C, G, pix_per_cta, sums_workspace);
+  if (int rc = check_launch("gn_stats_kernel")) return rc;
+  GnApplyParams p{x, x_batch_stride, sums_workspace, gamma, beta, N, HW, C, G, eps, relu, up, up_batch_stride, up_h, up_w,
+                  H, W, pos, out_f32, out_lp, out_lp_pos, out_batch_stride};
+  const int64_t total = (int64_t)N * HW * (C / 4);
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16));
+  using bf = __nv_bfloat16;
+  if (x_dtype == DVIS_F32 && lp_dtype == DVIS_F32) gn_apply_kernel<float, float><<<blocks, 256, 0, s>>>(p);
+  else if (x_dtype == DVIS_F32) gn_apply_kernel<float, bf><<<blocks, 256, 0, s>>>(p);
+  else if (lp_dtype == DVIS_F32) gn_apply_kernel<bf, float><<<blocks, 256, 0, s>>>(p);
+  else gn_apply_kernel<bf, bf><<<blocks, 256, 0, s>>>(p);
+  return check_launch("gn_apply_kernel");
+}

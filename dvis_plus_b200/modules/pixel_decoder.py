@@ -112,8 +112,8 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         w1, b1, w2, b2 = self._lp(dt)
         a = self.self_attn.forward_fused(q_lp, ctx["ref"], src_lp, ctx["shapes"], ctx["shapes_dev"], ctx["lsi_dev"])
         src32, src_lp, _ = ops.add_layernorm(a, src32, self.norm1.weight, self.norm1.bias, self.norm1.eps, lp_dtype=dt)
-        h = F.relu(F.linear(src_lp, w1, b1))
-        f = F.linear(h, w2, b2)
+        h = torch._addmm_activation(b1, src_lp.view(-1, src_lp.shape[-1]), w1.t())      # ReLU in the GEMM epilogue
+        f = F.linear(h, w2, b2).view(src_lp.shape)
         return ops.add_layernorm(f, src32, self.norm2.weight, self.norm2.bias, self.norm2.eps, lp_dtype=dt,
                                  pos=pos if next_needs_q else None)
 
@@ -199,15 +199,23 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
             memory = self.encoder(src.float(), ctx["shapes_dev"], ctx["lsi_dev"], valid, pos, None)
             return memory, ctx["shapes_dev"], ctx["lsi_dev"]
         dt = gemm_dtype()
-        run = dict(ctx)
-        run["ref"] = ctx["ref1"].expand(N, -1, -1, -1).contiguous()
         src32 = src.float().contiguous()
         src_lp = src32.to(dt)
         q_lp = (src32 + ctx["pos"][None]).to(dt)
+        return self.run_layers(src32, src_lp, q_lp, ctx), ctx["shapes_dev"], ctx["lsi_dev"]
+
+    def run_layers(self, src32, src_lp, q_lp, ctx):
+        """The encoder stack on prepared inputs: fp32 stream, GEMM-dtype copy, GEMM-dtype (src + pos).  -> (N,S,C) fp32."""
+        N = src32.shape[0]
+        run = dict(ctx)
+        key = ("ref", N)
+        if key not in ctx:
+            ctx[key] = ctx["ref1"].expand(N, -1, -1, -1).contiguous()
+        run["ref"] = ctx[key]
         n_layers = len(self.encoder.layers)
         for i, layer in enumerate(self.encoder.layers):
             src32, src_lp, q_lp = layer.forward_fused(src32, src_lp, q_lp, ctx["pos"], run, next_needs_q=i + 1 < n_layers)
-        return src32, ctx["shapes_dev"], ctx["lsi_dev"]
+        return src32
 
 
 class MSDeformAttnPixelDecoder(nn.Module):
@@ -279,9 +287,94 @@ class MSDeformAttnPixelDecoder(nn.Module):
         ret["common_stride"] = cfg.MODEL.SEM_SEG_HEAD.COMMON_STRIDE
         return ret
 
+    # -- inference path: channels-last tokens end to end ------------------------------------------------------
+    def _lp_weights(self, dt):
+        params = list(self.input_proj.parameters()) + [p for c in self.lateral_convs + self.output_convs for p in c.parameters()] \
+            + list(self.mask_features.parameters())
+        key = (dt, tuple(p._version for p in params), params[0].data_ptr())
+        c = getattr(self, "_dvis_lp", None)
+        if c is None or c[0] != key:
+            d = lambda t: None if t is None else t.detach().to(dt).contiguous()
+            c = (key, dict(
+                inproj=[(d(seq[0].weight.flatten(1)), d(seq[0].bias)) for seq in self.input_proj],
+                lateral=[(d(cv.weight.flatten(1)), d(cv.bias)) for cv in self.lateral_convs],
+                output=[(cv.weight.detach().to(dt).contiguous(memory_format=torch.channels_last), d(cv.bias)) for cv in self.output_convs],
+                mask=(d(self.mask_features.weight.flatten(1)), d(self.mask_features.bias))))
+            self._dvis_lp = c
+        return c[1]
+
+    @staticmethod
+    def _tokens(x, dt):
+        """(N, C, H, W) map -> (N, H*W, C) channels-last token view in the GEMM dtype (no copy when the producer already
+        emits channels_last, as Swin / ViT backbones natively do)."""
+        if x.dtype != dt or not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.to(dtype=dt, memory_format=torch.channels_last)
+        N, C, H, W = x.shape
+        return x.permute(0, 2, 3, 1).reshape(N, H * W, C)
+
+    def _fused_ok(self):
+        tf = self.transformer
+        attn = tf.encoder.layers[0].self_attn
+        return (self.conv_dim % 128 == 0 and attn.n_points == 4 and (attn.d_model // attn.n_heads) in (16, 32, 64)
+                and all(isinstance(seq[1], nn.GroupNorm) for seq in self.input_proj)
+                and all(isinstance(cv.norm, nn.GroupNorm) for cv in self.lateral_convs + self.output_convs)
+                and self.transformer_num_feature_levels >= self.maskformer_num_feature_levels)
+
+    def _forward_features_fused(self, features):
+        dt = gemm_dtype()
+        tf, C = self.transformer, self.conv_dim
+        lp = self._lp_weights(dt)
+        maps = [features[f] for f in self.transformer_in_features[::-1]]            # low -> high resolution
+        N, dev = maps[0].shape[0], maps[0].device
+        shapes = tuple((int(m.shape[2]), int(m.shape[3])) for m in maps)
+        ctx = tf._context(shapes, dev)
+        S = sum(h * w for h, w in shapes)
+        src32 = torch.empty(N, S, C, dtype=torch.float32, device=dev)
+        src_lp = torch.empty(N, S, C, dtype=dt, device=dev)
+        q_lp = torch.empty(N, S, C, dtype=dt, device=dev)
+        off, offsets = 0, []
+        for idx, (m, (h, w)) in enumerate(zip(maps, shapes)):
+            gn = self.input_proj[idx][1]
+            y = F.linear(self._tokens(m, dt), *lp["inproj"][idx])                    # 1x1 conv == per-pixel linear
+            sl = slice(off, off + h * w)
+            ops.groupnorm_nhwc(y, gn.num_groups, gn.weight, gn.bias, gn.eps, pos=ctx["pos"][sl],
+                               out_f32=src32[:, sl], out_lp=src_lp[:, sl], out_lp_pos=q_lp[:, sl])
+            offsets.append(off)
+            off += h * w
+        memory = tf.run_layers(src32, src_lp, q_lp, ctx)                              # (N, S, C) fp32
+        out = [memory[:, o:o + h * w].view(N, h, w, C).permute(0, 3, 1, 2) for o, (h, w) in zip(offsets, shapes)]
+        cur, cur_hw = memory[:, offsets[-1]:], shapes[-1]                             # highest-resolution encoder level
+        last_lp = None
+        for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
+            x = features[f]
+            H, W = int(x.shape[2]), int(x.shape[3])
+            lat, outc = self.lateral_convs[idx], self.output_convs[idx]
+            y = F.linear(self._tokens(x, dt), *lp["lateral"][idx])
+            z = torch.empty(N, H * W, C, dtype=dt, device=dev)
+            ops.groupnorm_nhwc(y, lat.norm.num_groups, lat.norm.weight, lat.norm.bias, lat.norm.eps,
+                               up=cur, up_hw=cur_hw, hw=(H, W), out_lp=z)               # GN(lateral) + upsample(top-down)
+            w3, b3 = lp["output"][idx]
+            c = F.conv2d(z.view(N, H, W, C).permute(0, 3, 1, 2), w3, b3, padding=1)
+            c = c.permute(0, 2, 3, 1).reshape(N, H * W, C)
+            last_lp = torch.empty(N, H * W, C, dtype=dt, device=dev)
+            more = idx + 1 < self.num_fpn_levels
+            nxt = torch.empty(N, H * W, C, dtype=torch.float32, device=dev) if more else None
+            ops.groupnorm_nhwc(c, outc.norm.num_groups, outc.norm.weight, outc.norm.bias, outc.norm.eps, relu=True,
+                               out_lp=last_lp, out_f32=nxt)
+            cur, cur_hw = nxt, (H, W)
+        if last_lp is None:                                                           # no FPN level: mask features from the encoder
+            H, W = shapes[-1]
+            last_lp = memory[:, offsets[-1]:].to(dt)
+        mf = F.linear(last_lp, *lp["mask"])                                           # (N, H*W, mask_dim)
+        mask_features = mf.view(N, H, W, self.mask_dim).permute(0, 3, 1, 2)           # NCHW shape, channels_last memory
+        return mask_features, out[0], out[:self.maskformer_num_feature_levels]
+
     def forward_features(self, features):
         """-> (mask_features (N, mask_dim, H/4, W/4), out[0], multi_scale_features[:3])  (py:314-358).
         On the inference path the returned maps are channels_last; mask_features is in the GEMM dtype."""
+        if _fast_path(next(iter(features.values()))) and self._fused_ok():
+            with torch.autocast("cuda", enabled=False):
+                return self._forward_features_fused(features)
         with torch.autocast("cuda", enabled=False):
             fast = _fast_path(next(iter(features.values())))
             dt = gemm_dtype() if fast else torch.float32

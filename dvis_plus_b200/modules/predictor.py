@@ -9,12 +9,16 @@ bilinear resizing is linear, so  interpolate(E @ F) == E @ interpolate(F)  and  
 the attention mask of each layer is therefore  (E @ F_l) < 0  with F_l = mask_features resized once per level.
 Set `materialize_aux_masks=True` (or run under autograd) to get the reference's every-layer `aux_outputs` masks.
 """
+import math
+
 import torch
 import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .blocks import MLP, CrossAttentionLayer, FFNLayer, SelfAttentionLayer, _fast_path, linear, sine_position_embedding
+from .blocks import (MLP, CrossAttentionLayer, FFNLayer, SelfAttentionLayer, _fast_path, add_norm, linear,
+                     sine_position_embedding)
+from .precision import gemm_dtype
 from .pixel_decoder import ConvNorm, _c2_xavier_fill, configurable
 
 try:  # optional registration, mirrors py:174
@@ -123,9 +127,118 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         logits = ops.mask_logits(mask_embed, level_feat, torch.float32)       # (B, Q, h, w) on the level's own grid
         return (logits < 0).flatten(2)
 
+    # ---- inference path ------------------------------------------------------------------------------
+    def _stacked(self, dt):
+        """GEMM-dtype weights grouped the way the fast path consumes them: the keys / values of the 3 layers that attend
+        to the same level come out of ONE GEMM each (their input, the level memory, is the same)."""
+        params = list(self.parameters())
+        key = (dt, tuple(p._version for p in params), params[0].data_ptr())
+        c = getattr(self, "_dvis_fast", None)
+        if c is None or c[0] != key:
+            C, L, nl = self.hidden_dim, self.num_layers, self.num_feature_levels
+            d = lambda t: t.detach().to(dt).contiguous()
+            ca = [m.multihead_attn for m in self.transformer_cross_attention_layers]
+            f = dict(wk=[], bk=[], wv=[], bv=[], layers_of_level=[])
+            for l in range(nl):
+                ids = list(range(l, L, nl))
+                f["layers_of_level"].append(ids)
+                f["wk"].append(d(torch.cat([ca[i].in_proj_weight[C:2 * C] for i in ids], 0)) if ids else None)
+                f["bk"].append(d(torch.cat([ca[i].in_proj_bias[C:2 * C] for i in ids], 0)) if ids else None)
+                f["wv"].append(d(torch.cat([ca[i].in_proj_weight[2 * C:] for i in ids], 0)) if ids else None)
+                f["bv"].append(d(torch.cat([ca[i].in_proj_bias[2 * C:] for i in ids], 0)) if ids else None)
+            f["wq"] = [d(m.in_proj_weight[:C]) for m in ca]
+            f["bq"] = [d(m.in_proj_bias[:C]) for m in ca]
+            c = (key, f)
+            self._dvis_fast = c
+        return c[1]
+
+    def _mask_embed_of(self, output):
+        return self.mask_embed(self.decoder_norm(output))
+
+    def _forward_fast(self, x, mask_features):
+        """Batch-first (B, L, C) formulation of forward() for inference: same arithmetic, but level memories are cast /
+        position-embedded once, K / V of the layers sharing a level are projected together, the attention mask stays a
+        (B, 1, Q, hw) additive bias (no per-head copies) and only the last layer's masks are produced at full resolution."""
+        dt = gemm_dtype()
+        f = self._stacked(dt)
+        C, H, L, nl = self.hidden_dim, self.num_heads, self.num_layers, self.num_feature_levels
+        dh = C // H
+        scale = 1.0 / math.sqrt(dh)
+        B = x[0].shape[0]
+        sizes, k_all, v_all, level_feats = [], [], [], []
+        for l in range(nl):
+            xl = x[l] if len(self.input_proj[l]) == 0 else self.input_proj[l](x[l])
+            h, w = xl.shape[-2:]
+            sizes.append((h, w))
+            tok = xl.permute(0, 2, 3, 1).reshape(B, h * w, C).float() + self.level_embed.weight[l]      # (B, hw, C)
+            n_of = len(f["layers_of_level"][l])
+            if n_of:
+                key_in = (tok + self._pos(h, w, tok.device)[:, 0][None]).to(dt)
+                k = F.linear(key_in, f["wk"][l], f["bk"][l]).view(B, h * w, n_of, H, dh)
+                v = F.linear(tok.to(dt), f["wv"][l], f["bv"][l]).view(B, h * w, n_of, H, dh)
+                k_all.append(k.permute(2, 0, 3, 1, 4))                                                # (n_of, B, H, hw, dh) views
+                v_all.append(v.permute(2, 0, 3, 1, 4))
+            else:
+                k_all.append(None)
+                v_all.append(None)
+            # mask features resized once to this level's grid: interpolate(E @ F) == E @ interpolate(F)
+            level_feats.append(F.interpolate(mask_features.float(), size=(h, w), mode="bilinear", align_corners=False)
+                               .to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+        query_embed = self.query_embed.weight[None]                                                    # (1, Q, C)
+        output = self.query_feat.weight[None].expand(B, -1, -1).contiguous()                           # (B, Q, C) fp32
+        Q = output.shape[1]
+
+        def attn_bias(level):
+            logits = ops.mask_logits(self._mask_embed_of(output), level_feats[level], torch.float32).flatten(2)   # (B, Q, hw)
+            m = logits < 0                                           # sigmoid(x) < 0.5  <=>  x < 0
+            m = m & ~m.all(-1, keepdim=True)                         # fully masked rows attend everywhere (py:297)
+            return torch.zeros(m.shape, dtype=dt, device=m.device).masked_fill_(m, float("-inf"))[:, None]
+
+        bias = attn_bias(0)
+        for i in range(L):
+            l = i % nl
+            j = i // nl
+            sa, ff, ca = self.transformer_self_attention_layers[i], self.transformer_ffn_layers[i], self.transformer_cross_attention_layers[i]
+            # masked cross-attention to level l
+            q = F.linear((output + query_embed).to(dt), f["wq"][i], f["bq"][i]).view(B, Q, H, dh).transpose(1, 2)
+            o = F.scaled_dot_product_attention(q, k_all[l][j], v_all[l][j], attn_mask=bias, scale=scale)
+            o = linear(ca.multihead_attn.out_proj, o.transpose(1, 2).reshape(B, Q, C))
+            output = add_norm(ca.norm, o, output)
+            # self-attention over the queries
+            m = sa.self_attn
+            w, b = m._weights(dt)
+            qk = F.linear((output + query_embed).to(dt), w[:2 * C], b[:2 * C]).view(B, Q, 2, H, dh)
+            v = F.linear(output.to(dt), w[2 * C:], b[2 * C:]).view(B, Q, H, dh)
+            o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2), scale=scale)
+            o = linear(m.out_proj, o.transpose(1, 2).reshape(B, Q, C))
+            output = add_norm(sa.norm, o, output)
+            # FFN
+            output = add_norm(ff.norm, linear(ff.linear2, linear(ff.linear1, output, relu=True)), output)
+            if i + 1 < L:
+                bias = attn_bias((i + 1) % nl)
+        normed = self.decoder_norm(output)
+        cls = linear(self.class_embed, normed).float()                                                 # (B, Q, K+1)
+        masks = ops.mask_logits(self.mask_embed(normed), mask_features, torch.float32)                 # (B, Q, H, W)
+        reid = self.reid_embed(normed).float()
+        b = B // self.num_frames if self.training else 1
+        t = B // b
+        to_bctq = lambda z: z.reshape(b, t, Q, z.shape[-1]).permute(0, 3, 1, 2)                        # (b t) q c -> b c t q
+        pe, re_, nn_ = to_bctq(normed), to_bctq(reid), to_bctq(output)
+        return {
+            "pred_logits": cls.reshape(b, t, Q, -1),
+            "pred_masks": masks.reshape(b, t, Q, *masks.shape[-2:]).permute(0, 2, 1, 3, 4),
+            "aux_outputs": [],
+            "pred_embds": torch.cat([pe, re_], dim=1),
+            "pred_embds_without_norm": torch.cat([nn_, re_], dim=1),
+            "pred_reid_embed": re_,
+            "mask_features": mask_features,
+        }
+
     def forward(self, x, mask_features, mask=None):
         assert len(x) == self.num_feature_levels
         del mask
+        if _fast_path(mask_features) and not self.materialize_aux_masks and self.hidden_dim % 128 == 0:
+            return self._forward_fast(x, mask_features)
         fast = _fast_path(mask_features) and not self.materialize_aux_masks
         src, pos, size_list = [], [], []
         for i in range(self.num_feature_levels):

@@ -17,7 +17,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .blocks import MLP, FFNLayer, ReferringCrossAttentionLayer, SelfAttentionLayer, _fast_path, linear
+from .blocks import MLP, FFNLayer, ReferringCrossAttentionLayer, SelfAttentionLayer, _fast_path, add_norm, linear
+from .precision import gemm_dtype
 from .pixel_decoder import _c2_xavier_fill
 
 
@@ -109,6 +110,9 @@ class ReferringTracker_noiser(nn.Module):
         self.last_reference = None
         # the reference passes noise_mode='hard' by default, which its Noiser asserts against; DVIS configs set it
         self.noiser = Noiser(noise_ratio=noise_ratio, mode=noise_mode if noise_mode != "hard" else "none")
+        self.use_fast_path = True      # inference: batched matching + CUDA-graph frame steps (set False for the eager loop)
+        self.use_cuda_graph = True
+        self._fast = None
 
     def _clear_memory(self):
         self.last_outputs = None
@@ -129,6 +133,8 @@ class ReferringTracker_noiser(nn.Module):
     def forward(self, frame_embeds, mask_features, resume=False, return_indices=False, frame_classes=None,
                 frame_embeds_no_norm=None, with_masks=True):
         """frame_embeds (b, c, t, q); mask_features (b, t, c, h, w) (may be None when with_masks=False)."""
+        if (not self.training) and _fast_path(frame_embeds) and frame_embeds.shape[0] == 1 and self.use_fast_path:
+            return self._forward_fast(frame_embeds, mask_features, resume, return_indices, frame_embeds_no_norm, with_masks)
         frame_embeds = frame_embeds.permute(2, 3, 0, 1).float()                  # t, q, b, c
         if frame_embeds_no_norm is not None:
             frame_embeds_no_norm = frame_embeds_no_norm.permute(2, 3, 0, 1).float()
@@ -206,3 +212,155 @@ class ReferringTracker_noiser(nn.Module):
         shape = mask_features.shape
         mf = F.conv2d(mask_features.flatten(0, 1).float(), self.mask_feature_proj.weight, self.mask_feature_proj.bias).reshape(shape)
         return outputs_class, torch.einsum("lbtqc,btchw->lbqthw", mask_embed, mf)
+
+
+    # ================================================================================================
+    # Inference fast path.  Same arithmetic as the loop in forward() (py:210-340), reorganised around what
+    # actually depends on what:
+    #   * the Hungarian chain depends only on the SEGMENTER's frame embeddings, never on tracker outputs
+    #     (noiser.py:43-56 gets last_frame_embeds = cur[indices], py:224,285): all T cost matrices come from one batched
+    #     GEMM and one device->host copy; each frame's assignment is solved against the un-permuted previous frame and
+    #     composed with the previous permutation (idx_t = sigma_t[idx_{t-1}]) -- T host syncs become 1;
+    #   * keys / values of the referring cross-attention depend only on the frame's own queries: projected for all
+    #     frames and all layers in one GEMM before the sequential part;
+    #   * for frames after the first the cross-attention query of every layer is the same `reference`
+    #     (py:278,293,313): the 6 layers' cross-attention cores run as one batched attention;
+    #   * the remaining strictly sequential per-frame chain is captured once in a CUDA graph and replayed per frame.
+    # ================================================================================================
+    def _stacked(self, dt):
+        L = self.num_layers
+        ca, sa, ff = self.transformer_cross_attention_layers, self.transformer_self_attention_layers, self.transformer_ffn_layers
+        params = [p for p in self.parameters()]
+        key = (dt, tuple(p._version for p in params), params[0].data_ptr())
+        if self._fast is None or self._fast["key"] != key:
+            C = self.decoder_norm.normalized_shape[0]
+            d = lambda t: t.detach().to(dt).contiguous()
+            f = dict(key=key, C=C)
+            f["wq"] = d(torch.cat([ca[j].multihead_attn.in_proj_weight[:C] for j in range(L)], 0))          # (L*C, C)
+            f["bq"] = d(torch.cat([ca[j].multihead_attn.in_proj_bias[:C] for j in range(L)], 0))
+            f["wkv"] = d(torch.cat([ca[j].multihead_attn.in_proj_weight[C:] for j in range(L)], 0))         # (L*2C, C)
+            f["bkv"] = d(torch.cat([ca[j].multihead_attn.in_proj_bias[C:] for j in range(L)], 0))
+            f["wo"] = d(torch.stack([ca[j].multihead_attn.out_proj.weight.t() for j in range(L)], 0))       # (L, C, C) = W^T
+            f["bo"] = d(torch.stack([ca[j].multihead_attn.out_proj.bias for j in range(L)], 0))[:, None, :]
+            self._fast = f
+            self._graphs = {}
+        return self._fast
+
+    def _match_all(self, cur, ref0):
+        """cur (T, Q, C) normalised-query embeddings of the window; ref0 (Q, C) reference of the first frame (the frame
+        itself at the start of a video, last_frame_embeds when resuming).  -> (T, Q) long indices, one host sync."""
+        from scipy.optimize import linear_sum_assignment
+        unit = lambda z: z / (z.norm(dim=-1, keepdim=True) + 1e-6)
+        n = unit(cur.float())
+        prev = torch.cat([unit(ref0.float())[None], n[:-1]], 0)
+        cost = (1 - torch.bmm(n, prev.transpose(1, 2))).cpu()                       # (T, Q_cur, Q_ref); the single sync
+        cost = torch.where(torch.isnan(cost), torch.zeros_like(cost), cost).numpy()
+        idx, out = None, []
+        for t in range(cost.shape[0]):
+            sigma = linear_sum_assignment(cost[t].T)[1]                             # ref row j -> cur column sigma[j]
+            idx = sigma if idx is None else sigma[idx]
+            out.append(idx)
+        return out
+
+    def _frame_body(self, f, ref_src, identity, kv, first):
+        """One frame of py:236-329 on (Q, C) tensors.  ref_src: last_outputs[-1] of the previous frame (or the frame key
+        for the first frame); identity: cur_no_norm[indices]; kv: (L, 2, H, Q, dh) projected keys / values.
+        Returns the stacked layer outputs (L, Q, C) fp32 and this frame's reference (Q, C) fp32 (py:276,279)."""
+        L, C, H = self.num_layers, f["C"], self.num_heads
+        dh = C // H
+        Q = identity.shape[0]
+        sa, ff = self.transformer_self_attention_layers, self.transformer_ffn_layers
+        ca = self.transformer_cross_attention_layers
+        scale = 1.0 / (dh ** 0.5)
+        outs = []
+        x = identity
+        reference = self.ref_proj(ref_src)                                                         # (Q, C)
+        if not first:
+            q_all = F.linear(reference, f["wq"], f["bq"]).view(Q, L, H, dh).permute(1, 2, 0, 3)  # (L, H, Q, dh)
+            o_all = F.scaled_dot_product_attention(q_all, kv[:, 0], kv[:, 1], scale=scale)        # (L, H, Q, dh)
+            o_all = torch.baddbmm(f["bo"], o_all.permute(0, 2, 1, 3).reshape(L, Q, C), f["wo"])   # (L, Q, C)
+        for j in range(L):
+            if first:
+                tgt = reference if j == 0 else self.ref_proj(x)
+                q = F.linear(tgt, f["wq"][j * C:(j + 1) * C], f["bq"][j * C:(j + 1) * C]).view(Q, H, dh).permute(1, 0, 2)
+                o = F.scaled_dot_product_attention(q[None], kv[j, 0][None], kv[j, 1][None], scale=scale)[0]
+                o = torch.addmm(f["bo"][j], o.permute(1, 0, 2).reshape(Q, C), f["wo"][j])
+            else:
+                o = o_all[j]
+            x = add_norm(ca[j].norm, o, x)
+            x = sa[j](x[:, None, :])[:, 0]
+            x = ff[j](x[:, None, :])[:, 0]
+            outs.append(x)
+        return torch.stack(outs, 0), reference.float()
+
+    def _graph_step(self, f, first, Q, dev):
+        """Capture `_frame_body` for (first / later) frames once; returns (graph, static inputs, static output)."""
+        key = (first, Q, str(dev), gemm_dtype())
+        g = self._graphs.get(key)
+        if g is None:
+            C, L, H = f["C"], self.num_layers, self.num_heads
+            s_ref = torch.zeros(Q, C, device=dev)
+            s_id = torch.zeros(Q, C, device=dev)
+            s_kv = torch.zeros(L, 2, H, Q, C // H, device=dev, dtype=gemm_dtype())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._frame_body(f, s_ref, s_id, s_kv, first)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                s_out, s_refout = self._frame_body(f, s_ref, s_id, s_kv, first)
+            g = (graph, s_ref, s_id, s_kv, s_out, s_refout)
+            self._graphs[key] = g
+        return g
+
+    def _forward_fast(self, frame_embeds, mask_features, resume, return_indices, frame_embeds_no_norm, with_masks):
+        dt = gemm_dtype()
+        f = self._stacked(dt)
+        L, C, H = self.num_layers, f["C"], self.num_heads
+        cur = frame_embeds[0].permute(1, 2, 0).float().contiguous()                       # (T, Q, C)
+        cur_nn = cur if frame_embeds_no_norm is None else frame_embeds_no_norm[0].permute(1, 2, 0).float().contiguous()
+        T, Q, _ = cur.shape
+        dev = cur.device
+        start_of_video = not resume
+        if start_of_video:
+            self._clear_memory()
+        ref0 = cur[0] if start_of_video else self.last_frame_embeds[:, 0, :]
+        indices = self._match_all(cur, ref0)
+        idx_dev = torch.as_tensor(np.stack(indices), device=dev, dtype=torch.long)         # (T, Q)
+        init = torch.gather(cur_nn, 1, idx_dev[..., None].expand(-1, -1, C))               # cur_nn[t][idx_t]
+        self.last_frame_embeds = torch.gather(cur[-1], 0, idx_dev[-1][:, None].expand(-1, C))[:, None, :]
+        # keys / values of all frames and layers: one GEMM
+        kv = F.linear(cur_nn.to(dt), f["wkv"], f["bkv"]).view(T, Q, L, 2, H, C // H).permute(0, 2, 3, 4, 1, 5).contiguous()
+        outs, refs = [], []
+        prev_last = None if start_of_video else self.last_outputs[-1][:, 0, :]
+        for t in range(T):
+            first = prev_last is None
+            ref_src = cur_nn[t] if first else prev_last
+            if self.use_cuda_graph:
+                graph, s_ref, s_id, s_kv, s_out, s_refout = self._graph_step(f, first, Q, dev)
+                s_ref.copy_(ref_src)
+                s_id.copy_(init[t])
+                s_kv.copy_(kv[t])
+                graph.replay()
+                layer_out, reference = s_out.clone(), s_refout.clone()
+            else:
+                layer_out, reference = self._frame_body(f, ref_src, init[t], kv[t], first)
+            refs.append(reference)
+            prev_last = layer_out[-1]
+            outs.append(layer_out)
+            last_stack = torch.cat([init[t][None], layer_out], 0)
+        self.last_outputs = last_stack[:, :, None, :]                                       # (1+L, q, b, c)
+        self.last_reference = refs[-1][:, None, :]
+        outputs = torch.stack([o[-1:] for o in outs], 0)[:, :, :, None, :]                  # (t, 1, q, b, c)  eval: last layer
+        all_refs = torch.stack(refs, 0)[:, :, None, :]                                      # (t, q, b, c)
+        outputs_class, outputs_masks = self.prediction(outputs, mask_features, all_refs, with_masks=with_masks)
+        out = {
+            "pred_logits": outputs_class[-1].transpose(1, 2),
+            "pred_masks": None if outputs_masks is None else outputs_masks[-1],
+            "aux_outputs": self._set_aux_loss(outputs_class, outputs_masks),
+            "pred_embds": outputs[:, -1].permute(2, 3, 0, 1),
+            "pred_references": all_refs.permute(2, 3, 0, 1),
+        }
+        return (out, indices) if return_indices else out

@@ -186,3 +186,38 @@ def add_layernorm(x, residual, weight, bias, eps=1e-5, *, want_f32=True, lp_dtyp
                   pos_rows, rows, C, float(eps), ptr(out_f32), ptr(out_lp), ptr(out_lp_pos),
                   _DTYPE[lp_dtype] if lp_dtype is not None else DVIS_F32, _stream())
     return out_f32, out_lp, out_lp_pos
+
+
+def groupnorm_nhwc(x, num_groups, weight, bias, eps=1e-5, *, relu=False, up=None, up_hw=None, hw=None, pos=None,
+                   out_f32=None, out_lp=None, out_lp_pos=None):
+    """GroupNorm over a channels-last (N, HW, C) map with fused upsample-add / ReLU / casts (dvis_groupnorm_nhwc).
+
+    x: (N, HW, C) f32|bf16, rows contiguous (batch stride free).  `up`: optional (N, h*w, C) f32 low-res map to add after
+    bilinear upsampling from `up_hw` = (h, w) to `hw` = (H, W).  Outputs are caller-provided (N, HW, C) views (any batch
+    stride, e.g. slices of an (N, S, C) token buffer): out_f32 f32, out_lp / out_lp_pos in their own dtype (same for
+    both); out_lp_pos additionally adds pos (HW, C) f32.
+    """
+    N, HW, C = x.shape
+    assert x.is_cuda and x.stride(2) == 1 and x.stride(1) == C
+    outs = [o for o in (out_f32, out_lp, out_lp_pos) if o is not None]
+    assert outs and all(o.shape == (N, HW, C) and o.stride(2) == 1 and o.stride(1) == C for o in outs)
+    obs = outs[0].stride(0)
+    assert all(o.stride(0) == obs for o in outs)
+    lp = out_lp if out_lp is not None else out_lp_pos
+    lp_dtype = lp.dtype if lp is not None else torch.float32
+    if out_lp is not None and out_lp_pos is not None:
+        assert out_lp.dtype == out_lp_pos.dtype
+    ws = torch.empty(2 * N * num_groups, dtype=torch.float64, device=x.device)
+    uh = uw = H = W = 0
+    if up is not None:
+        (uh, uw), (H, W) = up_hw, hw
+        assert up.dtype == torch.float32 and up.shape == (N, uh * uw, C) and up.stride(2) == 1 and up.stride(1) == C
+    if pos is not None:
+        assert pos.dtype == torch.float32 and pos.shape == (HW, C) and pos.is_contiguous()
+    w = weight if weight.dtype == torch.float32 else weight.float()
+    b = bias if bias.dtype == torch.float32 else bias.float()
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(x.device):
+        _lib.call("dvis_groupnorm_nhwc", x.data_ptr(), _DTYPE[x.dtype], x.stride(0), N, HW, C, num_groups, w.data_ptr(),
+                  b.data_ptr(), float(eps), int(relu), ws.data_ptr(), ptr(up), up.stride(0) if up is not None else 0,
+                  uh, uw, H, W, ptr(pos), ptr(out_f32), ptr(out_lp), ptr(out_lp_pos), _DTYPE[lp_dtype], obs, _stream())

@@ -110,6 +110,25 @@ int dvis_add_layernorm(const void *x, int x_dtype, const void *residual, int res
                        const float *beta, const float *pos, int64_t pos_rows, int64_t rows, int C, float eps,
                        float *out_f32, void *out_lp, void *out_lp_pos, int lp_dtype, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm over a channels-last (N, HW, C) map with fused epilogue:
+ *   y = GroupNorm_G(x) * gamma + beta  [+ bilinear_upsample(up) to (H, W), align_corners=False]  [ReLU]
+ * Replaces nn.GroupNorm(32, conv_dim) after the pixel decoder's 1x1 / 3x3 convs together with the FPN top-down add and
+ * the ReLU (P/mask2former/modeling/pixel_decoder/msdeformattn.py:213-226,262-286,321,346-351) and the flatten /
+ * transpose / cat / with_pos_embed that build the encoder inputs (:70-80,112-114).
+ *   x (N, HW, C) x_dtype, batch stride x_batch_stride elements; gamma, beta (C,) f32
+ *   sums_workspace: 2*N*G doubles of scratch (zeroed and filled by the call)
+ *   up: optional (N, up_h, up_w, C) f32 with batch stride up_batch_stride (needs H*W == HW), else NULL
+ *   outputs, each optional: out_f32; out_lp (lp_dtype); out_lp_pos = y + pos[pixel] (pos (HW, C) f32); all laid out as
+ *   (N, HW, C) with batch stride out_batch_stride elements (so a level can land in its slice of a token buffer).
+ * Constraints: C % 4 == 0, (C/G) % 4 == 0, C <= 1024, G <= 64; dtypes DVIS_F32 or DVIS_BF16.
+ */
+int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_stride, int N, int HW, int C, int G,
+                        const float *gamma, const float *beta, float eps, int relu, double *sums_workspace,
+                        const float *up, int64_t up_batch_stride, int up_h, int up_w, int H, int W, const float *pos,
+                        float *out_f32, void *out_lp, void *out_lp_pos, int lp_dtype, int64_t out_batch_stride,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

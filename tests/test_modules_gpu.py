@@ -200,3 +200,59 @@ def test_add_layernorm_kernel():
         assert (y32b - refb).abs().max() < 1e-5 * max(1.0, refb.abs().max().item())
         y32n, _, _ = ops.add_layernorm(x, None, w, b)
         assert (y32n - torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)).abs().max() < 1e-5 * 10
+
+
+@torch.no_grad()
+def test_groupnorm_nhwc_kernel():
+    from dvis_plus_b200 import ops
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    N, H, W, C, G = 3, 12, 20, 256, 32
+    x = torch.randn(N, H * W, C, device="cuda") * 2 + 0.5
+    w, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    ref = F.group_norm(x.transpose(1, 2).reshape(N, C, H, W), G, w, b, 1e-5)               # NCHW reference
+    ref_tok = ref.flatten(2).transpose(1, 2)
+    # plain, into a slice of a bigger token buffer, with pos
+    buf32 = torch.zeros(N, H * W + 7, C, device="cuda")
+    buf_lp = torch.zeros(N, H * W + 7, C, device="cuda", dtype=torch.bfloat16)
+    buf_q = torch.zeros_like(buf_lp)
+    pos = torch.randn(H * W, C, device="cuda")
+    ops.groupnorm_nhwc(x, G, w, b, pos=pos, out_f32=buf32[:, 7:], out_lp=buf_lp[:, 7:], out_lp_pos=buf_q[:, 7:])
+    assert (buf32[:, 7:] - ref_tok).abs().max() < 1e-4 * ref_tok.abs().max()
+    assert buf32[:, :7].abs().max() == 0
+    assert (buf_lp[:, 7:].float() - ref_tok).abs().max() < 1e-2 * ref_tok.abs().max()
+    assert (buf_q[:, 7:].float() - (ref_tok + pos)).abs().max() < 1e-2 * (ref_tok + pos).abs().max()
+    # upsample-add + relu, bf16 input
+    up = torch.randn(N, (H // 2) * (W // 2), C, device="cuda")
+    up_ref = F.interpolate(up.transpose(1, 2).reshape(N, C, H // 2, W // 2), size=(H, W), mode="bilinear", align_corners=False)
+    xb = x.bfloat16()
+    ref2 = F.relu(F.group_norm(xb.float().transpose(1, 2).reshape(N, C, H, W), G, w, b, 1e-5) + up_ref).flatten(2).transpose(1, 2)
+    out = torch.empty(N, H * W, C, device="cuda")
+    ops.groupnorm_nhwc(xb, G, w, b, relu=True, up=up, up_hw=(H // 2, W // 2), hw=(H, W), out_f32=out)
+    assert (out - ref2).abs().max() < 1e-4 * ref2.abs().max()
+
+
+@torch.no_grad()
+def test_predictor_fast_path_production_width():
+    """hidden_dim 256: the batch-first inference path against the oracle port (CPU, fp32)."""
+    from oracle import torch_port as tp
+    torch.manual_seed(0)
+    d = M.VideoMultiScaleMaskedTransformerDecoder_dvisPlus(
+        256, True, num_classes=7, hidden_dim=256, num_queries=20, nheads=8, dim_feedforward=512, dec_layers=4,
+        pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=1, num_reid_head_layers=3,
+        reid_hidden_dim=256).eval()
+    ms = [torch.randn(2, 256, 4, 6), torch.randn(2, 256, 8, 12), torch.randn(2, 256, 16, 24)]
+    mf = torch.randn(2, 256, 32, 48)
+    sd = {k: v.detach() for k, v in d.state_dict().items()}
+    ref = tp.predictor_forward(sd, ms, mf, num_layers=4)
+    d = d.cuda()
+    calls = _lib.launch_count
+    with precision("fp32"):
+        out = d(cuda(ms), mf.cuda())
+    assert _lib.launch_count > calls
+    for k in ("pred_logits", "pred_masks", "pred_embds", "pred_embds_without_norm"):
+        assert rel_err(out[k], ref[k]) < 5e-2, (k, rel_err(out[k], ref[k]))     # thresholded bf16 logits, see above
+    with precision("bf16"):
+        out = d(cuda(ms), mf.cuda())
+    for k in ("pred_logits", "pred_masks", "pred_embds"):
+        assert rel_err(out[k], ref[k]) < 8e-2, (k, rel_err(out[k], ref[k]))
