@@ -279,8 +279,11 @@ def main():
         n, tot = kern["dvis_msda_fused_forward"]
         us = tot / n * 1e3
         ach = msda_bytes / us / 1e3
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r1_ncu_msda_bf16_fused_and_pair_N8.txt
+        # (ncu --set full, 8 frames per launch: 173.1 + 62.3 MB) scaled to the frames of one launch here
+        traffic = int((173.107712e6 + 62.283008e6) / 8 * t_local)
         roof = {"kernel": "msda_fwd_staged_kernel (dvis_msda_fused_forward)", "bound": "hbm", "achieved": round(ach, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None, "us_per_launch": round(us, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic, "us_per_launch": round(us, 1),
                 "algorithmic_bytes_per_launch": msda_bytes, "peak_source": peak_src,
                 "share_of_step": round(tot / (ms_dev * args.steps), 4),
                 "other_kernels_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in kern.items()}}

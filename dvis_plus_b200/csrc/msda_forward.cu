@@ -14,6 +14,7 @@
 //   * the fused variant also does softmax(logits) and loc = ref + offset / (W, H) in registers, removing the
 //     sampling_locations / attention_weights round trip through HBM (OPS/modules/ms_deform_attn.py:101-112).
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -137,8 +138,8 @@ __device__ __forceinline__ float ldp<__nv_bfloat16>(const __nv_bfloat16 *p) {
 }
 
 // TP: dtype of the FUSED path's offsets / logits (float or bf16); unused for the plain op
-template <typename T, typename TO, int D, bool FUSED, typename TP = float>
-__global__ void __launch_bounds__(kThreads, 3) msda_fwd_staged_kernel(const MsdaParams p) {
+template <typename T, typename TO, int D, bool FUSED, typename TP = float, int MINB = 6, int UNROLL = 2>
+__global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const MsdaParams p) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;  // lanes per row
   constexpr int G = 32 / LPR;   // items per warp
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 3) msda_fwd_staged_kernel(const Msda
     for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
     const uint4 *so = reinterpret_cast<const uint4 *>(s_off) + il * LPs;
     const float4 *sw = s_wt + il * LPs;
-#pragma unroll 4
+#pragma unroll UNROLL
     for (int pt = 0; pt < LP; ++pt) {
       const uint4 o = so[pt];
       const float4 w = sw[pt];
@@ -326,11 +327,14 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
   p.lpc_shift = sh;
   const size_t smem = (size_t)p.items_per_cta * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
   auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP>;
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
+  {  // occupancy / unroll variants (DVIS_MSDA_VARIANT), kept for the micro-benchmark.  Default: 6 CTAs/SM, unroll 2
+     // (40 registers): measured 23 % faster than 3 CTAs/SM x unroll 4 (80 registers) -- the gather is latency bound.
+    static const int variant = getenv("DVIS_MSDA_VARIANT") ? atoi(getenv("DVIS_MSDA_VARIANT")) : 0;
+    if (variant == 1) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 3, 4>;
+    if (variant == 2) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 2>;
+    if (variant == 3) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 1>;
   }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   dim3 grid((per_batch + p.items_per_cta - 1) / p.items_per_cta, p.N);
   kern<<<grid, kThreads, smem, stream>>>(p);
   return check_launch("msda_fwd_staged_kernel");

@@ -112,6 +112,7 @@ class ReferringTracker_noiser(nn.Module):
         self.noiser = Noiser(noise_ratio=noise_ratio, mode=noise_mode if noise_mode != "hard" else "none")
         self.use_fast_path = True      # inference: batched matching + CUDA-graph frame steps (set False for the eager loop)
         self.use_cuda_graph = True
+        self.match_on_host = False     # True: SciPy linear_sum_assignment on the host instead of the GPU LAP kernel
         self._fast = None
 
     def _clear_memory(self):
@@ -248,19 +249,23 @@ class ReferringTracker_noiser(nn.Module):
 
     def _match_all(self, cur, ref0):
         """cur (T, Q, C) normalised-query embeddings of the window; ref0 (Q, C) reference of the first frame (the frame
-        itself at the start of a video, last_frame_embeds when resuming).  -> (T, Q) long indices, one host sync."""
-        from scipy.optimize import linear_sum_assignment
+        itself at the start of a video, last_frame_embeds when resuming).  -> (T, Q) int64 DEVICE tensor of indices.
+        All T assignment problems are solved concurrently on the GPU (dvis_lap_chain): no host sync at all."""
         unit = lambda z: z / (z.norm(dim=-1, keepdim=True) + 1e-6)
         n = unit(cur.float())
         prev = torch.cat([unit(ref0.float())[None], n[:-1]], 0)
-        cost = (1 - torch.bmm(n, prev.transpose(1, 2))).cpu()                       # (T, Q_cur, Q_ref); the single sync
-        cost = torch.where(torch.isnan(cost), torch.zeros_like(cost), cost).numpy()
-        idx, out = None, []
-        for t in range(cost.shape[0]):
-            sigma = linear_sum_assignment(cost[t].T)[1]                             # ref row j -> cur column sigma[j]
-            idx = sigma if idx is None else sigma[idx]
-            out.append(idx)
-        return out
+        cost = 1 - torch.bmm(prev, n.transpose(1, 2))                                # (T, Q_ref, Q_cur) == C.T of noiser.py:49-54
+        if self.match_on_host:                                                      # SciPy on the host (debug / cross-check)
+            from scipy.optimize import linear_sum_assignment
+            c = cost.cpu()
+            c = torch.where(torch.isnan(c), torch.zeros_like(c), c).numpy()
+            idx, out = None, []
+            for t in range(c.shape[0]):
+                sigma = linear_sum_assignment(c[t])[1]
+                idx = sigma if idx is None else sigma[idx]
+                out.append(idx)
+            return torch.as_tensor(np.stack(out), device=cur.device, dtype=torch.long)
+        return ops.lap_chain(cost)[1]
 
     def _frame_body(self, f, ref_src, identity, kv, first):
         """One frame of py:236-329 on (Q, C) tensors.  ref_src: last_outputs[-1] of the previous frame (or the frame key
@@ -327,8 +332,7 @@ class ReferringTracker_noiser(nn.Module):
         if start_of_video:
             self._clear_memory()
         ref0 = cur[0] if start_of_video else self.last_frame_embeds[:, 0, :]
-        indices = self._match_all(cur, ref0)
-        idx_dev = torch.as_tensor(np.stack(indices), device=dev, dtype=torch.long)         # (T, Q)
+        idx_dev = self._match_all(cur, ref0)                                               # (T, Q) on the device
         init = torch.gather(cur_nn, 1, idx_dev[..., None].expand(-1, -1, C))               # cur_nn[t][idx_t]
         self.last_frame_embeds = torch.gather(cur[-1], 0, idx_dev[-1][:, None].expand(-1, C))[:, None, :]
         # keys / values of all frames and layers: one GEMM
@@ -363,4 +367,4 @@ class ReferringTracker_noiser(nn.Module):
             "pred_embds": outputs[:, -1].permute(2, 3, 0, 1),
             "pred_references": all_refs.permute(2, 3, 0, 1),
         }
-        return (out, indices) if return_indices else out
+        return (out, [i for i in idx_dev.cpu().numpy()]) if return_indices else out

@@ -89,6 +89,28 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     return out
 
 
+def msda_pair_forward(value, spatial_shapes, level_start_index, offsets, logits, reference_points, num_heads,
+                      num_levels, num_points, item_order=None):
+    """Pair-packed bf16 fused forward: packs `value` (N,S,M,32) bf16 into x-adjacent corner pairs, then gathers 2 lines
+    per sampling point (dvis_msda_pack_pairs + dvis_msda_pair_forward).  Same contract as msda_fused_forward."""
+    N, S, M, D = value.shape
+    Lq = offsets.shape[1]
+    assert value.dtype == torch.bfloat16 and D == 32 and value.is_contiguous() and reference_points.is_contiguous()
+    assert offsets.dtype == logits.dtype and offsets.dtype in (torch.float32, torch.bfloat16)
+    assert offsets.stride(-1) == 1 and logits.stride(-1) == 1
+    assert offsets.stride(0) == offsets.stride(1) * Lq and logits.stride(0) == logits.stride(1) * Lq
+    pairs = torch.empty((N, S + 1, M, 2, D), dtype=torch.bfloat16, device=value.device)
+    out = torch.empty((N, Lq, M * D), dtype=torch.bfloat16, device=value.device)
+    order_ptr = item_order.data_ptr() if item_order is not None else None
+    with torch.cuda.device(value.device):
+        _lib.call("dvis_msda_pack_pairs", value.data_ptr(), N, S, M, D, pairs.data_ptr(), _stream())
+        _lib.call("dvis_msda_pair_forward", pairs.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                  offsets.data_ptr(), offsets.stride(1), logits.data_ptr(), logits.stride(1), _DTYPE[offsets.dtype],
+                  reference_points.data_ptr(), reference_points.shape[-1], N, S, M, D, num_levels, Lq, num_points,
+                  order_ptr, out.data_ptr(), _stream())
+    return out
+
+
 def install_as_reference_extension():
     """Register this module's op functions as the importable module `MultiScaleDeformableAttention`
     (OPS/setup.py:60) so the reference's `import MultiScaleDeformableAttention as MSDA` binds to them."""
@@ -221,3 +243,20 @@ def groupnorm_nhwc(x, num_groups, weight, bias, eps=1e-5, *, relu=False, up=None
         _lib.call("dvis_groupnorm_nhwc", x.data_ptr(), _DTYPE[x.dtype], x.stride(0), N, HW, C, num_groups, w.data_ptr(),
                   b.data_ptr(), float(eps), int(relu), ws.data_ptr(), ptr(up), up.stride(0) if up is not None else 0,
                   uh, uw, H, W, ptr(pos), ptr(out_f32), ptr(out_lp), ptr(out_lp_pos), _DTYPE[lp_dtype], obs, _stream())
+
+
+def lap_chain(cost, idx_init=None):
+    """Batched Hungarian matching + index chain on the device (dvis_lap_chain).
+    cost (T, n, n) f32 with rows = reference items, cols = current items -> (sigma (T,n), idx (T,n)) int64."""
+    assert cost.is_cuda and cost.dtype == torch.float32 and cost.dim() == 3 and cost.shape[1] == cost.shape[2]
+    cost = cost.contiguous()
+    T, n, _ = cost.shape
+    sigma = torch.empty((T, n), dtype=torch.int64, device=cost.device)
+    idx = torch.empty((T, n), dtype=torch.int64, device=cost.device)
+    if idx_init is not None:
+        assert idx_init.dtype == torch.int64 and idx_init.numel() == n and idx_init.is_cuda
+        idx_init = idx_init.contiguous()
+    with torch.cuda.device(cost.device):
+        _lib.call("dvis_lap_chain", cost.data_ptr(), T, n, idx_init.data_ptr() if idx_init is not None else None,
+                  sigma.data_ptr(), idx.data_ptr(), _stream())
+    return sigma, idx

@@ -82,6 +82,20 @@ int dvis_msda_fused_forward(const void *value, int value_dtype, const int64_t *s
                             int num_query, int num_point, const int32_t *item_order, void *out, int out_dtype,
                             void *stream);
 
+/* Pair-packed bf16 variant of the fused forward (same arithmetic as dvis_msda_fused_forward with bf16 value / output).
+ * dvis_msda_pack_pairs re-lays `value` (batch, S, M, 32) bf16 out as pairs (batch, S+1, M, 2, 32) bf16 with
+ * pairs[n, e, m] = [value[n, e-1, m], value[n, e, m]] (zeros outside [0, S)), so that the two x-adjacent bilinear
+ * corners share one 128-byte line; dvis_msda_pair_forward then gathers 2 lines per sampling point instead of 4.
+ * channels must be 32; num_levels * num_point <= 32; out (batch, num_query, M*32) bf16.
+ */
+int dvis_msda_pack_pairs(const void *value, int batch, int spatial_size, int num_heads, int channels, void *pairs,
+                         void *stream);
+int dvis_msda_pair_forward(const void *pairs, const int64_t *spatial_shapes, const int64_t *level_start,
+                           const void *offsets, int64_t offsets_stride, const void *logits, int64_t logits_stride,
+                           int param_dtype, const float *ref, int ref_dim, int batch, int spatial_size, int num_heads,
+                           int channels, int num_levels, int num_query, int num_point, const int32_t *item_order,
+                           void *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Mask logits:  out[b, q, p] = sum_c emb[b, q, c] * feat[b, p, c]      (tcgen05 / TMEM GEMM, TMA-fed)
  * Replaces torch.einsum("bqc,bchw->bqhw") of the mask head (P/dvis_Plus/video_mask2former_transformer_decoder.py:363)
@@ -128,6 +142,19 @@ int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_stride, int 
                         const float *up, int64_t up_batch_stride, int up_h, int up_w, int H, int W, const float *pos,
                         float *out_f32, void *out_lp, void *out_lp_pos, int lp_dtype, int64_t out_batch_stride,
                         void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched linear assignment + index chain for the tracker's frame-to-frame query matching.
+ * Replaces, for a whole window at once, the per-frame `C.cpu()` + scipy.optimize.linear_sum_assignment(C.T)[1] of
+ * Noiser.match_embds (P/dvis_Plus/noiser.py:43-56; called per frame at P/dvis_Plus/tracker.py:224,285).
+ *   cost   (T, n, n) f32: cost[t][r][c] = 1 - cos(reference item r of frame t, current item c of frame t), where the
+ *          reference items of frame t are frame t-1's items in their ORIGINAL order (frame 0: the window's reference);
+ *          NaN entries count as 0 (noiser.py:52)
+ *   sigma  (T, n) i64 out: per-frame optimal assignment, row r -> column sigma[t][r]
+ *   idx    (T, n) i64 out: the tracker's indices, idx[t] = sigma[t] o idx[t-1], idx[-1] = idx_init (NULL = identity)
+ * n <= 1024.  One CTA per frame; exact (double potentials), equal to SciPy's result whenever the optimum is unique.
+ */
+int dvis_lap_chain(const float *cost, int T, int n, const int64_t *idx_init, int64_t *sigma, int64_t *idx, void *stream);
 
 #ifdef __cplusplus
 }

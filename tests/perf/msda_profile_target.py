@@ -1,4 +1,4 @@
-"""Tiny driver for `ncu`: launches each MSDA variant a few times at the 720p size (N frames, chosen regime)."""
+"""Tiny driver for `ncu`: launches the bf16 fused MSDA variants a few times at the 720p size (N frames, chosen regime)."""
 import os
 import sys
 
@@ -18,8 +18,8 @@ M, L, P = 8, 3, 4
 S = sum(h * w for h, w in shapes)
 value, loc, attn, offsets, logits, ref = make_inputs(regime, N, shapes)
 order = tiled_item_order(shapes, M, "cuda")
+vb, ob, lb = value.bfloat16(), offsets.view(N, S, -1).bfloat16(), logits.view(N, S, -1).bfloat16()
 for _ in range(3):
-    ops.ms_deform_attn_forward(value, sh_t, lsi, loc, attn, 128)
-    ops.ms_deform_attn_forward(value, sh_t, lsi, loc, attn, 128, item_order=order)
-    ops.msda_fused_forward(value, sh_t, lsi, offsets.view(N, S, -1), logits.view(N, S, -1), ref, M, L, P, item_order=order)
+    ops.msda_fused_forward(vb, sh_t, lsi, ob, lb, ref, M, L, P, item_order=order)
+    ops.msda_pair_forward(vb, sh_t, lsi, ob, lb, ref, M, L, P, item_order=order)
 torch.cuda.synchronize()

@@ -256,3 +256,32 @@ def test_predictor_fast_path_production_width():
         out = d(cuda(ms), mf.cuda())
     for k in ("pred_logits", "pred_masks", "pred_embds"):
         assert rel_err(out[k], ref[k]) < 8e-2, (k, rel_err(out[k], ref[k]))
+
+
+def test_lap_chain_matches_scipy():
+    """GPU Hungarian (one CTA per frame) vs scipy.optimize.linear_sum_assignment, incl. the index chain of the tracker."""
+    from scipy.optimize import linear_sum_assignment
+    from dvis_plus_b200 import ops
+    torch.manual_seed(0)
+    for T, n in ((1, 1), (3, 7), (5, 33), (16, 200), (2, 300)):
+        emb = torch.randn(T + 1, n, 64)
+        emb = emb / emb.norm(dim=-1, keepdim=True)
+        emb[1:] = 0.7 * emb[:-1][:, torch.randperm(n)] + 0.3 * emb[1:]            # consecutive frames are related
+        cost = 1 - torch.bmm(emb[:-1], emb[1:].transpose(1, 2))                   # rows = previous frame, cols = current
+        cost[0, 0, 0] = float("nan")                                              # NaN -> 0 like noiser.py:52
+        sigma, idx = ops.lap_chain(cost.cuda())
+        c = torch.where(torch.isnan(cost), torch.zeros_like(cost), cost).numpy()
+        prev = None
+        for t in range(T):
+            ref = linear_sum_assignment(c[t])[1]
+            assert np.array_equal(sigma[t].cpu().numpy(), ref), (T, n, t)
+            prev = ref if prev is None else ref[prev]
+            assert np.array_equal(idx[t].cpu().numpy(), prev)
+    # adversarial: random uniform costs (long augmenting paths)
+    cost = torch.rand(4, 150, 150)
+    sigma, _ = ops.lap_chain(cost.cuda())
+    for t in range(4):
+        ref = linear_sum_assignment(cost[t].numpy())[1]
+        got = sigma[t].cpu().numpy()
+        assert sorted(got.tolist()) == list(range(150))
+        assert abs(cost[t].numpy()[np.arange(150), got].sum() - cost[t].numpy()[np.arange(150), ref].sum()) < 1e-4

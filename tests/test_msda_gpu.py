@@ -176,3 +176,36 @@ def test_fused_variant_vs_oracle(vdtype, odtype, ref_dim, L, D):
                                  out_dtype=odtype).float().cpu()
     tol = 1e-2 if odtype == torch.bfloat16 else 1e-4
     assert (out - ref).abs().max() <= tol * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize("ref_dim,L,pdt", [(2, 3, torch.bfloat16), (4, 3, torch.float32), (2, 1, torch.bfloat16), (2, 4, torch.float32)])
+def test_pair_packed_variant_vs_oracle(ref_dim, L, pdt):
+    """bf16 pair-packed kernel: same contract as the fused variant; checked against the oracle on bf16-rounded value."""
+    from dvis_plus_b200 import ops
+    torch.manual_seed(5)
+    shapes = torch.as_tensor([(13, 17), (7, 9), (4, 5), (2, 3)][:L])
+    S = int(shapes.prod(1).sum())
+    N, M, D, P, Lq = 2, 8, 32, 4, 61
+    value = torch.randn(N, S, M, D)
+    fused = (torch.randn(N, Lq, M * L * P * 3) * 1.5).to(pdt)
+    offsets, logits = fused[..., :M * L * P * 2], fused[..., M * L * P * 2:]
+    ref_pts = torch.rand(N, Lq, L, ref_dim) * 1.2 - 0.1          # some points fall outside the map
+    if ref_dim == 4:
+        ref_pts[..., 2:] = ref_pts[..., 2:].abs() * 0.4
+    aw = logits.float().reshape(N, Lq, M, L * P).softmax(-1).view(N, Lq, M, L, P)
+    off = offsets.float().reshape(N, Lq, M, L, P, 2)
+    if ref_dim == 2:
+        norm = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float()
+        loc = ref_pts[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = ref_pts[:, :, None, :, None, :2] + off / P * ref_pts[:, :, None, :, None, 2:] * 0.5
+    ref = _oracle(value.bfloat16().float(), shapes, loc.contiguous(), aw.contiguous())
+    dev = "cuda"
+    f = fused.to(dev)
+    out = ops.msda_pair_forward(value.to(dev).bfloat16(), shapes.to(dev), lsi_of(shapes).to(dev), f[..., :M * L * P * 2],
+                                f[..., M * L * P * 2:], ref_pts.to(dev), M, L, P).float().cpu()
+    assert (out - ref).abs().max() <= 1e-2 * max(1.0, ref.abs().max())
+    # and against the staged fused kernel on identical inputs (differs only by fp16 weights / bf16 output rounding)
+    out2 = ops.msda_fused_forward(value.to(dev).bfloat16(), shapes.to(dev), lsi_of(shapes).to(dev), f[..., :M * L * P * 2],
+                                  f[..., M * L * P * 2:], ref_pts.to(dev), M, L, P).float().cpu()
+    assert (out - out2).abs().max() <= 1e-2 * max(1.0, ref.abs().max())
