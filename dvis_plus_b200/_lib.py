@@ -25,6 +25,8 @@ SIGNATURES = {
     "dvis_mask_logits": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp],
     "dvis_groupnorm_nhwc": [_vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp,
                             _vp, _i, _i64, _vp],
+    "dvis_resize_bilinear_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
+    "dvis_attn_bias_from_logits": [_vp, _i64, _i, _vp, _i, _vp],
     "dvis_lap_chain": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "dvis_add_layernorm": [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _i64, _i, _f, _vp, _vp, _vp, _i, _vp],
 }

@@ -166,6 +166,9 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         scale = 1.0 / math.sqrt(dh)
         B = x[0].shape[0]
         sizes, k_all, v_all, level_feats = [], [], [], []
+        mf_lp = mask_features
+        if mf_lp.dtype != torch.bfloat16 or not mf_lp.is_contiguous(memory_format=torch.channels_last):
+            mf_lp = mf_lp.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         for l in range(nl):
             xl = x[l] if len(self.input_proj[l]) == 0 else self.input_proj[l](x[l])
             h, w = xl.shape[-2:]
@@ -182,17 +185,22 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
                 k_all.append(None)
                 v_all.append(None)
             # mask features resized once to this level's grid: interpolate(E @ F) == E @ interpolate(F)
-            level_feats.append(F.interpolate(mask_features.float(), size=(h, w), mode="bilinear", align_corners=False)
-                               .to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
-        query_embed = self.query_embed.weight[None]                                                    # (1, Q, C)
-        output = self.query_feat.weight[None].expand(B, -1, -1).contiguous()                           # (B, Q, C) fp32
-        Q = output.shape[1]
+            level_feats.append(ops.resize_bilinear_nhwc(mf_lp, (h, w)))
+        query_embed = self.query_embed.weight.detach().float().contiguous()                            # (Q, C)
+        Q = query_embed.shape[0]
+        dn = self.decoder_norm
+        out32 = self.query_feat.weight.detach().float()[None].expand(B, -1, -1).contiguous()           # (B, Q, C) fp32 stream
+        out_lp = out32.to(dt)
+        out_q = (out32 + query_embed[None]).to(dt)                                                     # with_pos_embed(tgt, query_pos)
 
         def attn_bias(level):
-            logits = ops.mask_logits(self._mask_embed_of(output), level_feats[level], torch.float32).flatten(2)   # (B, Q, hw)
-            m = logits < 0                                           # sigmoid(x) < 0.5  <=>  x < 0
-            m = m & ~m.all(-1, keepdim=True)                         # fully masked rows attend everywhere (py:297)
-            return torch.zeros(m.shape, dtype=dt, device=m.device).masked_fill_(m, float("-inf"))[:, None]
+            normed_lp = ops.add_layernorm(out32, None, dn.weight, dn.bias, dn.eps, want_f32=False, lp_dtype=dt)[1]
+            logits = ops.mask_logits(self.mask_embed(normed_lp), level_feats[level], torch.float32)   # (B, Q, h, w)
+            return ops.attn_bias_from_logits(logits.flatten(2), dt)[:, None]                           # (B, 1, Q, hw)
+
+        def ln(norm, x, want_lp=True, want_q=True):
+            return ops.add_layernorm(x, out32, norm.weight, norm.bias, norm.eps, lp_dtype=dt if (want_lp or want_q) else None,
+                                     pos=query_embed if want_q else None)
 
         bias = attn_bias(0)
         for i in range(L):
@@ -200,22 +208,23 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
             j = i // nl
             sa, ff, ca = self.transformer_self_attention_layers[i], self.transformer_ffn_layers[i], self.transformer_cross_attention_layers[i]
             # masked cross-attention to level l
-            q = F.linear((output + query_embed).to(dt), f["wq"][i], f["bq"][i]).view(B, Q, H, dh).transpose(1, 2)
+            q = F.linear(out_q, f["wq"][i], f["bq"][i]).view(B, Q, H, dh).transpose(1, 2)
             o = F.scaled_dot_product_attention(q, k_all[l][j], v_all[l][j], attn_mask=bias, scale=scale)
             o = linear(ca.multihead_attn.out_proj, o.transpose(1, 2).reshape(B, Q, C))
-            output = add_norm(ca.norm, o, output)
+            out32, out_lp, out_q = ln(ca.norm, o)
             # self-attention over the queries
             m = sa.self_attn
             w, b = m._weights(dt)
-            qk = F.linear((output + query_embed).to(dt), w[:2 * C], b[:2 * C]).view(B, Q, 2, H, dh)
-            v = F.linear(output.to(dt), w[2 * C:], b[2 * C:]).view(B, Q, H, dh)
+            qk = F.linear(out_q, w[:2 * C], b[:2 * C]).view(B, Q, 2, H, dh)
+            v = F.linear(out_lp, w[2 * C:], b[2 * C:]).view(B, Q, H, dh)
             o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2), scale=scale)
             o = linear(m.out_proj, o.transpose(1, 2).reshape(B, Q, C))
-            output = add_norm(sa.norm, o, output)
+            out32, out_lp, _ = ln(sa.norm, o, want_q=False)
             # FFN
-            output = add_norm(ff.norm, linear(ff.linear2, linear(ff.linear1, output, relu=True)), output)
+            out32, out_lp, out_q = ln(ff.norm, linear(ff.linear2, linear(ff.linear1, out_lp, relu=True)))
             if i + 1 < L:
                 bias = attn_bias((i + 1) % nl)
+        output = out32
         normed = self.decoder_norm(output)
         cls = linear(self.class_embed, normed).float()                                                 # (B, Q, K+1)
         masks = ops.mask_logits(self.mask_embed(normed), mask_features, torch.float32)                 # (B, Q, H, W)

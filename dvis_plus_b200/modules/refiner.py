@@ -43,8 +43,10 @@ class TemporalRefiner(nn.Module):
         """x (bq, c, t) -> conv(k5) -> ReLU -> conv(k3), replicate padding (py:44-52,116-119)."""
         c5, c3 = self.conv_short_aggregate_layers[i][0], self.conv_short_aggregate_layers[i][2]
         dt = gemm_dtype() if _fast_path(x) else x.dtype
-        y = F.conv1d(F.pad(x.to(dt), (2, 2), mode="replicate"), c5.weight.to(dt), c5.bias.to(dt))
-        y = F.conv1d(F.pad(F.relu(y), (1, 1), mode="replicate"), c3.weight.to(dt), c3.bias.to(dt))
+        x = x.to(dt)
+        rep = lambda z, k: torch.cat([z[..., :1].expand(-1, -1, k), z, z[..., -1:].expand(-1, -1, k)], dim=-1)   # replicate pad
+        y = F.conv1d(rep(x, 2), c5.weight.to(dt), c5.bias.to(dt))
+        y = F.conv1d(rep(F.relu(y), 1), c3.weight.to(dt), c3.bias.to(dt))
         return y
 
     def refine(self, instance_embeds, frame_embeds):

@@ -260,3 +260,26 @@ def lap_chain(cost, idx_init=None):
         _lib.call("dvis_lap_chain", cost.data_ptr(), T, n, idx_init.data_ptr() if idx_init is not None else None,
                   sigma.data_ptr(), idx.data_ptr(), _stream())
     return sigma, idx
+
+
+def resize_bilinear_nhwc(x, size):
+    """F.interpolate(x, size, mode="bilinear", align_corners=False) for a bf16 channels_last (N, C, h, w) map; returns a
+    bf16 channels_last (N, C, H, W) map (dvis_resize_bilinear_nhwc)."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    N, C, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _lib.call("dvis_resize_bilinear_nhwc", x.data_ptr(), N, h, w, C, out.data_ptr(), H, W, _stream())
+    return out
+
+
+def attn_bias_from_logits(logits, dtype=torch.bfloat16):
+    """(..., hw) f32 mask logits -> additive attention bias of the same shape: -inf where sigmoid(logit) < 0.5, rows that
+    would be fully masked reset to 0 (dvis_attn_bias_from_logits)."""
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
+    hw = logits.shape[-1]
+    bias = torch.empty(logits.shape, dtype=dtype, device=logits.device)
+    with torch.cuda.device(logits.device):
+        _lib.call("dvis_attn_bias_from_logits", logits.data_ptr(), logits.numel() // hw, hw, bias.data_ptr(), _DTYPE[dtype], _stream())
+    return bias

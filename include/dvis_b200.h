@@ -156,6 +156,17 @@ int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_stride, int 
  */
 int dvis_lap_chain(const float *cost, int T, int n, const int64_t *idx_init, int64_t *sigma, int64_t *idx, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Helpers of the masked-attention decoder's mask head (P/dvis_Plus/video_mask2former_transformer_decoder.py:358-374).
+ * dvis_resize_bilinear_nhwc: F.interpolate(mode="bilinear", align_corners=False) (py:367) of a channels-last bf16 map
+ *   in (N, h, w, C) -> out (N, H, W, C); C % 4 == 0.  Used once per attention level on mask_features:
+ *   interpolate(E @ F) == E @ interpolate(F).
+ * dvis_attn_bias_from_logits: logits (rows, hw) f32 -> additive attention bias (rows, hw) f32|bf16: -inf where
+ *   sigmoid(logit) < 0.5 (py:370-371), 0 elsewhere; a row that would be -inf everywhere becomes all 0 (py:297).
+ */
+int dvis_resize_bilinear_nhwc(const void *in, int N, int h, int w, int C, void *out, int H, int W, void *stream);
+int dvis_attn_bias_from_logits(const float *logits, int64_t rows, int hw, void *bias, int bias_dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,3 +285,23 @@ def test_lap_chain_matches_scipy():
         got = sigma[t].cpu().numpy()
         assert sorted(got.tolist()) == list(range(150))
         assert abs(cost[t].numpy()[np.arange(150), got].sum() - cost[t].numpy()[np.arange(150), ref].sum()) < 1e-4
+
+
+@torch.no_grad()
+def test_resize_and_attn_bias_kernels():
+    from dvis_plus_b200 import ops
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.randn(3, 64, 23, 40, device="cuda").to(torch.bfloat16, memory_format=torch.channels_last)
+    for size in ((12, 20), (6, 10), (46, 80), (5, 7)):
+        ref = F.interpolate(x.float(), size=size, mode="bilinear", align_corners=False)
+        out = ops.resize_bilinear_nhwc(x, size)
+        assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+        assert (out.float() - ref).abs().max() < 1e-2 * ref.abs().max()
+    logits = torch.randn(4, 9, 333, device="cuda")
+    logits[1, 3] = -logits[1, 3].abs() - 0.1          # a fully masked row -> must become all zeros (decoder.py:297)
+    bias = ops.attn_bias_from_logits(logits, torch.float32)
+    m = logits.sigmoid() < 0.5
+    m[m.all(-1)] = False
+    ref = torch.zeros_like(logits).masked_fill_(m, float("-inf"))
+    assert torch.equal(bias, ref) and bias[1, 3].abs().max() == 0
