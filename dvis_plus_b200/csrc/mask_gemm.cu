@@ -38,6 +38,7 @@ struct MaskGemmParams {
   int B, Q, Qpad, KB;   // KB = C / 64
   int64_t HW;
   int tiles_per_batch, total_tiles, stages;
+  int *row_open;        // kBias epilogue: row_open[b*Q + q] = 1 if some pixel of the row has logit >= 0
 };
 
 struct __align__(8) Barriers {
@@ -57,7 +58,10 @@ __device__ __forceinline__ __nv_bfloat16 cvt_logit<__nv_bfloat16>(uint32_t bits)
 }
 
 // kTmaStore = false: direct (still coalesced) global stores for outputs whose row pitch is not a multiple of 16 bytes
-template <typename TO, bool kTmaStore>
+// kBias = true: the epilogue writes the additive attention bias of the masked-attention decoder instead of the logits:
+// -inf where sigmoid(logit) < 0.5 <=> logit < 0, else 0 (decoder.py:370-371), and records per (b, q) row whether any pixel
+// stays open so that fully masked rows can be reset afterwards (decoder.py:297).
+template <typename TO, bool kTmaStore, bool kBias = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_emb,
                  const __grid_constant__ CUtensorMap tmap_out, const MaskGemmParams p) {
@@ -165,6 +169,16 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
         uint32_t r[32];
         tmem_ld_32x32(taddr + c0, r);
         tmem_ld_wait();
+        if constexpr (kBias) {
+          const bool pix_ok = (int64_t)tile * kTileM + px < p.HW;
+#pragma unroll
+          for (int i = 0; i < kEpiCols; ++i) {
+            const bool open = pix_ok && !(__uint_as_float(r[i]) < 0.f);
+            const unsigned any = __ballot_sync(0xffffffffu, open);
+            if (any && lane == 0 && c0 + i < p.Q) p.row_open[b * p.Q + c0 + i] = 1;
+            r[i] = open ? 0u : 0xff800000u;                 // 0.0f / -inf
+          }
+        }
         if constexpr (kTmaStore) {
           TO *buf = sOut + (n_chunk & 1) * (kEpiCols * kTileM);
           if (issuer) tma_store_wait_read<1>();          // the store that last read this buffer (2 chunks ago) is done
@@ -219,8 +233,41 @@ int encode_map(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int e
 
 using namespace dvis;
 
+namespace dvis {
+namespace {
+// rows whose every position is masked attend everywhere: reset them to 0 (decoder.py:297)
+template <typename TB>
+__global__ void __launch_bounds__(256) reset_closed_rows_kernel(const int *__restrict__ row_open, TB *__restrict__ bias, int64_t HW) {
+  const int64_t row = blockIdx.x;
+  if (row_open[row]) return;
+  TB *b = bias + row * HW;
+  for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) b[i] = TB(0.f);
+}
+}  // namespace
+int mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
+                     int *row_open, void *stream);
+}  // namespace dvis
+
 extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out,
                                 int out_dtype, void *stream) {
+  return mask_gemm_launch(emb, feat, B, Q, C, HW, out, out_dtype, nullptr, stream);
+}
+
+extern "C" int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias,
+                                   int bias_dtype, int *row_open_workspace, void *stream) {
+  DVIS_REQUIRE(row_open_workspace, "mask_attn_bias: null workspace");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(row_open_workspace, 0, sizeof(int) * size_t(B) * Q, s);
+  if (int rc = mask_gemm_launch(emb, feat, B, Q, C, HW, bias, bias_dtype, row_open_workspace, stream)) return rc;
+  if (bias_dtype == DVIS_F32)
+    reset_closed_rows_kernel<float><<<B * Q, 256, 0, s>>>(row_open_workspace, static_cast<float *>(bias), HW);
+  else
+    reset_closed_rows_kernel<__nv_bfloat16><<<B * Q, 256, 0, s>>>(row_open_workspace, static_cast<__nv_bfloat16 *>(bias), HW);
+  return check_launch("reset_closed_rows_kernel");
+}
+
+int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
+                           int *row_open, void *stream) {
   DVIS_REQUIRE(emb && feat && out, "mask_logits: null pointer argument");
   DVIS_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_logits: sizes must be positive");
   DVIS_REQUIRE(C % kBlockK == 0 && C <= 512, "mask_logits: C must be a multiple of 64 and <= 512 (got %d)", C);
@@ -232,6 +279,7 @@ extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q,
 
   MaskGemmParams p{};
   p.out = out; p.B = B; p.Q = Q; p.Qpad = (Q + 15) & ~15; p.KB = C / kBlockK; p.HW = HW;
+  p.row_open = row_open;
   p.tiles_per_batch = int((HW + kTileM - 1) / kTileM);
   p.total_tiles = p.tiles_per_batch * B;
   const int b_bytes = p.KB * p.Qpad * 128;
@@ -255,13 +303,18 @@ extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q,
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = std::min(p.total_tiles, kNumSMs);
-#define DVIS_LAUNCH(TO, TMA)                                                                                   \
-  do {                                                                                                         \
-    cudaFuncSetAttribute(mask_gemm_kernel<TO, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));    \
-    mask_gemm_kernel<TO, TMA><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);                         \
+#define DVIS_LAUNCH(TO, TMA, BIAS)                                                                                   \
+  do {                                                                                                               \
+    cudaFuncSetAttribute(mask_gemm_kernel<TO, TMA, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));    \
+    mask_gemm_kernel<TO, TMA, BIAS><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);                         \
   } while (0)
-  if (out_dtype == DVIS_F32) { if (tma_store) DVIS_LAUNCH(float, true); else DVIS_LAUNCH(float, false); }
-  else { if (tma_store) DVIS_LAUNCH(__nv_bfloat16, true); else DVIS_LAUNCH(__nv_bfloat16, false); }
+#define DVIS_LAUNCH_T(TO)                                                                            \
+  do {                                                                                               \
+    if (row_open) { if (tma_store) DVIS_LAUNCH(TO, true, true); else DVIS_LAUNCH(TO, false, true); } \
+    else { if (tma_store) DVIS_LAUNCH(TO, true, false); else DVIS_LAUNCH(TO, false, false); }        \
+  } while (0)
+  if (out_dtype == DVIS_F32) DVIS_LAUNCH_T(float); else DVIS_LAUNCH_T(__nv_bfloat16);
+#undef DVIS_LAUNCH_T
 #undef DVIS_LAUNCH
   return check_launch("mask_gemm_kernel");
 }

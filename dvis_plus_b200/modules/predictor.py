@@ -195,8 +195,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
 
         def attn_bias(level):
             normed_lp = ops.add_layernorm(out32, None, dn.weight, dn.bias, dn.eps, want_f32=False, lp_dtype=dt)[1]
-            logits = ops.mask_logits(self.mask_embed(normed_lp), level_feats[level], torch.float32)   # (B, Q, h, w)
-            return ops.attn_bias_from_logits(logits.flatten(2), dt)[:, None]                           # (B, 1, Q, hw)
+            return ops.mask_attn_bias(self.mask_embed(normed_lp), level_feats[level], dt)[:, None]   # (B, 1, Q, hw)
 
         def ln(norm, x, want_lp=True, want_q=True):
             return ops.add_layernorm(x, out32, norm.weight, norm.bias, norm.eps, lp_dtype=dt if (want_lp or want_q) else None,

@@ -342,7 +342,7 @@ class ReferringTracker_noiser(nn.Module):
         for t in range(T):
             first = prev_last is None
             ref_src = cur_nn[t] if first else prev_last
-            if self.use_cuda_graph:
+            if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
                 graph, s_ref, s_id, s_kv, s_out, s_refout = self._graph_step(f, first, Q, dev)
                 s_ref.copy_(ref_src)
                 s_id.copy_(init[t])

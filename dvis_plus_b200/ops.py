@@ -283,3 +283,21 @@ def attn_bias_from_logits(logits, dtype=torch.bfloat16):
     with torch.cuda.device(logits.device):
         _lib.call("dvis_attn_bias_from_logits", logits.data_ptr(), logits.numel() // hw, hw, bias.data_ptr(), _DTYPE[dtype], _stream())
     return bias
+
+
+def mask_attn_bias(mask_embed, level_features, dtype=torch.bfloat16):
+    """Attention bias of the masked-attention decoder straight from the tcgen05 mask GEMM (dvis_mask_attn_bias):
+    mask_embed (B,Q,C); level_features (B,C,h,w) bf16 channels_last = mask_features resized to the attention level.
+    -> (B, Q, h*w) `dtype`: -inf where sigmoid(E @ F) < 0.5, rows that would be fully masked reset to 0."""
+    B, Q, C = mask_embed.shape
+    _, _, h, w = level_features.shape
+    assert level_features.dtype == torch.bfloat16 and level_features.is_contiguous(memory_format=torch.channels_last)
+    emb = mask_embed.to(torch.bfloat16).contiguous()
+    if Q > 256:
+        return attn_bias_from_logits(mask_logits(mask_embed, level_features, torch.float32).flatten(2), dtype)
+    bias = torch.empty((B, Q, h * w), dtype=dtype, device=emb.device)
+    ws = torch.empty(B * Q, dtype=torch.int32, device=emb.device)
+    with torch.cuda.device(emb.device):
+        _lib.call("dvis_mask_attn_bias", emb.data_ptr(), level_features.data_ptr(), B, Q, C, h * w, bias.data_ptr(),
+                  _DTYPE[dtype], ws.data_ptr(), _stream())
+    return bias

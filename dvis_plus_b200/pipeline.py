@@ -55,6 +55,27 @@ class OfflineClipRunner:
         return self.temporal_stage(seg, mask_features)
 
     @torch.no_grad()
+    def segment_stage(self, features):
+        """Per-frame stage on this rank's frames: -> (packed query block (t_local, Q, 2C+K+1) fp32, mask_features)."""
+        mask_features, _, multi_scale = self.pixel_decoder.forward_features(features)
+        seg = self.predictor(multi_scale, mask_features)
+        return self.pack_queries(seg), mask_features
+
+    @torch.no_grad()
+    def temporal_from_block(self, block, mask_features, C):
+        """Tracker + refiner + final masks from the GATHERED query block (T, Q, 2C+K+1) and local mask features."""
+        t_local = mask_features.shape[0]
+        frame_embds, frame_embds_no_norm, _ = self.unpack_queries(block, C)
+        track = self.tracker(frame_embds, None, resume=False, frame_embeds_no_norm=frame_embds_no_norm, with_masks=False)
+        outputs = self.refiner.refine(track["pred_embds"], frame_embds_no_norm)
+        dec = self.refiner.decoder_norm(outputs[:, -1:]).permute(1, 3, 0, 2, 4)
+        logits = self.refiner.pred_class(dec)[-1].transpose(1, 2)
+        t0 = self.rank * t_local
+        masks = self.refiner.predict_masks(outputs[t0:t0 + t_local], mask_features[None])
+        return {"pred_logits": logits, "pred_masks": masks, "pred_embds": dec[0].permute(0, 3, 1, 2),
+                "online_pred_logits": track["pred_logits"]}
+
+    @torch.no_grad()
     def temporal_stage(self, seg, mask_features):
         """Exchange + tracker + refiner + final masks, given this rank's segmenter outputs (`seg`: the predictor's
         dict for t_local frames) and its local mask features (t_local, C, H, W)."""
@@ -72,3 +93,94 @@ class OfflineClipRunner:
         masks = self.refiner.predict_masks(outputs[t0:t0 + t_local], mask_features[None])
         return {"pred_logits": logits, "pred_masks": masks, "pred_embds": dec[0].permute(0, 3, 1, 2),
                 "online_pred_logits": track["pred_logits"]}
+
+
+class GraphedClipRunner:
+    """The clip pipeline as CUDA graphs, software-pipelined across clips.
+
+    Stage A (pixel decoder + predictor on this rank's frames) and stage B (tracker + refiner + final masks) are each
+    captured once into a CUDA graph; the NCCL all-gather of the query block runs between them.  Nothing in either stage
+    synchronises with the host (the Hungarian matching runs on the GPU), so a step is 2 graph launches + 1 collective
+    instead of ~2000 kernel launches -- which is what keeps the host off the critical path when the per-rank work shrinks
+    with the number of GPUs.  With `depth` = 2 two instances alternate and stage B of clip i (latency-bound, tiny kernels)
+    overlaps stage A of clip i+1 (bandwidth / tensor bound) on a second stream.
+    """
+
+    def __init__(self, runner: OfflineClipRunner, example_features, depth=2):
+        self.r = runner
+        self.depth = depth
+        self.slots = []
+        self.stream_a = torch.cuda.Stream()
+        self.stream_b = torch.cuda.Stream(priority=-1)           # latency-bound stage: its tiny kernels go first
+        self.stream_c = torch.cuda.Stream()                      # host -> device copies of the next clip's inputs
+        self.n = 0
+        self.captured_launches = 0
+        dev = next(iter(example_features.values())).device
+        with torch.no_grad():
+            for _ in range(2):                                   # populate caches / autotune outside capture
+                blk, mf = runner.segment_stage(example_features)
+                runner.temporal_from_block(runner.gather_queries(blk), mf, self._C(blk))
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        for _ in range(depth):
+            n0 = _lib.launch_count
+            slot = {"in": {k: v.clone() for k, v in example_features.items()}}
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, stream=self.stream_a), torch.no_grad():
+                slot["block"], slot["mf"] = runner.segment_stage(slot["in"])
+            slot["ga"] = ga
+            slot["gathered"] = torch.empty((runner.world * slot["block"].shape[0],) + tuple(slot["block"].shape[1:]),
+                                           dtype=slot["block"].dtype, device=dev)
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, stream=self.stream_b), torch.no_grad():
+                slot["out"] = runner.temporal_from_block(slot["gathered"], slot["mf"], self._C(slot["block"]))
+            slot["gb"] = gb
+            slot["ev_a"] = torch.cuda.Event()
+            slot["ev_b"] = torch.cuda.Event()
+            slot["ev_c"] = torch.cuda.Event()
+            self.captured_launches = _lib.launch_count - n0       # libdvis_b200 kernels inside one clip's two graphs
+            self.slots.append(slot)
+        torch.cuda.synchronize(dev)
+
+    def _C(self, block):
+        K1 = self.r.refiner.class_embed.out_features
+        return (block.shape[-1] - K1) // 2
+
+    def submit(self, features=None, d2h=None):
+        """Enqueue one clip.  `features`: optional host (pinned) tensors copied into the slot's input buffers on the
+        copy stream first; `d2h`: optional dict name -> pinned host tensor that receives slot["out"][name] after stage B.
+        Returns the slot; its `out` is valid once slot["ev_b"] has completed."""
+        slot = self.slots[self.n % self.depth]
+        self.n += 1
+        cur = torch.cuda.current_stream()
+        if features is not None:
+            self.stream_c.wait_stream(cur)
+            self.stream_c.wait_event(slot["ev_a"])                # the slot's previous stage A has consumed its inputs
+            with torch.cuda.stream(self.stream_c):
+                for k, v in features.items():
+                    slot["in"][k].copy_(v, non_blocking=True)
+                slot["ev_c"].record(self.stream_c)
+            self.stream_a.wait_event(slot["ev_c"])
+        self.stream_a.wait_stream(cur)
+        self.stream_a.wait_event(slot["ev_b"])                    # this slot's previous clip has finished with its buffers
+        with torch.cuda.stream(self.stream_a):
+            slot["ga"].replay()
+            slot["ev_a"].record(self.stream_a)
+        self.stream_b.wait_event(slot["ev_a"])
+        with torch.cuda.stream(self.stream_b):
+            if self.r.world > 1:
+                dist.all_gather_into_tensor(slot["gathered"], slot["block"], group=self.r.group)
+            else:
+                slot["gathered"].copy_(slot["block"])
+            slot["gb"].replay()
+            if d2h is not None:
+                for k, v in d2h.items():
+                    v.copy_(slot["out"][k], non_blocking=True)
+            slot["ev_b"].record(self.stream_b)
+        return slot
+
+    def wait_all(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.stream_a)
+        cur.wait_stream(self.stream_b)
+        cur.wait_stream(self.stream_c)

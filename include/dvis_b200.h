@@ -156,6 +156,14 @@ int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_stride, int 
  */
 int dvis_lap_chain(const float *cost, int T, int n, const int64_t *idx_init, int64_t *sigma, int64_t *idx, void *stream);
 
+/* Same GEMM with the masked-attention decoder's threshold fused into the epilogue
+ * (P/dvis_Plus/video_mask2former_transformer_decoder.py:370-371 and :297): writes, instead of the logits, the additive
+ * attention bias (B, Q, HW) in bias_dtype (DVIS_F32 | DVIS_BF16): -inf where sigmoid(logit) < 0.5, 0 elsewhere, rows that
+ * would be -inf everywhere reset to 0.  row_open_workspace: B*Q ints of scratch.  `feat` is mask_features already
+ * resized to the attention level (interpolate(E @ F) == E @ interpolate(F)). */
+int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias, int bias_dtype,
+                        int *row_open_workspace, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Helpers of the masked-attention decoder's mask head (P/dvis_Plus/video_mask2former_transformer_decoder.py:358-374).
  * dvis_resize_bilinear_nhwc: F.interpolate(mode="bilinear", align_corners=False) (py:367) of a channels-last bf16 map

@@ -71,3 +71,20 @@ def test_mask_logits_720p_full_size_properties():
     ref = torch.einsum("bqc,bpc->bqp", emb1.float().cpu().double(), fs.double()).float()
     got = o1.reshape(B, Q, H * W)[:, :, idx.cuda()].cpu()
     assert (got - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_mask_attn_bias_fused_epilogue(dtype):
+    """Threshold fused into the GEMM epilogue == attn_bias_from_logits(mask_logits(...)); includes a fully masked row."""
+    from dvis_plus_b200 import ops
+    emb, feat = _case(3, 50, 64, 23, 40, seed=9)
+    emb[1, 7] = 0
+    emb[1, 7, 0] = -50.0
+    feat[1, 0] = feat[1, 0].abs() + 0.1              # row (1,7): every logit < 0 -> must come out as all zeros
+    e, f = emb.cuda(), feat.cuda().to(torch.bfloat16, memory_format=torch.channels_last)
+    logits = ops.mask_logits(e, f, torch.float32).flatten(2)
+    assert (logits[1, 7] < 0).all()
+    ref = ops.attn_bias_from_logits(logits, dtype)
+    got = ops.mask_attn_bias(e, f, dtype)
+    assert torch.equal(got, ref)
+    assert got[1, 7].abs().max() == 0 and torch.isinf(got).any()
