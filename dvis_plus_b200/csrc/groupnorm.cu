@@ -81,33 +81,36 @@ struct GnApplyParams {
   int64_t out_batch_stride;  // elements between batch items of every output
 };
 
+// grid (pixel chunks, N); a thread owns 4 fixed channels (its group's mean / rstd and gamma / beta stay in registers) and
+// walks pixels with stride blockDim / (C/4)
 template <typename T, typename TL>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, int pix_per_cta) {
   const int quads = p.C / 4;
-  const int64_t total = (int64_t)p.N * p.HW * quads;
-  const float inv_cnt = 1.f / (float(p.HW) * float(p.C / p.G));
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cq = int(i % quads);
-    const int64_t np = i / quads;
-    const int pix = int(np % p.HW), n = int(np / p.HW);
-    const int c = cq * 4, g = c / (p.C / p.G);
-    const double su = p.sums[((size_t)n * p.G + g) * 2], sq = p.sums[((size_t)n * p.G + g) * 2 + 1];
-    const float mean = float(su * inv_cnt);
-    const float var = fmaxf(float(sq * inv_cnt - (su * inv_cnt) * (su * inv_cnt)), 0.f);
-    const float rstd = rsqrtf(var + p.eps);
-    const float4 v = ld4<T>(static_cast<const T *>(p.x) + (size_t)n * p.x_batch_stride + (size_t)pix * p.C + c);
-    const float4 ga = *reinterpret_cast<const float4 *>(p.gamma + c), be = *reinterpret_cast<const float4 *>(p.beta + c);
-    float4 y = make_float4((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y,
-                           (v.z - mean) * rstd * ga.z + be.z, (v.w - mean) * rstd * ga.w + be.w);
-    if (p.up) {
+  const int cq = threadIdx.x % quads, pl = threadIdx.x / quads, prow = blockDim.x / quads;
+  if (pl >= prow) return;
+  const int n = blockIdx.y;
+  const int c = cq * 4, g = c / (p.C / p.G);
+  const double inv_cnt = 1.0 / (double(p.HW) * double(p.C / p.G));
+  const double su = p.sums[((size_t)n * p.G + g) * 2] * inv_cnt, sq = p.sums[((size_t)n * p.G + g) * 2 + 1] * inv_cnt;
+  const float mean = float(su);
+  const float rstd = rsqrtf(fmaxf(float(sq - su * su), 0.f) + p.eps);
+  const float4 ga = *reinterpret_cast<const float4 *>(p.gamma + c), be = *reinterpret_cast<const float4 *>(p.beta + c);
+  const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+  const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+  const T *xn = static_cast<const T *>(p.x) + (size_t)n * p.x_batch_stride + c;
+  const float *u = p.up ? p.up + (size_t)n * p.up_batch_stride + c : nullptr;
+  const float ry = float(p.uh) / float(max(p.H, 1)), rx = float(p.uw) / float(max(p.W, 1));
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, p.HW);
+  for (int pix = p0 + pl; pix < p1; pix += prow) {
+    const float4 v = ld4<T>(xn + (size_t)pix * p.C);
+    float4 y = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+    if (u) {
       // F.interpolate(mode="bilinear", align_corners=False): src = (dst + 0.5) * in/out - 0.5, clamped at 0
       const int oy = pix / p.W, ox = pix - oy * p.W;
-      const float fy = fmaxf((oy + 0.5f) * (float(p.uh) / float(p.H)) - 0.5f, 0.f);
-      const float fx = fmaxf((ox + 0.5f) * (float(p.uw) / float(p.W)) - 0.5f, 0.f);
-      const int y0 = int(fy), x0 = int(fx);
+      const float fy = fmaxf((oy + 0.5f) * ry - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * rx - 0.5f, 0.f);
+      const int y0 = min(int(fy), p.uh - 1), x0 = min(int(fx), p.uw - 1);
       const int y1 = min(y0 + 1, p.uh - 1), x1 = min(x0 + 1, p.uw - 1);
       const float ly = fy - y0, lx = fx - x0;
-      const float *u = p.up + (size_t)n * p.up_batch_stride + c;
       const float4 a = *reinterpret_cast<const float4 *>(u + ((size_t)y0 * p.uw + x0) * p.C);
       const float4 b = *reinterpret_cast<const float4 *>(u + ((size_t)y0 * p.uw + x1) * p.C);
       const float4 cc = *reinterpret_cast<const float4 *>(u + ((size_t)y1 * p.uw + x0) * p.C);
@@ -159,12 +162,12 @@ extern "C" int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_s
   if (int rc = check_launch("gn_stats_kernel")) return rc;
   GnApplyParams p{x, x_batch_stride, sums_workspace, gamma, beta, N, HW, C, G, eps, relu, up, up_batch_stride, up_h, up_w,
                   H, W, pos, out_f32, out_lp, out_lp_pos, out_batch_stride};
-  const int64_t total = (int64_t)N * HW * (C / 4);
-  const int blocks = int(std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16));
+  const int apply_pix = 64;                                     // 16 pixels per thread row at C = 256
+  dim3 agrid((HW + apply_pix - 1) / apply_pix, N);
   using bf = __nv_bfloat16;
-  if (x_dtype == DVIS_F32 && lp_dtype == DVIS_F32) gn_apply_kernel<float, float><<<blocks, 256, 0, s>>>(p);
-  else if (x_dtype == DVIS_F32) gn_apply_kernel<float, bf><<<blocks, 256, 0, s>>>(p);
-  else if (lp_dtype == DVIS_F32) gn_apply_kernel<bf, float><<<blocks, 256, 0, s>>>(p);
-  else gn_apply_kernel<bf, bf><<<blocks, 256, 0, s>>>(p);
+  if (x_dtype == DVIS_F32 && lp_dtype == DVIS_F32) gn_apply_kernel<float, float><<<agrid, 256, 0, s>>>(p, apply_pix);
+  else if (x_dtype == DVIS_F32) gn_apply_kernel<float, bf><<<agrid, 256, 0, s>>>(p, apply_pix);
+  else if (lp_dtype == DVIS_F32) gn_apply_kernel<bf, float><<<agrid, 256, 0, s>>>(p, apply_pix);
+  else gn_apply_kernel<bf, bf><<<agrid, 256, 0, s>>>(p, apply_pix);
   return check_launch("gn_apply_kernel");
 }

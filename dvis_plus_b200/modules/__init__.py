@@ -5,3 +5,5 @@ from .pixel_decoder import MSDeformAttnPixelDecoder  # noqa: F401
 from .predictor import VideoMultiScaleMaskedTransformerDecoder_dvisPlus  # noqa: F401
 from .tracker import ReferringTracker_noiser  # noqa: F401
 from .refiner import TemporalRefiner  # noqa: F401
+from .daq import SlotCrossAttentionLayer, VideoInstanceCutter  # noqa: F401
+from .daq import TemporalRefiner as DAQTemporalRefiner  # noqa: F401

@@ -156,5 +156,77 @@ def main():
                                   pred_logits=o["pred_logits"], pred_masks=o["pred_masks"], pred_embds=o["pred_embds"]))
 
 
+class cuda_to_cpu:
+    """The DAQ reference hard-codes `.to("cuda")` (D/dvis_daq/track_module.py:757,779): while generating fixtures on this
+    GPU-less box the harness maps that device string to "cpu"; the reference source itself stays untouched."""
+
+    def __enter__(self):
+        self._orig = torch.Tensor.to
+        orig = self._orig
+
+        def to(t, *args, **kwargs):
+            args = tuple("cpu" if (isinstance(a, str) and a.startswith("cuda")) else a for a in args)
+            if isinstance(kwargs.get("device"), str) and kwargs["device"].startswith("cuda"):
+                kwargs["device"] = "cpu"
+            return orig(t, *args, **kwargs)
+        torch.Tensor.to = to
+
+    def __exit__(self, *exc):
+        torch.Tensor.to = self._orig
+
+
+@torch.no_grad()
+def main_daq():
+    import random
+    R = rl.load()
+    # 10. DVIS-DAQ tracker inference: hidden 64, 2 layers, num_new_ins = fQ new-instance queries (track_module.py:640-641), 3 slots; T=4 frames as windows [0:3],[3:4]
+    torch.manual_seed(7)
+    random.seed(7)
+    C, fQ, T, H, W = 64, 10, 4, 16, 24
+    cut = R.VideoInstanceCutter(hidden_dim=C, feedforward_dim=128, num_head=8, decoder_layer_num=2, mask_dim=C, num_classes=5,
+                                num_new_ins=fQ, inference_select_threshold=0.1, kick_out_frame_num=2, num_slots=3,
+                                keep_threshold=0.01, ovis_infer=True).eval()
+    torch.nn.init.normal_(cut.class_embed.weight, std=0.5)          # spread the scores so that some queries are (in)valid
+    seg_query_feat = torch.nn.Embedding(fQ, C)
+    fe = torch.randn(1, C, T, fQ)
+    mf = torch.randn(1, T, C, H, W)
+    valid = [[torch.rand(fQ) > 0.4] for _ in range(T)]
+    pm = [[torch.randn(fQ, H, W)] for _ in range(T)]
+    info = lambda a, b: {"seg_query_feat": seg_query_feat, "valid": valid[a:b], "pred_masks": pm[a:b]}
+    with cuda_to_cpu():
+        cut.inference(fe[:, :, :3], mf[:, :3], info(0, 3), 0, resume=False, to_store="cpu")
+        cut.inference(fe[:, :, 3:], mf[:, 3:], info(3, 4), 3, resume=True, to_store="cpu")
+    seqs = []
+    for sid in cut.memory_seq_ids:
+        s = cut.video_ins_hub[sid]
+        seqs.append(dict(sT=s.sT, dead=s.dead, appearance=list(s.appearance), embeds=torch.stack(s.embeds),
+                         pred_logits=torch.stack(s.pred_logits), pred_masks=torch.stack(s.pred_masks),
+                         pos=s.similarity_guided_pos_embed))
+    save("daq_tracker_small.pt", dict(state_dict=cut.state_dict(), seg_query_feat=seg_query_feat.weight.detach(), frame_embeds=fe,
+                                      mask_features=mf, valid=[v[0] for v in valid], pred_masks=[p[0] for p in pm], seqs=seqs,
+                                      track_queries=cut.track_queries, track_embeds=cut.track_embeds, seed=7))
+
+    # 11. SlotCrossAttentionLayer alone
+    torch.manual_seed(8)
+    sl = R.SlotCrossAttentionLayer(d_model=C, nhead=8).eval()
+    tgt, mem, qp, sq = torch.randn(7, 1, C), torch.randn(10, 1, C), torch.randn(7, 1, C), torch.randn(7, 1, C)
+    save("daq_slot_layer.pt", dict(state_dict=sl.state_dict(), tgt=tgt, memory=mem, query_pos=qp, slot_query=sq,
+                                   out=sl(tgt, mem, query_pos=qp, slot_query=sq)))
+
+    # 12. DAQ TemporalRefiner (no local conv branch, like the released configs), eval
+    torch.manual_seed(9)
+    rf = R.DAQTemporalRefiner(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=C,
+                              class_num=5, windows=3, use_local_attn=False).eval()
+    Tn, Q = 5, 9
+    inst, fr, mfeat = torch.randn(1, C, Tn, Q), torch.randn(1, C, Tn, Q), torch.randn(1, Tn, C, H, W)
+    o = rf(inst, torch.zeros(1, Q, Tn, dtype=torch.bool), fr, mfeat, None)
+    save("daq_refiner_small.pt", dict(state_dict=rf.state_dict(), instance_embeds=inst, frame_embeds=fr, mask_features=mfeat,
+                                      pred_logits=o["pred_logits"], pred_masks=o["pred_masks"], pred_embds=o["pred_embds"]))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "daq":
+        main_daq()
+    else:
+        main()
+        main_daq()

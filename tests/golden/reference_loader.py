@@ -129,6 +129,7 @@ def install():
     _ns("mask2former_video.modeling", f"{P}/mask2former_video/modeling")
     _ns("mask2former_video.modeling.transformer_decoder", f"{P}/mask2former_video/modeling/transformer_decoder")
     _ns("dvis_Plus", f"{P}/dvis_Plus")
+    _ns("dvis_daq", f"{REF_ROOT}/DVIS_DAQ/dvis_daq")
     _installed = True
 
 
@@ -142,7 +143,13 @@ def load():
     dec = importlib.import_module("dvis_Plus.video_mask2former_transformer_decoder")
     trk = importlib.import_module("dvis_Plus.tracker")
     rfn = importlib.import_module("dvis_Plus.refiner")
+    daq_trk = importlib.import_module("dvis_daq.track_module")
+    daq_rfn = importlib.import_module("dvis_daq.refiner")
+    daq_slot = importlib.import_module("dvis_daq.slot_attention")
     return types.SimpleNamespace(
+        VideoInstanceCutter=daq_trk.VideoInstanceCutter,
+        DAQTemporalRefiner=daq_rfn.TemporalRefiner,
+        SlotCrossAttentionLayer=daq_slot.SlotCrossAttentionLayer,
         ms_deform_attn_core_pytorch=ops_func.ms_deform_attn_core_pytorch,
         MSDeformAttn=ops_mod.MSDeformAttn,
         MSDeformAttnPixelDecoder=pix.MSDeformAttnPixelDecoder,
