@@ -235,9 +235,10 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
   using V = decltype(Vec16<T>::v);
   const char *vb = reinterpret_cast<const char *>(static_cast<const T *>(p.value) + (size_t)n * p.S * M * D) + j * 16;
   for (int il = warp * G + g; il < nitems; il += kWarps * G) {
-    float acc[VEC];
+    // accumulators as f32x2 pairs: Blackwell's packed FFMA2 (fma.rn.f32x2) halves the FMA issue slots
+    float2 acc2[VEC / 2];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int k = 0; k < VEC / 2; ++k) acc2[k] = make_float2(0.f, 0.f);
     const uint4 *so = reinterpret_cast<const uint4 *>(s_off) + il * LPs;
     const float4 *sw = s_wt + il * LPs;
 #pragma unroll UNROLL
@@ -249,14 +250,18 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
       v01.v = __ldg(reinterpret_cast<const V *>(vb + o.y));
       v10.v = __ldg(reinterpret_cast<const V *>(vb + o.z));
       v11.v = __ldg(reinterpret_cast<const V *>(vb + o.w));
+      const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y), wz = make_float2(w.z, w.z), ww = make_float2(w.w, w.w);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        acc[k] = fmaf(w.x, v00.get(k), acc[k]);
-        acc[k] = fmaf(w.y, v01.get(k), acc[k]);
-        acc[k] = fmaf(w.z, v10.get(k), acc[k]);
-        acc[k] = fmaf(w.w, v11.get(k), acc[k]);
+      for (int k = 0; k < VEC / 2; ++k) {
+        acc2[k] = __ffma2_rn(wx, make_float2(v00.get(2 * k), v00.get(2 * k + 1)), acc2[k]);
+        acc2[k] = __ffma2_rn(wy, make_float2(v01.get(2 * k), v01.get(2 * k + 1)), acc2[k]);
+        acc2[k] = __ffma2_rn(wz, make_float2(v10.get(2 * k), v10.get(2 * k + 1)), acc2[k]);
+        acc2[k] = __ffma2_rn(ww, make_float2(v11.get(2 * k), v11.get(2 * k + 1)), acc2[k]);
       }
     }
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC / 2; ++k) { acc[2 * k] = acc2[k].x; acc[2 * k + 1] = acc2[k].y; }
     const int item = s_item[il];
     const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
     TO *dst = static_cast<TO *>(p.out) + (((size_t)n * p.Lq + q) * M + m) * (size_t)D + j * VEC;

@@ -209,3 +209,28 @@ def test_pair_packed_variant_vs_oracle(ref_dim, L, pdt):
     out2 = ops.msda_fused_forward(value.to(dev).bfloat16(), shapes.to(dev), lsi_of(shapes).to(dev), f[..., :M * L * P * 2],
                                   f[..., M * L * P * 2:], ref_pts.to(dev), M, L, P).float().cpu()
     assert (out - out2).abs().max() <= 1e-2 * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize("kind", ["injector", "extractor"])
+def test_vit_adapter_call_site_shapes(kind):
+    """Second consumer of the op: ViT-Adapter Injector / Extractor (P/mask2former/modeling/backbones_vitAdapter/
+    adapter.py:101-165, deform_inputs :39-58): d_model 1024 / 16 heads -> D=64; Injector: queries = ViT tokens (1 level grid),
+    values = 3-level pyramid; Extractor: queries = pyramid tokens, values = 1 level; Lq != S in both."""
+    from dvis_plus_b200 import ops
+    torch.manual_seed(2)
+    M, D, P = 16, 64, 4
+    if kind == "injector":
+        shapes = torch.as_tensor([(16, 24), (8, 12), (4, 6)])     # 1/8, 1/16, 1/32 pyramid
+        Lq = 8 * 12                                               # ViT tokens at 1/16
+    else:
+        shapes = torch.as_tensor([(8, 12)])
+        Lq = 16 * 24 + 8 * 12 + 4 * 6
+    L = shapes.shape[0]
+    S = int(shapes.prod(1).sum())
+    value = torch.randn(2, S, M, D)
+    loc = torch.rand(2, Lq, M, L, P, 2)
+    attn = torch.rand(2, Lq, M, L, P).flatten(-2).softmax(-1).view(2, Lq, M, L, P)
+    out = _run(value, shapes, loc, attn)
+    ref = _oracle(value, shapes, loc, attn)
+    assert out.shape == (2, Lq, M * D)
+    assert (out - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max())
