@@ -34,7 +34,11 @@ def linear(layer: nn.Linear, x, relu=False):
     w, b = layer.weight, layer.bias
     if w.dtype != dt:
         w, b = _cast_cached(layer, dt)
-    y = F.linear(x.to(dt), w, b)
+    x = x.to(dt)
+    if relu and b is not None and x.is_cuda and not torch.is_grad_enabled():
+        # bias + ReLU in the GEMM epilogue (cuBLASLt RELU_BIAS) instead of a separate elementwise kernel
+        return torch._addmm_activation(b, x.reshape(-1, x.shape[-1]), w.t()).view(*x.shape[:-1], w.shape[0])
+    y = F.linear(x, w, b)
     return F.relu(y) if relu else y
 
 

@@ -17,7 +17,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .blocks import MLP, FFNLayer, ReferringCrossAttentionLayer, SelfAttentionLayer, _fast_path, add_norm, linear
+from .blocks import (MLP, FFNLayer, ReferringCrossAttentionLayer, SelfAttentionLayer, _cast_cached, _fast_path, add_norm,
+                     linear)
 from .precision import gemm_dtype
 from .pixel_decoder import _c2_xavier_fill
 
@@ -274,28 +275,56 @@ class ReferringTracker_noiser(nn.Module):
         L, C, H = self.num_layers, f["C"], self.num_heads
         dh = C // H
         Q = identity.shape[0]
+        dt = f["wq"].dtype
         sa, ff = self.transformer_self_attention_layers, self.transformer_ffn_layers
         ca = self.transformer_cross_attention_layers
         scale = 1.0 / (dh ** 0.5)
+        fused_ln = C % 128 == 0
+
+        def ln(norm, x, res32):
+            """LayerNorm(x + res) -> (fp32 stream, GEMM-dtype copy) in one kernel."""
+            if fused_ln:
+                y32, ylp, _ = ops.add_layernorm(x.contiguous(), res32, norm.weight, norm.bias, norm.eps, lp_dtype=dt)
+                return y32, ylp
+            y32 = F.layer_norm(x.float() + res32, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
+            return y32, y32.to(dt)
+
+        def lin(layer, x_lp, relu=False):
+            w, b = _cast_cached(layer, dt) if layer.weight.dtype != dt else (layer.weight, layer.bias)
+            if relu:
+                return torch._addmm_activation(b, x_lp, w.t())          # bias + ReLU in the GEMM epilogue
+            return torch.addmm(b, x_lp, w.t())
+
+        def ref_mlp(x_lp):
+            n = self.ref_proj.num_layers
+            for i, layer in enumerate(self.ref_proj.layers):
+                x_lp = lin(layer, x_lp, relu=i < n - 1)
+            return x_lp
+
         outs = []
-        x = identity
-        reference = self.ref_proj(ref_src)                                                         # (Q, C)
+        x32 = identity
+        reference = ref_mlp(ref_src.to(dt))                                                           # (Q, C)
         if not first:
-            q_all = F.linear(reference, f["wq"], f["bq"]).view(Q, L, H, dh).permute(1, 2, 0, 3)  # (L, H, Q, dh)
-            o_all = F.scaled_dot_product_attention(q_all, kv[:, 0], kv[:, 1], scale=scale)        # (L, H, Q, dh)
-            o_all = torch.baddbmm(f["bo"], o_all.permute(0, 2, 1, 3).reshape(L, Q, C), f["wo"])   # (L, Q, C)
+            q_all = F.linear(reference, f["wq"], f["bq"]).view(Q, L, H, dh).permute(1, 2, 0, 3)      # (L, H, Q, dh)
+            o_all = F.scaled_dot_product_attention(q_all, kv[:, 0], kv[:, 1], scale=scale)            # (L, H, Q, dh)
+            o_all = torch.baddbmm(f["bo"], o_all.permute(0, 2, 1, 3).reshape(L, Q, C), f["wo"])       # (L, Q, C)
+        x_lp = None
         for j in range(L):
             if first:
-                tgt = reference if j == 0 else self.ref_proj(x)
+                tgt = reference if j == 0 else ref_mlp(x_lp)
                 q = F.linear(tgt, f["wq"][j * C:(j + 1) * C], f["bq"][j * C:(j + 1) * C]).view(Q, H, dh).permute(1, 0, 2)
                 o = F.scaled_dot_product_attention(q[None], kv[j, 0][None], kv[j, 1][None], scale=scale)[0]
                 o = torch.addmm(f["bo"][j], o.permute(1, 0, 2).reshape(Q, C), f["wo"][j])
             else:
                 o = o_all[j]
-            x = add_norm(ca[j].norm, o, x)
-            x = sa[j](x[:, None, :])[:, 0]
-            x = ff[j](x[:, None, :])[:, 0]
-            outs.append(x)
+            x32, x_lp = ln(ca[j].norm, o, x32)
+            m = sa[j].self_attn
+            w, b = m._weights(dt)
+            qkv = torch.addmm(b, x_lp, w.t()).view(Q, 3, H, dh).permute(1, 2, 0, 3)                    # (3, H, Q, dh)
+            o = F.scaled_dot_product_attention(qkv[0][None], qkv[1][None], qkv[2][None], scale=scale)[0]
+            x32, x_lp = ln(sa[j].norm, lin(m.out_proj, o.permute(1, 0, 2).reshape(Q, C)), x32)
+            x32, x_lp = ln(ff[j].norm, lin(ff[j].linear2, lin(ff[j].linear1, x_lp, relu=True)), x32)
+            outs.append(x32)
         return torch.stack(outs, 0), reference.float()
 
     def _graph_step(self, f, first, Q, dev):
