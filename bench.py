@@ -186,7 +186,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = max(1, args.cpu_sample_frames)
+        sample = max(4, args.cpu_sample_frames)     # 4 frames per step: ~5-20 s of host work per step
         fps, dt = run_cpu_reference(sample, max(1, min(args.steps, 3)), min(args.warmup, 1), Q)
         line = {"impl": "reference", "metric": "frames/sec (720p, T=16, Q=200) pixel-decoder+mask+refiner", "value": round(fps, 4),
                 "unit": "frames/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": min(args.warmup, 1),
@@ -288,9 +288,17 @@ def main():
     ms_latency = s.elapsed_time(e) / n_lat
     launches = (graphed.captured_launches if graphed is not None else sum(v[0] for v in kern.values()) // n_lat) * args.steps
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing NCCL down rank by rank (ProcessGroupNCCL teardown can wait on peers that already left):
+        one last barrier so rank 0 has printed, then a hard exit on every rank."""
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -330,8 +338,7 @@ def main():
                     "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": round(ms_e2e, 3)},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
