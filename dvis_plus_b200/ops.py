@@ -301,3 +301,20 @@ def mask_attn_bias(mask_embed, level_features, dtype=torch.bfloat16):
         _lib.call("dvis_mask_attn_bias", emb.data_ptr(), level_features.data_ptr(), B, Q, C, h * w, bias.data_ptr(),
                   _DTYPE[dtype], ws.data_ptr(), _stream())
     return bias
+
+
+def mha_core(q, k, v, scale):
+    """softmax(scale * q k^T) v for short sequences (dvis_mha_core).
+
+    q (B, Lq, H, Dh), k / v (B, Lk, H, Dh): bf16 views with contiguous (H, Dh) (any row / batch stride, e.g. slices of a
+    packed QKV projection).  Returns a contiguous (B, Lq, H*Dh) bf16 tensor."""
+    B, Lq, H, Dh = q.shape
+    Lk = k.shape[1]
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.is_cuda and t.stride(3) == 1 and t.stride(2) == Dh, "heads must be packed (H, Dh)"
+    out = torch.empty((B, Lq, H * Dh), dtype=torch.bfloat16, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.call("dvis_mha_core", q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                  v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), H * Dh, Lq * H * Dh, B, Lq, Lk, H, Dh,
+                  float(scale), _stream())
+    return out

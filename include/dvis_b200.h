@@ -109,6 +109,20 @@ int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int
                      int out_dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused multi-head attention core for the short query sequences of tracker / refiner / predictor self-attention
+ * (what nn.MultiheadAttention does between its projections inside SelfAttentionLayer / CrossAttentionLayer /
+ * ReferringCrossAttentionLayer, P/mask2former_video/modeling/transformer_decoder/video_mask2former_transformer_decoder.py:46,104;
+ * P/dvis_Plus/tracker.py:45):
+ *   out[b, i, h, :] = softmax_j(scale * q[b,i,h,:] . k[b,j,h,:]) @ v[b,j,h,:]
+ * q (B, Lq, H, Dh), k / v (B, Lk, H, Dh), out (B, Lq, H, Dh), all bf16; *_row = elements between consecutive sequence
+ * positions, *_batch = elements between batch items (heads are Dh apart), so q / k / v may be slices of one packed
+ * projection.  Dh must be 32 or 64; K and V of one (batch, head) must fit in shared memory (Lk <= ~380 at Dh = 64).
+ */
+int dvis_mha_core(const void *q, int64_t q_row, int64_t q_batch, const void *k, int64_t k_row, int64_t k_batch,
+                  const void *v, int64_t v_row, int64_t v_batch, void *out, int64_t o_row, int64_t o_batch, int B,
+                  int Lq, int Lk, int H, int Dh, float scale, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * y = LayerNorm(x + residual) * gamma + beta over the last dim C, one pass.
  * The post-norm residual blocks of the path: MSDeformAttnTransformerEncoderLayer.forward
  * (P/mask2former/modeling/pixel_decoder/msdeformattn.py:118-119,125-126) and SelfAttentionLayer / CrossAttentionLayer /

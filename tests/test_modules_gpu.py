@@ -156,6 +156,7 @@ def test_mask_head_golden_and_lowres_equivalence(golden):
 def test_tracker_golden(golden, mode, tol):
     g = golden("tracker_small.pt")
     t = build_tracker(g).cuda()
+    t.use_custom_attention = mode == "bf16"      # also exercise the hand-written attention core (off by default)
     fe, fn, mf = g["frame_embeds"].cuda(), g["frame_embeds_no_norm"].cuda(), g["mask_features"].cuda()
     with precision(mode):
         o1, i1 = t(fe[:, :, :2], mf[:, :2], resume=False, return_indices=True, frame_embeds_no_norm=fn[:, :, :2])
@@ -305,3 +306,28 @@ def test_resize_and_attn_bias_kernels():
     m[m.all(-1)] = False
     ref = torch.zeros_like(logits).masked_fill_(m, float("-inf"))
     assert torch.equal(bias, ref) and bias[1, 3].abs().max() == 0
+
+
+@pytest.mark.parametrize("B,Lq,Lk,H,dh", [(1, 200, 200, 8, 64), (6, 200, 200, 8, 64), (3, 16, 16, 8, 64), (2, 37, 53, 4, 32),
+                                         (16, 200, 200, 8, 32), (1, 1, 300, 8, 64)])
+@torch.no_grad()
+def test_mha_core_kernel(B, Lq, Lk, H, dh):
+    """dvis_mha_core vs an fp32 softmax(QK^T)V on the same bf16 inputs, with q / k / v as strided slices of packed
+    projections (the layouts the tracker uses)."""
+    from dvis_plus_b200 import ops
+    import torch.nn.functional as F
+    torch.manual_seed(B * 1000 + Lq)
+    C = H * dh
+    if Lq == Lk:
+        qkv = torch.randn(B, Lq, 3, H, dh, device="cuda").bfloat16()                 # packed self-attention projection
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    else:
+        q = torch.randn(Lq, B, H, dh, device="cuda").bfloat16().permute(1, 0, 2, 3)  # batch-strided query
+        kv = torch.randn(B, Lk, 2, H, dh, device="cuda").bfloat16()
+        k, v = kv[:, :, 0], kv[:, :, 1]
+    scale = dh ** -0.5
+    out = ops.mha_core(q, k, v, scale)
+    ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2), scale=scale)
+    ref = ref.transpose(1, 2).reshape(B, Lq, C)
+    assert out.shape == (B, Lq, C)
+    assert (out.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
