@@ -8,10 +8,11 @@
 //   * a group of LPR = D*sizeof(T)/16 lanes owns one (query, head) item and reads each corner row of D
 //     channels as one 16-byte load per lane (a full 128-byte line for D=32 fp32); a warp carries
 //     G = 32/LPR independent items, so no cross-lane reduction is needed at all;
-//   * all P points of a level are issued back to back (4*P independent 16-byte loads in flight per lane);
+//   * per-point offsets and bilinear x attention weights are computed ONCE per (item, point) by one thread into shared
+//     memory (phase 1) and then consumed by the lanes that gather (phase 2): 2 LDS.128 + 4 LDG.128 + 8 FFMA2 per point;
 //   * a CTA walks a contiguous chunk of an optional `item_order` permutation -- the host orders items as
-//     2-D query tiles per head so that the lines a CTA touches stay L1-resident (see host/locality.py);
-//   * the fused variant also does softmax(logits) and loc = ref + offset / (W, H) in registers, removing the
+//     2-D query tiles per head so that the lines a CTA touches stay L1-resident (dvis_plus_b200/locality.py);
+//   * the fused variant also does softmax(logits) and loc = ref + offset / (W, H) in the kernel, removing the
 //     sampling_locations / attention_weights round trip through HBM (OPS/modules/ms_deform_attn.py:101-112).
 #include <algorithm>
 #include <cstdlib>
@@ -42,18 +43,6 @@ struct MsdaParams {
   int items_per_cta;
   int m_shift, p_shift, lpc_shift;  // log2(M), log2(P) or -1 when not a power of two; log2(next_pow2(L*P))
 };
-
-template <typename T>
-__device__ __forceinline__ Vec16<T> ldg16(const T *p) {
-  Vec16<T> r;
-  r.v = __ldg(reinterpret_cast<const decltype(r.v) *>(p));
-  return r;
-}
-
-template <typename T>
-struct AccOf { using type = float; };
-template <>
-struct AccOf<double> { using type = double; };
 
 template <typename T>
 struct LocType { using type = float; };   // plain-op loc/attn dtype for value dtype T (bf16 value is fused-only)
