@@ -39,6 +39,7 @@ struct MaskGemmParams {
   int64_t HW;
   int tiles_per_batch, total_tiles, stages;
   int *row_open;        // kBias epilogue: row_open[b*Q + q] = 1 if some pixel of the row has logit >= 0
+  int64_t out_batch;    // elements between batch items of `out` (Q*HW when dense; larger for a query slice)
 };
 
 struct __align__(8) Barriers {
@@ -194,7 +195,7 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
         } else {
           const int64_t pix = (int64_t)tile * kTileM + px;
           if (pix < p.HW) {
-            TO *dst = static_cast<TO *>(p.out) + ((int64_t)b * p.Q + c0) * p.HW + pix;
+            TO *dst = static_cast<TO *>(p.out) + (int64_t)b * p.out_batch + (int64_t)c0 * p.HW + pix;
             const int nq = min(kEpiCols, p.Q - c0);
             for (int i = 0; i < nq; ++i) dst[(int64_t)i * p.HW] = cvt_logit<TO>(r[i]);
           }
@@ -214,11 +215,11 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
 
 // 3-D map over a dense (batch, rows, inner) tensor; box = (box_inner, box_rows, 1)
 int encode_map(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int esize, uint64_t inner, uint64_t rows,
-               uint64_t batch, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
+               uint64_t batch, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz, uint64_t batch_stride = 0) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(DVIS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[3] = {inner, rows, batch};
-  const cuuint64_t strides[2] = {inner * esize, inner * rows * esize};   // bytes, dims 1..2
+  const cuuint64_t strides[2] = {inner * esize, (batch_stride ? batch_stride : inner * rows) * esize};   // bytes, dims 1..2
   const cuuint32_t box[3] = {box_inner, box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr,
@@ -245,12 +246,19 @@ __global__ void __launch_bounds__(256) reset_closed_rows_kernel(const int *__res
 }
 }  // namespace
 int mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
-                     int *row_open, void *stream);
+                     int *row_open, void *stream, int64_t emb_batch = 0, int64_t out_batch = 0);
 }  // namespace dvis
 
 extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out,
                                 int out_dtype, void *stream) {
   return mask_gemm_launch(emb, feat, B, Q, C, HW, out, out_dtype, nullptr, stream);
+}
+
+extern "C" int dvis_mask_logits_strided(const void *emb, int64_t emb_batch_stride, const void *feat, int B, int Q, int C,
+                                        int64_t HW, void *out, int64_t out_batch_stride, int out_dtype, void *stream) {
+  DVIS_REQUIRE(emb_batch_stride >= (int64_t)Q * C && out_batch_stride >= (int64_t)Q * HW, "mask_logits_strided: batch strides too small");
+  DVIS_REQUIRE(emb_batch_stride % 8 == 0, "mask_logits_strided: emb batch stride must be a multiple of 8 elements (16 bytes)");
+  return mask_gemm_launch(emb, feat, B, Q, C, HW, out, out_dtype, nullptr, stream, emb_batch_stride, out_batch_stride);
 }
 
 extern "C" int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias,
@@ -267,7 +275,7 @@ extern "C" int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int
 }
 
 int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
-                           int *row_open, void *stream) {
+                           int *row_open, void *stream, int64_t emb_batch, int64_t out_batch) {
   DVIS_REQUIRE(emb && feat && out, "mask_logits: null pointer argument");
   DVIS_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_logits: sizes must be positive");
   DVIS_REQUIRE(C % kBlockK == 0 && C <= 512, "mask_logits: C must be a multiple of 64 and <= 512 (got %d)", C);
@@ -280,11 +288,12 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
   MaskGemmParams p{};
   p.out = out; p.B = B; p.Q = Q; p.Qpad = (Q + 15) & ~15; p.KB = C / kBlockK; p.HW = HW;
   p.row_open = row_open;
+  p.out_batch = out_batch ? out_batch : (int64_t)Q * HW;
   p.tiles_per_batch = int((HW + kTileM - 1) / kTileM);
   p.total_tiles = p.tiles_per_batch * B;
   const int b_bytes = p.KB * p.Qpad * 128;
   const int esize = out_dtype == DVIS_F32 ? 4 : 2;
-  const bool tma_store = aligned16(out) && (HW * esize) % 16 == 0;   // TMA needs a 16-byte row pitch
+  const bool tma_store = aligned16(out) && (HW * esize) % 16 == 0 && (p.out_batch * esize) % 16 == 0;   // TMA: 16-byte pitches
   const int stage_out_bytes = 2 * kEpiCols * kTileM * esize;
   const int budget = 225 * 1024 - b_bytes - 1024 - stage_out_bytes - int(sizeof(Barriers));
   p.stages = std::min(kMaxStages, budget / kStageBytes);
@@ -293,10 +302,11 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
 
   CUtensorMap tm_feat, tm_emb, tm_out;
   if (int rc = encode_map(&tm_feat, feat, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, HW, B, kBlockK, kTileM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  if (int rc = encode_map(&tm_emb, emb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, Q, B, kBlockK, p.Qpad, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = encode_map(&tm_emb, emb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, Q, B, kBlockK, p.Qpad, CU_TENSOR_MAP_SWIZZLE_128B,
+                          emb_batch)) return rc;
   if (tma_store) {
     if (int rc = encode_map(&tm_out, out, out_dtype == DVIS_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                            esize, HW, Q, B, kTileM, kEpiCols, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+                            esize, HW, Q, B, kTileM, kEpiCols, CU_TENSOR_MAP_SWIZZLE_NONE, p.out_batch)) return rc;
   } else {
     tm_out = tm_emb;   // unused by the direct-store variant; any valid map
   }

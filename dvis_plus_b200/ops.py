@@ -166,18 +166,16 @@ def mask_logits(mask_embed, mask_features, out_dtype=torch.float32):
     emb = mask_embed.to(torch.bfloat16).contiguous()
     out = torch.empty((B, Q, H, W), dtype=out_dtype, device=feat.device)
     with torch.cuda.device(feat.device):
-        for q0 in range(0, Q, 256):
-            q1 = min(Q, q0 + 256)
-            if q0 == 0 and q1 == Q:
-                e, o = emb, out
-                _lib.call("dvis_mask_logits", e.data_ptr(), feat.data_ptr(), B, Q, C, H * W, o.data_ptr(),
-                          _DTYPE[out_dtype], _stream())
-            else:
-                # a query slice of a (B,Q,HW) output is not one dense block: run per batch element
-                for b in range(B):
-                    e = emb[b, q0:q1].contiguous()
-                    _lib.call("dvis_mask_logits", e.data_ptr(), feat[b].data_ptr(), 1, q1 - q0, C, H * W,
-                              out[b, q0:q1].data_ptr(), _DTYPE[out_dtype], _stream())
+        if Q <= 256:
+            _lib.call("dvis_mask_logits", emb.data_ptr(), feat.data_ptr(), B, Q, C, H * W, out.data_ptr(),
+                      _DTYPE[out_dtype], _stream())
+        else:
+            # query slices of <= 256 (a multiple of 8 so the slice starts stay 16-byte aligned), computed in place
+            es_in, es_out = emb.element_size(), out.element_size()
+            for q0 in range(0, Q, 256):
+                q1 = min(Q, q0 + 256)
+                _lib.call("dvis_mask_logits_strided", emb.data_ptr() + q0 * C * es_in, Q * C, feat.data_ptr(), B, q1 - q0, C,
+                          H * W, out.data_ptr() + q0 * H * W * es_out, Q * H * W, _DTYPE[out_dtype], _stream())
     return out
 
 

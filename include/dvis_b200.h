@@ -170,6 +170,12 @@ int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_stride, int 
  */
 int dvis_lap_chain(const float *cost, int T, int n, const int64_t *idx_init, int64_t *sigma, int64_t *idx, void *stream);
 
+/* Strided form for query slices: emb (B, Q, C) with `emb_batch_stride` elements between batch items (a multiple of 8) and
+ * out (B, Q, HW) with `out_batch_stride` elements between batch items, so a slice [q0, q1) of a larger query set can be
+ * computed in place (used to split Q > 256, e.g. the DAQ stress size Q = 300, into two launches). */
+int dvis_mask_logits_strided(const void *emb, int64_t emb_batch_stride, const void *feat, int B, int Q, int C, int64_t HW,
+                             void *out, int64_t out_batch_stride, int out_dtype, void *stream);
+
 /* Same GEMM with the masked-attention decoder's threshold fused into the epilogue
  * (P/dvis_Plus/video_mask2former_transformer_decoder.py:370-371 and :297): writes, instead of the logits, the additive
  * attention bias (B, Q, HW) in bias_dtype (DVIS_F32 | DVIS_BF16): -inf where sigmoid(logit) < 0.5, 0 elsewhere, rows that

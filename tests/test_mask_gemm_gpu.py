@@ -47,10 +47,12 @@ def test_mask_logits_golden_mask_head(golden):
 
 def test_mask_logits_accepts_nchw_fp32_and_splits_queries():
     from dvis_plus_b200 import ops
-    emb, feat = _case(2, 300, 64, 9, 16, seed=5)      # Q=300 > 256 (DAQ stress size)
-    ref = torch.einsum("bqc,bchw->bqhw", emb, feat)
-    out = ops.mask_logits(emb.cuda(), feat.cuda()).cpu()
-    assert (out - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    for (B, H, W, dt) in ((2, 9, 16, torch.float32), (3, 5, 7, torch.float32), (2, 12, 20, torch.bfloat16)):
+        emb, feat = _case(B, 300, 64, H, W, seed=5)   # Q=300 > 256 (DAQ stress size): two in-place query slices
+        ref = torch.einsum("bqc,bchw->bqhw", emb, feat)
+        out = ops.mask_logits(emb.cuda(), feat.cuda(), dt).float().cpu()
+        tol = 1e-3 if dt == torch.float32 else 1e-2
+        assert (out - ref).abs().max().item() <= tol * ref.abs().max().item()
 
 
 def test_mask_logits_720p_full_size_properties():
