@@ -40,6 +40,7 @@ struct MaskGemmParams {
   int tiles_per_batch, total_tiles, stages;
   int *row_open;        // kBias epilogue: row_open[b*Q + q] = 1 if some pixel of the row has logit >= 0
   int64_t out_batch;    // elements between batch items of `out` (Q*HW when dense; larger for a query slice)
+  int epi_bufs;         // output staging tiles in flight (2..4): depth of the TMA-store pipeline
 };
 
 struct __align__(8) Barriers {
@@ -71,9 +72,9 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
   const int b_block_bytes = p.Qpad * 128;                       // one emb k-block
   uint8_t *sB = smem;
   uint8_t *sA = smem + p.KB * b_block_bytes;                    // 1024-aligned because Qpad % 8 == 0
-  // two output staging tiles [kEpiCols queries][128 pixels] for the TMA store (row-major, no swizzle)
+  // epi_bufs output staging tiles [kEpiCols queries][128 pixels] for the TMA store (row-major, no swizzle)
   TO *sOut = reinterpret_cast<TO *>(sA + p.stages * kStageBytes);
-  Barriers *bars = reinterpret_cast<Barriers *>(reinterpret_cast<uint8_t *>(sOut) + 2 * kEpiCols * kTileM * sizeof(TO));
+  Barriers *bars = reinterpret_cast<Barriers *>(reinterpret_cast<uint8_t *>(sOut) + p.epi_bufs * kEpiCols * kTileM * sizeof(TO));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -181,8 +182,12 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
           }
         }
         if constexpr (kTmaStore) {
-          TO *buf = sOut + (n_chunk & 1) * (kEpiCols * kTileM);
-          if (issuer) tma_store_wait_read<1>();          // the store that last read this buffer (2 chunks ago) is done
+          TO *buf = sOut + (n_chunk % p.epi_bufs) * (kEpiCols * kTileM);
+          if (issuer) {                                  // the store that last read this buffer (epi_bufs chunks ago) is done
+            if (p.epi_bufs == 4) tma_store_wait_read<3>();
+            else if (p.epi_bufs == 3) tma_store_wait_read<2>();
+            else tma_store_wait_read<1>();
+          }
           named_barrier_sync(1, kEpiThreads);
 #pragma unroll
           for (int i = 0; i < kEpiCols; ++i) buf[i * kTileM + px] = cvt_logit<TO>(r[i]);
@@ -294,8 +299,13 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
   const int b_bytes = p.KB * p.Qpad * 128;
   const int esize = out_dtype == DVIS_F32 ? 4 : 2;
   const bool tma_store = aligned16(out) && (HW * esize) % 16 == 0 && (p.out_batch * esize) % 16 == 0;   // TMA: 16-byte pitches
-  const int stage_out_bytes = 2 * kEpiCols * kTileM * esize;
-  const int budget = 225 * 1024 - b_bytes - 1024 - stage_out_bytes - int(sizeof(Barriers));
+  // deepest store pipeline (up to 4 staging tiles) that still leaves >= 4 A stages
+  int stage_out_bytes = 0, budget = 0;
+  for (p.epi_bufs = 4; p.epi_bufs >= 2; --p.epi_bufs) {
+    stage_out_bytes = p.epi_bufs * kEpiCols * kTileM * esize;
+    budget = 225 * 1024 - b_bytes - 1024 - stage_out_bytes - int(sizeof(Barriers));
+    if (budget / kStageBytes >= 4 || p.epi_bufs == 2) break;
+  }
   p.stages = std::min(kMaxStages, budget / kStageBytes);
   if (p.stages < 2) return fail(DVIS_ERR_UNSUPPORTED, "mask_logits: Q=%d, C=%d do not fit in shared memory", Q, C);
   const size_t smem = 1024 + b_bytes + size_t(p.stages) * kStageBytes + stage_out_bytes + sizeof(Barriers);
