@@ -42,6 +42,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         self.num_heads = nheads
         self.num_layers = dec_layers
         self.hidden_dim = hidden_dim
+        self.pre_norm = pre_norm
         self.transformer_self_attention_layers = nn.ModuleList()
         self.transformer_cross_attention_layers = nn.ModuleList()
         self.transformer_ffn_layers = nn.ModuleList()
@@ -170,7 +171,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         if mf_lp.dtype != torch.bfloat16 or not mf_lp.is_contiguous(memory_format=torch.channels_last):
             mf_lp = mf_lp.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         for l in range(nl):
-            xl = x[l] if len(self.input_proj[l]) == 0 else self.input_proj[l](x[l])
+            xl = self.input_proj[l](x[l])   # empty nn.Sequential is the identity
             h, w = xl.shape[-2:]
             sizes.append((h, w))
             tok = xl.permute(0, 2, 3, 1).reshape(B, h * w, C).float() + self.level_embed.weight[l]      # (B, hw, C)
@@ -245,7 +246,8 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
     def forward(self, x, mask_features, mask=None):
         assert len(x) == self.num_feature_levels
         del mask
-        if _fast_path(mask_features) and not self.materialize_aux_masks and self.hidden_dim % 128 == 0:
+        # the fused path is written for the post-norm blocks every DVIS config uses; pre-norm takes the generic loop
+        if _fast_path(mask_features) and not self.materialize_aux_masks and self.hidden_dim % 128 == 0 and not self.pre_norm:
             return self._forward_fast(x, mask_features)
         fast = _fast_path(mask_features) and not self.materialize_aux_masks
         src, pos, size_list = [], [], []
@@ -253,7 +255,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
             H, W = x[i].shape[-2:]
             size_list.append((H, W))
             pos.append(self._pos(H, W, x[i].device))
-            s = x[i] if len(self.input_proj[i]) == 0 else self.input_proj[i](x[i])
+            s = self.input_proj[i](x[i])
             s = s.flatten(2).float() + self.level_embed.weight[i][None, :, None]
             src.append(s.permute(2, 0, 1))                                    # (hw, B, C)
         bs = src[0].shape[1]

@@ -224,9 +224,33 @@ def main_daq():
                                       pred_logits=o["pred_logits"], pred_masks=o["pred_masks"], pred_embds=o["pred_embds"]))
 
 
+@torch.no_grad()
+def main_variants():
+    """Less common constructor variants the drop-ins also mirror: pre-norm blocks, DAQ refiner with the conv branch."""
+    R = rl.load()
+    g = torch.load(os.path.join(HERE, "predictor_small.pt"), weights_only=False)
+    torch.manual_seed(10)
+    dec = R.Decoder_dvisPlus(64, True, num_classes=5, hidden_dim=64, num_queries=12, nheads=8, dim_feedforward=128,
+                             dec_layers=2, pre_norm=True, mask_dim=64, enforce_input_project=True, num_frames=2,
+                             num_reid_head_layers=0, reid_hidden_dim=64).eval()
+    out = dec(g["multi_scale"], g["mask_features"])
+    save("predictor_prenorm_small.pt", dict(state_dict=dec.state_dict(), pred_logits=out["pred_logits"], pred_masks=out["pred_masks"],
+                                            pred_embds=out["pred_embds"], pred_embds_without_norm=out["pred_embds_without_norm"]))
+    torch.manual_seed(11)
+    rf = R.DAQTemporalRefiner(hidden_channel=64, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=64,
+                              class_num=5, windows=4, use_local_attn=True).eval()
+    inst, fr, mfeat = torch.randn(1, 64, 6, 7), torch.randn(1, 64, 6, 7), torch.randn(1, 6, 64, 8, 12)
+    o = rf(inst, torch.zeros(1, 7, 6, dtype=torch.bool), fr, mfeat, None)
+    save("daq_refiner_localattn_small.pt", dict(state_dict=rf.state_dict(), instance_embeds=inst, frame_embeds=fr, mask_features=mfeat,
+                                                pred_logits=o["pred_logits"], pred_masks=o["pred_masks"], pred_embds=o["pred_embds"]))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "daq":
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        main_variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == "daq":
         main_daq()
     else:
         main()
         main_daq()
+        main_variants()

@@ -103,3 +103,30 @@ def test_msdeformattn_module_api(golden):
     assert fresh.sampling_offsets.weight.abs().max() == 0 and fresh.attention_weights.weight.abs().max() == 0
     b = fresh.sampling_offsets.bias.view(8, 3, 4, 2)
     assert torch.allclose(b[0, 0, :, 0], torch.tensor([1., 2., 3., 4.])) and torch.allclose(b[2, 1, :, 1], torch.tensor([1., 2., 3., 4.]))
+
+
+@torch.no_grad()
+def test_prenorm_predictor_variant_cpu(golden):
+    """pre_norm=True blocks, enforce_input_project=True (1x1 convs), no ReID head: constructor variants of
+    P/dvis_Plus/video_mask2former_transformer_decoder.py:177-230 that the DVIS configs do not use but the API offers."""
+    g = golden("predictor_prenorm_small.pt")
+    base = golden("predictor_small.pt")
+    d = M.VideoMultiScaleMaskedTransformerDecoder_dvisPlus(
+        64, True, num_classes=5, hidden_dim=64, num_queries=12, nheads=8, dim_feedforward=128, dec_layers=2, pre_norm=True,
+        mask_dim=64, enforce_input_project=True, num_frames=2, num_reid_head_layers=0, reid_hidden_dim=64).eval()
+    assert not any(d.load_state_dict(g["state_dict"]))
+    out = d(base["multi_scale"], base["mask_features"])
+    for k in ("pred_logits", "pred_masks", "pred_embds", "pred_embds_without_norm"):
+        close(out[k], g[k])
+
+
+@torch.no_grad()
+def test_daq_refiner_with_local_conv_branch_cpu(golden):
+    g = golden("daq_refiner_localattn_small.pt")
+    rf = M.DAQTemporalRefiner(hidden_channel=64, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=64,
+                              class_num=5, windows=4, use_local_attn=True).eval()
+    assert not any(rf.load_state_dict(g["state_dict"]))
+    o = rf(g["instance_embeds"], None, g["frame_embeds"], g["mask_features"], None)
+    close(o["pred_logits"], g["pred_logits"])
+    close(o["pred_masks"], g["pred_masks"])
+    close(o["pred_embds"], g["pred_embds"])

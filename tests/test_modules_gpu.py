@@ -234,6 +234,23 @@ def test_groupnorm_nhwc_kernel():
 
 
 @torch.no_grad()
+def test_predictor_prenorm_variant_golden(golden):
+    """pre_norm=True + enforce_input_project + no ReID head: runs the generic loop (the fused path is post-norm only)."""
+    g, base = golden("predictor_prenorm_small.pt"), golden("predictor_small.pt")
+    d = M.VideoMultiScaleMaskedTransformerDecoder_dvisPlus(
+        64, True, num_classes=5, hidden_dim=64, num_queries=12, nheads=8, dim_feedforward=128, dec_layers=2, pre_norm=True,
+        mask_dim=64, enforce_input_project=True, num_frames=2, num_reid_head_layers=0, reid_hidden_dim=64).eval()
+    d.load_state_dict(g["state_dict"])
+    d = d.cuda()
+    calls = _lib.launch_count
+    with precision("fp32"):
+        out = d(cuda(base["multi_scale"]), base["mask_features"].cuda())
+    assert _lib.launch_count > calls
+    for k in ("pred_logits", "pred_masks", "pred_embds", "pred_embds_without_norm"):
+        assert rel_err(out[k], g[k]) < 5e-2, (k, rel_err(out[k], g[k]))     # thresholded bf16 logits, see above
+
+
+@torch.no_grad()
 def test_predictor_fast_path_production_width():
     """hidden_dim 256: the batch-first inference path against the oracle port (CPU, fp32)."""
     from oracle import torch_port as tp
