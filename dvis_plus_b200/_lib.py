@@ -31,6 +31,12 @@ SIGNATURES = {
     "dvis_mask_logits_strided": [_vp, _i64, _vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp],
     "dvis_mask_attn_bias": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp, _vp],
     "dvis_mha_core": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp],
+    "dvis_class_scores": [_vp, _vp, _i, _i, _vp, _vp],
+    "dvis_vis_topk": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "dvis_vis_masks": [_vp, _i, _i64, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "dvis_vps_argmax": [_vp, _i, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "dvis_vps_paint": [_vp, _vp, _i64, _vp, _vp],
+    "dvis_vss_argmax": [_vp, _i, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "dvis_add_layernorm": [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _i64, _i, _f, _vp, _vp, _vp, _i, _vp],
 }
 

@@ -1,0 +1,396 @@
+// Fused video post-processing: what DVIS_Plus_online.inference_video_vis / _vps / _vss do
+// after the final mask GEMM (P/dvis_Plus/meta_architecture.py:818-979).
+//
+// The reference materialises, per kept query and frame, the mask logits at the padded input resolution (fp32), crops
+// them, resizes again to the output resolution (fp32), and only then thresholds / arg-maxes: ~8 bytes of HBM traffic per
+// full-resolution pixel and query, twice.  Here the whole chain is evaluated per OUTPUT pixel straight from the stride-4
+// logits (which stay L2-resident: 235 KB per query-frame at 720p), so the only full-resolution traffic is the result:
+// 1 byte per pixel (vis masks), 4 bytes per pixel and frame (vps ids), 8 bytes per pixel and frame (vss labels).
+// All of it is gather/elementwise work: HBM-write bound, no tensor cores (the vss class contraction is the exception,
+// see vss_argmax_kernel).  The per-pixel arithmetic lives in resize_core.cuh.
+#include <algorithm>
+
+#include "common.cuh"
+#include "resize_core.cuh"
+
+namespace dvis {
+namespace {
+
+using rc::Geom;
+using rc::Plane;
+using rc::Tap;
+
+template <typename T>
+struct Raw;  // storage type the core's ld_elem understands
+template <>
+struct Raw<float> { using type = float; };
+template <>
+struct Raw<__nv_bfloat16> { using type = uint16_t; };
+
+// ---- class scores + top-k ----------------------------------------------------------------------------------------
+// scores[q, c] = softmax(cls[q, :])[c]; for c < K1 - 1 optionally max'ed with softmax(aux[q, :])[c]   (py:823-827,873-876)
+__device__ void class_scores_rows(const float *__restrict__ cls, const float *__restrict__ aux, int Q, int K1,
+                                  float *__restrict__ scores, int warp, int num_warps, int lane) {
+  for (int q = warp; q < Q; q += num_warps) {
+    const float *rows[2] = {cls + (size_t)q * K1, aux ? aux + (size_t)q * K1 : nullptr};
+    float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.f, 0.f};
+    for (int r = 0; r < 2; ++r) {
+      if (!rows[r]) continue;
+      for (int c = lane; c < K1; c += 32) mx[r] = fmaxf(mx[r], rows[r][c]);
+      for (int o = 16; o; o >>= 1) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+      for (int c = lane; c < K1; c += 32) sum[r] += expf(rows[r][c] - mx[r]);
+      for (int o = 16; o; o >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+    }
+    for (int c = lane; c < K1; c += 32) {
+      float s = expf(rows[0][c] - mx[0]) / sum[0];
+      if (rows[1] && c < K1 - 1) s = fmaxf(s, expf(rows[1][c] - mx[1]) / sum[1]);
+      scores[(size_t)q * K1 + c] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) class_scores_kernel(const float *cls, const float *aux, int Q, int K1, float *scores) {
+  class_scores_rows(cls, aux, Q, K1, scores, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5),
+                    threadIdx.x & 31);
+}
+
+// One CTA: class scores, then max_num rounds of a block-wide arg-max over the Q x (K1 - 1) object scores
+// (larger score first, lower flat index on ties), each winner removed before the next round (py:831-835).
+__global__ void __launch_bounds__(1024) vis_topk_kernel(const float *cls, const float *aux, int Q, int K1, int max_num,
+                                                        float *scores, float *out_scores, int64_t *out_labels,
+                                                        int64_t *out_query) {
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  class_scores_rows(cls, aux, Q, K1, scores, warp, blockDim.x >> 5, lane);
+  __syncthreads();
+  const int K = K1 - 1, n = Q * K;
+  for (int r = 0; r < max_num; ++r) {
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int j = tid; j < n; j += blockDim.x) {
+      const float v = scores[(size_t)(j / K) * K1 + (j % K)];
+      if (v > best) { best = v; arg = j; }                       // ascending j per thread: first maximum kept
+    }
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+    }
+    if (lane == 0) { s_val[warp] = best; s_idx[warp] = arg; }
+    __syncthreads();
+    if (warp == 0) {
+      best = lane < (blockDim.x >> 5) ? s_val[lane] : -INFINITY;
+      arg = lane < (blockDim.x >> 5) ? s_idx[lane] : 0x7fffffff;
+      for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+      }
+      if (lane == 0) {
+        out_scores[r] = best;
+        out_labels[r] = arg % K;
+        out_query[r] = arg / K;
+        scores[(size_t)(arg / K) * K1 + (arg % K)] = -INFINITY;  // taken
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- vis masks -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread4(uint32_t b) {  // bit i -> byte i
+  return (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21);
+}
+
+constexpr int kStripPx = 8;     // output pixels per thread and row: one 8-byte store
+constexpr int kStripWarps = 4;  // warps per CTA, each walking its own band of rows
+
+// Second resize is the identity (output size == un-padded input size, the benchmark's 720p case): one bilinear sample
+// per pixel.  A warp covers 256 consecutive pixels of a row and walks `rows_per_warp` rows, re-reading its source rows
+// only when they change (every 4th output row at the 4x up-scale of the stride-4 logits).
+template <typename T>
+__global__ void __launch_bounds__(32 * kStripWarps) vis_masks_strip_kernel(const T *__restrict__ logits, int64_t q_stride,
+                                                                           int64_t t_stride, const int64_t *__restrict__ sel,
+                                                                           int frames, Geom g, int rows_per_warp,
+                                                                           uint8_t *__restrict__ out) {
+  using R = typename Raw<T>::type;
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int plane = blockIdx.z, n = plane / frames, t = plane % frames;
+  const int ox0 = (blockIdx.x * 32 + lane) * kStripPx;
+  const int oy_begin = (blockIdx.y * kStripWarps + warp) * rows_per_warp;
+  const int oy_end = min(oy_begin + rows_per_warp, g.Ho);
+  if (ox0 >= g.Wo || oy_begin >= oy_end) return;
+  const int64_t q = sel ? sel[n] : n;
+  Plane<R> pl;
+  pl.p = reinterpret_cast<const R *>(logits) + q * q_stride + t * t_stride;
+  pl.w = g.w;
+  rc::Strip<kStripPx, R> strip;
+  strip.init(g, ox0);
+  uint8_t *o = out + (int64_t)plane * g.Ho * g.Wo + ox0;
+  const bool vec = (g.Wo % kStripPx == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
+  for (int oy = oy_begin; oy < oy_end; ++oy) {
+    const uint32_t bits = strip.row(pl, g, oy);
+    uint8_t *orow = o + (int64_t)oy * g.Wo;
+    if (vec) {
+      *reinterpret_cast<uint2 *>(orow) = make_uint2(spread4(bits & 15u), spread4(bits >> 4));
+    } else {
+      for (int i = 0; i < kStripPx; ++i)
+        if (ox0 + i < g.Wo) orow[i] = uint8_t((bits >> i) & 1u);
+    }
+  }
+}
+
+// General chain (second resize changes the size): every output pixel evaluates up to four first-stage samples.
+template <typename T>
+__global__ void __launch_bounds__(128) vis_masks_two_stage_kernel(const T *__restrict__ logits, int64_t q_stride,
+                                                                   int64_t t_stride, const int64_t *__restrict__ sel,
+                                                                   int frames, Geom g, uint8_t *__restrict__ out) {
+  using R = typename Raw<T>::type;
+  const int plane = blockIdx.z, n = plane / frames, t = plane % frames;
+  const int oy = blockIdx.y;
+  const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (ox0 >= g.Wo) return;
+  const int64_t q = sel ? sel[n] : n;
+  Plane<R> pl;
+  pl.p = reinterpret_cast<const R *>(logits) + q * q_stride + t * t_stride;
+  pl.w = g.w;
+  const Tap t2y = rc::make_tap(oy, g.s2y, g.Hc);
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (ox0 + i < g.Wo) {
+      const Tap t2x = rc::make_tap(ox0 + i, g.s2x, g.Wc);
+      bits |= uint32_t(rc::two_stage<false>(pl, g, t2y, t2x) > 0.f) << i;
+    }
+  }
+  uint8_t *orow = out + ((int64_t)plane * g.Ho + oy) * g.Wo + ox0;
+  if ((g.Wo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+    *reinterpret_cast<uint32_t *>(orow) = spread4(bits);
+  } else {
+    for (int i = 0; i < 4; ++i)
+      if (ox0 + i < g.Wo) orow[i] = uint8_t((bits >> i) & 1u);
+  }
+}
+
+// ---- vps ---------------------------------------------------------------------------------------------------------
+// One thread per output pixel of frame blockIdx.z.  win[t, y, x] = k (winner's probability >= 0.5) or ~k (< 0.5);
+// areas[0:n] = #pixels won by k (py:923), areas[n:2n] = #pixels with probability_k >= 0.5 (py:924),
+// areas[2n:3n] = #pixels won by k with probability_k >= 0.5 (py:925-926).
+struct AreaVisitor {
+  int *cnt;
+  int n_keep;
+  bool active;
+  int lane;
+  __device__ __forceinline__ void operator()(int k, float v) const {
+    const unsigned m = __ballot_sync(0xffffffffu, active && v >= 0.5f);
+    if (lane == 0 && m) atomicAdd(&cnt[n_keep + k], __popc(m));
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) vps_argmax_kernel(const T *__restrict__ logits, int64_t q_stride, int64_t t_stride,
+                                                         const int64_t *__restrict__ keep_idx,
+                                                         const float *__restrict__ keep_score, int n_keep, Geom g,
+                                                         int32_t *__restrict__ win, unsigned long long *__restrict__ areas) {
+  using R = typename Raw<T>::type;
+  extern __shared__ int cnt[];  // 3 * n_keep
+  for (int i = threadIdx.x; i < 3 * n_keep; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y, t = blockIdx.z;
+  const bool active = ox < g.Wo;
+  const Tap t2y = rc::make_tap(oy, g.s2y, g.Hc);
+  const Tap t2x = rc::make_tap(active ? ox : g.Wo - 1, g.s2x, g.Wc);
+  AreaVisitor visit;
+  visit.cnt = cnt;
+  visit.n_keep = n_keep;
+  visit.active = active;
+  visit.lane = threadIdx.x & 31;
+  bool solid = false;
+  const int best = rc::vps_pixel(reinterpret_cast<const R *>(logits) + t * t_stride, q_stride, keep_idx, keep_score, n_keep,
+                                 g, t2y, t2x, &solid, visit);
+  if (active) {
+    atomicAdd(&cnt[best], 1);
+    if (solid) atomicAdd(&cnt[2 * n_keep + best], 1);
+    win[((int64_t)t * g.Ho + oy) * g.Wo + ox] = solid ? best : ~best;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * n_keep; i += blockDim.x)
+    if (cnt[i]) atomicAdd(&areas[i], (unsigned long long)cnt[i]);
+}
+
+// panoptic[i] = segment id of the pixel's winner if the winner's probability is >= 0.5, else 0 (py:925,934,939)
+__global__ void __launch_bounds__(256) vps_paint_kernel(const int32_t *__restrict__ win, const int32_t *__restrict__ seg_of_k,
+                                                        int64_t total, int32_t *__restrict__ panoptic) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t k = win[i];
+    panoptic[i] = k >= 0 ? seg_of_k[k] : 0;
+  }
+}
+
+// ---- vss ---------------------------------------------------------------------------------------------------------
+// semseg[c] = sum_q mask_cls[q, c] * probability_q (py:972), label = first arg-max over c (py:973).  One thread per
+// output pixel: the Q resized probabilities of the pixel are computed once into the thread's own shared-memory column,
+// then the K classes are accumulated 8 at a time (mask_cls reads are warp-uniform).  fp32 CUDA-core math, the same
+// precision as the reference's einsum; the contraction is K x Q MACs per pixel and would sit on the tensor pipe with
+// tf32 operands -- left as the next step for this kernel, see DESIGN.md.
+constexpr int kVssThreads = 128;
+constexpr int kVssClasses = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kVssThreads) vss_argmax_kernel(const T *__restrict__ logits, int64_t q_stride,
+                                                                 int64_t t_stride, const float *__restrict__ mask_cls,
+                                                                 int64_t cls_stride, int Q, int K, Geom g,
+                                                                 int64_t *__restrict__ out) {
+  using R = typename Raw<T>::type;
+  extern __shared__ float probs[];  // [Q][kVssThreads]
+  const int ox = blockIdx.x * kVssThreads + threadIdx.x, oy = blockIdx.y, t = blockIdx.z;
+  if (ox >= g.Wo) return;           // no block-wide synchronisation below: every thread owns its column
+  const Tap t2y = rc::make_tap(oy, g.s2y, g.Hc);
+  const Tap t2x = rc::make_tap(ox, g.s2x, g.Wc);
+  float *mine = probs + threadIdx.x;
+  for (int q = 0; q < Q; ++q) {
+    Plane<R> pl;
+    pl.p = reinterpret_cast<const R *>(logits) + q * q_stride + t * t_stride;
+    pl.w = g.w;
+    mine[q * kVssThreads] = rc::two_stage<true>(pl, g, t2y, t2x);
+  }
+  float best = 0.f;
+  int arg = 0;
+  for (int c0 = 0; c0 < K; c0 += kVssClasses) {
+    float acc[kVssClasses];
+#pragma unroll
+    for (int j = 0; j < kVssClasses; ++j) acc[j] = 0.f;
+    for (int q = 0; q < Q; ++q) {
+      const float m = mine[q * kVssThreads];
+      const float *row = mask_cls + q * cls_stride + c0;
+#pragma unroll
+      for (int j = 0; j < kVssClasses; ++j)
+        if (c0 + j < K) acc[j] += __ldg(row + j) * m;
+    }
+#pragma unroll
+    for (int j = 0; j < kVssClasses; ++j)
+      if (c0 + j < K && (c0 + j == 0 || acc[j] > best)) { best = acc[j]; arg = c0 + j; }
+  }
+  out[((int64_t)t * g.Ho + oy) * g.Wo + ox] = arg;
+}
+
+int check_geom(const char *who, int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo) {
+  DVIS_REQUIRE(frames > 0 && h > 0 && w > 0 && H1 > 0 && W1 > 0 && Ho > 0 && Wo > 0, "%s: sizes must be positive", who);
+  DVIS_REQUIRE(Hc > 0 && Wc > 0 && Hc <= H1 && Wc <= W1, "%s: crop (%d, %d) must lie inside the first resize (%d, %d)", who, Hc, Wc, H1, W1);
+  DVIS_REQUIRE(Ho <= 65535 && frames <= 65535, "%s: output height and frame count are limited to 65535 per launch", who);
+  return DVIS_OK;
+}
+
+}  // namespace
+}  // namespace dvis
+
+using namespace dvis;
+
+extern "C" int dvis_class_scores(const float *pred_cls, const float *aux_cls, int Q, int K1, float *scores, void *stream) {
+  DVIS_REQUIRE(pred_cls && scores, "class_scores: null pointer argument");
+  DVIS_REQUIRE(Q > 0 && K1 > 1, "class_scores: need Q > 0 and at least one class besides no-object");
+  class_scores_kernel<<<(Q + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred_cls, aux_cls, Q, K1, scores);
+  return check_launch("class_scores_kernel");
+}
+
+extern "C" int dvis_vis_topk(const float *pred_cls, const float *aux_cls, int Q, int K1, int max_num, float *scores_workspace,
+                             float *out_scores, int64_t *out_labels, int64_t *out_query, void *stream) {
+  DVIS_REQUIRE(pred_cls && scores_workspace && out_scores && out_labels && out_query, "vis_topk: null pointer argument");
+  DVIS_REQUIRE(Q > 0 && K1 > 1, "vis_topk: need Q > 0 and at least one class besides no-object");
+  // torch.topk raises for k larger than the number of candidates (py:831)
+  DVIS_REQUIRE(max_num > 0 && (int64_t)max_num <= (int64_t)Q * (K1 - 1), "vis_topk: selected index k out of range (max_num %d, %lld scores)",
+               max_num, (long long)Q * (K1 - 1));
+  DVIS_REQUIRE((int64_t)Q * (K1 - 1) < (int64_t)1 << 31, "vis_topk: too many scores");
+  vis_topk_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(pred_cls, aux_cls, Q, K1, max_num, scores_workspace,
+                                                                     out_scores, out_labels, out_query);
+  return check_launch("vis_topk_kernel");
+}
+
+extern "C" int dvis_vis_masks(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *sel,
+                              int n_sel, int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo,
+                              uint8_t *out, void *stream) {
+  DVIS_REQUIRE(logits && out, "vis_masks: null pointer argument");
+  DVIS_REQUIRE(n_sel > 0, "vis_masks: nothing selected");
+  if (int rc_ = check_geom("vis_masks", frames, h, w, H1, W1, Hc, Wc, Ho, Wo)) return rc_;
+  DVIS_REQUIRE((int64_t)n_sel * frames <= 65535, "vis_masks: n_sel * frames is limited to 65535 per launch");
+  const Geom g = rc::make_geom(h, w, H1, W1, Hc, Wc, Ho, Wo);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned planes = unsigned(n_sel * frames);
+  if (Ho == Hc && Wo == Wc) {
+    // rows per warp: enough CTAs to fill the machine a few times over, bands long enough to reuse source rows
+    const int rows_per_warp = 16;
+    const dim3 grid((Wo + 32 * kStripPx - 1) / (32 * kStripPx), (Ho + kStripWarps * rows_per_warp - 1) / (kStripWarps * rows_per_warp), planes);
+    const dim3 block(32, kStripWarps);
+    if (logits_dtype == DVIS_F32)
+      vis_masks_strip_kernel<float><<<grid, block, 0, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
+    else if (logits_dtype == DVIS_BF16)
+      vis_masks_strip_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
+    else
+      return fail(DVIS_ERR_UNSUPPORTED, "vis_masks: logits dtype must be f32 or bf16");
+    return check_launch("vis_masks_strip_kernel");
+  }
+  const dim3 grid((Wo + 128 * 4 - 1) / (128 * 4), Ho, planes);
+  if (logits_dtype == DVIS_F32)
+    vis_masks_two_stage_kernel<float><<<grid, 128, 0, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, out);
+  else if (logits_dtype == DVIS_BF16)
+    vis_masks_two_stage_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, out);
+  else
+    return fail(DVIS_ERR_UNSUPPORTED, "vis_masks: logits dtype must be f32 or bf16");
+  return check_launch("vis_masks_two_stage_kernel");
+}
+
+extern "C" int dvis_vps_argmax(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *keep_idx,
+                               const float *keep_score, int n_keep, int frames, int h, int w, int H1, int W1, int Hc, int Wc,
+                               int Ho, int Wo, int32_t *win, unsigned long long *areas, void *stream) {
+  DVIS_REQUIRE(logits && keep_idx && keep_score && win && areas, "vps_argmax: null pointer argument");
+  DVIS_REQUIRE(n_keep > 0 && n_keep <= 4096, "vps_argmax: 1 <= n_keep <= 4096");
+  if (int rc_ = check_geom("vps_argmax", frames, h, w, H1, W1, Hc, Wc, Ho, Wo)) return rc_;
+  const Geom g = rc::make_geom(h, w, H1, W1, Hc, Wc, Ho, Wo);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(areas, 0, sizeof(unsigned long long) * 3 * n_keep, s);
+  if (e != cudaSuccess) return fail(DVIS_ERR_CUDA, "vps_argmax: memset: %s", cudaGetErrorString(e));
+  const dim3 grid((Wo + 127) / 128, Ho, frames);
+  const size_t smem = sizeof(int) * 3 * n_keep;
+  if (logits_dtype == DVIS_F32)
+    vps_argmax_kernel<float><<<grid, 128, smem, s>>>(static_cast<const float *>(logits), q_stride, t_stride, keep_idx, keep_score, n_keep, g, win, areas);
+  else if (logits_dtype == DVIS_BF16)
+    vps_argmax_kernel<__nv_bfloat16><<<grid, 128, smem, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, keep_idx, keep_score, n_keep, g, win, areas);
+  else
+    return fail(DVIS_ERR_UNSUPPORTED, "vps_argmax: logits dtype must be f32 or bf16");
+  return check_launch("vps_argmax_kernel");
+}
+
+extern "C" int dvis_vps_paint(const int32_t *win, const int32_t *seg_of_k, int64_t total, int32_t *panoptic, void *stream) {
+  DVIS_REQUIRE(win && seg_of_k && panoptic, "vps_paint: null pointer argument");
+  DVIS_REQUIRE(total > 0, "vps_paint: nothing to paint");
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16));
+  vps_paint_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(win, seg_of_k, total, panoptic);
+  return check_launch("vps_paint_kernel");
+}
+
+extern "C" int dvis_vss_argmax(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const float *mask_cls,
+                               int64_t cls_stride, int Q, int K, int frames, int h, int w, int H1, int W1, int Hc, int Wc,
+                               int Ho, int Wo, int64_t *out, void *stream) {
+  DVIS_REQUIRE(logits && mask_cls && out, "vss_argmax: null pointer argument");
+  DVIS_REQUIRE(Q > 0 && K > 0 && cls_stride >= K, "vss_argmax: need Q > 0, K > 0, cls_stride >= K");
+  if (int rc_ = check_geom("vss_argmax", frames, h, w, H1, W1, Hc, Wc, Ho, Wo)) return rc_;
+  const size_t smem = sizeof(float) * (size_t)Q * kVssThreads;
+  if (smem > 200 * 1024) return fail(DVIS_ERR_UNSUPPORTED, "vss_argmax: Q = %d needs %zu bytes of shared memory (limit 400 queries)", Q, smem);
+  const Geom g = rc::make_geom(h, w, H1, W1, Hc, Wc, Ho, Wo);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const dim3 grid((Wo + kVssThreads - 1) / kVssThreads, Ho, frames);
+  cudaError_t e;
+  if (logits_dtype == DVIS_F32) {
+    e = cudaFuncSetAttribute(vss_argmax_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return fail(DVIS_ERR_CUDA, "vss_argmax: shared memory opt-in: %s", cudaGetErrorString(e));
+    vss_argmax_kernel<float><<<grid, kVssThreads, smem, s>>>(static_cast<const float *>(logits), q_stride, t_stride, mask_cls, cls_stride, Q, K, g, out);
+  } else if (logits_dtype == DVIS_BF16) {
+    e = cudaFuncSetAttribute(vss_argmax_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return fail(DVIS_ERR_CUDA, "vss_argmax: shared memory opt-in: %s", cudaGetErrorString(e));
+    vss_argmax_kernel<__nv_bfloat16><<<grid, kVssThreads, smem, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, mask_cls, cls_stride, Q, K, g, out);
+  } else {
+    return fail(DVIS_ERR_UNSUPPORTED, "vss_argmax: logits dtype must be f32 or bf16");
+  }
+  return check_launch("vss_argmax_kernel");
+}

@@ -195,6 +195,55 @@ int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, 
 int dvis_resize_bilinear_nhwc(const void *in, int N, int h, int w, int C, void *out, int H, int W, void *stream);
 int dvis_attn_bias_from_logits(const float *logits, int64_t rows, int hw, void *bias, int bias_dtype, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Video post-processing: what DVIS_Plus_online.inference_video_vis / _vps / _vss do after the final mask GEMM
+ * (P/dvis_Plus/meta_architecture.py:818-868, 870-956, 958-979; same code in D/dvis_daq/meta_architecture.py:704-).
+ * The resize chain  logits (h, w) --bilinear--> (H1, W1) = padded network input --crop--> (Hc, Wc) = image without
+ * padding --[sigmoid]--> --bilinear--> (Ho, Wo)  (F.interpolate(mode="bilinear", align_corners=False) twice,
+ * py:838-844) is evaluated per OUTPUT pixel from the stride-4 logits; no full-resolution float tensor is ever written.
+ * `logits` is a (queries, frames, h, w) view of f32 or bf16 mask logits with contiguous (h, w) planes: element
+ * strides `q_stride` between queries and `t_stride` between frames (the frame-major (T, Q, HW) output of
+ * dvis_mask_logits has q_stride = HW, t_stride = Q*HW).
+ */
+
+/* scores[q, c] = softmax(pred_cls[q, :])[c]; for c < K1-1 max'ed with softmax(aux_cls[q, :])[c] when aux_cls != NULL
+ * (py:823-827, 873-876, 962-965).  pred_cls, aux_cls, scores: (Q, K1) f32, K1 = classes + 1 (no-object last). */
+int dvis_class_scores(const float *pred_cls, const float *aux_cls, int Q, int K1, float *scores, void *stream);
+
+/* VIS instance selection (py:823-835): class scores as above, then the max_num largest of the Q*(K1-1) object scores.
+ * Output r (score descending; ties: lower flat index first -- torch.topk(sorted=False) leaves the order open):
+ * out_scores[r], out_labels[r] = flat % (K1-1), out_query[r] = flat / (K1-1).  scores_workspace: Q*K1 floats
+ * (receives the scores, selected entries overwritten with -inf).  Fails like torch.topk if max_num > Q*(K1-1). */
+int dvis_vis_topk(const float *pred_cls, const float *aux_cls, int Q, int K1, int max_num, float *scores_workspace,
+                  float *out_scores, int64_t *out_labels, int64_t *out_query, void *stream);
+
+/* VIS masks (py:836-846): out[n, t] = resize_chain(logits[sel[n], t]) > 0 as bytes 0/1 (torch.bool layout),
+ * out (n_sel, frames, Ho, Wo).  sel: n_sel int64 query indices on the device, NULL = queries 0..n_sel-1.
+ * n_sel*frames <= 65535 and Ho <= 65535 per call. */
+int dvis_vis_masks(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *sel, int n_sel,
+                   int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo, uint8_t *out, void *stream);
+
+/* VPS (py:889-926): per output pixel the arg-max over the kept queries k of keep_score[k] * sigmoid-resized mask
+ * (cur_prob_masks.argmax(0), first maximum), plus the three pixel counts the segment filter needs, so the host loop
+ * (py:919-949) runs on 3*n_keep integers instead of n_keep full-resolution reductions with a sync each.
+ *   keep_idx (n_keep) int64 query indices, keep_score (n_keep) f32 -- on the device
+ *   win (frames, Ho, Wo) int32 out: k if the winner's own probability is >= 0.5 (the pixel belongs to `mask`, py:925),
+ *       ~k (negative) if it is below
+ *   areas (3, n_keep) uint64 out: [0] pixels won by k (py:923), [1] pixels with probability_k >= 0.5 (py:924),
+ *       [2] pixels won by k with probability_k >= 0.5 (py:925-926); zeroed by the call
+ * dvis_vps_paint then writes panoptic[i] = win[i] >= 0 ? seg_of_k[win[i]] : 0 (py:934,939; seg_of_k[k] = 0 drops k). */
+int dvis_vps_argmax(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *keep_idx,
+                    const float *keep_score, int n_keep, int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho,
+                    int Wo, int32_t *win, unsigned long long *areas, void *stream);
+int dvis_vps_paint(const int32_t *win, const int32_t *seg_of_k, int64_t total, int32_t *panoptic, void *stream);
+
+/* VSS (py:968-975): out[t, y, x] = argmax_c sum_q mask_cls[q, c] * sigmoid-resized mask_q (einsum "qc,qthw->cthw" +
+ * max(0), first maximum).  mask_cls (Q, K) f32 with row stride cls_stride (>= K; the scores of dvis_class_scores
+ * without their last column: cls_stride = K + 1).  out (frames, Ho, Wo) int64.  Q <= 400. */
+int dvis_vss_argmax(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const float *mask_cls,
+                    int64_t cls_stride, int Q, int K, int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho,
+                    int Wo, int64_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,3 +159,20 @@ def load():
         TemporalRefiner=rfn.TemporalRefiner,
         ShapeSpec=_ShapeSpec,
     )
+
+
+def load_meta_architecture():
+    """Import P/dvis_Plus/meta_architecture.py (the post-processing methods inference_video_vis / vps / vss and
+    post_processing live on the meta-architecture classes, py:255-301,758-979).  The file's imports of Detectron2
+    structures, the criterion and the matcher are stubbed: none of them is touched by those methods."""
+    install()
+    import importlib
+    _mod("detectron2.data", MetadataCatalog=types.SimpleNamespace(get=lambda name: types.SimpleNamespace()))
+    sys.modules["detectron2.modeling"].__dict__.update(
+        META_ARCH_REGISTRY=_Registry("META_ARCH"), build_backbone=None, build_sem_seg_head=None)
+    _mod("detectron2.modeling.backbone", Backbone=nn.Module)
+    _mod("detectron2.structures", Boxes=object, ImageList=object, Instances=object, BitMasks=object)
+    _mod("mask2former_video.modeling.criterion", VideoSetCriterion=object)
+    _mod("mask2former_video.modeling.matcher", VideoHungarianMatcher=object, VideoHungarianMatcher_Consistent=object)
+    _ns("mask2former_video.utils", f"{P}/mask2former_video/utils")
+    return importlib.import_module("dvis_Plus.meta_architecture")

@@ -69,10 +69,21 @@ def test_product_never_imports_the_oracle_or_the_reference():
     assert src.count("from oracle") == 1 and "def cpu_reference_step" in src.split("from oracle")[0].splitlines()[-2]
 
 
+def test_product_has_no_host_implementation_of_the_postprocessing_kernels():
+    """tests/hostcore compiles csrc/resize_core.cuh for the host as a CHECKER; the product must not: no python file of the
+    package mentions it and libdvis_b200.so exports none of its symbols."""
+    import ctypes
+    from dvis_plus_b200 import _lib
+    assert not [p for p in _py_files("dvis_plus_b200") if "hostcore" in open(p).read()]
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in ("hostcore_vis_masks", "hostcore_vps_argmax", "hostcore_vss_argmax"):
+        assert not hasattr(lib, name)
+
+
 def test_gpu_tests_do_not_read_the_reference_tree():
     """/root/reference does not exist on the GPU box: only the fixture generators and the explicitly skipped drop-in test
     may mention it."""
-    allowed = {"reference_loader.py", "make_golden.py", "test_dropin_reference.py", "test_oracle_properties.py"}
+    allowed = {"reference_loader.py", "make_golden.py", "make_golden_postprocess.py", "test_dropin_reference.py", "test_oracle_properties.py"}
     bad = [p for p in _py_files("tests") if os.path.basename(p) not in allowed and "/root/reference" in open(p).read()]
     assert not bad, bad
 

@@ -1,0 +1,217 @@
+"""-m gpu parity tests of the post-processing kernels (csrc/postproc.cu) through the C ABI: against the oracle
+(oracle/postprocess_port.py, torch CPU) on identical seeded inputs, against golden outputs of the unmodified reference
+methods, and -- at the benchmark's full size -- through size-independent properties.
+
+Tolerance: thresholded / arg-maxed outputs must be IDENTICAL except at pixels where the oracle's own margin is below
+1e-4 (fp32 interpolation rounds differently on every implementation; the reference's CPU and CUDA kernels disagree there
+too); the number of such pixels is bounded as well.  See tests/postproc_util.py."""
+import pytest
+import torch
+
+from dvis_plus_b200 import ops
+from dvis_plus_b200.modules.postprocess import VideoPostProcessor
+from oracle import postprocess_port as pp
+from postproc_util import assert_labels_match, assert_masks_match, sort_instances
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+GEOMS = [  # (h, w), first resize, image size, output size
+    ((12, 20), (48, 80), (45, 78), (45, 78)),      # identity second resize: strip kernel, byte-store tail
+    ((12, 20), (48, 80), (45, 78), (67, 117)),     # up-scaling second resize
+    ((12, 20), (48, 80), (45, 78), (30, 52)),      # down-scaling second resize, width % 4 == 0
+    ((12, 20), (48, 80), (48, 80), (48, 80)),      # strip kernel, 8-byte vector stores
+    ((7, 9), (28, 36), (25, 33), (25, 33)),        # odd sizes
+    ((23, 40), (92, 160), (90, 160), (180, 320)),  # exact 2x second resize
+    ((5, 6), (20, 24), (20, 24), (3, 2)),          # output smaller than the logits
+    ((46, 80), (184, 320), (180, 320), (180, 320)),  # several row bands and strips per plane
+]
+
+
+def test_class_scores_and_topk():
+    g = torch.Generator().manual_seed(0)
+    for Q, K, max_num, use_aux in ((200, 25, 10, True), (200, 25, 20, False), (100, 40, 100, True), (7, 3, 21, False), (300, 124, 50, True)):
+        cls = torch.randn(Q, K + 1, generator=g) * 3
+        aux = torch.randn(Q, K + 1, generator=g) * 3 if use_aux else None
+        ref = pp.vis_scores(cls, aux)
+        full = cls.softmax(-1)
+        sc = ops.class_scores(cls.to(DEV), None if aux is None else aux.to(DEV)).cpu()
+        torch.testing.assert_close(sc[:, :-1], ref, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(sc[:, -1], full[:, -1], rtol=1e-5, atol=1e-7)
+        s, l, q = (t.cpu() for t in ops.vis_topk(cls.to(DEV), max_num, None if aux is None else aux.to(DEV)))
+        rs, ri = ref.flatten().topk(max_num, sorted=True)
+        torch.testing.assert_close(s, rs, rtol=1e-5, atol=1e-7)
+        assert (s[:-1] >= s[1:]).all()                                  # score descending
+        flat = q * K + l
+        assert flat.unique().numel() == max_num                         # no entry selected twice
+        torch.testing.assert_close(ref.flatten()[flat], rs, rtol=1e-5, atol=1e-7)   # same multiset of scores
+        gap = (rs[:-1] - rs[1:]).min().item() if max_num > 1 else 1.0
+        if gap > 1e-5:
+            assert torch.equal(flat, ri)
+    with pytest.raises(RuntimeError, match="out of range"):              # torch.topk raises too (py:831)
+        ops.vis_topk(torch.randn(3, 4, device=DEV), 10)
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_vis_masks_vs_oracle(geom, dtype):
+    (h, w), first, img, out = geom
+    g = torch.Generator().manual_seed(h * 100 + w)
+    masks = (torch.randn(6, 3, h, w, generator=g) * 3).to(dtype)
+    sel = torch.tensor([4, 0, 4, 5], dtype=torch.int64)
+    ours = ops.vis_masks(masks.to(DEV), sel.to(DEV), first, img, out)
+    assert ours.dtype == torch.bool and ours.shape == (4, 3, *out)
+    ref = pp.resize_chain(masks[sel].float(), img, out[0], out[1], first)
+    assert_masks_match(ours, ref > 0, ref)
+    # all queries, frame-major storage (T, Q, h, w) viewed as (Q, T, h, w): the layout the mask GEMM produces
+    fm = masks.to(DEV).transpose(0, 1).contiguous().transpose(0, 1)
+    ours2 = ops.vis_masks(fm, None, first, img, out)
+    ref2 = pp.resize_chain(masks.float(), img, out[0], out[1], first)
+    assert_masks_match(ours2, ref2 > 0, ref2)
+
+
+def test_vis_module_vs_reference_golden(golden):
+    g = golden("postprocess_vis.pt")
+    for name, c in g["cases"].items():
+        Ho, Wo = c["output_size"]
+        post = VideoPostProcessor(g["num_classes"], num_queries=12, max_num=c["max_num"])
+        aux = g["aux_cls"].to(DEV) if c["use_aux"] else None
+        out = post.inference_video_task(g["pred_cls"].to(DEV), g["pred_masks"].to(DEV), g["img_size"], Ho, Wo,
+                                        g["first_resize_size"], g["pred_id"], aux_pred_cls=aux)
+        assert all(not m.is_cuda and m.dtype == torch.bool for m in out["pred_masks"])
+        s, l, i, m = sort_instances(out["pred_scores"], out["pred_labels"], out["pred_ids"], torch.stack(out["pred_masks"]))
+        rs, rl, ri, rm = sort_instances(c["pred_scores"], c["pred_labels"], c["pred_ids"], c["pred_masks"])
+        torch.testing.assert_close(s, rs, rtol=1e-5, atol=1e-7)
+        assert torch.equal(l, rl) and torch.equal(i, ri), name
+        o = pp.inference_video_vis(g["pred_cls"], g["pred_masks"], g["img_size"], Ho, Wo, g["first_resize_size"], g["pred_id"],
+                                   g["num_classes"], c["max_num"], aux_pred_cls=g["aux_cls"] if c["use_aux"] else None, return_logits=True)
+        _, _, _, lg = sort_instances(o["pred_scores"], o["pred_labels"], o["pred_ids"], o["resized_logits"])
+        assert_masks_match(m, rm, lg)
+    empty = VideoPostProcessor(5).inference_video_vis(g["pred_cls"][:0].to(DEV), g["pred_masks"][:0].to(DEV), g["img_size"], 45, 78,
+                                                      g["first_resize_size"], g["pred_id"][:0])
+    assert empty["pred_masks"] == [] and empty["pred_scores"] == []
+
+
+def _blob_logits(Q, T, h, w, gen):
+    coarse = torch.randn(Q, T, max(h // 8, 2), max(w // 8, 2), generator=gen) * 6.0
+    fine = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bicubic", align_corners=False)
+    return fine + 0.3 * torch.randn(Q, T, h, w, generator=gen) - 1.0
+
+
+@pytest.mark.parametrize("case", ["720p_identity", "480p_to_720p"])
+def test_vis_masks_full_size(case):
+    """BASELINE metric size (720p, T=16, 10 of Q=200 queries kept) and a real two-resize geometry (480p inference of a
+    720p video), against the oracle on the host; plus properties that need no oracle."""
+    gen = torch.Generator().manual_seed(5)
+    if case == "720p_identity":
+        Q, T, (h, w), first, img, out = 24, 16, (184, 320), (736, 1280), (720, 1280), (720, 1280)
+    else:
+        Q, T, (h, w), first, img, out = 24, 4, (120, 216), (480, 864), (480, 854), (720, 1280)
+    masks = _blob_logits(Q, T, h, w, gen)
+    sel = torch.randperm(Q, generator=gen)[:10]
+    d = masks.to(DEV)
+    ours = ops.vis_masks(d, sel.to(DEV), first, img, out)
+    ref = pp.resize_chain(masks[sel], img, out[0], out[1], first)
+    assert_masks_match(ours, ref > 0, ref, max_boundary_frac=1e-4)
+    assert 0.02 < ours.float().mean().item() < 0.98                      # a non-trivial pattern was compared
+    # bf16 logits (what the bf16 mask GEMM emits): same decision as the oracle on the bf16-rounded values
+    ours_bf = ops.vis_masks(d.bfloat16(), sel.to(DEV), first, img, out)
+    ref_bf = pp.resize_chain(masks[sel].bfloat16().float(), img, out[0], out[1], first)
+    assert_masks_match(ours_bf, ref_bf > 0, ref_bf, max_boundary_frac=1e-4)
+    # properties: negation flips every pixel whose value is not exactly 0; a positive shift only adds pixels;
+    # constant logits give constant masks; selection commutes with the kernel
+    neg = ops.vis_masks(-d, sel.to(DEV), first, img, out)
+    assert (neg & ours).sum().item() == 0 and (~(neg | ours)).float().mean().item() < 1e-4
+    shifted = ops.vis_masks(d + 0.5, sel.to(DEV), first, img, out)
+    assert (ours & ~shifted).sum().item() == 0 and shifted.sum() > ours.sum()
+    ones = ops.vis_masks(torch.full_like(d[:2], 0.25), None, first, img, out)
+    assert ones.all() and not ops.vis_masks(torch.full_like(d[:2], -0.25), None, first, img, out).any()
+    assert torch.equal(ops.vis_masks(d, None, first, img, out)[sel.to(DEV)], ours)
+
+
+@pytest.mark.parametrize("geom", GEOMS[:5])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_vps_argmax_vs_oracle(geom, dtype):
+    (h, w), first, img, out = geom
+    g = torch.Generator().manual_seed(7 + h)
+    masks = (torch.randn(9, 2, h, w, generator=g) * 3).to(dtype)
+    keep_idx = torch.tensor([1, 3, 4, 8], dtype=torch.int64)
+    keep_score = torch.tensor([0.9, 0.5, 0.7, 0.95])
+    win, areas = ops.vps_argmax(masks.to(DEV), keep_idx.to(DEV), keep_score.to(DEV), first, img, out)
+    win, areas = win.cpu(), areas.cpu()
+    cur = pp.resize_chain(masks[keep_idx].float(), img, out[0], out[1], first, sigmoid=True)
+    prob = keep_score.view(-1, 1, 1, 1) * cur
+    ref_ids = prob.argmax(0)
+    ids = torch.where(win >= 0, win, ~win).long()
+    assert_labels_match(ids, ref_ids, prob, tol=1e-4)
+    same = ids == ref_ids
+    margin = (cur.gather(0, ref_ids[None])[0] - 0.5).abs()
+    assert ((win >= 0) == (cur.gather(0, ref_ids[None])[0] >= 0.5))[same & (margin > 1e-4)].all()
+    n = keep_idx.numel()
+    ref_areas = torch.stack([torch.stack([(ref_ids == k).sum() for k in range(n)]),
+                             torch.stack([(cur[k] >= 0.5).sum() for k in range(n)]),
+                             torch.stack([((ref_ids == k) & (cur[k] >= 0.5)).sum() for k in range(n)])])
+    assert (areas - ref_areas).abs().max().item() <= 3, (areas, ref_areas)
+    assert areas[0].sum().item() == ref_ids.numel()
+    # painting: segment ids through the winner map
+    seg = torch.tensor([5, 0, 7, 7], dtype=torch.int32)
+    pan = ops.vps_paint(win.to(DEV), seg.to(DEV)).cpu()
+    assert torch.equal(pan, torch.where(win >= 0, seg[win.clamp(min=0).long()], torch.zeros_like(win)))
+
+
+def test_vps_module_vs_reference_golden(golden):
+    g = golden("postprocess_vps.pt")
+    for name, c in g["cases"].items():
+        Ho, Wo = c["output_size"]
+        post = VideoPostProcessor(g["num_classes"], object_mask_threshold=c["object_mask_threshold"],
+                                  overlap_threshold=c["overlap_threshold"], num_thing_classes=g["num_thing_classes"], task="vps")
+        out = post.inference_video_task(g["pred_cls"].to(DEV), g["pred_masks"].to(DEV), g["img_size"], Ho, Wo,
+                                        g["first_resize_size"], g["pred_id"], aux_pred_cls=g["aux_cls"].to(DEV) if c["use_aux"] else None)
+        assert out["segments_infos"] == c["segments_infos"], name
+        assert [int(i) for i in out["pred_ids"]] == c["pred_ids"], name
+        assert out["pred_masks"].dtype == torch.int32 and not out["pred_masks"].is_cuda
+        assert (out["pred_masks"] != c["pred_masks"]).float().mean().item() < 1e-3, name
+
+
+@pytest.mark.parametrize("geom", GEOMS[:4])
+@pytest.mark.parametrize("K", [5, 19, 124])
+def test_vss_argmax_vs_oracle(geom, K):
+    (h, w), first, img, out = geom
+    g = torch.Generator().manual_seed(3 + K)
+    Q = 10 if K < 100 else 100
+    masks = torch.randn(Q, 2, h, w, generator=g) * 3
+    cls = torch.randn(Q, K + 1, generator=g) * 2
+    scores = ops.class_scores(cls.to(DEV))
+    ours = ops.vss_argmax(masks.to(DEV), scores[:, :-1], first, img, out)
+    ref = pp.inference_video_vss(cls, masks, img, out[0], out[1], first, return_scores=True)
+    assert ours.dtype == torch.int64
+    assert_labels_match(ours, ref["pred_masks"], ref["semseg"], tol=1e-4)
+    ours_bf = ops.vss_argmax(masks.to(DEV).bfloat16(), scores[:, :-1], first, img, out)
+    ref_bf = pp.inference_video_vss(cls, masks.bfloat16().float(), img, out[0], out[1], first, return_scores=True)
+    assert_labels_match(ours_bf, ref_bf["pred_masks"], ref_bf["semseg"], tol=1e-4)
+
+
+def test_vss_module_vs_reference_golden(golden):
+    g = golden("postprocess_vss.pt")
+    for name, c in g["cases"].items():
+        Ho, Wo = c["output_size"]
+        aux = g["aux_cls"] if c["use_aux"] else None
+        out = VideoPostProcessor(g["num_classes"], task="vss").inference_video_task(
+            g["pred_cls"].to(DEV), g["pred_masks"].to(DEV), g["img_size"], Ho, Wo, g["first_resize_size"], None,
+            aux_pred_cls=None if aux is None else aux.to(DEV))
+        ref = pp.inference_video_vss(g["pred_cls"], g["pred_masks"], g["img_size"], Ho, Wo, g["first_resize_size"], aux_pred_cls=aux,
+                                     return_scores=True)
+        assert_labels_match(out["pred_masks"], c["pred_masks"], ref["semseg"], tol=1e-4)
+
+
+def test_post_processing_vs_reference_golden(golden):
+    g = golden("postprocess_logits.pt")
+    post = VideoPostProcessor(5)
+    outs, aux = post.post_processing(dict(pred_logits=g["pred_logits"].to(DEV), pred_masks=g["pred_masks"].to(DEV)),
+                                     aux_logits=g["aux_logits"].to(DEV))
+    torch.testing.assert_close(outs["pred_logits"].cpu(), g["dvis_logits"], rtol=0, atol=1e-6)
+    torch.testing.assert_close(aux.cpu(), g["dvis_aux"], rtol=0, atol=1e-6)
+    mv = post.post_processing_minvis(dict(pred_logits=g["pred_logits"].to(DEV), pred_masks=g["pred_masks"].to(DEV),
+                                          pred_embds=g["pred_embds"].to(DEV)))
+    torch.testing.assert_close(mv["pred_logits"].cpu(), g["minvis_logits"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(mv["pred_masks"].cpu(), g["minvis_masks"])        # GPU Hungarian == SciPy on the reference's input
