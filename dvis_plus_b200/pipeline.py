@@ -76,6 +76,38 @@ class OfflineClipRunner:
                 "online_pred_logits": track["pred_logits"]}
 
     @torch.no_grad()
+    def vis_from_block(self, block, mask_features, C, post, img_size, output_size, first_resize_size=None):
+        """Tracker + refiner + the video-instance post-processing of DVIS_Plus_offline.forward's eval branch
+        (P/dvis_Plus/meta_architecture.py:1377-1396 -> post_processing py:758-772 -> inference_video_vis py:818-868), fused
+        around the final mask GEMM: the `max_num` instances are selected from the time-averaged class logits FIRST, so the
+        GEMM produces max_num (not Q) masks per frame, and the resize chain + threshold runs straight from those stride-4
+        logits (ops.vis_masks).  The reference computes all Q masks for all frames, moves them to the host in fp32, and
+        up-samples the selected ones to the padded image size twice.
+
+        block: the gathered (T, Q, 2C+K+1) query block; mask_features: THIS rank's (t_local, C_m, h, w) features;
+        post: modules.postprocess.VideoPostProcessor (task "vis").  Nothing here synchronises with the host.
+        -> dict of DEVICE tensors: pred_scores (n,), pred_labels (n,), pred_ids (n,) -- identical on all ranks -- and
+        pred_masks (n, t_local, H_out, W_out) bool for this rank's frames."""
+        from . import ops
+        t_local = mask_features.shape[0]
+        frame_embds, frame_embds_no_norm, _ = self.unpack_queries(block, C)
+        track = self.tracker(frame_embds, None, resume=False, frame_embeds_no_norm=frame_embds_no_norm, with_masks=False)
+        outputs = self.refiner.refine(track["pred_embds"], frame_embds_no_norm)           # (T, l, q, 1, c)
+        dec = self.refiner.decoder_norm(outputs[:, -1:]).permute(1, 3, 0, 2, 4)           # (1, 1, T, q, c)
+        logits = self.refiner.pred_class(dec)[-1].transpose(1, 2)                         # (1, T, q, K+1)
+        mean_logits = logits[0].float().mean(0)                                           # post_processing, py:763-767
+        aux_logits = track["pred_logits"][0].float().mean(0)
+        scores, labels, query = post.select_vis(mean_logits, aux_logits)
+        t0 = self.rank * t_local
+        sel = dec[0, 0, t0:t0 + t_local].index_select(1, query)                           # (t_local, n, c)
+        emb = self.refiner.mask_embed(sel).float()
+        low = self.refiner._masks(emb[None, None], mask_features[None])[0, 0]             # (n, t_local, h, w), frame-major storage
+        h, w = low.shape[-2:]
+        first = first_resize_size if first_resize_size is not None else (4 * h, 4 * w)    # stride-4 mask features
+        masks = ops.vis_masks(low, None, first, img_size, output_size)
+        return {"pred_scores": scores, "pred_labels": labels, "pred_ids": query, "pred_masks": masks}
+
+    @torch.no_grad()
     def temporal_stage(self, seg, mask_features):
         """Exchange + tracker + refiner + final masks, given this rank's segmenter outputs (`seg`: the predictor's
         dict for t_local frames) and its local mask features (t_local, C, H, W)."""

@@ -215,3 +215,44 @@ def test_post_processing_vs_reference_golden(golden):
                                           pred_embds=g["pred_embds"].to(DEV)))
     torch.testing.assert_close(mv["pred_logits"].cpu(), g["minvis_logits"], rtol=1e-5, atol=1e-6)
     assert torch.equal(mv["pred_masks"].cpu(), g["minvis_masks"])        # GPU Hungarian == SciPy on the reference's input
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("out_size", [(60, 90), (90, 135)])
+def test_pipeline_vis_from_block_equals_postprocessing_all_masks(out_size):
+    """Selecting the instances BEFORE the final mask GEMM (OfflineClipRunner.vis_from_block) gives the same result as the
+    reference order: all Q masks -> post_processing -> inference_video_vis."""
+    from dvis_plus_b200 import _lib, modules as M
+    from dvis_plus_b200.modules.precision import precision
+    from dvis_plus_b200.pipeline import OfflineClipRunner
+    T, Q, C, K, H, W = 4, 24, 64, 5, 16, 24
+    torch.manual_seed(0)
+    trk = M.ReferringTracker_noiser(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=64,
+                                    class_num=K, noise_mode="none").eval().to(DEV)
+    rfn = M.TemporalRefiner(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=64, class_num=K,
+                            windows=2).eval().to(DEV)
+    g = torch.Generator().manual_seed(1)
+    seg = dict(pred_embds=torch.randn(1, C, T, Q, generator=g).to(DEV), pred_embds_without_norm=torch.randn(1, C, T, Q, generator=g).to(DEV),
+               pred_logits=torch.randn(1, T, Q, K + 1, generator=g).to(DEV))
+    mf = torch.randn(T, 64, H, W, generator=g).to(DEV).to(torch.bfloat16, memory_format=torch.channels_last)
+    runner = OfflineClipRunner(None, None, trk, rfn)
+    post = VideoPostProcessor(K, num_queries=Q, max_num=10)
+    img = (60, 90)
+    n0 = _lib.launch_count
+    with precision("bf16"):
+        block = runner.pack_queries(seg)
+        fused = runner.vis_from_block(block, mf, C, post, img, out_size)
+        full = runner.temporal_from_block(block, mf, C)
+    assert _lib.launch_count - n0 > 10, "libdvis_b200 kernels did not run"
+    outs, aux = post.post_processing(dict(pred_logits=full["pred_logits"], pred_masks=full["pred_masks"]),
+                                     aux_logits=full["online_pred_logits"])
+    ref = post.inference_video_vis(outs["pred_logits"][0], outs["pred_masks"][0], img, *out_size, (4 * H, 4 * W), outs["ids"][0],
+                                   aux_pred_cls=aux)
+    torch.testing.assert_close(fused["pred_scores"].cpu(), torch.tensor(ref["pred_scores"]), rtol=1e-5, atol=1e-7)
+    assert fused["pred_labels"].tolist() == ref["pred_labels"] and fused["pred_ids"].tolist() == ref["pred_ids"]
+    assert fused["pred_masks"].shape == (10, T, *out_size) and fused["pred_masks"].dtype == torch.bool
+    assert (fused["pred_masks"].cpu() != torch.stack(ref["pred_masks"])).float().mean().item() < 1e-3
+    # and the masks agree with the oracle's resize chain applied to the pipeline's own stride-4 logits
+    low = outs["pred_masks"][0][torch.tensor(ref["pred_ids"], device=DEV)].float().cpu()
+    chain = pp.resize_chain(low, img, out_size[0], out_size[1], (4 * H, 4 * W))
+    assert_masks_match(fused["pred_masks"], chain > 0, chain, tol=1e-3, max_boundary_frac=5e-3)

@@ -121,3 +121,34 @@ def test_cpu_tensors_raise():
     post = VideoPostProcessor(5)
     with pytest.raises(RuntimeError, match="no CPU path"):
         post.inference_video_vis(torch.randn(4, 6), torch.randn(4, 2, 8, 8), (30, 30), 30, 30, (32, 32), torch.arange(4))
+
+
+def test_pipeline_vis_from_block_equals_postprocessing_all_masks(doubles):
+    """OfflineClipRunner.vis_from_block selects the instances BEFORE the final mask GEMM; the result must equal running the
+    reference order (all Q masks -> post_processing -> inference_video_vis) on the same tracker / refiner outputs."""
+    from dvis_plus_b200 import modules as M
+    from dvis_plus_b200.pipeline import OfflineClipRunner
+    T, Q, C, K, H, W = 4, 10, 64, 5, 8, 12
+    torch.manual_seed(0)
+    trk = M.ReferringTracker_noiser(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=32,
+                                    class_num=K, noise_mode="none").eval()
+    rfn = M.TemporalRefiner(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=32, class_num=K,
+                            windows=2).eval()
+    g = torch.Generator().manual_seed(1)
+    seg = dict(pred_embds=torch.randn(1, C, T, Q, generator=g), pred_embds_without_norm=torch.randn(1, C, T, Q, generator=g),
+               pred_logits=torch.randn(1, T, Q, K + 1, generator=g))
+    mf = torch.randn(T, 32, H, W, generator=g)
+    runner = OfflineClipRunner(None, None, trk, rfn)
+    post = VideoPostProcessor(K, num_queries=Q, max_num=6)
+    img, out_size = (30, 45), (41, 60)
+    block = runner.pack_queries(seg)
+    fused = runner.vis_from_block(block, mf, C, post, img, out_size)
+    full = runner.temporal_from_block(block, mf, C)
+    outs, aux = post.post_processing(dict(pred_logits=full["pred_logits"], pred_masks=full["pred_masks"]),
+                                     aux_logits=full["online_pred_logits"])
+    ref = post.inference_video_vis(outs["pred_logits"][0], outs["pred_masks"][0], img, *out_size, (4 * H, 4 * W), outs["ids"][0],
+                                   aux_pred_cls=aux)
+    torch.testing.assert_close(fused["pred_scores"], torch.tensor(ref["pred_scores"]), rtol=1e-6, atol=1e-7)
+    assert fused["pred_labels"].tolist() == ref["pred_labels"] and fused["pred_ids"].tolist() == ref["pred_ids"]
+    assert fused["pred_masks"].shape == (6, T, *out_size)
+    assert (fused["pred_masks"] != torch.stack(ref["pred_masks"])).float().mean().item() < 1e-4
