@@ -141,35 +141,39 @@ __global__ void __launch_bounds__(32 * kStripWarps) vis_masks_strip_kernel(const
   }
 }
 
-// General chain (second resize changes the size): every output pixel evaluates up to four first-stage samples.
+// General chain (second resize changes the size): the same walk with two cache levels (rc::Strip2) -- source rows and
+// intermediate rows are each computed once per strip when they first enter, instead of 16 source reads per output pixel.
+constexpr int kStrip2Px = 4;    // output pixels per thread and row: one 4-byte store, a warp stores 128 contiguous bytes
+
 template <typename T>
-__global__ void __launch_bounds__(128) vis_masks_two_stage_kernel(const T *__restrict__ logits, int64_t q_stride,
-                                                                   int64_t t_stride, const int64_t *__restrict__ sel,
-                                                                   int frames, Geom g, uint8_t *__restrict__ out) {
+__global__ void __launch_bounds__(32 * kStripWarps) vis_masks_two_stage_kernel(const T *__restrict__ logits, int64_t q_stride,
+                                                                               int64_t t_stride, const int64_t *__restrict__ sel,
+                                                                               int frames, Geom g, int rows_per_warp,
+                                                                               uint8_t *__restrict__ out) {
   using R = typename Raw<T>::type;
+  const int lane = threadIdx.x, warp = threadIdx.y;
   const int plane = blockIdx.z, n = plane / frames, t = plane % frames;
-  const int oy = blockIdx.y;
-  const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (ox0 >= g.Wo) return;
+  const int ox0 = (blockIdx.x * 32 + lane) * kStrip2Px;
+  const int oy_begin = (blockIdx.y * kStripWarps + warp) * rows_per_warp;
+  const int oy_end = min(oy_begin + rows_per_warp, g.Ho);
+  if (ox0 >= g.Wo || oy_begin >= oy_end) return;
   const int64_t q = sel ? sel[n] : n;
   Plane<R> pl;
   pl.p = reinterpret_cast<const R *>(logits) + q * q_stride + t * t_stride;
   pl.w = g.w;
-  const Tap t2y = rc::make_tap(oy, g.s2y, g.Hc);
-  uint32_t bits = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (ox0 + i < g.Wo) {
-      const Tap t2x = rc::make_tap(ox0 + i, g.s2x, g.Wc);
-      bits |= uint32_t(rc::two_stage<false>(pl, g, t2y, t2x) > 0.f) << i;
+  rc::Strip2<kStrip2Px, R> strip;
+  strip.init(g, ox0);
+  uint8_t *o = out + (int64_t)plane * g.Ho * g.Wo + ox0;
+  const bool vec = (g.Wo % kStrip2Px == 0) && ((reinterpret_cast<uintptr_t>(out) & 3u) == 0);
+  for (int oy = oy_begin; oy < oy_end; ++oy) {
+    const uint32_t bits = strip.row(pl, g, oy);
+    uint8_t *orow = o + (int64_t)oy * g.Wo;
+    if (vec) {
+      *reinterpret_cast<uint32_t *>(orow) = spread4(bits);
+    } else {
+      for (int i = 0; i < kStrip2Px; ++i)
+        if (ox0 + i < g.Wo) orow[i] = uint8_t((bits >> i) & 1u);
     }
-  }
-  uint8_t *orow = out + ((int64_t)plane * g.Ho + oy) * g.Wo + ox0;
-  if ((g.Wo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
-    *reinterpret_cast<uint32_t *>(orow) = spread4(bits);
-  } else {
-    for (int i = 0; i < 4; ++i)
-      if (ox0 + i < g.Wo) orow[i] = uint8_t((bits >> i) & 1u);
   }
 }
 
@@ -330,11 +334,13 @@ extern "C" int dvis_vis_masks(const void *logits, int logits_dtype, int64_t q_st
       return fail(DVIS_ERR_UNSUPPORTED, "vis_masks: logits dtype must be f32 or bf16");
     return check_launch("vis_masks_strip_kernel");
   }
-  const dim3 grid((Wo + 128 * 4 - 1) / (128 * 4), Ho, planes);
+  const int rows_per_warp = 24;
+  const dim3 grid((Wo + 32 * kStrip2Px - 1) / (32 * kStrip2Px), (Ho + kStripWarps * rows_per_warp - 1) / (kStripWarps * rows_per_warp), planes);
+  const dim3 block(32, kStripWarps);
   if (logits_dtype == DVIS_F32)
-    vis_masks_two_stage_kernel<float><<<grid, 128, 0, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, out);
+    vis_masks_two_stage_kernel<float><<<grid, block, 0, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
   else if (logits_dtype == DVIS_BF16)
-    vis_masks_two_stage_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, out);
+    vis_masks_two_stage_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
   else
     return fail(DVIS_ERR_UNSUPPORTED, "vis_masks: logits dtype must be f32 or bf16");
   return check_launch("vis_masks_two_stage_kernel");

@@ -155,6 +155,78 @@ struct Strip {
   }
 };
 
+// ---- two-resize strip walker (general chain, no sigmoid) -----------------------------------------------------------
+// Same walk as Strip, for a second resize that changes the size.  Per thread: PX output pixels need 2*PX columns of the
+// intermediate (cropped, first-resize) image -- ix0 / ix1 of every pixel -- in two intermediate rows (iy0, iy1), and every
+// intermediate row needs two source rows.  Both levels are cached and shifted as the walk moves down: a source row is
+// read (2 loads per intermediate column) only when it first enters, an intermediate row is blended from the two cached
+// source rows only when it first enters.  All cache decisions depend on row indices only, i.e. are warp-uniform.
+// The arithmetic per value is exactly the two nested bilinear formulas of the reference (see the file header).
+template <int PX, typename T>
+struct Strip2 {
+  float w2x0[PX], w2x1[PX];     // second-resize x weights of the PX output pixels
+  Tap ctap[2 * PX];             // first-resize x taps of intermediate columns (ix0_0, ix1_0, ix0_1, ix1_1, ...)
+  float lowA[2 * PX], lowB[2 * PX];   // horizontally blended source rows ya / yb at the intermediate columns
+  float midA[2 * PX], midB[2 * PX];   // intermediate rows ma / mb at the intermediate columns
+  int ya, yb, ma, mb;
+
+  DVIS_HD void init(const Geom &g, int ox0) {
+    DVIS_UNROLL
+    for (int i = 0; i < PX; ++i) {
+      const int ox = ox0 + i < g.Wo ? ox0 + i : g.Wo - 1;   // columns past the edge are computed but never stored
+      const Tap t2 = make_tap(ox, g.s2x, g.Wc);
+      w2x0[i] = t2.w0;
+      w2x1[i] = t2.w1;
+      ctap[2 * i] = make_tap(t2.i0, g.s1x, g.w);
+      ctap[2 * i + 1] = make_tap(t2.i1, g.s1x, g.w);
+    }
+    ya = yb = ma = mb = -1;
+  }
+  DVIS_HD void load_low(const Plane<T> &pl, int y, float *dst) {
+    DVIS_UNROLL
+    for (int j = 0; j < 2 * PX; ++j) dst[j] = ctap[j].w0 * pl.at(y, ctap[j].i0) + ctap[j].w1 * pl.at(y, ctap[j].i1);
+  }
+  DVIS_HD void copy(float *dst, const float *src) {
+    DVIS_UNROLL
+    for (int j = 0; j < 2 * PX; ++j) dst[j] = src[j];
+  }
+  // make (lowA, lowB) hold source rows (y0, y1)
+  DVIS_HD void ensure_low(const Plane<T> &pl, int y0, int y1) {
+    if (ya == y0 && yb == y1) return;
+    if (yb == y0) { copy(lowA, lowB); ya = yb; }
+    else if (ya != y0) { load_low(pl, y0, lowA); ya = y0; }
+    if (ya == y1) { copy(lowB, lowA); yb = ya; }
+    else if (yb != y1) { load_low(pl, y1, lowB); yb = y1; }
+  }
+  DVIS_HD void make_mid(const Plane<T> &pl, const Geom &g, int iy, float *dst) {
+    const Tap ty = make_tap(iy, g.s1y, g.h);
+    ensure_low(pl, ty.i0, ty.i1);
+    DVIS_UNROLL
+    for (int j = 0; j < 2 * PX; ++j) dst[j] = ty.w0 * lowA[j] + ty.w1 * lowB[j];
+  }
+  // make (midA, midB) hold intermediate rows (i0, i1)
+  DVIS_HD void ensure_mid(const Plane<T> &pl, const Geom &g, int i0, int i1) {
+    if (ma == i0 && mb == i1) return;
+    if (mb == i0) { copy(midA, midB); ma = mb; }
+    else if (ma != i0) { make_mid(pl, g, i0, midA); ma = i0; }
+    if (ma == i1) { copy(midB, midA); mb = ma; }
+    else if (mb != i1) { make_mid(pl, g, i1, midB); mb = i1; }
+  }
+  // -> bit i of the result = (chain value of pixel ox0 + i on row oy) > 0
+  DVIS_HD uint32_t row(const Plane<T> &pl, const Geom &g, int oy) {
+    const Tap t2y = make_tap(oy, g.s2y, g.Hc);
+    ensure_mid(pl, g, t2y.i0, t2y.i1);
+    uint32_t bits = 0;
+    DVIS_UNROLL
+    for (int i = 0; i < PX; ++i) {
+      const float v = t2y.w0 * (w2x0[i] * midA[2 * i] + w2x1[i] * midA[2 * i + 1]) +
+                      t2y.w1 * (w2x0[i] * midB[2 * i] + w2x1[i] * midB[2 * i + 1]);
+      bits |= uint32_t(v > 0.f) << i;
+    }
+    return bits;
+  }
+};
+
 // ---- vps: per-pixel arg-max over the kept queries of score * probability (py:897,917) -----------------------------
 // visit(k, v) is called with every kept query's resized probability (for the "original area" counts, py:924).
 // Returns the winner (first maximum, like torch.argmax) and whether ITS probability is >= 0.5 (py:925).

@@ -39,11 +39,17 @@ void vis_masks(const R *logits, int64_t q_stride, int64_t t_stride, const int64_
           }
         }
     } else {                                                  // vis_masks_two_stage_kernel
-      for (int oy = 0; oy < g.Ho; ++oy) {
-        const Tap t2y = make_tap(oy, g.s2y, g.Hc);
-        for (int ox = 0; ox < g.Wo; ++ox)
-          o[(int64_t)oy * g.Wo + ox] = uint8_t(two_stage<false>(pl, g, t2y, make_tap(ox, g.s2x, g.Wc)) > 0.f);
-      }
+      constexpr int PX2 = 4, rows2 = 24;                      // postproc.cu: kStrip2Px, rows_per_warp
+      for (int oy_begin = 0; oy_begin < g.Ho; oy_begin += rows2)
+        for (int ox0 = 0; ox0 < g.Wo; ox0 += PX2) {
+          Strip2<PX2, R> strip;
+          strip.init(g, ox0);
+          for (int oy = oy_begin; oy < std::min(oy_begin + rows2, g.Ho); ++oy) {
+            const uint32_t bits = strip.row(pl, g, oy);
+            for (int i = 0; i < PX2; ++i)
+              if (ox0 + i < g.Wo) o[(int64_t)oy * g.Wo + ox0 + i] = uint8_t((bits >> i) & 1u);
+          }
+        }
     }
   }
 }

@@ -21,6 +21,9 @@ GEOMS = [  # (h, w), first resize, image size, output size
     ((7, 9), (28, 36), (25, 33), (25, 33)),        # odd sizes, strip tail
     ((23, 40), (92, 160), (90, 160), (180, 320)),  # exact 2x second resize
     ((5, 6), (20, 24), (20, 24), (3, 2)),          # output smaller than the logits
+    ((12, 20), (48, 80), (45, 78), (200, 301)),    # strong up-scale: intermediate rows reused over many output rows
+    ((30, 30), (120, 120), (118, 119), (17, 13)),  # strong down-scale: source rows jump, nothing is reused
+    ((46, 80), (184, 320), (180, 320), (100, 177)),  # several row bands per plane, odd width
 ]
 
 

@@ -24,6 +24,9 @@ GEOMS = [  # (h, w), first resize, image size, output size
     ((7, 9), (28, 36), (25, 33), (25, 33)),        # odd sizes
     ((23, 40), (92, 160), (90, 160), (180, 320)),  # exact 2x second resize
     ((5, 6), (20, 24), (20, 24), (3, 2)),          # output smaller than the logits
+    ((12, 20), (48, 80), (45, 78), (200, 301)),    # strong up-scale: intermediate rows reused over many output rows
+    ((30, 30), (120, 120), (118, 119), (17, 13)),  # strong down-scale: source rows jump, nothing is reused
+    ((46, 80), (184, 320), (180, 320), (100, 177)),  # several row bands per plane, odd width
     ((46, 80), (184, 320), (180, 320), (180, 320)),  # several row bands and strips per plane
 ]
 
@@ -100,33 +103,35 @@ def _blob_logits(Q, T, h, w, gen):
 
 @pytest.mark.parametrize("case", ["720p_identity", "480p_to_720p"])
 def test_vis_masks_full_size(case):
-    """BASELINE metric size (720p, T=16, 10 of Q=200 queries kept) and a real two-resize geometry (480p inference of a
-    720p video), against the oracle on the host; plus properties that need no oracle."""
+    """BASELINE metric size (720p, T=16, 10 of the queries kept) and a real two-resize geometry (480p inference of a 720p
+    video).  The oracle (F.interpolate on the host) checks a few frames; size-independent properties cover all of them."""
     gen = torch.Generator().manual_seed(5)
     if case == "720p_identity":
         Q, T, (h, w), first, img, out = 24, 16, (184, 320), (736, 1280), (720, 1280), (720, 1280)
     else:
-        Q, T, (h, w), first, img, out = 24, 4, (120, 216), (480, 864), (480, 854), (720, 1280)
+        Q, T, (h, w), first, img, out = 24, 8, (120, 216), (480, 864), (480, 854), (720, 1280)
     masks = _blob_logits(Q, T, h, w, gen)
     sel = torch.randperm(Q, generator=gen)[:10]
-    d = masks.to(DEV)
-    ours = ops.vis_masks(d, sel.to(DEV), first, img, out)
-    ref = pp.resize_chain(masks[sel], img, out[0], out[1], first)
-    assert_masks_match(ours, ref > 0, ref, max_boundary_frac=1e-4)
-    assert 0.02 < ours.float().mean().item() < 0.98                      # a non-trivial pattern was compared
+    d, dsel = masks.to(DEV), sel.to(DEV)
+    ours = ops.vis_masks(d, dsel, first, img, out)
+    assert ours.shape == (10, T, *out) and 0.02 < ours.float().mean().item() < 0.98     # a non-trivial pattern
+    frames = [0, T // 2, T - 1]                                            # oracle on 3 frames x 4 instances
+    ref = pp.resize_chain(masks[sel[:4]][:, frames], img, out[0], out[1], first)
+    assert_masks_match(ours[:4][:, frames], ref > 0, ref, max_boundary_frac=1e-4)
     # bf16 logits (what the bf16 mask GEMM emits): same decision as the oracle on the bf16-rounded values
-    ours_bf = ops.vis_masks(d.bfloat16(), sel.to(DEV), first, img, out)
-    ref_bf = pp.resize_chain(masks[sel].bfloat16().float(), img, out[0], out[1], first)
-    assert_masks_match(ours_bf, ref_bf > 0, ref_bf, max_boundary_frac=1e-4)
-    # properties: negation flips every pixel whose value is not exactly 0; a positive shift only adds pixels;
-    # constant logits give constant masks; selection commutes with the kernel
-    neg = ops.vis_masks(-d, sel.to(DEV), first, img, out)
+    ours_bf = ops.vis_masks(d.bfloat16(), dsel, first, img, out)
+    ref_bf = pp.resize_chain(masks[sel[:4]][:, frames].bfloat16().float(), img, out[0], out[1], first)
+    assert_masks_match(ours_bf[:4][:, frames], ref_bf > 0, ref_bf, max_boundary_frac=1e-4)
+    # properties over the full size: negation flips every pixel whose value is not exactly 0; a positive shift only adds
+    # pixels; constant logits give constant masks; selection commutes with the kernel; frames / instances are independent
+    neg = ops.vis_masks(-d, dsel, first, img, out)
     assert (neg & ours).sum().item() == 0 and (~(neg | ours)).float().mean().item() < 1e-4
-    shifted = ops.vis_masks(d + 0.5, sel.to(DEV), first, img, out)
+    shifted = ops.vis_masks(d + 0.5, dsel, first, img, out)
     assert (ours & ~shifted).sum().item() == 0 and shifted.sum() > ours.sum()
-    ones = ops.vis_masks(torch.full_like(d[:2], 0.25), None, first, img, out)
-    assert ones.all() and not ops.vis_masks(torch.full_like(d[:2], -0.25), None, first, img, out).any()
-    assert torch.equal(ops.vis_masks(d, None, first, img, out)[sel.to(DEV)], ours)
+    assert ops.vis_masks(torch.full_like(d[:2], 0.25), None, first, img, out).all()
+    assert not ops.vis_masks(torch.full_like(d[:2], -0.25), None, first, img, out).any()
+    assert torch.equal(ops.vis_masks(d, None, first, img, out)[dsel], ours)
+    assert torch.equal(ops.vis_masks(d[:, 3:5], dsel[2:7], first, img, out), ours[2:7, 3:5])
 
 
 @pytest.mark.parametrize("geom", GEOMS[:5])
@@ -243,7 +248,7 @@ def test_pipeline_vis_from_block_equals_postprocessing_all_masks(out_size):
         block = runner.pack_queries(seg)
         fused = runner.vis_from_block(block, mf, C, post, img, out_size)
         full = runner.temporal_from_block(block, mf, C)
-    assert _lib.launch_count - n0 > 10, "libdvis_b200 kernels did not run"
+    assert _lib.launch_count - n0 >= 4, "libdvis_b200 kernels did not run"
     outs, aux = post.post_processing(dict(pred_logits=full["pred_logits"], pred_masks=full["pred_masks"]),
                                      aux_logits=full["online_pred_logits"])
     ref = post.inference_video_vis(outs["pred_logits"][0], outs["pred_masks"][0], img, *out_size, (4 * H, 4 * W), outs["ids"][0],
