@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 BACKBONE_CHANNELS = {  # only input_proj / lateral conv widths depend on the backbone
     "swinl": dict(res2=192, res3=384, res4=768, res5=1536),
     "r50": dict(res2=256, res3=512, res4=1024, res5=2048),
+    "vitl": dict(res2=1024, res3=1024, res4=1024, res5=1024),   # ViT-Adapter-L (D/dvis_daq/.../adapter.py:619-624), config 5
 }
 STRIDES = dict(res2=4, res3=8, res4=16, res5=32)
 IMG_H, IMG_W = 736, 1280          # 720p padded to a multiple of 32 (P/dvis_Plus/meta_architecture.py:187,639)
