@@ -77,6 +77,9 @@ __global__ void __launch_bounds__(1024) lap_kernel(const float *__restrict__ cos
       __syncthreads();
       const double delta = red[0].v;
       const int j1 = red[0].j;
+      // read the exit condition BEFORE the barrier below: once a thread leaves the loop, thread 0 starts rewriting p[]
+      // (augmentation) and a slower warp must not see the updated p[j1]
+      const bool reached_free_column = p[j1] == 0;
       // update potentials: tree columns (incl. j0, which joins the tree now) move with their rows
       for (int j = tid; j <= n; j += nthr) {
         if (used[j] || j == j0) { u[p[j]] += delta; v[j] -= delta; }
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(1024) lap_kernel(const float *__restrict__ cos
       }
       if (tid == 0) { used[j0] = 1; s_j0 = j1; }
       __syncthreads();
-      if (p[j1] == 0) break;
+      if (reached_free_column) break;
     }
     // augment along the alternating path
     if (tid == 0) {

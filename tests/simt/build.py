@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE ONLY.  Turn CUDA-core kernels of dvis_plus_b200/csrc into a g++ build on top of the SIMT emulator
+(tests/simt/simt_shim.h): tests/simt/_build/libdvis_simt.so exports the SAME C-ABI entry points as libdvis_b200.so for the
+translated files, operating on host memory.
+
+Source transforms (textual, the kernels themselves are untouched):
+  * project headers (`#include "x.cuh"`) are inlined once; <cuda_runtime.h> / <cuda_bf16.h> are replaced by the shim
+  * `kernel<<<grid, block, smem, stream>>>(args);`   ->  SIMT_LAUNCH((kernel), grid, block, smem, stream, args);
+  * `extern __shared__ T name[];`                    ->  T *name = reinterpret_cast<T *>(simt::dyn_smem());
+"""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "dvis_plus_b200", "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+OUT_DIR = os.path.join(HERE, "_build")
+OUT = os.path.join(OUT_DIR, "libdvis_simt.so")
+FILES = ["postproc.cu", "lap.cu"]          # CUDA-core kernels only (no tcgen05 / TMA / vector atomics)
+
+
+def _split_top_level(s):
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "(<[{":
+            depth += 1
+        elif ch in ")>]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+def _inline(path, seen):
+    out = []
+    for line in open(path).read().splitlines():
+        m = re.match(r'\s*#include\s+"([\w.]+)"', line)
+        if m:
+            name = m.group(1)
+            for d in (CSRC, INCLUDE):
+                if os.path.exists(os.path.join(d, name)):
+                    if name not in seen:
+                        seen.add(name)
+                        out.append(f"// ---- inlined {name}")
+                        out.extend(_inline(os.path.join(d, name), seen))
+                    break
+            else:
+                raise RuntimeError(f"{path}: cannot resolve include {name}")
+            continue
+        if re.match(r"\s*#include\s+<cuda(_runtime|_bf16)\.h>", line):
+            continue
+        if re.match(r"\s*#pragma\s+once", line):
+            continue
+        out.append(line)
+    return out
+
+
+def translate(cu):
+    src = "\n".join(_inline(os.path.join(CSRC, cu), set()))
+    src = re.sub(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\s*\[\s*\]\s*;",
+                 r"\1 *\2 = reinterpret_cast<\1 *>(simt::dyn_smem());", src)
+
+    def launch(m):
+        cfg = _split_top_level(m.group(2))
+        assert len(cfg) == 4, f"{cu}: launch configuration must have 4 entries: {m.group(0)}"
+        return f"SIMT_LAUNCH(({m.group(1)}), {cfg[0]}, {cfg[1]}, {cfg[2]}, {cfg[3]}, {m.group(3)});"
+
+    src, n = re.subn(r"([A-Za-z_][\w:]*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\)\s*;", launch, src, flags=re.S)
+    assert n > 0, f"{cu}: no kernel launch found"
+    return f'#include "simt_shim.h"\n#define DVIS_SIMT_EMULATION 1\n{src}\n', n
+
+
+def build(force=False):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + \
+           [os.path.join(INCLUDE, "dvis_b200.h"), os.path.join(HERE, "simt_shim.h"), os.path.abspath(__file__)]
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
+        return OUT
+    units = []
+    for cu in FILES:
+        text, _ = translate(cu)
+        path = os.path.join(OUT_DIR, cu[:-3] + "_simt.cpp")
+        with open(path, "w") as fh:
+            fh.write(text)
+        units.append(path)
+    glue = os.path.join(OUT_DIR, "glue_simt.cpp")
+    with open(glue, "w") as fh:          # what csrc/api.cu provides in the real library
+        fh.write('namespace dvis { char *last_error_buffer() { static thread_local char buf[512] = {0}; return buf; } }\n'
+                 'extern "C" const char *dvis_last_error(void) { return dvis::last_error_buffer(); }\n'
+                 '#include "simt_shim.h"\nextern "C" void simt_set_jitter(int one_in) { simt::g_jitter = one_in; }\n')
+    cmd = ["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas",
+           "-Wno-attributes", f"-I{HERE}", f"-I{INCLUDE}"] + units + [glue, "-o", OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed:\n{r.stdout[-3000:]}\n{r.stderr[-6000:]}")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True))
