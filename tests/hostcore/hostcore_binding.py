@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-import build as _build  # noqa: E402
+import hostcore_build as _build  # noqa: E402
 
 _lib = None
 _DT = {torch.float32: 0, torch.bfloat16: 2}

@@ -3,7 +3,7 @@
 // dvis_plus_b200/csrc/resize_core.cuh is written as host/device inline code; this file compiles it with plain g++ and
 // drives it with the same work decomposition as the kernels in dvis_plus_b200/csrc/postproc.cu (planes x row bands x
 // strips, one call per output pixel), so the CPU test-suite can check that arithmetic against the oracle
-// (oracle/postprocess_port.py) and the reference's golden vectors without a GPU.  Built by tests/hostcore/build.py into
+// (oracle/postprocess_port.py) and the reference's golden vectors without a GPU.  Built by tests/hostcore/hostcore_build.py into
 // tests/hostcore/_build/ (git-ignored); never linked into, loaded by or shipped with libdvis_b200.so.
 #include <stdint.h>
 

@@ -8,11 +8,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-import importlib.util  # noqa: E402
-
-_spec = importlib.util.spec_from_file_location("simt_build", os.path.join(os.path.dirname(os.path.abspath(__file__)), "build.py"))
-_build = importlib.util.module_from_spec(_spec)
-_spec.loader.exec_module(_build)
+import simt_build as _build  # noqa: E402
 
 from dvis_plus_b200 import _lib as product_binding  # noqa: E402  (signatures only; the product library is not loaded)
 

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- a minimal SIMT emulator so that the CPU test-suite can execute the CUDA-core kernels of
 // libdvis_b200 (csrc/postproc.cu, csrc/lap.cu: no tensor cores, no TMA) from their ORIGINAL sources without a GPU.
 //
-// tests/simt/build.py turns a .cu file into a g++ translation unit (kernel launches `k<<<g, b, s, st>>>(args)` become
+// tests/simt/simt_build.py turns a .cu file into a g++ translation unit (kernel launches `k<<<g, b, s, st>>>(args)` become
 // SIMT_LAUNCH(...), `extern __shared__` arrays become pointers into a per-block buffer) and includes this header instead
 // of <cuda_runtime.h> / <cuda_bf16.h>.  Every CUDA thread of a block runs as an OS thread; blocks run one after the other.
 // __syncthreads() and the warp collectives (__shfl_xor_sync, __ballot_sync, __any_sync) are rendezvous points

@@ -11,7 +11,7 @@ from oracle import postprocess_port as pp
 from postproc_util import assert_labels_match, assert_masks_match
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcore"))
-import binding as hc  # noqa: E402
+import hostcore_binding as hc  # noqa: E402
 
 GEOMS = [  # (h, w), first resize, image size, output size
     ((12, 20), (48, 80), (45, 78), (45, 78)),      # identity second resize: strip walker

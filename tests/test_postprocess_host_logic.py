@@ -16,7 +16,7 @@ from oracle import postprocess_port as pp
 from postproc_util import assert_labels_match, assert_masks_match, sort_instances
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcore"))
-import binding as hc  # noqa: E402
+import hostcore_binding as hc  # noqa: E402
 
 
 @pytest.fixture

@@ -15,7 +15,7 @@ from oracle import postprocess_port as pp
 from postproc_util import assert_labels_match, assert_masks_match
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
-import binding as simt  # noqa: E402
+import simt_binding as simt  # noqa: E402
 
 pytestmark = pytest.mark.timeout(900)          # an emulated kernel that dead-locks must fail, not hang the suite
 
