@@ -108,3 +108,95 @@ def lap_chain(cost, idx_init=None):
 def set_jitter(one_in):
     """Race shaker: delay roughly one in `one_in` threads after every __syncthreads() (0 = off)."""
     lib().simt_set_jitter(int(one_in))
+
+
+# ---- the remaining CUDA-core entry points (same argument order as dvis_plus_b200/ops.py) ------------------------------------
+ENTRY_POINTS += ("dvis_msda_forward", "dvis_msda_backward", "dvis_msda_fused_forward", "dvis_add_layernorm", "dvis_groupnorm_nhwc",
+                 "dvis_resize_bilinear_nhwc", "dvis_attn_bias_from_logits", "dvis_mha_core", "dvis_msda_pack_pairs",
+                 "dvis_msda_pair_forward")
+_DT[torch.float64] = 1
+
+
+def msda_forward(value, shapes, lsi, loc, attn, item_order=None):
+    N, S, M, D = value.shape
+    L, Lq, P = shapes.shape[0], loc.shape[1], loc.shape[4]
+    out = torch.full((N, Lq, M * D), float("nan"), dtype=value.dtype)
+    call("dvis_msda_forward", _p(value), _p(shapes), _p(lsi), _p(loc), _p(attn), N, S, M, D, L, Lq, P, _DT[value.dtype],
+         _p(item_order), _p(out), None)
+    return out
+
+
+def msda_backward(value, shapes, lsi, loc, attn, grad_out):
+    N, S, M, D = value.shape
+    L, Lq, P = shapes.shape[0], loc.shape[1], loc.shape[4]
+    gv, gl, ga = torch.zeros_like(value), torch.zeros_like(loc), torch.zeros_like(attn)
+    call("dvis_msda_backward", _p(value), _p(shapes), _p(lsi), _p(loc), _p(attn), _p(grad_out), N, S, M, D, L, Lq, P,
+         _DT[value.dtype], _p(gv), _p(gl), _p(ga), None)
+    return gv, gl, ga
+
+
+def msda_fused_forward(value, shapes, lsi, offsets, logits, ref, L, P, item_order=None, out_dtype=None, pair=False):
+    """offsets (N, Lq, M*L*P*2), logits (N, Lq, M*L*P) -- possibly column slices of one tensor; ref (N, Lq, L, 2|4) f32."""
+    N, S, M, D = value.shape
+    Lq = offsets.shape[1]
+    out_dtype = out_dtype or value.dtype
+    out = torch.full((N, Lq, M * D), float("nan"), dtype=out_dtype)
+    if pair:
+        pairs = torch.zeros((N, S + 1, M, 2, D), dtype=torch.bfloat16)
+        call("dvis_msda_pack_pairs", _p(value), N, S, M, D, _p(pairs), None)
+        call("dvis_msda_pair_forward", _p(pairs), _p(shapes), _p(lsi), _p(offsets), offsets.stride(1), _p(logits), logits.stride(1),
+             _DT[offsets.dtype], _p(ref), ref.shape[-1], N, S, M, D, L, Lq, P, _p(item_order), _p(out), None)
+        return out
+    call("dvis_msda_fused_forward", _p(value), _DT[value.dtype], _p(shapes), _p(lsi), _p(offsets), offsets.stride(1), _p(logits),
+         logits.stride(1), _DT[offsets.dtype], _p(ref), ref.shape[-1], N, S, M, D, L, Lq, P, _p(item_order), _p(out),
+         _DT[out_dtype], None)
+    return out
+
+
+def add_layernorm(x, residual, weight, bias, eps=1e-5, lp_dtype=None, pos=None):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out32 = torch.full(x.shape, float("nan"), dtype=torch.float32)
+    lp = torch.zeros(x.shape, dtype=lp_dtype) if lp_dtype is not None else None
+    lpp = torch.zeros(x.shape, dtype=lp_dtype) if pos is not None else None
+    call("dvis_add_layernorm", _p(x), _DT[x.dtype], _p(residual), _DT[residual.dtype] if residual is not None else 0, _p(weight),
+         _p(bias), _p(pos), pos.numel() // C if pos is not None else 0, rows, C, float(eps), _p(out32), _p(lp), _p(lpp),
+         _DT[lp_dtype] if lp_dtype is not None else 0, None)
+    return out32, lp, lpp
+
+
+def groupnorm_nhwc(x, G, weight, bias, eps=1e-5, relu=False, up=None, up_hw=None, hw=None, pos=None, lp_dtype=torch.bfloat16):
+    N, HW, C = x.shape
+    ws = torch.empty(2 * N * G, dtype=torch.float64)
+    out32 = torch.full((N, HW, C), float("nan"), dtype=torch.float32)
+    lp = torch.zeros((N, HW, C), dtype=lp_dtype)
+    lpp = torch.zeros((N, HW, C), dtype=lp_dtype) if pos is not None else None
+    uh, uw = up_hw if up is not None else (0, 0)
+    H, W = hw if up is not None else (0, 0)
+    call("dvis_groupnorm_nhwc", _p(x), _DT[x.dtype], x.stride(0), N, HW, C, G, _p(weight), _p(bias), float(eps), int(relu), _p(ws),
+         _p(up), up.stride(0) if up is not None else 0, uh, uw, H, W, _p(pos), _p(out32), _p(lp), _p(lpp), _DT[lp_dtype],
+         out32.stride(0), None)
+    return out32, lp, lpp
+
+
+def resize_bilinear_nhwc(x_nhwc, size):
+    N, h, w, C = x_nhwc.shape
+    out = torch.zeros((N, size[0], size[1], C), dtype=torch.bfloat16)
+    call("dvis_resize_bilinear_nhwc", _p(x_nhwc), N, h, w, C, _p(out), size[0], size[1], None)
+    return out
+
+
+def attn_bias_from_logits(logits, dtype=torch.float32):
+    hw = logits.shape[-1]
+    bias = torch.full(logits.shape, 7.0, dtype=dtype)
+    call("dvis_attn_bias_from_logits", _p(logits), logits.numel() // hw, hw, _p(bias), _DT[dtype], None)
+    return bias
+
+
+def mha_core(q, k, v, scale):
+    B, Lq, H, Dh = q.shape
+    Lk = k.shape[1]
+    out = torch.zeros((B, Lq, H * Dh), dtype=torch.bfloat16)
+    call("dvis_mha_core", _p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1), v.stride(0), _p(out),
+         H * Dh, Lq * H * Dh, B, Lq, Lk, H, Dh, float(scale), None)
+    return out

@@ -17,7 +17,10 @@ CSRC = os.path.join(ROOT, "dvis_plus_b200", "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 OUT_DIR = os.path.join(HERE, "_build")
 OUT = os.path.join(OUT_DIR, "libdvis_simt.so")
-FILES = ["postproc.cu", "lap.cu"]          # CUDA-core kernels only (no tcgen05 / TMA / vector atomics)
+# every CUDA-core kernel file of the library; csrc/mask_gemm.cu (tcgen05 / TMEM / TMA) and csrc/api.cu (driver entry
+# points) have no CPU meaning and stay out
+FILES = ["postproc.cu", "lap.cu", "msda_forward.cu", "msda_backward.cu", "layernorm.cu", "groupnorm.cu", "mask_aux.cu",
+         "attention.cu", "msda_pair.cu"]
 
 
 def _split_top_level(s):
@@ -52,7 +55,7 @@ def _inline(path, seen):
             else:
                 raise RuntimeError(f"{path}: cannot resolve include {name}")
             continue
-        if re.match(r"\s*#include\s+<cuda(_runtime|_bf16)\.h>", line):
+        if re.match(r"\s*#include\s+<cuda(_runtime|_bf16|_fp16)\.h>", line):
             continue
         if re.match(r"\s*#pragma\s+once", line):
             continue

@@ -32,6 +32,9 @@ struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
+struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
@@ -65,6 +68,18 @@ struct __nv_bfloat16 {
 struct __nv_bfloat162 { __nv_bfloat16 x, y; };
 inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{__nv_bfloat16(a), __nv_bfloat16(b)}; }
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float __bfloat162float(__nv_bfloat16 b) { return float(b); }
+inline float __expf(float x) { return std::exp(x); }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+// packed f32x2 fused multiply-add (fma.rn.f32x2): two independent fmaf
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+// fp16 pairs (csrc/msda_pair.cu)
+struct __half2 { _Float16 x, y; };
+inline __half2 __floats2half2_rn(float a, float b) { return __half2{(_Float16)a, (_Float16)b}; }
+inline float __low2float(__half2 h) { return float(h.x); }
+inline float __high2float(__half2 h) { return float(h.y); }
+#define __align__(n) alignas(n)
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline int min(int a, int b) { return a < b ? a : b; }
@@ -172,6 +187,26 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
 inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0; }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+namespace simt {
+template <typename F, typename U>
+inline F atomic_add_fp(F *p, F v) {          // compare-and-swap loop on the value's bit pattern
+  static_assert(sizeof(F) == sizeof(U), "bit pattern type");
+  U *up = reinterpret_cast<U *>(p);
+  U old = __atomic_load_n(up, __ATOMIC_RELAXED), desired;
+  F cur;
+  do {
+    std::memcpy(&cur, &old, sizeof(F));
+    const F sum = cur + v;
+    std::memcpy(&desired, &sum, sizeof(F));
+  } while (!__atomic_compare_exchange_n(up, &old, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  return cur;
+}
+}  // namespace simt
+inline float atomicAdd(float *p, float v) { return simt::atomic_add_fp<float, uint32_t>(p, v); }
+inline double atomicAdd(double *p, double v) { return simt::atomic_add_fp<double, uint64_t>(p, v); }
+inline float4 atomicAdd(float4 *p, float4 v) {   // 16-byte vector atomic (red.global.add.v4.f32): four independent adds
+  return float4{atomicAdd(&p->x, v.x), atomicAdd(&p->y, v.y), atomicAdd(&p->z, v.z), atomicAdd(&p->w, v.w)};
+}
 
 #define SIMT_LAUNCH(kernel, grid, block, smem, stream, ...) \
   simt::launch(dim3(grid), dim3(block), size_t(smem), [&] { kernel(__VA_ARGS__); })

@@ -1,0 +1,186 @@
+"""MSDA forward / backward, the fused LayerNorm / GroupNorm kernels, the mask-head helpers and the small attention core,
+executed from their ORIGINAL .cu sources by the SIMT emulator (tests/simt/) through the C-ABI entry points, against the
+plain-C oracle / torch on CPU.  Same purpose as tests/test_simt_kernels.py: launch geometry, thread -> item mapping,
+shared-memory staging and barrier protocols are checked without a GPU.  Tolerances are the ones the -m gpu tests use."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import c_oracle
+from oracle import torch_port as tp
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+import simt_binding as simt  # noqa: E402
+
+pytestmark = pytest.mark.timeout(900)
+
+
+def lsi_of(shapes):
+    return torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+
+
+def msda_case(dtype, N, M, D, Lq, shapes, P, seed=0, spread=1.4):
+    g = torch.Generator().manual_seed(seed)
+    sh = torch.as_tensor(shapes, dtype=torch.long)
+    S, L = int(sh.prod(1).sum()), len(shapes)
+    value = torch.randn(N, S, M, D, generator=g, dtype=dtype)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g, dtype=dtype) * spread - (spread - 1) / 2      # partly outside [0, 1]
+    attn = torch.rand(N, Lq, M, L, P, generator=g, dtype=dtype).flatten(-2).softmax(-1).view(N, Lq, M, L, P)
+    return value, sh, lsi_of(sh), loc, attn
+
+
+@pytest.mark.parametrize("D", [8, 32, 64])
+def test_msda_forward_staged_kernel(D):
+    value, sh, lsi, loc, attn = msda_case(torch.float32, 2, 8, D, 37, ((12, 20), (6, 10), (3, 5)), 4)
+    ref = c_oracle.msda_forward(value.numpy(), sh.numpy(), lsi.numpy(), loc.numpy(), attn.numpy())
+    out = simt.msda_forward(value, sh, lsi, loc, attn)
+    assert np.abs(out.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    order = torch.randperm(37 * 8, generator=torch.Generator().manual_seed(1)).int()          # any item order gives the same result
+    out2 = simt.msda_forward(value, sh, lsi, loc, attn, item_order=order)
+    assert torch.equal(out2, out)
+
+
+def test_msda_forward_generic_kernel_fp64_and_odd_dim():
+    value, sh, lsi, loc, attn = msda_case(torch.float64, 1, 2, 6, 9, ((6, 4), (3, 2)), 2)
+    ref = c_oracle.msda_forward(value.numpy(), sh.numpy(), lsi.numpy(), loc.numpy(), attn.numpy())
+    assert np.allclose(simt.msda_forward(value, sh, lsi, loc, attn).numpy(), ref, rtol=1e-12, atol=1e-13)
+    v32, _, _, l32, a32 = msda_case(torch.float32, 1, 2, 6, 9, ((6, 4), (3, 2)), 2)
+    ref32 = c_oracle.msda_forward(v32.numpy(), sh.numpy(), lsi.numpy(), l32.numpy(), a32.numpy())
+    assert np.allclose(simt.msda_forward(v32, sh, lsi, l32, a32).numpy(), ref32, rtol=1e-5, atol=1e-6)
+
+
+def test_msda_forward_reference_golden(golden):
+    g = golden("msda_optest.pt")                                                               # OPS/test.py shapes + seed
+    out = simt.msda_forward(g["value32"], g["shapes"], g["lsi"], g["loc32"], g["attn32"])
+    assert (out - g["out32"]).abs().max() < 1e-6                                                # OPS/test.py:59 uses 1e-2 / 1e-3
+    out64 = simt.msda_forward(g["value64"], g["shapes"], g["lsi"], g["loc64"], g["attn64"])
+    assert torch.allclose(out64, g["out64"])                                                    # OPS/test.py:43
+
+
+@pytest.mark.parametrize("D,dtype", [(32, torch.float32), (8, torch.float32), (6, torch.float64)])
+def test_msda_backward_kernels(D, dtype):
+    value, sh, lsi, loc, attn = msda_case(dtype, 1, 4, D, 21, ((8, 12), (4, 6)), 4, seed=3)
+    go = torch.randn(1, 21, 4 * D, generator=torch.Generator().manual_seed(5), dtype=dtype)
+    rv, rl, ra = c_oracle.msda_backward(value.numpy(), sh.numpy(), lsi.numpy(), loc.numpy(), attn.numpy(), go.numpy())
+    gv, gl, ga = simt.msda_backward(value, sh, lsi, loc, attn, go)
+    tol = 1e-10 if dtype == torch.float64 else 2e-4
+    for ours, ref in ((gv, rv), (gl, rl), (ga, ra)):
+        assert np.abs(ours.numpy() - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("vdt,odt,pdt,ref_dim", [(torch.float32, torch.float32, torch.float32, 2),
+                                                 (torch.bfloat16, torch.bfloat16, torch.bfloat16, 2),
+                                                 (torch.bfloat16, torch.float32, torch.float32, 4)])
+def test_msda_fused_forward_kernel(vdt, odt, pdt, ref_dim):
+    N, M, D, L, P = 2, 8, 32, 3, 4
+    shapes = ((12, 20), (6, 10), (3, 5))
+    sh = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(sh.prod(1).sum())
+    g = torch.Generator().manual_seed(11)
+    value = torch.randn(N, S, M, D, generator=g).to(vdt)
+    fused = (torch.randn(N, S, M * L * P * 3, generator=g) * torch.cat([torch.full((M * L * P * 2,), 3.0), torch.ones(M * L * P)])).to(pdt)
+    offsets, logits = fused[..., :M * L * P * 2], fused[..., M * L * P * 2:]                    # column slices of one linear output
+    ref_pts = torch.rand(N, S, L, ref_dim, generator=g)
+    if ref_dim == 4:
+        ref_pts[..., 2:] *= 0.3
+    out = simt.msda_fused_forward(value, sh, lsi_of(sh), offsets, logits, ref_pts, L, P, out_dtype=odt)
+    # oracle: OPS/modules/ms_deform_attn.py:103-112 on the same (rounded) operands
+    off = offsets.float().view(N, S, M, L, P, 2)
+    aw = logits.float().view(N, S, M, L * P).softmax(-1).view(N, S, M, L, P)
+    if ref_dim == 2:
+        norm = torch.stack([sh[:, 1], sh[:, 0]], -1).float()
+        loc = ref_pts[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = ref_pts[:, :, None, :, None, :2] + off / P * ref_pts[:, :, None, :, None, 2:] * 0.5
+    ref = c_oracle.msda_forward(value.float().numpy(), sh.numpy(), lsi_of(sh).numpy(), loc.numpy(), aw.numpy())
+    tol = 2e-5 if odt == torch.float32 and vdt == torch.float32 else 1e-2
+    assert np.abs(out.float().numpy() - ref).max() <= tol * max(1.0, np.abs(ref).max())
+    if vdt == torch.bfloat16 and odt == torch.bfloat16:
+        pair = simt.msda_fused_forward(value, sh, lsi_of(sh), offsets, logits, ref_pts, L, P, pair=True)
+        assert np.abs(pair.float().numpy() - ref).max() <= 1.5e-2 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("C", [128, 256, 512])
+def test_add_layernorm_kernel(C):
+    g = torch.Generator().manual_seed(C)
+    x, r = torch.randn(13, 5, C, generator=g), torch.randn(13, 5, C, generator=g)
+    w, b, pos = torch.randn(C, generator=g), torch.randn(C, generator=g), torch.randn(5, C, generator=g)
+    ref = F.layer_norm(x + r, (C,), w, b, 1e-5)
+    y32, ylp, ypos = simt.add_layernorm(x, r, w, b, lp_dtype=torch.bfloat16, pos=pos)
+    assert (y32 - ref).abs().max() < 1e-5 * max(1.0, ref.abs().max().item())
+    assert (ylp.float() - ref).abs().max() < 1e-2 * ref.abs().max()
+    assert (ypos.float() - (ref + pos)).abs().max() < 1e-2 * (ref + pos).abs().max()
+    yb, _, _ = simt.add_layernorm(x.bfloat16(), None, w, b)
+    refb = F.layer_norm(x.bfloat16().float(), (C,), w, b, 1e-5)
+    assert (yb - refb).abs().max() < 1e-5 * max(1.0, refb.abs().max().item())
+
+
+def test_groupnorm_nhwc_kernel_with_fused_upsample_add_relu():
+    g = torch.Generator().manual_seed(2)
+    N, C, G, H, W, uh, uw = 2, 128, 32, 8, 12, 4, 6
+    x = torch.randn(N, H * W, C, generator=g)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    up = torch.randn(N, uh * uw, C, generator=g)
+    pos = torch.randn(H * W, C, generator=g)
+    nchw = x.transpose(1, 2).reshape(N, C, H, W)
+    ref = F.group_norm(nchw, G, w, b, 1e-5) + F.interpolate(up.transpose(1, 2).reshape(N, C, uh, uw), size=(H, W), mode="bilinear",
+                                                            align_corners=False)
+    ref = F.relu(ref).flatten(2).transpose(1, 2)
+    y32, ylp, ypos = simt.groupnorm_nhwc(x, G, w, b, relu=True, up=up, up_hw=(uh, uw), hw=(H, W), pos=pos)
+    assert (y32 - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert (ylp.float() - ref).abs().max() < 1e-2 * ref.abs().max()
+    assert (ypos.float() - (ref + pos)).abs().max() < 1e-2 * (ref + pos).abs().max()
+    plain, _, _ = simt.groupnorm_nhwc(x.bfloat16(), G, w, b)
+    refp = F.group_norm(x.bfloat16().float().transpose(1, 2).reshape(N, C, H, W), G, w, b, 1e-5).flatten(2).transpose(1, 2)
+    assert (plain - refp).abs().max() < 2e-5 * max(1.0, refp.abs().max().item())
+
+
+def test_mask_head_helper_kernels():
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 16, 5, 7, generator=g).bfloat16()
+    out = simt.resize_bilinear_nhwc(x.permute(0, 2, 3, 1).contiguous(), (9, 13))
+    ref = F.interpolate(x.float(), size=(9, 13), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max() < 1e-2 * ref.abs().max()
+    logits = torch.randn(3, 4, 50, generator=g)
+    logits[1, 2] = -logits[1, 2].abs() - 0.1                                                    # a fully masked row attends everywhere
+    bias = simt.attn_bias_from_logits(logits)
+    ref_mask = logits.sigmoid() < 0.5
+    ref_mask[ref_mask.all(-1)] = False
+    assert torch.equal(torch.isinf(bias) & (bias < 0), ref_mask) and (bias[~ref_mask] == 0).all()
+
+
+@pytest.mark.parametrize("Dh", [32, 64])
+def test_mha_core_kernel(Dh):
+    g = torch.Generator().manual_seed(Dh)
+    B, Lq, Lk, H = 2, 19, 23, 4
+    qkv = torch.randn(B, Lk, 3, H, Dh, generator=g).bfloat16()                                  # q / k / v: slices of one projection
+    q, k, v = qkv[:, :Lq, 0], qkv[:, :, 1], qkv[:, :, 2]
+    out = simt.mha_core(q, k, v, 1 / math.sqrt(Dh))
+    ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2))
+    ref = ref.transpose(1, 2).reshape(B, Lq, H * Dh)
+    assert (out.float() - ref).abs().max() < 2e-2 * ref.abs().max()
+
+
+def test_shared_memory_protocols_under_jitter():
+    """Race shaker (tests/simt/simt_shim.h): random threads are delayed after every __syncthreads(); kernels whose phases
+    hand data over through shared memory must not change their results."""
+    value, sh, lsi, loc, attn = msda_case(torch.float32, 1, 8, 32, 23, ((8, 12), (4, 6)), 4, seed=9)
+    calm = simt.msda_forward(value, sh, lsi, loc, attn)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 48, 128, generator=g)
+    w, b = torch.randn(128, generator=g), torch.randn(128, generator=g)
+    gn_calm = simt.groupnorm_nhwc(x, 32, w, b)[0]
+    qkv = torch.randn(1, 21, 3, 2, 32, generator=g).bfloat16()
+    mha_calm = simt.mha_core(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 0.17)
+    simt.set_jitter(4)
+    try:
+        assert torch.equal(simt.msda_forward(value, sh, lsi, loc, attn), calm)
+        assert (simt.groupnorm_nhwc(x, 32, w, b)[0] - gn_calm).abs().max() < 1e-5      # atomics: summation order may differ
+        assert torch.equal(simt.mha_core(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 0.17), mha_calm)
+    finally:
+        simt.set_jitter(0)
