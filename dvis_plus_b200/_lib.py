@@ -28,6 +28,7 @@ SIGNATURES = {
     "dvis_resize_bilinear_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
     "dvis_attn_bias_from_logits": [_vp, _i64, _i, _vp, _i, _vp],
     "dvis_lap_chain": [_vp, _i, _i, _vp, _vp, _vp, _vp],
+    "dvis_lap_rect": [_vp, _i, _i, _i, _vp, _vp],
     "dvis_mask_logits_strided": [_vp, _i64, _vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp],
     "dvis_mask_attn_bias": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp, _vp],
     "dvis_mha_core": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp],

@@ -117,6 +117,9 @@ class VideoInstanceCutter(nn.Module):
         self.kick_out_frame_num, self.mask_nms_thr = kick_out_frame_num, mask_nms_thr
         self.match_score_thr, self.keep_threshold = match_score_thr, keep_threshold
         self.memory_seq_ids = []
+        # track x query assignment: SciPy on the host like the reference (default this round), or the GPU Hungarian kernel
+        # (ops.lap_rect, no host copy of the cost matrix) with match_on_host = False
+        self.match_on_host = True
         self._clear_memory()
 
     def _clear_memory(self):
@@ -148,13 +151,17 @@ class VideoInstanceCutter(nn.Module):
         return torch.empty((0, 1, self.hidden_dim), dtype=torch.float32, device=dev)
 
     def match_with_embeds(self, trc_queries_feat, seg_queries_feat):
-        """track_module.py:749-759: nearest segmenter query per track query, Hungarian-assigned where possible."""
-        from scipy.optimize import linear_sum_assignment
+        """track_module.py:749-759: nearest segmenter query per track query, Hungarian-assigned where possible.  On the
+        device the (tracks x queries) assignment runs in the GPU Hungarian kernel (ops.lap_rect): no `C.cpu()` sync."""
         t, s = trc_queries_feat.detach()[:, 0, :].float(), seg_queries_feat.detach()[:, 0, :].float()
         t = t / (t.norm(dim=1)[:, None] + 1e-6)
         s = s / (s.norm(dim=1)[:, None] + 1e-6)
         C = 1 - torch.mm(t, s.transpose(0, 1))
         least = torch.min(C, dim=1)[1]
+        if _fast_path(C) and not self.match_on_host and 0 < C.shape[0] <= 1024 and 0 < C.shape[1] <= 1024:
+            assigned = ops.lap_rect(C)
+            return torch.where(assigned >= 0, assigned, least)
+        from scipy.optimize import linear_sum_assignment
         rows, cols = linear_sum_assignment(C.cpu())
         least[torch.as_tensor(rows, device=least.device)] = torch.as_tensor(cols, dtype=torch.int64, device=least.device)
         return least

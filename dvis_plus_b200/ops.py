@@ -260,6 +260,19 @@ def lap_chain(cost, idx_init=None):
     return sigma, idx
 
 
+def lap_rect(cost):
+    """Rectangular Hungarian matching on the device (dvis_lap_rect): cost (rows, cols) or (B, rows, cols) f32 ->
+    row_to_col int64 of shape (rows,) / (B, rows): the assigned column per row, -1 where a row stays unmatched."""
+    assert cost.is_cuda and cost.dtype == torch.float32 and cost.dim() in (2, 3)
+    c = cost.contiguous()
+    B = 1 if c.dim() == 2 else c.shape[0]
+    rows, cols = c.shape[-2:]
+    out = torch.empty(c.shape[:-1], dtype=torch.int64, device=c.device)
+    with torch.cuda.device(c.device):
+        _lib.call("dvis_lap_rect", c.data_ptr(), B, rows, cols, out.data_ptr(), _stream())
+    return out
+
+
 def resize_bilinear_nhwc(x, size):
     """F.interpolate(x, size, mode="bilinear", align_corners=False) for a bf16 channels_last (N, C, h, w) map; returns a
     bf16 channels_last (N, C, H, W) map (dvis_resize_bilinear_nhwc)."""

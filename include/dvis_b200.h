@@ -170,6 +170,13 @@ int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_stride, int 
  */
 int dvis_lap_chain(const float *cost, int T, int n, const int64_t *idx_init, int64_t *sigma, int64_t *idx, void *stream);
 
+/* Rectangular linear assignment, batched: cost (B, rows, cols) f32 row-major -> row_to_col (B, rows) i64, the column
+ * assigned to each row, -1 for a row left unmatched (only when rows > cols); min(rows, cols) pairs of minimum total cost,
+ * i.e. scipy.optimize.linear_sum_assignment(cost) as a dense map.  Replaces the `C.cpu()` + SciPy call of DVIS-DAQ's
+ * VideoInstanceCutter.match_with_embeds (D/dvis_daq/track_module.py:749-759: track queries x segmenter queries).
+ * rows, cols <= 1024; NaN entries count as 0. */
+int dvis_lap_rect(const float *cost, int B, int rows, int cols, int64_t *row_to_col, void *stream);
+
 /* Strided form for query slices: emb (B, Q, C) with `emb_batch_stride` elements between batch items (a multiple of 8) and
  * out (B, Q, HW) with `out_batch_stride` elements between batch items, so a slice [q0, q1) of a larger query set can be
  * computed in place (used to split Q > 256, e.g. the DAQ stress size Q = 300, into two launches). */

@@ -113,7 +113,7 @@ def set_jitter(one_in):
 # ---- the remaining CUDA-core entry points (same argument order as dvis_plus_b200/ops.py) ------------------------------------
 ENTRY_POINTS += ("dvis_msda_forward", "dvis_msda_backward", "dvis_msda_fused_forward", "dvis_add_layernorm", "dvis_groupnorm_nhwc",
                  "dvis_resize_bilinear_nhwc", "dvis_attn_bias_from_logits", "dvis_mha_core", "dvis_msda_pack_pairs",
-                 "dvis_msda_pair_forward")
+                 "dvis_msda_pair_forward", "dvis_lap_rect")
 _DT[torch.float64] = 1
 
 
@@ -199,4 +199,12 @@ def mha_core(q, k, v, scale):
     out = torch.zeros((B, Lq, H * Dh), dtype=torch.bfloat16)
     call("dvis_mha_core", _p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1), v.stride(0), _p(out),
          H * Dh, Lq * H * Dh, B, Lq, Lk, H, Dh, float(scale), None)
+    return out
+
+
+def lap_rect(cost):
+    c = cost.float().contiguous()
+    B = 1 if c.dim() == 2 else c.shape[0]
+    out = torch.full(c.shape[:-1], -7, dtype=torch.int64)
+    call("dvis_lap_rect", _p(c), B, c.shape[-2], c.shape[-1], _p(out), None)
     return out

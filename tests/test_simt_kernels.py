@@ -134,6 +134,29 @@ def test_lap_chain_kernel_vs_scipy():
             assert np.array_equal(idx[t].numpy(), prev)
 
 
+@pytest.mark.parametrize("jitter", [0, 5])
+def test_lap_rect_kernel_vs_scipy(jitter):
+    """Rectangular assignment (DVIS-DAQ track x query matching): rows < cols, rows > cols (solved through the transpose,
+    unmatched rows = -1), square, single row / column; batched."""
+    from scipy.optimize import linear_sum_assignment
+    g = torch.Generator().manual_seed(12)
+    simt.set_jitter(jitter)
+    try:
+        for B, rows, cols in ((2, 7, 19), (2, 19, 7), (1, 12, 12), (1, 1, 9), (1, 9, 1), (1, 40, 70)):
+            cost = torch.rand(B, rows, cols, generator=g)
+            got = simt.lap_rect(cost)
+            for b in range(B):
+                r, c = linear_sum_assignment(cost[b].numpy())
+                ref = np.full(rows, -1, dtype=np.int64)
+                ref[r] = c
+                assert np.array_equal(got[b].numpy(), ref), (rows, cols)
+        assert simt.lap_rect(torch.rand(5, 8, generator=g)).shape == (5,)
+    finally:
+        simt.set_jitter(0)
+    with pytest.raises(RuntimeError, match="1024"):
+        simt.lap_rect(torch.zeros(1, 2, 2000))
+
+
 def test_barrier_protocols_under_jitter():
     """Race shaker: the kernels that communicate through shared memory (block arg-max of the top-k, vps area counters,
     the Hungarian kernel) give the same results when random threads are delayed after every __syncthreads()."""

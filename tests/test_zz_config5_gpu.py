@@ -72,3 +72,29 @@ def test_config5_postprocessing_1080p():
     neg = ops.vis_masks(-d, dsel, first, img, out)
     assert (neg & ours).sum().item() == 0 and (~(neg | ours)).float().mean().item() < 1e-4
     assert torch.equal(ops.vis_masks(d[:, 1:3], dsel[5:9], first, img, out), ours[5:9, 1:3])
+
+
+@torch.no_grad()
+def test_daq_track_query_matching_on_device():
+    """D/dvis_daq/track_module.py:749-759 on the GPU Hungarian kernel (ops.lap_rect) == SciPy on the host, at DAQ sizes
+    (up to ~100 tracks x 100-200 segmenter queries, both orientations), and through VideoInstanceCutter.match_with_embeds."""
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+    from dvis_plus_b200 import modules as M
+    g = torch.Generator().manual_seed(21)
+    for rows, cols in ((37, 100), (100, 100), (150, 100), (1, 200), (300, 300)):
+        cost = torch.rand(rows, cols, generator=g)
+        got = ops.lap_rect(cost.cuda()).cpu().numpy()
+        r, c = linear_sum_assignment(cost.numpy())
+        ref = np.full(rows, -1, dtype=np.int64)
+        ref[r] = c
+        assert np.array_equal(got, ref), (rows, cols)
+    batched = torch.rand(4, 20, 33, generator=g)
+    got = ops.lap_rect(batched.cuda()).cpu()
+    for b in range(4):
+        assert np.array_equal(got[b].numpy(), linear_sum_assignment(batched[b].numpy())[1])
+    cutter = M.VideoInstanceCutter(hidden_dim=64, feedforward_dim=128, num_head=8, decoder_layer_num=1, mask_dim=64, num_classes=5).cuda().eval()
+    trc, seg = torch.randn(30, 1, 64, generator=g).cuda(), torch.randn(100, 1, 64, generator=g).cuda()
+    host = cutter.match_with_embeds(trc, seg)
+    cutter.match_on_host = False
+    assert torch.equal(cutter.match_with_embeds(trc, seg), host)
