@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--queries", type=int, default=200)
-    ap.add_argument("--cpu-sample-frames", type=int, default=1)
+    ap.add_argument("--cpu-sample-frames", type=int, default=8)   # ~10 s of host work on the GPU box (16 cores)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs / no pipelining across clips (debug)")
     args = ap.parse_args()
