@@ -184,3 +184,44 @@ def test_shared_memory_protocols_under_jitter():
         assert torch.equal(simt.mha_core(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 0.17), mha_calm)
     finally:
         simt.set_jitter(0)
+
+
+def test_msda_forward_edge_cases():
+    """Boundary behaviour of the sampling (cuh:38-89, 290-293): points exactly on / outside the map edges, a single query,
+    L*P > 32 (generic kernel), D = 128, ragged item counts (Lq*M not a multiple of the 64 items of a CTA)."""
+    # every point outside (-1, size): the output is exactly zero
+    value, sh, lsi, loc, attn = msda_case(torch.float32, 1, 4, 32, 5, ((6, 9),), 4)
+    out = simt.msda_forward(value, sh, lsi, loc * 0 - 0.5, attn)
+    assert torch.equal(out, torch.zeros_like(out))
+    # points exactly on the pixel-centre lattice and on the outer borders 0 and 1
+    g = torch.Generator().manual_seed(4)
+    H, W = 6, 9
+    xs = torch.tensor([0.0, 0.5 / W, 1.0 - 0.5 / W, 1.0, 3.5 / W, -1e-7, 1.0 + 1e-7, 0.999999])
+    ys = torch.tensor([0.0, 0.5 / H, 1.0 - 0.5 / H, 1.0, 2.5 / H, 1.0, 0.0, 0.5])
+    loc = torch.stack([xs, ys], -1).view(1, 1, 1, 1, 8, 2).expand(1, 3, 4, 1, 8, 2).contiguous()
+    attn = torch.rand(1, 3, 4, 1, 8, generator=g)
+    ref = c_oracle.msda_forward(value.numpy(), sh.numpy(), lsi.numpy(), loc.numpy(), attn.numpy())
+    out = simt.msda_forward(value, sh, lsi, loc, attn)
+    assert np.abs(out.numpy() - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    # L*P = 40 > 32 -> generic kernel; D = 128 -> 32 lanes per row; Lq*M = 33*3 = 99 items (ragged last CTA); one query
+    for M, D, Lq, shapes, P in ((2, 16, 7, ((4, 5), (3, 3), (2, 4), (2, 2), (1, 3)), 8), (3, 128, 33, ((5, 7), (3, 4)), 4),
+                                (8, 32, 1, ((4, 4),), 4)):
+        value, sh, lsi, loc, attn = msda_case(torch.float32, 2, M, D, Lq, shapes, P, seed=M)
+        ref = c_oracle.msda_forward(value.numpy(), sh.numpy(), lsi.numpy(), loc.numpy(), attn.numpy())
+        out = simt.msda_forward(value, sh, lsi, loc, attn)
+        assert np.abs(out.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), (M, D, Lq)
+
+
+def test_msda_argument_checks():
+    v = torch.zeros(1, 4, 1, 8)
+    sh, lsi = torch.tensor([[2, 2]]), torch.zeros(1, dtype=torch.long)
+    loc, attn, out = torch.zeros(1, 1, 1, 1, 1, 2), torch.zeros(1, 1, 1, 1, 1), torch.zeros(1, 1, 8)
+    with pytest.raises(RuntimeError, match="null"):
+        simt.call("dvis_msda_forward", None, sh.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(), 1, 4, 1, 8, 1, 1, 1, 0,
+                  None, out.data_ptr(), None)
+    with pytest.raises(RuntimeError, match="float/double only"):
+        simt.call("dvis_msda_forward", v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(), 1, 4, 1, 8, 1, 1, 1,
+                  2, None, out.data_ptr(), None)
+    with pytest.raises(RuntimeError, match="num_levels"):
+        simt.call("dvis_msda_forward", v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(), 1, 4, 1, 8, 9, 1, 1,
+                  0, None, out.data_ptr(), None)
