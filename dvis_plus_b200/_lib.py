@@ -35,6 +35,7 @@ SIGNATURES = {
     "dvis_class_scores": [_vp, _vp, _i, _i, _vp, _vp],
     "dvis_vis_topk": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "dvis_vis_masks": [_vp, _i, _i64, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "dvis_vis_masks_packed": [_vp, _i, _i64, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "dvis_vps_argmax": [_vp, _i, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "dvis_vps_paint": [_vp, _vp, _i64, _vp, _vp],
     "dvis_vss_argmax": [_vp, _i, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],

@@ -109,7 +109,9 @@ constexpr int kStripWarps = 4;  // warps per CTA, each walking its own band of r
 // Second resize is the identity (output size == un-padded input size, the benchmark's 720p case): one bilinear sample
 // per pixel.  A warp covers 256 consecutive pixels of a row and walks `rows_per_warp` rows, re-reading its source rows
 // only when they change (every 4th output row at the 4x up-scale of the stride-4 logits).
-template <typename T>
+// kPacked: one BIT per pixel instead of one byte -- out (planes, Ho, ceil(Wo / 8)), bit i of byte b = pixel 8 * b + i
+// (numpy.unpackbits(bitorder="little")), bits past Wo are 0: 8x less to write and to copy to the host.
+template <typename T, bool kPacked>
 __global__ void __launch_bounds__(32 * kStripWarps) vis_masks_strip_kernel(const T *__restrict__ logits, int64_t q_stride,
                                                                            int64_t t_stride, const int64_t *__restrict__ sel,
                                                                            int frames, Geom g, int rows_per_warp,
@@ -127,6 +129,14 @@ __global__ void __launch_bounds__(32 * kStripWarps) vis_masks_strip_kernel(const
   pl.w = g.w;
   rc::Strip<kStripPx, R> strip;
   strip.init(g, ox0);
+  if constexpr (kPacked) {
+    static_assert(kStripPx == 8, "one byte of 8 pixels per thread");
+    const int Wb = (g.Wo + 7) >> 3;
+    const uint32_t valid = ox0 + 8 <= g.Wo ? 0xffu : (1u << (g.Wo - ox0)) - 1u;          // pixels of this byte inside the row
+    uint8_t *ob = out + (int64_t)plane * g.Ho * Wb + (ox0 >> 3);
+    for (int oy = oy_begin; oy < oy_end; ++oy) ob[(int64_t)oy * Wb] = uint8_t(strip.row(pl, g, oy) & valid);
+    return;
+  }
   uint8_t *o = out + (int64_t)plane * g.Ho * g.Wo + ox0;
   const bool vec = (g.Wo % kStripPx == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
   for (int oy = oy_begin; oy < oy_end; ++oy) {
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(32 * kStripWarps) vis_masks_strip_kernel(const
 // intermediate rows are each computed once per strip when they first enter, instead of 16 source reads per output pixel.
 constexpr int kStrip2Px = 4;    // output pixels per thread and row: one 4-byte store, a warp stores 128 contiguous bytes
 
-template <typename T>
+template <typename T, bool kPacked>
 __global__ void __launch_bounds__(32 * kStripWarps) vis_masks_two_stage_kernel(const T *__restrict__ logits, int64_t q_stride,
                                                                                int64_t t_stride, const int64_t *__restrict__ sel,
                                                                                int frames, Geom g, int rows_per_warp,
@@ -156,13 +166,29 @@ __global__ void __launch_bounds__(32 * kStripWarps) vis_masks_two_stage_kernel(c
   const int ox0 = (blockIdx.x * 32 + lane) * kStrip2Px;
   const int oy_begin = (blockIdx.y * kStripWarps + warp) * rows_per_warp;
   const int oy_end = min(oy_begin + rows_per_warp, g.Ho);
-  if (ox0 >= g.Wo || oy_begin >= oy_end) return;
+  if (oy_begin >= oy_end) return;                       // warp-uniform
+  // packed: lanes past the row end stay (their columns are clamped, their bits masked off) -- the nibble exchange below
+  // needs every lane of the warp
+  if (!kPacked && ox0 >= g.Wo) return;
   const int64_t q = sel ? sel[n] : n;
   Plane<R> pl;
   pl.p = reinterpret_cast<const R *>(logits) + q * q_stride + t * t_stride;
   pl.w = g.w;
   rc::Strip2<kStrip2Px, R> strip;
   strip.init(g, ox0);
+  if constexpr (kPacked) {
+    static_assert(kStrip2Px == 4, "two lanes of 4 pixels per byte");
+    const int Wb = (g.Wo + 7) >> 3;
+    const int left = g.Wo - ox0;                                                           // pixels of this nibble inside the row
+    const uint32_t valid = left >= 4 ? 0xfu : left > 0 ? (1u << left) - 1u : 0u;
+    uint8_t *ob = out + (int64_t)plane * g.Ho * Wb + (ox0 >> 3);
+    for (int oy = oy_begin; oy < oy_end; ++oy) {
+      const uint32_t mine = strip.row(pl, g, oy) & valid;
+      const uint32_t hi = __shfl_down_sync(0xffffffffu, mine, 1);                          // the odd neighbour's nibble
+      if ((lane & 1) == 0 && ox0 < g.Wo) ob[(int64_t)oy * Wb] = uint8_t(mine | (hi << 4));
+    }
+    return;
+  }
   uint8_t *o = out + (int64_t)plane * g.Ho * g.Wo + ox0;
   const bool vec = (g.Wo % kStrip2Px == 0) && ((reinterpret_cast<uintptr_t>(out) & 3u) == 0);
   for (int oy = oy_begin; oy < oy_end; ++oy) {
@@ -311,39 +337,51 @@ extern "C" int dvis_vis_topk(const float *pred_cls, const float *aux_cls, int Q,
   return check_launch("vis_topk_kernel");
 }
 
-extern "C" int dvis_vis_masks(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *sel,
-                              int n_sel, int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo,
-                              uint8_t *out, void *stream) {
+namespace dvis {
+namespace {
+template <bool kPacked>
+int launch_vis_masks(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *sel, int n_sel,
+                     int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo, uint8_t *out, void *stream) {
   DVIS_REQUIRE(logits && out, "vis_masks: null pointer argument");
   DVIS_REQUIRE(n_sel > 0, "vis_masks: nothing selected");
   if (int rc_ = check_geom("vis_masks", frames, h, w, H1, W1, Hc, Wc, Ho, Wo)) return rc_;
   DVIS_REQUIRE((int64_t)n_sel * frames <= 65535, "vis_masks: n_sel * frames is limited to 65535 per launch");
+  if (logits_dtype != DVIS_F32 && logits_dtype != DVIS_BF16) return fail(DVIS_ERR_UNSUPPORTED, "vis_masks: logits dtype must be f32 or bf16");
   const Geom g = rc::make_geom(h, w, H1, W1, Hc, Wc, Ho, Wo);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned planes = unsigned(n_sel * frames);
+  const dim3 block(32, kStripWarps);
   if (Ho == Hc && Wo == Wc) {
     // rows per warp: enough CTAs to fill the machine a few times over, bands long enough to reuse source rows
     const int rows_per_warp = 16;
     const dim3 grid((Wo + 32 * kStripPx - 1) / (32 * kStripPx), (Ho + kStripWarps * rows_per_warp - 1) / (kStripWarps * rows_per_warp), planes);
-    const dim3 block(32, kStripWarps);
     if (logits_dtype == DVIS_F32)
-      vis_masks_strip_kernel<float><<<grid, block, 0, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
-    else if (logits_dtype == DVIS_BF16)
-      vis_masks_strip_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
+      vis_masks_strip_kernel<float, kPacked><<<grid, block, 0, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
     else
-      return fail(DVIS_ERR_UNSUPPORTED, "vis_masks: logits dtype must be f32 or bf16");
+      vis_masks_strip_kernel<__nv_bfloat16, kPacked><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
     return check_launch("vis_masks_strip_kernel");
   }
   const int rows_per_warp = 24;
   const dim3 grid((Wo + 32 * kStrip2Px - 1) / (32 * kStrip2Px), (Ho + kStripWarps * rows_per_warp - 1) / (kStripWarps * rows_per_warp), planes);
-  const dim3 block(32, kStripWarps);
   if (logits_dtype == DVIS_F32)
-    vis_masks_two_stage_kernel<float><<<grid, block, 0, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
-  else if (logits_dtype == DVIS_BF16)
-    vis_masks_two_stage_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
+    vis_masks_two_stage_kernel<float, kPacked><<<grid, block, 0, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
   else
-    return fail(DVIS_ERR_UNSUPPORTED, "vis_masks: logits dtype must be f32 or bf16");
+    vis_masks_two_stage_kernel<__nv_bfloat16, kPacked><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out);
   return check_launch("vis_masks_two_stage_kernel");
+}
+}  // namespace
+}  // namespace dvis
+
+extern "C" int dvis_vis_masks(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *sel,
+                              int n_sel, int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo,
+                              uint8_t *out, void *stream) {
+  return launch_vis_masks<false>(logits, logits_dtype, q_stride, t_stride, sel, n_sel, frames, h, w, H1, W1, Hc, Wc, Ho, Wo, out, stream);
+}
+
+extern "C" int dvis_vis_masks_packed(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *sel,
+                                     int n_sel, int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo,
+                                     uint8_t *out, void *stream) {
+  return launch_vis_masks<true>(logits, logits_dtype, q_stride, t_stride, sel, n_sel, frames, h, w, H1, W1, Hc, Wc, Ho, Wo, out, stream);
 }
 
 extern "C" int dvis_vps_argmax(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *keep_idx,

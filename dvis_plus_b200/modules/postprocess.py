@@ -76,6 +76,8 @@ class VideoPostProcessor:
         only max_num (not Q) masks per frame are ever computed (pipeline.OfflineClipRunner.vis_inference)."""
         return ops.vis_topk(pred_cls, self.max_num, aux_pred_cls)
 
+    packed_transfer = True    # bool masks cross PCIe as 1 bit per pixel and are unpacked on the host (8x less device->host)
+
     def inference_video_vis(self, pred_cls, pred_masks, img_size, output_height, output_width, first_resize_size, pred_id,
                             aux_pred_cls=None, masks_on_device=False):
         """py:818-868.  pred_cls (Q, K+1); pred_masks (Q, T, h, w) f32|bf16 device view (any query / frame strides);
@@ -83,12 +85,18 @@ class VideoPostProcessor:
         (`masks_on_device=True` keeps them on the GPU as one (n, T, H_out, W_out) tensor's rows)."""
         if len(pred_cls) > 0:
             scores, labels, query = self.select_vis(pred_cls, aux_pred_cls)
-            masks = ops.vis_masks(pred_masks, query, first_resize_size, img_size, (output_height, output_width))
+            out_size = (output_height, output_width)
+            if masks_on_device or not self.packed_transfer:
+                masks = ops.vis_masks(pred_masks, query, first_resize_size, img_size, out_size)
+                masks = masks if masks_on_device else masks.cpu()
+            else:
+                masks = ops.unpack_masks(ops.vis_masks(pred_masks, query, first_resize_size, img_size, out_size, packed=True).cpu(),
+                                         output_width)
             pred_ids = torch.as_tensor(pred_id, device=query.device)[query]
             out_scores = scores.tolist()
             out_labels = labels.tolist()
             out_ids = pred_ids.tolist()
-            out_masks = [m for m in (masks if masks_on_device else masks.cpu())]
+            out_masks = [m for m in masks]
         else:
             out_scores, out_labels, out_masks, out_ids = [], [], [], []
         return {"image_size": (output_height, output_width), "pred_scores": out_scores, "pred_labels": out_labels,

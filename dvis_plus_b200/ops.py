@@ -384,16 +384,19 @@ def vis_topk(pred_cls, max_num, aux_pred_cls=None):
     return scores, labels, query
 
 
-def vis_masks(pred_masks, sel, first_resize_size, img_size, out_size, out=None):
+def vis_masks(pred_masks, sel, first_resize_size, img_size, out_size, out=None, packed=False):
     """bool masks (n, T, Ho, Wo) = resize_chain(pred_masks[sel]) > 0 straight from the stride-4 logits (dvis_vis_masks).
-    pred_masks (Q, T, h, w) f32|bf16 view (any query / frame strides); sel (n,) int64 device tensor or None (all)."""
+    pred_masks (Q, T, h, w) f32|bf16 view (any query / frame strides); sel (n,) int64 device tensor or None (all).
+    packed=True: one bit per pixel instead, uint8 (n, T, Ho, ceil(Wo/8)), little bit order (dvis_vis_masks_packed; see
+    unpack_masks) -- 8x less to write and to copy to the host."""
     m, qs, ts = _mask_view(pred_masks)
     n = m.shape[0] if sel is None else sel.numel()
     T = m.shape[1]
     Ho, Wo = int(out_size[0]), int(out_size[1])
+    row = (Wo + 7) // 8 if packed else Wo
     if out is None:
-        out = torch.empty((n, T, Ho, Wo), dtype=torch.bool, device=m.device)
-    assert out.dtype == torch.bool and out.is_contiguous() and out.shape == (n, T, Ho, Wo)
+        out = torch.empty((n, T, Ho, row), dtype=torch.uint8 if packed else torch.bool, device=m.device)
+    assert out.dtype == (torch.uint8 if packed else torch.bool) and out.is_contiguous() and out.shape == (n, T, Ho, row)
     if n == 0:
         return out
     if sel is not None:
@@ -401,6 +404,7 @@ def vis_masks(pred_masks, sel, first_resize_size, img_size, out_size, out=None):
         sel = sel.contiguous()
     geom = _geom_args(m, first_resize_size, img_size, out_size)
     per_call = max(1, 65535 // T)                     # grid.z limit: n_sel * frames <= 65535 per launch
+    entry = "dvis_vis_masks_packed" if packed else "dvis_vis_masks"
     with torch.cuda.device(m.device):
         for n0 in range(0, n, per_call):
             n1 = min(n, n0 + per_call)
@@ -408,9 +412,16 @@ def vis_masks(pred_masks, sel, first_resize_size, img_size, out_size, out=None):
                 base, sel_ptr = m.data_ptr(), sel.data_ptr() + 8 * n0
             else:
                 base, sel_ptr = m.data_ptr() + n0 * qs * m.element_size(), None
-            _lib.call("dvis_vis_masks", base, _DTYPE[m.dtype], qs, ts, sel_ptr, n1 - n0, T, *geom,
-                      out.data_ptr() + n0 * T * Ho * Wo, _stream())
+            _lib.call(entry, base, _DTYPE[m.dtype], qs, ts, sel_ptr, n1 - n0, T, *geom, out.data_ptr() + n0 * T * Ho * row, _stream())
     return out
+
+
+def unpack_masks(packed, width):
+    """Host side of vis_masks(packed=True): (..., Ho, ceil(Wo/8)) uint8 CPU tensor -> (..., Ho, Wo) bool CPU tensor."""
+    import numpy as np
+    assert not packed.is_cuda and packed.dtype == torch.uint8
+    bits = np.unpackbits(packed.numpy(), axis=-1, bitorder="little")[..., :width]
+    return torch.from_numpy(bits).bool()
 
 
 def vps_argmax(pred_masks, keep_idx, keep_score, first_resize_size, img_size, out_size):

@@ -230,6 +230,13 @@ int dvis_vis_topk(const float *pred_cls, const float *aux_cls, int Q, int K1, in
 int dvis_vis_masks(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *sel, int n_sel,
                    int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo, uint8_t *out, void *stream);
 
+/* Same masks as ONE BIT per pixel: out (n_sel, frames, Ho, ceil(Wo/8)) bytes, bit i of byte b = pixel 8*b + i of the row
+ * (numpy.unpackbits(..., bitorder="little")), bits past Wo are 0.  8x less HBM write and device->host traffic for results
+ * that are consumed on the host (the reference moves its bool masks to the CPU, py:851). */
+int dvis_vis_masks_packed(const void *logits, int logits_dtype, int64_t q_stride, int64_t t_stride, const int64_t *sel,
+                          int n_sel, int frames, int h, int w, int H1, int W1, int Hc, int Wc, int Ho, int Wo, uint8_t *out,
+                          void *stream);
+
 /* VPS (py:889-926): per output pixel the arg-max over the kept queries k of keep_score[k] * sigmoid-resized mask
  * (cur_prob_masks.argmax(0), first maximum), plus the three pixel counts the segment filter needs, so the host loop
  * (py:919-949) runs on 3*n_keep integers instead of n_keep full-resolution reductions with a sync each.

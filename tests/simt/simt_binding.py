@@ -14,7 +14,7 @@ from dvis_plus_b200 import _lib as product_binding  # noqa: E402  (signatures on
 
 _DT = {torch.float32: 0, torch.bfloat16: 2}
 _lib = None
-ENTRY_POINTS = ("dvis_class_scores", "dvis_vis_topk", "dvis_vis_masks", "dvis_vps_argmax", "dvis_vps_paint",
+ENTRY_POINTS = ("dvis_class_scores", "dvis_vis_topk", "dvis_vis_masks", "dvis_vis_masks_packed", "dvis_vps_argmax", "dvis_vps_paint",
                 "dvis_vss_argmax", "dvis_lap_chain")
 
 
@@ -71,6 +71,16 @@ def vis_masks(m, sel, first, img, out_size):
     call("dvis_vis_masks", _p(m), _DT[m.dtype], m.stride(0), m.stride(1), _p(sel), n, T, *_geom(m, first, img, out_size), _p(out), None)
     assert int(out.max()) <= 1, "unwritten output pixels"
     return out.bool()
+
+
+def vis_masks_packed(m, sel, first, img, out_size):
+    assert m.stride(3) == 1 and m.stride(2) == m.shape[3]
+    n = m.shape[0] if sel is None else sel.numel()
+    T = m.shape[1]
+    out = torch.full((n, T, out_size[0], (out_size[1] + 7) // 8), 0xAA, dtype=torch.uint8)
+    call("dvis_vis_masks_packed", _p(m), _DT[m.dtype], m.stride(0), m.stride(1), _p(sel), n, T, *_geom(m, first, img, out_size),
+         _p(out), None)
+    return out
 
 
 def vps_argmax(m, keep_idx, keep_score, first, img, out_size):

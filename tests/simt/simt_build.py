@@ -96,11 +96,22 @@ def build(force=False):
         fh.write('namespace dvis { char *last_error_buffer() { static thread_local char buf[512] = {0}; return buf; } }\n'
                  'extern "C" const char *dvis_last_error(void) { return dvis::last_error_buffer(); }\n'
                  '#include "simt_shim.h"\nextern "C" void simt_set_jitter(int one_in) { simt::g_jitter = one_in; }\n')
-    cmd = ["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas",
-           "-Wno-attributes", f"-I{HERE}", f"-I{INCLUDE}"] + units + [glue, "-o", OUT]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    flags = ["-O1", "-std=c++20", "-fPIC", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
+             f"-I{HERE}", f"-I{INCLUDE}"]
+
+    def compile_one(src):
+        obj = src[:-4] + ".o"
+        r = subprocess.run(["g++"] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed on {src}:\n{r.stdout[-3000:]}\n{r.stderr[-6000:]}")
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        objs = list(ex.map(compile_one, units + [glue]))
+    r = subprocess.run(["g++", "-shared", "-pthread"] + objs + ["-o", OUT], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError(f"g++ failed:\n{r.stdout[-3000:]}\n{r.stderr[-6000:]}")
+        raise RuntimeError(f"link failed:\n{r.stdout[-3000:]}\n{r.stderr[-6000:]}")
     return OUT
 
 

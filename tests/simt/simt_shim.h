@@ -175,6 +175,7 @@ inline void __syncthreads() { simt::syncthreads(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_barrier().arrive_and_wait(); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return simt::exchange(v, (simt::t_linear & 31) ^ lane_mask); }
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return simt::exchange(v, src); }
+template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned delta) { return simt::exchange(v, (simt::t_linear & 31) + int(delta)); }
 inline unsigned __ballot_sync(unsigned, bool pred) {
   simt::g_block->slot[simt::t_linear] = pred ? 1 : 0;
   simt::warp_barrier().arrive_and_wait();

@@ -261,3 +261,33 @@ def test_pipeline_vis_from_block_equals_postprocessing_all_masks(out_size):
     low = outs["pred_masks"][0][torch.tensor(ref["pred_ids"], device=DEV)].float().cpu()
     chain = pp.resize_chain(low, img, out_size[0], out_size[1], (4 * H, 4 * W))
     assert_masks_match(fused["pred_masks"], chain > 0, chain, tol=1e-3, max_boundary_frac=5e-3)
+
+
+@pytest.mark.parametrize("geom", [GEOMS[0], GEOMS[1], GEOMS[3], GEOMS[5], GEOMS[8], GEOMS[10]])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_vis_masks_packed(geom, dtype):
+    """One bit per pixel (dvis_vis_masks_packed): exactly the byte kernel's masks, packed little-endian with zero padding."""
+    import numpy as np
+    (h, w), first, img, out = geom
+    g = torch.Generator().manual_seed(h * 10 + w)
+    masks = (torch.randn(5, 3, h, w, generator=g) * 3).to(dtype).to(DEV)
+    sel = torch.tensor([3, 1, 4], dtype=torch.int64, device=DEV)
+    ref = ops.vis_masks(masks, sel, first, img, out).cpu()
+    packed = ops.vis_masks(masks, sel, first, img, out, packed=True).cpu()
+    assert packed.dtype == torch.uint8 and packed.shape == (3, 3, out[0], (out[1] + 7) // 8)
+    assert np.array_equal(packed.numpy(), np.packbits(ref.numpy(), axis=-1, bitorder="little"))
+    assert torch.equal(ops.unpack_masks(packed, out[1]), ref)
+
+
+def test_vis_module_packed_transfer_equals_plain(golden):
+    g = golden("postprocess_vis.pt")
+    c = g["cases"]["up_aux"]
+    Ho, Wo = c["output_size"]
+    outs = []
+    for packed in (True, False):
+        post = VideoPostProcessor(g["num_classes"], num_queries=12, max_num=c["max_num"])
+        post.packed_transfer = packed
+        outs.append(post.inference_video_vis(g["pred_cls"].to(DEV), g["pred_masks"].to(DEV), g["img_size"], Ho, Wo,
+                                             g["first_resize_size"], g["pred_id"], aux_pred_cls=g["aux_cls"].to(DEV)))
+    assert outs[0]["pred_scores"] == outs[1]["pred_scores"] and outs[0]["pred_ids"] == outs[1]["pred_ids"]
+    assert torch.equal(torch.stack(outs[0]["pred_masks"]), torch.stack(outs[1]["pred_masks"]))

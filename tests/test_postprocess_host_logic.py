@@ -46,7 +46,14 @@ def doubles(monkeypatch):
 
     monkeypatch.setattr(ops, "class_scores", class_scores)
     monkeypatch.setattr(ops, "vis_topk", vis_topk)
-    monkeypatch.setattr(ops, "vis_masks", lambda m, sel, first, img, out: hc.vis_masks(m, sel, first, img, out))
+    def vis_masks(m, sel, first, img, out, packed=False):
+        masks = hc.vis_masks(m, sel, first, img, out)
+        if not packed:
+            return masks
+        import numpy as np
+        return torch.from_numpy(np.packbits(masks.numpy(), axis=-1, bitorder="little"))
+
+    monkeypatch.setattr(ops, "vis_masks", vis_masks)
     monkeypatch.setattr(ops, "vps_argmax", lambda m, ki, ks, first, img, out: hc.vps_argmax(m, ki, ks, first, img, out))
     monkeypatch.setattr(ops, "vps_paint", lambda win, seg: torch.where(win >= 0, seg[win.clamp(min=0).long()], torch.zeros_like(win)))
     monkeypatch.setattr(ops, "vss_argmax", lambda m, mc, first, img, out: hc.vss_argmax(m, mc, first, img, out))

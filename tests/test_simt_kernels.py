@@ -70,6 +70,21 @@ def test_vis_masks_kernels(geom, dtype):
     assert_masks_match(ours2, ref2 > 0, ref2, tol=2e-5, max_boundary_frac=1e-3)
 
 
+@pytest.mark.parametrize("geom", GEOMS)
+def test_vis_masks_packed_kernels(geom):
+    """One bit per pixel: identical to packing the byte kernel's result (little bit order, zero padding bits)."""
+    (h, w), first, img, out = geom
+    g = torch.Generator().manual_seed(h * 10 + w)
+    masks = torch.randn(4, 2, h, w, generator=g) * 3
+    sel = torch.tensor([3, 1], dtype=torch.int64)
+    ref = simt.vis_masks(masks, sel, first, img, out)
+    packed = simt.vis_masks_packed(masks, sel, first, img, out)
+    assert packed.shape == (2, 2, out[0], (out[1] + 7) // 8)
+    assert np.array_equal(packed.numpy(), np.packbits(ref.numpy(), axis=-1, bitorder="little"))
+    from dvis_plus_b200 import ops
+    assert torch.equal(ops.unpack_masks(packed, out[1]), ref)
+
+
 def test_vis_masks_argument_checks():
     m = torch.randn(2, 2, 4, 4)
     with pytest.raises(RuntimeError, match="crop"):
