@@ -159,3 +159,18 @@ def test_pipeline_vis_from_block_equals_postprocessing_all_masks(doubles):
     assert fused["pred_labels"].tolist() == ref["pred_labels"] and fused["pred_ids"].tolist() == ref["pred_ids"]
     assert fused["pred_masks"].shape == (6, T, *out_size)
     assert (fused["pred_masks"] != torch.stack(ref["pred_masks"])).float().mean().item() < 1e-4
+
+
+def test_vis_packed_transfer_gives_the_same_result(golden, doubles):
+    g = golden("postprocess_vis.pt")
+    c = g["cases"]["up_aux"]
+    Ho, Wo = c["output_size"]
+    outs = []
+    for packed in (True, False):
+        post = VideoPostProcessor(g["num_classes"], num_queries=12, max_num=c["max_num"])
+        post.packed_transfer = packed
+        outs.append(post.inference_video_vis(g["pred_cls"], g["pred_masks"], g["img_size"], Ho, Wo, g["first_resize_size"], g["pred_id"],
+                                             aux_pred_cls=g["aux_cls"]))
+    assert outs[0]["pred_scores"] == outs[1]["pred_scores"] and outs[0]["pred_ids"] == outs[1]["pred_ids"]
+    assert all(m.dtype == torch.bool and m.shape == (3, Ho, Wo) for m in outs[0]["pred_masks"])
+    assert torch.equal(torch.stack(outs[0]["pred_masks"]), torch.stack(outs[1]["pred_masks"]))
