@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "dvis_plus_b200", "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 OUT_DIR = os.path.join(HERE, "_build")
-OUT = os.path.join(OUT_DIR, "libdvis_simt.so")
+OUT = os.path.join(OUT_DIR, "libdvis_simt_%s.so" % os.environ["SIMT_SANITIZE"] if os.environ.get("SIMT_SANITIZE") else "libdvis_simt.so")
 # every CUDA-core kernel file of the library; csrc/mask_gemm.cu (tcgen05 / TMEM / TMA) and csrc/api.cu (driver entry
 # points) have no CPU meaning and stay out
 FILES = ["postproc.cu", "lap.cu", "msda_forward.cu", "msda_backward.cu", "layernorm.cu", "groupnorm.cu", "mask_aux.cu",
@@ -98,9 +98,12 @@ def build(force=False):
                  '#include "simt_shim.h"\nextern "C" void simt_set_jitter(int one_in) { simt::g_jitter = one_in; }\n')
     flags = ["-O1", "-std=c++20", "-fPIC", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
              f"-I{HERE}", f"-I{INCLUDE}"]
+    sanitize = os.environ.get("SIMT_SANITIZE")        # "address": out-of-bounds checks on every emulated load / store
+    if sanitize:                                      # (run the tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so))
+        flags += [f"-fsanitize={sanitize}", "-fno-omit-frame-pointer", "-g"]
 
     def compile_one(src):
-        obj = src[:-4] + ".o"
+        obj = src[:-4] + (".%s.o" % sanitize if sanitize else ".o")
         r = subprocess.run(["g++"] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"g++ failed on {src}:\n{r.stdout[-3000:]}\n{r.stderr[-6000:]}")
@@ -109,7 +112,8 @@ def build(force=False):
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(compile_one, units + [glue]))
-    r = subprocess.run(["g++", "-shared", "-pthread"] + objs + ["-o", OUT], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-pthread"] + ([f"-fsanitize={sanitize}"] if sanitize else []) + objs + ["-o", OUT],
+                       capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout[-3000:]}\n{r.stderr[-6000:]}")
     return OUT
