@@ -84,7 +84,7 @@ __device__ __forceinline__ int *lap_solve(const float *__restrict__ a, int n, in
       const bool reached_free_column = p[j1] == 0;
       // update potentials: tree columns (incl. j0, which joins the tree now) move with their rows
       for (int j = tid; j <= m; j += nthr) {
-        if (used[j] || j == j0) { u[p[j]] += delta; v[j] -= delta; }
+        if (j == j0 || used[j]) { u[p[j]] += delta; v[j] -= delta; }   // j0 first: thread 0 sets used[j0] below, unsynchronised
         else minv[j] -= delta;
       }
       if (tid == 0) { used[j0] = 1; s_j0 = j1; }
