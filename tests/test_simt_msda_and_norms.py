@@ -12,7 +12,6 @@ import torch
 import torch.nn.functional as F
 
 from oracle import c_oracle
-from oracle import torch_port as tp
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
 import simt_binding as simt  # noqa: E402
