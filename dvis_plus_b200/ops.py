@@ -417,10 +417,10 @@ def vis_masks(pred_masks, sel, first_resize_size, img_size, out_size, out=None, 
 
 
 def unpack_masks(packed, width):
-    """Host side of vis_masks(packed=True): (..., Ho, ceil(Wo/8)) uint8 CPU tensor -> (..., Ho, Wo) bool CPU tensor."""
+    """Host side of vis_masks(packed=True): (..., Ho, ceil(Wo/8)) uint8 tensor -> (..., Ho, Wo) bool CPU tensor."""
     import numpy as np
-    assert not packed.is_cuda and packed.dtype == torch.uint8
-    bits = np.unpackbits(packed.numpy(), axis=-1, bitorder="little")[..., :width]
+    assert packed.dtype == torch.uint8
+    bits = np.unpackbits(packed.cpu().numpy(), axis=-1, bitorder="little")[..., :width]
     return torch.from_numpy(bits).bool()
 
 

@@ -23,6 +23,55 @@ FILES = ["postproc.cu", "lap.cu", "msda_forward.cu", "msda_backward.cu", "layern
          "attention.cu", "msda_pair.cu"]
 
 
+# What csrc/api.cu provides in the real library, plus TEST DOUBLES (plain loops, not emulation) for the entry points of
+# csrc/mask_gemm.cu -- the tcgen05 / TMEM / TMA kernel has no CPU meaning; the doubles let module-level tests run the
+# product's host code end to end on the emulated device (tests/simt/emulated_device.py).
+GLUE = r'''
+#include "simt_shim.h"
+#include "dvis_b200.h"
+namespace dvis { char *last_error_buffer() { static thread_local char buf[512] = {0}; return buf; } }
+extern "C" const char *dvis_last_error(void) { return dvis::last_error_buffer(); }
+extern "C" int dvis_abi_version(void) { return DVIS_B200_ABI_VERSION; }
+extern "C" void simt_set_jitter(int one_in) { simt::g_jitter = one_in; }
+
+namespace {
+template <typename TO>
+void mask_gemm_double(const __nv_bfloat16 *emb, int64_t emb_batch, const __nv_bfloat16 *feat, int B, int Q, int C, int64_t HW,
+                      TO *out, int64_t out_batch, bool bias) {
+  for (int b = 0; b < B; ++b)
+    for (int q = 0; q < Q; ++q) {
+      bool any_open = false;
+      TO *row = out + b * out_batch + (int64_t)q * HW;
+      for (int64_t p = 0; p < HW; ++p) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc += float(emb[b * emb_batch + (int64_t)q * C + c]) * float(feat[((int64_t)b * HW + p) * C + c]);
+        if (bias) { const bool open = !(acc < 0.f); any_open |= open; acc = open ? 0.f : -INFINITY; }
+        row[p] = TO(acc);
+      }
+      if (bias && !any_open) for (int64_t p = 0; p < HW; ++p) row[p] = TO(0.f);
+    }
+}
+}  // namespace
+extern "C" int dvis_mask_logits_strided(const void *emb, int64_t emb_batch_stride, const void *feat, int B, int Q, int C, int64_t HW,
+                                        void *out, int64_t out_batch_stride, int out_dtype, void *) {
+  const auto *e = static_cast<const __nv_bfloat16 *>(emb), *f = static_cast<const __nv_bfloat16 *>(feat);
+  if (out_dtype == DVIS_F32) mask_gemm_double(e, emb_batch_stride, f, B, Q, C, HW, static_cast<float *>(out), out_batch_stride, false);
+  else mask_gemm_double(e, emb_batch_stride, f, B, Q, C, HW, static_cast<__nv_bfloat16 *>(out), out_batch_stride, false);
+  return 0;
+}
+extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype, void *s) {
+  return dvis_mask_logits_strided(emb, (int64_t)Q * C, feat, B, Q, C, HW, out, (int64_t)Q * HW, out_dtype, s);
+}
+extern "C" int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias, int bias_dtype, int *,
+                                   void *) {
+  const auto *e = static_cast<const __nv_bfloat16 *>(emb), *f = static_cast<const __nv_bfloat16 *>(feat);
+  if (bias_dtype == DVIS_F32) mask_gemm_double(e, (int64_t)Q * C, f, B, Q, C, HW, static_cast<float *>(bias), (int64_t)Q * HW, true);
+  else mask_gemm_double(e, (int64_t)Q * C, f, B, Q, C, HW, static_cast<__nv_bfloat16 *>(bias), (int64_t)Q * HW, true);
+  return 0;
+}
+'''
+
+
 def _split_top_level(s):
     parts, depth, cur = [], 0, ""
     for ch in s:
@@ -92,10 +141,8 @@ def build(force=False):
             fh.write(text)
         units.append(path)
     glue = os.path.join(OUT_DIR, "glue_simt.cpp")
-    with open(glue, "w") as fh:          # what csrc/api.cu provides in the real library
-        fh.write('namespace dvis { char *last_error_buffer() { static thread_local char buf[512] = {0}; return buf; } }\n'
-                 'extern "C" const char *dvis_last_error(void) { return dvis::last_error_buffer(); }\n'
-                 '#include "simt_shim.h"\nextern "C" void simt_set_jitter(int one_in) { simt::g_jitter = one_in; }\n')
+    with open(glue, "w") as fh:
+        fh.write(GLUE)
     flags = ["-O1", "-std=c++20", "-fPIC", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
              f"-I{HERE}", f"-I{INCLUDE}"]
     sanitize = os.environ.get("SIMT_SANITIZE")        # "address": out-of-bounds checks on every emulated load / store
