@@ -79,3 +79,70 @@ def test_pack_unpack_roundtrip():
     assert block.shape == (T, Q, 2 * C + K + 1)
     e, n, l = OfflineClipRunner.unpack_queries(block, C)
     assert torch.equal(e, seg["pred_embds"]) and torch.equal(n, seg["pred_embds_without_norm"]) and torch.equal(l, seg["pred_logits"])
+
+
+# ---- the B200 fast path of the frame-sharded pipeline, world size 2, on the emulated device -------------------------------
+def _vis_inputs():
+    g = torch.Generator().manual_seed(3)
+    seg = dict(pred_embds=torch.randn(1, C, T, Q, generator=g), pred_embds_without_norm=torch.randn(1, C, T, Q, generator=g),
+               pred_logits=torch.randn(1, T, Q, K + 1, generator=g))
+    mf = torch.randn(T, 64, H, W, generator=g).to(torch.bfloat16, memory_format=torch.channels_last)
+    return seg, mf
+
+
+def _vis_models():
+    from dvis_plus_b200.modules.postprocess import VideoPostProcessor
+    torch.manual_seed(0)
+    trk = M.ReferringTracker_noiser(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=64,
+                                    class_num=K, noise_mode="none").eval()
+    trk.use_cuda_graph = False
+    rfn = M.TemporalRefiner(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=64, class_num=K,
+                            windows=2).eval()
+    return trk, rfn, VideoPostProcessor(K, num_queries=Q, max_num=4)
+
+
+def _run_vis(runner, post, seg, mf):
+    """Kernels run from their original sources on the SIMT emulator (tests/simt/emulated_device.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+    from emulated_device import emulated_b200
+    from dvis_plus_b200.modules.precision import precision
+    with emulated_b200(), torch.no_grad(), precision("bf16"):
+        block = runner.gather_queries(runner.pack_queries(seg))          # the one collective of the path (gloo here, NCCL on the box)
+        return runner.vis_from_block(block, mf, C, post, (4 * H - 3, 4 * W - 2), (5 * H, 5 * W + 1))
+
+
+def _vis_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        trk, rfn, post = _vis_models()
+        runner = OfflineClipRunner(None, None, trk, rfn)
+        seg, mf = _vis_inputs()
+        t = T // world
+        seg_r, mf_r = _slice(seg, mf, rank * t, (rank + 1) * t)
+        out = _run_vis(runner, post, seg_r, mf_r.contiguous(memory_format=torch.channels_last))
+        torch.save(dict(out), os.path.join(out_dir, f"vis_rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_sharded_vis_postprocessing_world2_on_the_emulated_device():
+    """vis_from_block (instance selection before the final mask GEMM + fused resize / threshold) with the frames split over
+    two ranks: scores / labels / ids identical on both ranks and equal to the single-process result, masks = the two ranks'
+    frame blocks side by side."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_vis_worker, args=(2, port, d), nprocs=2, join=True)
+        r0 = torch.load(os.path.join(d, "vis_rank0.pt"))
+        r1 = torch.load(os.path.join(d, "vis_rank1.pt"))
+    trk, rfn, post = _vis_models()
+    seg, mf = _vis_inputs()
+    ref = _run_vis(OfflineClipRunner(None, None, trk, rfn), post, seg, mf)
+    for k in ("pred_scores", "pred_labels", "pred_ids"):
+        assert torch.equal(r0[k], r1[k]) and torch.equal(r0[k], ref[k]), k
+    masks = torch.cat([r0["pred_masks"], r1["pred_masks"]], dim=1)      # (n, T, H_out, W_out): rank order == frame order
+    assert masks.shape == ref["pred_masks"].shape == (4, T, 5 * H, 5 * W + 1)
+    assert torch.equal(masks, ref["pred_masks"])
