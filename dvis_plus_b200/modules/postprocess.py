@@ -7,6 +7,7 @@ the same signatures and result dictionaries:
 
     post_processing            DVIS_Plus_online.post_processing        py:758-772   (mean class logits + query ids)
     post_processing_minvis     MinVIS.post_processing                  py:255-301   (frame-by-frame Hungarian re-ordering)
+    inference_video            MinVIS.inference_video                  py:361-401
     inference_video_vis        DVIS_Plus_online.inference_video_vis    py:818-868
     inference_video_vps        DVIS_Plus_online.inference_video_vps    py:870-956
     inference_video_vss        DVIS_Plus_online.inference_video_vss    py:958-979
@@ -103,6 +104,16 @@ class VideoPostProcessor:
             out_scores, out_labels, out_masks, out_ids = [], [], [], []
         return {"image_size": (output_height, output_width), "pred_scores": out_scores, "pred_labels": out_labels,
                 "pred_masks": out_masks, "pred_ids": out_ids, "task": "vis"}
+
+    def inference_video(self, pred_cls, pred_masks, img_size, output_height, output_width, first_resize_size, masks_on_device=False):
+        """MinVIS.inference_video (py:361-401): the ten best (query, class) pairs, no ids, no online scores."""
+        saved, self.max_num = self.max_num, 10                                   # py:369 hard-codes topk(10)
+        try:
+            out = self.inference_video_vis(pred_cls, pred_masks, img_size, output_height, output_width, first_resize_size,
+                                           torch.arange(len(pred_cls)), masks_on_device=masks_on_device)
+        finally:
+            self.max_num = saved
+        return {k: out[k] for k in ("image_size", "pred_scores", "pred_labels", "pred_masks")}
 
     def inference_video_vss(self, pred_cls, pred_masks, img_size, output_height, output_width, first_resize_size,
                             pred_id=None, aux_pred_cls=None, masks_on_device=False):

@@ -127,6 +127,36 @@ class OfflineClipRunner:
                 "online_pred_logits": track["pred_logits"]}
 
 
+class OnlineClipRunner:
+    """DVIS_Plus_online.run_window_inference (P/dvis_Plus/meta_architecture.py:774-816) between the backbone and the
+    post-processing: windows of `window_size` frames go through the segmenter head (pixel decoder + predictor) and the
+    referring tracker, which carries its state from window to window (`resume=True` from the second window on, or from the
+    first when `keep` continues a previous call, py:793-797).  The reference moves every window's logits / masks / embeddings
+    to the host in fp32 (py:800-802) to save GPU memory; here they stay on the device for the fused post-processing
+    (modules.postprocess.VideoPostProcessor).  BASELINE config 3 (T=5 clip, Q=200, tracker cross-attention)."""
+
+    def __init__(self, pixel_decoder, predictor, tracker, window_size=30):
+        self.pixel_decoder, self.predictor, self.tracker = pixel_decoder, predictor, tracker
+        self.window_size = window_size
+
+    @torch.no_grad()
+    def __call__(self, features, keep=False):
+        """features: backbone maps of the clip, dict name -> (T, C_i, H_i, W_i).
+        -> pred_logits (1, T, Q, K+1), pred_masks (1, Q, T, H/4, W/4), pred_embds (1, C, T, Q)."""
+        T = next(iter(features.values())).shape[0]
+        logits, masks, embds = [], [], []
+        for i, start in enumerate(range(0, T, self.window_size)):
+            window = {k: v[start:start + self.window_size] for k, v in features.items()}
+            mask_features, _, multi_scale = self.pixel_decoder.forward_features(window)
+            out = self.predictor(multi_scale, mask_features)
+            track = self.tracker(out["pred_embds"], mask_features.unsqueeze(0), resume=(i != 0 or keep),
+                                 frame_embeds_no_norm=out["pred_embds_without_norm"])
+            logits.append(track["pred_logits"].float())
+            masks.append(track["pred_masks"])
+            embds.append(track["pred_embds"].float())
+        return {"pred_logits": torch.cat(logits, dim=1), "pred_masks": torch.cat(masks, dim=2), "pred_embds": torch.cat(embds, dim=2)}
+
+
 class GraphedClipRunner:
     """The clip pipeline as CUDA graphs, software-pipelined across clips.
 
