@@ -77,9 +77,8 @@ class VideoPostProcessor:
         only max_num (not Q) masks per frame are ever computed (pipeline.OfflineClipRunner.vis_inference)."""
         return ops.vis_topk(pred_cls, self.max_num, aux_pred_cls)
 
-    # True: bool masks cross PCIe as 1 bit per pixel and are unpacked on the host (8x less device->host).  Off by default
-    # until the packed kernels have been timed on a B200 (they are parity-checked in the SIMT emulator and by -m gpu tests).
-    packed_transfer = False
+    # bool masks cross PCIe as 1 bit per pixel and are unpacked on the host (8x less device->host); False copies bytes
+    packed_transfer = True
 
     def inference_video_vis(self, pred_cls, pred_masks, img_size, output_height, output_width, first_resize_size, pred_id,
                             aux_pred_cls=None, masks_on_device=False):
