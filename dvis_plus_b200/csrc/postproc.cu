@@ -9,6 +9,8 @@
 // All of it is gather/elementwise work: HBM-write bound, no tensor cores (the vss class contraction is the exception,
 // see vss_argmax_kernel).  The per-pixel arithmetic lives in resize_core.cuh.
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "resize_core.cuh"
@@ -203,6 +205,79 @@ __global__ void __launch_bounds__(32 * kStripWarps) vis_masks_two_stage_kernel(c
   }
 }
 
+// CTA-tiled variant of both strip kernels (selected with DVIS_VIS_MASKS_TILED=1; not yet timed on a B200, the strip
+// kernels above are the measured default).  The strip kernels stall on dependent L2 loads every time a source row enters
+// (26 % / 7 % of the HBM roofline); here the source window of the CTA's whole output tile is staged in shared memory once
+// -- one coalesced, latency-exposed read per CTA, converted to f32 -- and the very same walkers then run on the window,
+// so the results are bit-identical to the strip kernels'.
+template <typename T, bool kTwoStage, bool kPacked>
+__global__ void __launch_bounds__(32 * kStripWarps) vis_masks_tiled_kernel(const T *__restrict__ logits, int64_t q_stride,
+                                                                           int64_t t_stride, const int64_t *__restrict__ sel,
+                                                                           int frames, Geom g, int rows_per_warp,
+                                                                           uint8_t *__restrict__ out) {
+  using R = typename Raw<T>::type;
+  constexpr int PX = kTwoStage ? kStrip2Px : kStripPx;
+  extern __shared__ float s_win[];
+  const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+  const int plane = blockIdx.z, n = plane / frames, t = plane % frames;
+  const int64_t q = sel ? sel[n] : n;
+  const R *src = reinterpret_cast<const R *>(logits) + q * q_stride + t * t_stride;
+  // the CTA's output tile and its source window
+  const int tx0 = blockIdx.x * 32 * PX, tx1 = min(tx0 + 32 * PX, g.Wo) - 1;
+  const int ty0 = blockIdx.y * kStripWarps * rows_per_warp, ty1 = min(ty0 + kStripWarps * rows_per_warp, g.Ho) - 1;
+  int r_lo, r_hi, c_lo, c_hi;
+  rc::source_range(ty0, ty1, kTwoStage, g.s2y, g.Hc, g.s1y, g.h, &r_lo, &r_hi);
+  rc::source_range(tx0, tx1, kTwoStage, g.s2x, g.Wc, g.s1x, g.w, &c_lo, &c_hi);
+  const int ww = c_hi - c_lo + 1, cells = (r_hi - r_lo + 1) * ww;      // the host sized the dynamic shared memory for this
+  for (int i = tid; i < cells; i += 32 * kStripWarps) {
+    const int y = i / ww, x = i - y * ww;
+    s_win[i] = rc::ld_elem(src + (int64_t)(r_lo + y) * g.w + c_lo + x);
+  }
+  __syncthreads();
+  rc::Window pl;
+  pl.p = s_win;
+  pl.w = ww;
+  pl.y0 = r_lo;
+  pl.x0 = c_lo;
+
+  const int ox0 = tx0 + lane * PX;
+  const int oy_begin = ty0 + warp * rows_per_warp;
+  const int oy_end = min(oy_begin + rows_per_warp, g.Ho);
+  if (oy_begin >= oy_end) return;                                        // warp-uniform
+  if (!(kTwoStage && kPacked) && ox0 >= g.Wo) return;                    // packed two-stage: every lane feeds the nibble exchange
+  typename std::conditional<kTwoStage, rc::Strip2<PX, R>, rc::Strip<PX, R>>::type strip;
+  strip.init(g, ox0);
+  if constexpr (kPacked) {
+    const int Wb = (g.Wo + 7) >> 3;
+    const int left = g.Wo - ox0;
+    const uint32_t valid = left >= PX ? (1u << PX) - 1u : left > 0 ? (1u << left) - 1u : 0u;
+    uint8_t *ob = out + (int64_t)plane * g.Ho * Wb + (ox0 >> 3);
+    for (int oy = oy_begin; oy < oy_end; ++oy) {
+      const uint32_t mine = strip.row(pl, g, oy) & valid;
+      if constexpr (kTwoStage) {
+        const uint32_t hi = __shfl_down_sync(0xffffffffu, mine, 1);
+        if ((lane & 1) == 0 && ox0 < g.Wo) ob[(int64_t)oy * Wb] = uint8_t(mine | (hi << 4));
+      } else {
+        ob[(int64_t)oy * Wb] = uint8_t(mine);
+      }
+    }
+    return;
+  }
+  uint8_t *o = out + (int64_t)plane * g.Ho * g.Wo + ox0;
+  const bool vec = (g.Wo % PX == 0) && ((reinterpret_cast<uintptr_t>(out) & (PX - 1)) == 0);
+  for (int oy = oy_begin; oy < oy_end; ++oy) {
+    const uint32_t bits = strip.row(pl, g, oy);
+    uint8_t *orow = o + (int64_t)oy * g.Wo;
+    if (vec) {
+      if constexpr (PX == 8) *reinterpret_cast<uint2 *>(orow) = make_uint2(spread4(bits & 15u), spread4(bits >> 4));
+      else *reinterpret_cast<uint32_t *>(orow) = spread4(bits);
+    } else {
+      for (int i = 0; i < PX; ++i)
+        if (ox0 + i < g.Wo) orow[i] = uint8_t((bits >> i) & 1u);
+    }
+  }
+}
+
 // ---- vps ---------------------------------------------------------------------------------------------------------
 // One thread per output pixel of frame blockIdx.z.  win[t, y, x] = k (winner's probability >= 0.5) or ~k (< 0.5);
 // areas[0:n] = #pixels won by k (py:923), areas[n:2n] = #pixels with probability_k >= 0.5 (py:924),
@@ -351,6 +426,36 @@ int launch_vis_masks(const void *logits, int logits_dtype, int64_t q_stride, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned planes = unsigned(n_sel * frames);
   const dim3 block(32, kStripWarps);
+  const char *tiled_env = getenv("DVIS_VIS_MASKS_TILED");
+  if (tiled_env && atoi(tiled_env) != 0) {
+    const bool two = !(Ho == Hc && Wo == Wc);
+    const int px = two ? kStrip2Px : kStripPx, rows_per_warp = two ? 24 : 16;
+    const int tile_w = 32 * px, tile_h = kStripWarps * rows_per_warp;
+    // exact size of the largest source window over all tile rows / tile columns (a few hundred make_tap evaluations)
+    int max_rows = 0, max_cols = 0, lo, hi;
+    for (int y0 = 0; y0 < Ho; y0 += tile_h) {
+      rc::source_range(y0, std::min(y0 + tile_h, Ho) - 1, two, g.s2y, g.Hc, g.s1y, g.h, &lo, &hi);
+      max_rows = std::max(max_rows, hi - lo + 1);
+    }
+    for (int x0 = 0; x0 < Wo; x0 += tile_w) {
+      rc::source_range(x0, std::min(x0 + tile_w, Wo) - 1, two, g.s2x, g.Wc, g.s1x, g.w, &lo, &hi);
+      max_cols = std::max(max_cols, hi - lo + 1);
+    }
+    const size_t smem = sizeof(float) * (size_t)max_rows * max_cols;
+    if (smem <= 48 * 1024) {                    // strongly down-scaling chains have windows too large to stage: strip kernels
+      const dim3 grid((Wo + tile_w - 1) / tile_w, (Ho + tile_h - 1) / tile_h, planes);
+#define DVIS_TILED(TWO)                                                                                                          \
+      do {                                                                                                                       \
+        if (logits_dtype == DVIS_F32)                                                                                            \
+          vis_masks_tiled_kernel<float, TWO, kPacked><<<grid, block, smem, s>>>(static_cast<const float *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out); \
+        else                                                                                                                     \
+          vis_masks_tiled_kernel<__nv_bfloat16, TWO, kPacked><<<grid, block, smem, s>>>(static_cast<const __nv_bfloat16 *>(logits), q_stride, t_stride, sel, frames, g, rows_per_warp, out); \
+      } while (0)
+      if (two) DVIS_TILED(true); else DVIS_TILED(false);
+#undef DVIS_TILED
+      return check_launch("vis_masks_tiled_kernel");
+    }
+  }
   if (Ho == Hc && Wo == Wc) {
     // rows per warp: enough CTAs to fill the machine a few times over, bands long enough to reuse source rows
     const int rows_per_warp = 16;

@@ -88,6 +88,13 @@ struct Plane {
   DVIS_HD float at(int y, int x) const { return ld_elem(p + (int64_t)y * w + x); }
 };
 
+// a rectangular window [y0, y0 + rows) x [x0, x0 + w) of a plane, staged as f32 (shared memory on the device)
+struct Window {
+  const float *p;
+  int w, y0, x0;
+  DVIS_HD float at(int y, int x) const { return p[(y - y0) * w + (x - x0)]; }
+};
+
 template <typename T>
 DVIS_HD float bilinear(const Plane<T> &pl, const Tap &ty, const Tap &tx) {
   return ty.w0 * (tx.w0 * pl.at(ty.i0, tx.i0) + tx.w1 * pl.at(ty.i0, tx.i1)) +
@@ -137,7 +144,8 @@ struct Strip {
     y1 = -1;
   }
   // -> bit i of the result = (resized logit of pixel ox0 + i on row oy) > 0
-  DVIS_HD uint32_t row(const Plane<T> &pl, const Geom &g, int oy) {
+  template <typename PL>
+  DVIS_HD uint32_t row(const PL &pl, const Geom &g, int oy) {
     const Tap ty = make_tap(oy, g.s1y, g.h);
     if (ty.i0 != y0 || ty.i1 != y1) {
       y0 = ty.i0;
@@ -182,7 +190,8 @@ struct Strip2 {
     }
     ya = yb = ma = mb = -1;
   }
-  DVIS_HD void load_low(const Plane<T> &pl, int y, float *dst) {
+  template <typename PL>
+  DVIS_HD void load_low(const PL &pl, int y, float *dst) {
     DVIS_UNROLL
     for (int j = 0; j < 2 * PX; ++j) dst[j] = ctap[j].w0 * pl.at(y, ctap[j].i0) + ctap[j].w1 * pl.at(y, ctap[j].i1);
   }
@@ -191,21 +200,24 @@ struct Strip2 {
     for (int j = 0; j < 2 * PX; ++j) dst[j] = src[j];
   }
   // make (lowA, lowB) hold source rows (y0, y1)
-  DVIS_HD void ensure_low(const Plane<T> &pl, int y0, int y1) {
+  template <typename PL>
+  DVIS_HD void ensure_low(const PL &pl, int y0, int y1) {
     if (ya == y0 && yb == y1) return;
     if (yb == y0) { copy(lowA, lowB); ya = yb; }
     else if (ya != y0) { load_low(pl, y0, lowA); ya = y0; }
     if (ya == y1) { copy(lowB, lowA); yb = ya; }
     else if (yb != y1) { load_low(pl, y1, lowB); yb = y1; }
   }
-  DVIS_HD void make_mid(const Plane<T> &pl, const Geom &g, int iy, float *dst) {
+  template <typename PL>
+  DVIS_HD void make_mid(const PL &pl, const Geom &g, int iy, float *dst) {
     const Tap ty = make_tap(iy, g.s1y, g.h);
     ensure_low(pl, ty.i0, ty.i1);
     DVIS_UNROLL
     for (int j = 0; j < 2 * PX; ++j) dst[j] = ty.w0 * lowA[j] + ty.w1 * lowB[j];
   }
   // make (midA, midB) hold intermediate rows (i0, i1)
-  DVIS_HD void ensure_mid(const Plane<T> &pl, const Geom &g, int i0, int i1) {
+  template <typename PL>
+  DVIS_HD void ensure_mid(const PL &pl, const Geom &g, int i0, int i1) {
     if (ma == i0 && mb == i1) return;
     if (mb == i0) { copy(midA, midB); ma = mb; }
     else if (ma != i0) { make_mid(pl, g, i0, midA); ma = i0; }
@@ -213,7 +225,8 @@ struct Strip2 {
     else if (mb != i1) { make_mid(pl, g, i1, midB); mb = i1; }
   }
   // -> bit i of the result = (chain value of pixel ox0 + i on row oy) > 0
-  DVIS_HD uint32_t row(const Plane<T> &pl, const Geom &g, int oy) {
+  template <typename PL>
+  DVIS_HD uint32_t row(const PL &pl, const Geom &g, int oy) {
     const Tap t2y = make_tap(oy, g.s2y, g.Hc);
     ensure_mid(pl, g, t2y.i0, t2y.i1);
     uint32_t bits = 0;
@@ -226,6 +239,18 @@ struct Strip2 {
     return bits;
   }
 };
+
+// Source index range [lo, hi] touched by output indices [o0, o1] of one axis (taps are monotone in the output index).
+// two_stage: through the second resize (crop size `mid`, scale s2) and then the first (source size `in`, scale s1).
+DVIS_HD void source_range(int o0, int o1, bool two_stage, float s2, int mid, float s1, int in, int *lo, int *hi) {
+  int a = o0, b = o1;
+  if (two_stage) {
+    a = make_tap(o0, s2, mid).i0;
+    b = make_tap(o1, s2, mid).i1;
+  }
+  *lo = make_tap(a, s1, in).i0;
+  *hi = make_tap(b, s1, in).i1;
+}
 
 // ---- vps: per-pixel arg-max over the kept queries of score * probability (py:897,917) -----------------------------
 // visit(k, v) is called with every kept query's resized probability (for the "original area" counts, py:924).

@@ -49,6 +49,13 @@ def main():
                 tmed, _ = timeit(lambda: torch_chain(m[sel], first, img, out), iters=5 if quick else 20, flush=flush)
                 row["torch_sequence_us_median"] = round(tmed, 1)
                 row["speedup_vs_torch_sequence"] = round(tmed / med, 2)
+            # the shared-memory tile variant (DVIS_VIS_MASKS_TILED=1), same call
+            os.environ["DVIS_VIS_MASKS_TILED"] = "1"
+            same = bool(torch.equal(ops.vis_masks(m, sel, first, img, out), ours))
+            tmed, _ = timeit(lambda: ops.vis_masks(m, sel, first, img, out), iters=10 if quick else 30, flush=flush)
+            pmed, _ = timeit(lambda: ops.vis_masks(m, sel, first, img, out, packed=True), iters=10 if quick else 30, flush=flush)
+            os.environ["DVIS_VIS_MASKS_TILED"] = "0"
+            row.update(tiled_us_median=round(tmed, 1), tiled_packed_us_median=round(pmed, 1), tiled_equals_default=same)
             res.append(row)
             print(row, flush=True)
     if not quick:

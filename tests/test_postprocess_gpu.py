@@ -291,3 +291,18 @@ def test_vis_module_packed_transfer_equals_plain(golden):
                                              g["first_resize_size"], g["pred_id"], aux_pred_cls=g["aux_cls"].to(DEV)))
     assert outs[0]["pred_scores"] == outs[1]["pred_scores"] and outs[0]["pred_ids"] == outs[1]["pred_ids"]
     assert torch.equal(torch.stack(outs[0]["pred_masks"]), torch.stack(outs[1]["pred_masks"]))
+
+
+@pytest.mark.parametrize("geom", [GEOMS[0], GEOMS[1], GEOMS[3], GEOMS[5], GEOMS[8], GEOMS[10]])
+def test_vis_masks_tiled_variant_is_bit_identical(geom, monkeypatch):
+    """DVIS_VIS_MASKS_TILED=1 (source window of the CTA's tile staged in shared memory): same bytes / bits as the default."""
+    (h, w), first, img, out = geom
+    g = torch.Generator().manual_seed(h * 7 + w)
+    masks = (torch.randn(5, 3, h, w, generator=g) * 3).to(DEV)
+    sel = torch.tensor([3, 0, 4], dtype=torch.int64, device=DEV)
+    ref, ref_p = ops.vis_masks(masks, sel, first, img, out), ops.vis_masks(masks, sel, first, img, out, packed=True)
+    ref_b = ops.vis_masks(masks.bfloat16(), sel, first, img, out)
+    monkeypatch.setenv("DVIS_VIS_MASKS_TILED", "1")
+    assert torch.equal(ops.vis_masks(masks, sel, first, img, out), ref)
+    assert torch.equal(ops.vis_masks(masks, sel, first, img, out, packed=True), ref_p)
+    assert torch.equal(ops.vis_masks(masks.bfloat16(), sel, first, img, out), ref_b)

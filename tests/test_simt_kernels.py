@@ -85,6 +85,36 @@ def test_vis_masks_packed_kernels(geom):
     assert torch.equal(ops.unpack_masks(packed, out[1]), ref)
 
 
+@pytest.mark.parametrize("geom", GEOMS)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_vis_masks_tiled_variant_is_bit_identical(geom, dtype, monkeypatch):
+    """DVIS_VIS_MASKS_TILED=1: the CTA stages its source window in shared memory and runs the same walkers on it --
+    byte and packed results equal the default strip kernels' exactly (strongly down-scaling chains fall back to them)."""
+    (h, w), first, img, out = geom
+    g = torch.Generator().manual_seed(h * 7 + w)
+    masks = (torch.randn(4, 2, h, w, generator=g) * 3).to(dtype)
+    sel = torch.tensor([3, 0, 3], dtype=torch.int64)
+    fm = masks.transpose(0, 1).contiguous().transpose(0, 1)
+    ref, ref_p, ref_fm = simt.vis_masks(masks, sel, first, img, out), simt.vis_masks_packed(masks, sel, first, img, out), \
+        simt.vis_masks(fm, None, first, img, out)
+    monkeypatch.setenv("DVIS_VIS_MASKS_TILED", "1")
+    assert torch.equal(simt.vis_masks(masks, sel, first, img, out), ref)
+    assert torch.equal(simt.vis_masks_packed(masks, sel, first, img, out), ref_p)
+    assert torch.equal(simt.vis_masks(fm, None, first, img, out), ref_fm)
+
+
+def test_vis_masks_tiled_variant_falls_back_when_the_window_is_too_large(monkeypatch):
+    """A strongly down-scaling chain over a large source: one tile's source window (120 x 216 floats) exceeds 48 KB of
+    shared memory, the launcher keeps the strip kernel."""
+    h, w, first, img, out = 120, 216, (480, 864), (480, 854), (60, 107)
+    masks = torch.randn(1, 1, h, w, generator=torch.Generator().manual_seed(2)) * 3
+    ref = simt.vis_masks(masks, None, first, img, out)
+    monkeypatch.setenv("DVIS_VIS_MASKS_TILED", "1")
+    assert torch.equal(simt.vis_masks(masks, None, first, img, out), ref)
+    chain = pp.resize_chain(masks, img, out[0], out[1], first)
+    assert_masks_match(ref, chain > 0, chain, tol=2e-5, max_boundary_frac=1e-3)
+
+
 def test_vis_masks_argument_checks():
     m = torch.randn(2, 2, 4, 4)
     with pytest.raises(RuntimeError, match="crop"):
