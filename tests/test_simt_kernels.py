@@ -165,7 +165,7 @@ def test_vss_kernel(geom, K):
 def test_lap_chain_kernel_vs_scipy():
     from scipy.optimize import linear_sum_assignment
     g = torch.Generator().manual_seed(4)
-    for T, n in ((3, 5), (2, 33), (2, 70)):
+    for T, n in ((3, 5), (2, 33), (1, 45)):
         cost = torch.rand(T, n, n, generator=g)
         cost[0, 1, 2] = float("nan")                                    # NaN counts as 0 (noiser.py:52)
         init = torch.randperm(n, generator=g)
