@@ -157,6 +157,84 @@ class OnlineClipRunner:
         return {"pred_logits": torch.cat(logits, dim=1), "pred_masks": torch.cat(masks, dim=2), "pred_embds": torch.cat(embds, dim=2)}
 
 
+class DAQOnlineRunner:
+    """DVIS_DAQ_online.run_window_inference (D/dvis_daq/meta_architecture.py:488-597) between the backbone and the
+    post-processing -- BASELINE config 5's clip loop.  Windows of 5 frames (hard-coded in the reference, py:491) go through
+    the segmenter head; its confident queries (class score above `aux_inference_select_thr`, py:515-516) are offered to the
+    VideoInstanceCutter as candidates for new instances; the cutter keeps one VideoInstanceSequence per object in its hub.
+    After the last window every sequence that lived for at least `noise_frame_num` frames (or is still alive at the clip
+    end, py:540-544) becomes one row of the outputs: time-averaged class logits, per-frame masks (-1e4 where the object
+    does not exist), per-frame logits, a padding mask.  Dead sequences leave the hub (py:576-577).
+
+    `segment(window_features)` defaults to pixel decoder + predictor; mask logits stay wherever `to_store` says
+    (the reference parks them on the host; "cpu" reproduces that, None keeps them on the device)."""
+
+    window_size = 5
+
+    def __init__(self, pixel_decoder, predictor, cutter, num_classes, aux_inference_select_thr, noise_frame_num=2, segment=None,
+                 to_store=None):
+        self.pixel_decoder, self.predictor, self.cutter = pixel_decoder, predictor, cutter
+        self.num_classes, self.select_thr, self.noise_frame_num = num_classes, aux_inference_select_thr, noise_frame_num
+        self.segment = segment if segment is not None else self._segment
+        self.to_store = to_store
+
+    def _segment(self, window):
+        mask_features, _, multi_scale = self.pixel_decoder.forward_features(window)
+        return self.predictor(multi_scale, mask_features)
+
+    @torch.no_grad()
+    def __call__(self, features, keep=False, long_video_start_fidx=-1):
+        """features: dict name -> (T, C_i, H_i, W_i) backbone maps of the clip (anything `segment` can slice by frame).
+        -> the reference's dict: pred_logits (1, n, K+1), pred_masks (1, n, T, h, w), pred_ids (1, n), shape,
+        padding_masks (1, n, T), full_logits (1, n, T, K+1); empty lists when no instance survives."""
+        video_start = max(long_video_start_fidx, 0)
+        num_frames = next(iter(features.values())).shape[0]
+        H = W = dev = None
+        for i, start in enumerate(range(0, num_frames, self.window_size)):
+            out = self.segment({k: v[start:start + self.window_size] for k, v in features.items()})
+            frame_embds = out["pred_embds"]                                              # (1, c, t, q)
+            mask_features = out["mask_features"].unsqueeze(0)
+            logits = out["pred_logits"][0].float()                                       # (t, q, K+1)
+            masks = out["pred_masks"][0].transpose(0, 1)                                 # (t, q, h, w)
+            H, W, dev = mask_features.shape[-2], mask_features.shape[-1], frame_embds.device
+            valid = logits.softmax(dim=-1)[..., :-1].max(dim=-1)[0] > self.select_thr    # (t, q)
+            frame_info = {"pred_logits": [[l] for l in logits], "pred_masks": [[m] for m in masks], "valid": [[v] for v in valid],
+                          "seg_query_feat": self.predictor.query_feat, "seg_query_embed": self.predictor.query_embed}
+            self.cutter.inference(frame_embds, mask_features, frame_info, video_start + start, resume=(i != 0 or keep),
+                                  to_store=self.to_store if self.to_store is not None else dev)
+        store = self.to_store if self.to_store is not None else dev
+        rows, dead = [], []
+        for seq_id, seq in self.cutter.video_ins_hub.items():
+            n = len(seq.pred_masks)
+            if n < self.noise_frame_num and seq.sT + n < video_start + num_frames:       # too short and already gone: noise
+                continue
+            first = max(video_start - seq.sT, 0)                                         # frames before this clip are skipped
+            if first >= n:
+                continue
+            full_masks = torch.full((num_frames, H, W), -1e4, dtype=torch.float32, device=store)
+            full_logits = torch.full((num_frames, self.num_classes + 1), -1e4, dtype=torch.float32, device=dev)
+            full_logits[:, -1] = 1.0
+            padding = torch.ones(num_frames, dtype=torch.bool)
+            t0 = seq.sT + first - video_start
+            full_masks[t0:t0 + n - first] = torch.stack(seq.pred_masks[first:]).to(full_masks)
+            seq_logits = torch.stack(seq.pred_logits[first:]).to(full_logits)
+            full_logits[t0:t0 + n - first] = seq_logits
+            padding[t0:t0 + n - first] = False
+            rows.append((seq_logits.mean(0), full_masks, full_logits, padding, seq_id))
+            if seq.dead:
+                dead.append(seq_id)
+        for seq_id in dead:                                                              # long videos: free finished objects
+            self.cutter.video_ins_hub.pop(seq_id)
+        if rows:
+            outputs = {"pred_logits": torch.stack([r[0] for r in rows])[None], "pred_masks": torch.stack([r[1] for r in rows])[None],
+                       "pred_ids": torch.as_tensor([r[4] for r in rows], dtype=torch.int64)[None],
+                       "padding_masks": torch.stack([r[3] for r in rows])[None], "full_logits": torch.stack([r[2] for r in rows])[None]}
+        else:
+            outputs = {"pred_logits": [], "pred_masks": [], "pred_ids": [], "padding_masks": [], "full_logits": []}
+        outputs["shape"] = (H, W)
+        return outputs
+
+
 class GraphedClipRunner:
     """The clip pipeline as CUDA graphs, software-pipelined across clips.
 

@@ -176,3 +176,16 @@ def load_meta_architecture():
     _mod("mask2former_video.modeling.matcher", VideoHungarianMatcher=object, VideoHungarianMatcher_Consistent=object)
     _ns("mask2former_video.utils", f"{P}/mask2former_video/utils")
     return importlib.import_module("dvis_Plus.meta_architecture")
+
+
+def load_daq_meta_architecture():
+    """Import D/dvis_daq/meta_architecture.py (DVIS_DAQ_online.run_window_inference, py:488-597) with the same kind of
+    stubs: pycocotools and the DAQ criterion / matcher are never touched by the inference window loop."""
+    load_meta_architecture()
+    import importlib
+    _mod("pycocotools")
+    _mod("pycocotools.mask")
+    sys.modules["pycocotools"].mask = sys.modules["pycocotools.mask"]
+    _mod("dvis_daq.matcher", FrameMatcher=object, NewInsHungarianMatcher=object)
+    _mod("dvis_daq.criterion", DAQCriterion=object)
+    return importlib.import_module("dvis_daq.meta_architecture")

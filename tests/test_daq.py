@@ -96,3 +96,40 @@ def test_daq_refiner_gpu(golden):
     close(o["pred_logits"], g["pred_logits"], 1e-3)
     close(o["pred_embds"], g["pred_embds"], 1e-3)
     close(o["pred_masks"], g["pred_masks"], 1e-2)
+
+
+@torch.no_grad()
+def test_daq_online_window_loop_matches_reference(golden):
+    """pipeline.DAQOnlineRunner against the unmodified DVIS_DAQ_online.run_window_inference (fixture:
+    tests/golden/make_golden_daq_runner.py): same surviving instances, ids, averaged logits, per-frame masks / logits and
+    padding masks; dead sequences are dropped from the hub."""
+    import types
+    from dvis_plus_b200.pipeline import DAQOnlineRunner
+    g = golden("daq_runner_small.pt")
+    seg, K = g["seg"], g["num_classes"]
+    C, fQ = seg["pred_embds"].shape[1], seg["pred_embds"].shape[3]
+    cut = M.VideoInstanceCutter(hidden_dim=C, feedforward_dim=128, num_head=8, decoder_layer_num=2, mask_dim=C, num_classes=K,
+                                num_new_ins=fQ, inference_select_threshold=0.1, kick_out_frame_num=2, num_slots=3,
+                                keep_threshold=0.01, ovis_infer=True).eval()
+    assert not any(cut.load_state_dict(g["state_dict"]))
+    emb = torch.nn.Embedding(fQ, C)
+    emb.weight.data.copy_(g["query_feat"])
+    predictor = types.SimpleNamespace(query_feat=emb, query_embed=emb)
+
+    def segment(window):                          # the fixture's precomputed segmenter outputs, sliced by frame index
+        idx = window["frames"]
+        return {"pred_embds": seg["pred_embds"][:, :, idx], "mask_features": seg["mask_features"][idx],
+                "pred_logits": seg["pred_logits"][:, idx], "pred_masks": seg["pred_masks"][:, :, idx]}
+
+    random.seed(g["seed"])
+    runner = DAQOnlineRunner(None, predictor, cut, K, g["aux_inference_select_thr"], g["noise_frame_num"], segment=segment,
+                             to_store="cpu")
+    T = seg["pred_embds"].shape[2]
+    out, ref = runner({"frames": torch.arange(T)}), g["out"]
+    assert out["shape"] == ref["shape"]
+    assert torch.equal(out["pred_ids"], ref["pred_ids"])
+    assert torch.equal(out["padding_masks"], ref["padding_masks"])
+    close(out["pred_logits"], ref["pred_logits"])
+    close(out["full_logits"], ref["full_logits"])
+    close(out["pred_masks"], ref["pred_masks"])
+    assert all(not s.dead for s in cut.video_ins_hub.values())
