@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=8)   # ~10 s of host work on the GPU box (16 cores)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs / no pipelining across clips (debug)")
+    ap.add_argument("--temporal", default="replicated", choices=["replicated", "round_robin"],
+                    help="N > 1: tracker + refiner replicated on every rank (default, measured) or owned round-robin per clip "
+                         "with one broadcast (pipeline.RoundRobinClipRunner; not yet timed on a multi-GPU box)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -234,7 +237,15 @@ def main():
     d2h = {"pred_masks": masks_host, "pred_logits": logits_host}
     d2h_bytes = sum(v.numel() * v.element_size() for v in d2h.values())
 
-    graphed = None if args.eager else GraphedClipRunner(runner, resident, depth=2)
+    if args.eager:
+        graphed = None
+    elif args.temporal == "round_robin":
+        from dvis_plus_b200.pipeline import RoundRobinClipRunner
+        graphed = RoundRobinClipRunner(runner, resident)
+        config["parallelism"] += "; temporal stage owned round-robin per clip + 1 broadcast"
+        config["execution"] = "3 CUDA graphs per clip (per-frame, temporal on the owner rank, masks), %d clips in flight" % graphed.depth
+    else:
+        graphed = GraphedClipRunner(runner, resident, depth=2)
 
     def run_steps(n, mode):
         """n clips back to back; every clip's results are complete when this returns (after the closing barrier)."""

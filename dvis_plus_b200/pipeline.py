@@ -75,6 +75,34 @@ class OfflineClipRunner:
         return {"pred_logits": logits, "pred_masks": masks, "pred_embds": dec[0].permute(0, 3, 1, 2),
                 "online_pred_logits": track["pred_logits"]}
 
+    # -- the temporal stage in two halves (RoundRobinClipRunner runs the first half on ONE rank per clip) -------------------
+    @torch.no_grad()
+    def temporal_payload(self, block, C):
+        """Tracker + refiner on the gathered query block -> one contiguous fp32 (T, Q, Cm + 2(K+1) + C) tensor
+        [mask embeddings | refined class logits | online (tracker) class logits | refined query embeddings]: everything a
+        rank needs to finish the clip's masks for its own frames."""
+        frame_embds, frame_embds_no_norm, _ = self.unpack_queries(block, C)
+        track = self.tracker(frame_embds, None, resume=False, frame_embeds_no_norm=frame_embds_no_norm, with_masks=False)
+        outputs = self.refiner.refine(track["pred_embds"], frame_embds_no_norm)           # (T, l, q, 1, c)
+        dec = self.refiner.decoder_norm(outputs[:, -1:]).permute(1, 3, 0, 2, 4)           # (1, 1, T, q, c)
+        logits = self.refiner.pred_class(dec)[-1].transpose(1, 2)                         # (1, T, q, K+1)
+        emb = self.refiner.mask_embed(dec).float()                                        # (1, 1, T, q, Cm)
+        return torch.cat([emb[0, 0], logits[0].float(), track["pred_logits"][0].float(), dec[0, 0].float()], dim=-1).contiguous()
+
+    @torch.no_grad()
+    def outputs_from_payload(self, payload, mask_features, C):
+        """The second half: this rank's masks from the payload's mask embeddings and its local mask features; the clip-level
+        tensors are sliced out of the payload.  Same dictionary as temporal_from_block."""
+        t_local = mask_features.shape[0]
+        K1 = self.refiner.class_embed.out_features
+        Cm = payload.shape[-1] - 2 * K1 - C
+        t0 = self.rank * t_local
+        emb = payload[t0:t0 + t_local, :, :Cm]
+        masks = self.refiner._masks(emb[None, None], mask_features[None])[-1]            # (1, q, t_local, h, w)
+        return {"pred_logits": payload[None, :, :, Cm:Cm + K1], "pred_masks": masks,
+                "pred_embds": payload[..., Cm + 2 * K1:].permute(2, 0, 1)[None],
+                "online_pred_logits": payload[None, :, :, Cm + K1:Cm + 2 * K1]}
+
     @torch.no_grad()
     def vis_from_block(self, block, mask_features, C, post, img_size, output_size, first_resize_size=None):
         """Tracker + refiner + the video-instance post-processing of DVIS_Plus_offline.forward's eval branch
@@ -320,6 +348,155 @@ class GraphedClipRunner:
         return slot
 
     def wait_all(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.stream_a)
+        cur.wait_stream(self.stream_b)
+        cur.wait_stream(self.stream_c)
+
+
+class RoundRobinClipRunner:
+    """Streams of clips over the G GPUs of one box with the temporal stage OWNED round-robin instead of replicated.
+
+    OfflineClipRunner / GraphedClipRunner run tracker + refiner on every rank (identical results, no extra exchange): right
+    for the latency of one clip, but for a stream of clips it is the Amdahl term of the strong scaling -- at 8 GPUs the
+    replicated ~8 ms dwarf the 1.5 ms a rank spends on its two frames.  Here clip n's temporal stage runs only on rank
+    n mod G; its result (mask embeddings + class logits, 3-10 MB) is broadcast and every rank finishes the masks of its
+    own frames.  Per clip and rank that is 1/G of a temporal stage, overlapped with the other ranks' per-frame work:
+
+        stream A   seg(n)  gather(n)  seg(n+1)  gather(n+1) ...                  (all ranks, every clip)
+        stream B   [temporal(n) if n mod G == rank]  broadcast(n)  masks(n) ...  (2nd communicator: broadcasts never
+                                                                                   queue behind the all-gathers)
+
+    Every rank issues the same collectives in the same order on each communicator.  `depth` slots (default G + 2) bound
+    the clips in flight.  With CUDA tensors the three stages are captured into CUDA graphs per slot (like
+    GraphedClipRunner); on CPU tensors (gloo, tests) everything runs eagerly and synchronously.  Results are identical to
+    the replicated runners' (tests/test_pipeline_dist.py, world size 2)."""
+
+    def __init__(self, runner: OfflineClipRunner, example_features, depth=None, graphs=True):
+        self.r = runner
+        self.world, self.rank = runner.world, runner.rank
+        self.depth = depth or self.world + 2
+        self.n = 0
+        self.cuda = next(iter(example_features.values())).is_cuda
+        self.graphs = graphs and self.cuda
+        # a second communicator for the broadcasts (every rank must create it, in the same order)
+        self.group_bc = dist.new_group(ranks=list(range(self.world))) if self.world > 1 else None
+        self.captured_launches = 0
+        self.slots = []
+        if self.cuda:
+            self.stream_a, self.stream_b, self.stream_c = torch.cuda.Stream(), torch.cuda.Stream(priority=-1), torch.cuda.Stream()
+            with torch.no_grad():
+                for _ in range(2):                                   # populate caches / autotune outside capture
+                    blk, mf = runner.segment_stage(example_features)
+                    runner.outputs_from_payload(runner.temporal_payload(runner.gather_queries(blk), self._C(blk)), mf, self._C(blk))
+            torch.cuda.synchronize()
+        for _ in range(self.depth):
+            self.slots.append(self._make_slot(example_features))
+        if self.cuda:
+            torch.cuda.synchronize()
+
+    def _C(self, block):
+        return (block.shape[-1] - self.r.refiner.class_embed.out_features) // 2
+
+    def _payload_shape(self, gathered):
+        K1 = self.r.refiner.class_embed.out_features
+        Cm = self.r.refiner.mask_embed.layers[-1].out_features
+        return (gathered.shape[0], gathered.shape[1], Cm + 2 * K1 + self._C(gathered))
+
+    def _make_slot(self, example_features):
+        r = self.r
+        slot = {"in": {k: v.clone() for k, v in example_features.items()}}
+        if not self.graphs:
+            if self.cuda:                                             # eager on the device: static exchange buffers
+                with torch.no_grad():
+                    blk, _ = r.segment_stage(slot["in"])
+                slot["gathered"] = blk.new_zeros((self.world * blk.shape[0],) + tuple(blk.shape[1:]))
+                slot["payload"] = blk.new_zeros(self._payload_shape(slot["gathered"]))
+                slot.update(ev_a=torch.cuda.Event(), ev_b=torch.cuda.Event(), ev_c=torch.cuda.Event())
+            return slot
+        from . import _lib
+        n0 = _lib.launch_count
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga, stream=self.stream_a), torch.no_grad():
+            slot["block"], slot["mf"] = r.segment_stage(slot["in"])
+        C = self._C(slot["block"])
+        slot["gathered"] = torch.zeros((self.world * slot["block"].shape[0],) + tuple(slot["block"].shape[1:]),
+                                       dtype=slot["block"].dtype, device=slot["block"].device)
+        gt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gt, stream=self.stream_b), torch.no_grad():
+            slot["payload"] = r.temporal_payload(slot["gathered"], C)
+        gm = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gm, stream=self.stream_b), torch.no_grad():
+            slot["out"] = r.outputs_from_payload(slot["payload"], slot["mf"], C)
+        slot.update(ga=ga, gt=gt, gm=gm, ev_a=torch.cuda.Event(), ev_b=torch.cuda.Event(), ev_c=torch.cuda.Event())
+        self.captured_launches = _lib.launch_count - n0      # one clip's kernels if this rank owned every temporal stage
+        return slot
+
+    def _exchange(self, slot, owner):
+        if self.world > 1:
+            dist.broadcast(slot["payload"], src=owner, group=self.group_bc)
+
+    @torch.no_grad()
+    def submit(self, features=None, d2h=None):
+        """Enqueue one clip (same contract as GraphedClipRunner.submit).  Returns the slot; slot["out"] is valid once
+        slot["ev_b"] has completed (immediately on CPU)."""
+        r = self.r
+        slot = self.slots[self.n % self.depth]
+        owner = self.n % self.world
+        self.n += 1
+        if not self.cuda:                                             # eager, synchronous (gloo / tests)
+            feats = features if features is not None else slot["in"]
+            slot["block"], slot["mf"] = r.segment_stage(feats)
+            C = self._C(slot["block"])
+            slot["gathered"] = r.gather_queries(slot["block"])
+            slot["payload"] = r.temporal_payload(slot["gathered"], C) if owner == self.rank else \
+                slot["gathered"].new_empty(self._payload_shape(slot["gathered"]))
+            self._exchange(slot, owner)
+            slot["out"] = r.outputs_from_payload(slot["payload"], slot["mf"], C)
+            return slot
+        cur = torch.cuda.current_stream()
+        if features is not None:
+            self.stream_c.wait_stream(cur)
+            self.stream_c.wait_event(slot["ev_a"])                    # the slot's previous stage A has consumed its inputs
+            with torch.cuda.stream(self.stream_c):
+                for k, v in features.items():
+                    slot["in"][k].copy_(v, non_blocking=True)
+                slot["ev_c"].record(self.stream_c)
+            self.stream_a.wait_event(slot["ev_c"])
+        self.stream_a.wait_stream(cur)
+        self.stream_a.wait_event(slot["ev_b"])                        # the slot's previous clip is completely finished
+        with torch.cuda.stream(self.stream_a):
+            if self.graphs:
+                slot["ga"].replay()
+            else:
+                slot["block"], slot["mf"] = r.segment_stage(slot["in"])
+            if self.world > 1:
+                dist.all_gather_into_tensor(slot["gathered"], slot["block"], group=r.group)
+            else:
+                slot["gathered"].copy_(slot["block"])
+            slot["ev_a"].record(self.stream_a)
+        self.stream_b.wait_event(slot["ev_a"])
+        with torch.cuda.stream(self.stream_b):
+            C = self._C(slot["block"])
+            if owner == self.rank:
+                if self.graphs:
+                    slot["gt"].replay()
+                else:
+                    slot["payload"].copy_(r.temporal_payload(slot["gathered"], C))
+            self._exchange(slot, owner)
+            if self.graphs:
+                slot["gm"].replay()
+            else:
+                slot["out"] = r.outputs_from_payload(slot["payload"], slot["mf"], C)
+            if d2h is not None:
+                for k, v in d2h.items():
+                    v.copy_(slot["out"][k], non_blocking=True)
+            slot["ev_b"].record(self.stream_b)
+        return slot
+
+    def wait_all(self):
+        if not self.cuda:
+            return
         cur = torch.cuda.current_stream()
         cur.wait_stream(self.stream_a)
         cur.wait_stream(self.stream_b)

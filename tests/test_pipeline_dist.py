@@ -146,3 +146,64 @@ def test_frame_sharded_vis_postprocessing_world2_on_the_emulated_device():
     masks = torch.cat([r0["pred_masks"], r1["pred_masks"]], dim=1)      # (n, T, H_out, W_out): rank order == frame order
     assert masks.shape == ref["pred_masks"].shape == (4, T, 5 * H, 5 * W + 1)
     assert torch.equal(masks, ref["pred_masks"])
+
+
+# ---- round-robin ownership of the temporal stage for streams of clips -----------------------------------------------------
+def _clip(i):
+    g = torch.Generator().manual_seed(100 + i)
+    seg = dict(pred_embds=torch.randn(1, C, T, Q, generator=g), pred_embds_without_norm=torch.randn(1, C, T, Q, generator=g),
+               pred_logits=torch.randn(1, T, Q, K + 1, generator=g))
+    return seg, torch.randn(T, 32, H, W, generator=g)
+
+
+class _SegmentStub:
+    """Stands in for pixel decoder + predictor: the 'features' of a clip ARE its (sliced) segmenter outputs."""
+
+    def forward_features(self, feats):
+        return feats["mask_features"], None, feats
+
+
+def _rr_worker(rank, world, port, out_dir):
+    from dvis_plus_b200.pipeline import RoundRobinClipRunner
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        trk, rfn = _models()
+        runner = OfflineClipRunner(_SegmentStub(), lambda ms, mf: {k: v for k, v in ms.items() if k != "mask_features"}, trk, rfn)
+        t = T // world
+
+        def local(i):
+            seg, mf = _clip(i)
+            seg_r, mf_r = _slice(seg, mf, rank * t, (rank + 1) * t)
+            return dict(seg_r, mask_features=mf_r)
+        rr = RoundRobinClipRunner(runner, local(0))
+        assert rr.depth == world + 2 and not rr.cuda
+        outs = []
+        for i in range(5):                                            # owners: 0, 1, 0, 1, 0
+            outs.append({k: v.clone() for k, v in rr.submit(local(i))["out"].items()})
+        rr.wait_all()
+        torch.save(outs, os.path.join(out_dir, f"rr_rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_round_robin_temporal_ownership_world2_matches_replicated():
+    """RoundRobinClipRunner: clip n's tracker + refiner run on rank n mod 2 only and are broadcast; every clip's results
+    equal the single-process (replicated) pipeline's."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_rr_worker, args=(2, port, d), nprocs=2, join=True)
+        r0 = torch.load(os.path.join(d, "rr_rank0.pt"))
+        r1 = torch.load(os.path.join(d, "rr_rank1.pt"))
+    trk, rfn = _models()
+    single = OfflineClipRunner(None, None, trk, rfn)
+    for i in range(5):
+        seg, mf = _clip(i)
+        ref = single.temporal_stage(seg, mf)
+        for k in ("pred_logits", "pred_embds", "online_pred_logits"):
+            assert torch.equal(r0[i][k], r1[i][k]), (i, k)            # both ranks hold the owner's result
+            assert torch.allclose(r0[i][k], ref[k], atol=1e-6), (i, k)
+        masks = torch.cat([r0[i]["pred_masks"], r1[i]["pred_masks"]], dim=2)
+        assert torch.allclose(masks, ref["pred_masks"], atol=1e-5), i
