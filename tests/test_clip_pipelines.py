@@ -1,4 +1,4 @@
-"""pipeline.OnlineClipRunner = DVIS_Plus_online.run_window_inference between backbone and post-processing
+"""Clip-level runners on the emulated device.  pipeline.OnlineClipRunner = DVIS_Plus_online.run_window_inference between backbone and post-processing
 (P/dvis_Plus/meta_architecture.py:774-816): windows through the segmenter head and the referring tracker with state carried
 across windows.  Checked against the oracle port chained the same way (oracle/torch_port.py, `state=`), on the modules'
 autograd / CPU branch in fp32 and on the emulated device (B200 fast path, bf16 GEMMs)."""
@@ -112,3 +112,27 @@ def test_online_windows_on_the_emulated_device_and_vis_postprocessing():
         assert len(res["pred_masks"]) == 4 and res["pred_masks"][0].shape == (T, 45, 91) and res["task"] == "vis"
         mv = post.inference_video(o["pred_logits"][0], o["pred_masks"][0], (30, 60), 45, 91, (32, 64))
         assert set(mv) == {"image_size", "pred_scores", "pred_labels", "pred_masks"} and len(mv["pred_masks"]) == 10
+
+
+@pytest.mark.timeout(1200)
+@torch.no_grad()
+def test_offline_clip_runner_on_the_emulated_device_vs_oracle_chain():
+    """The benchmark's pipeline (OfflineClipRunner.__call__: pixel decoder -> predictor -> tracker -> refiner -> final mask
+    GEMM) end to end on the emulated device against the same chain of oracle functions bench.py times as the CPU baseline."""
+    from emulated_device import emulated_b200
+    from dvis_plus_b200.pipeline import OfflineClipRunner
+    pd, dec, trk, feats = build()
+    torch.manual_seed(5)
+    rfn = M.TemporalRefiner(hidden_channel=2 * HID, feedforward_channel=256, num_head=8, decoder_layer_num=2, mask_dim=HID,
+                            class_num=K, windows=T).eval()
+    dec.num_frames = T
+    sd = lambda m: {k: v.detach().float() for k, v in m.state_dict().items()}
+    mf, _, ms = tp.pixel_decoder_forward_features(sd(pd), feats, num_layers=2)
+    seg = tp.predictor_forward(sd(dec), ms, mf, num_layers=3)
+    trk_ref = tp.tracker_forward(sd(trk), seg["pred_embds"], None, seg["pred_embds_without_norm"], num_layers=2, with_masks=False)
+    ref = tp.refiner_forward(sd(rfn), trk_ref["pred_embds"], seg["pred_embds_without_norm"], mf[None], num_layers=2)
+    with emulated_b200(), precision("fp32"):
+        out = OfflineClipRunner(pd, dec, trk, rfn)(feats)
+    assert out["pred_masks"].shape == ref["pred_masks"].shape == (1, Q, T, 8, 16)
+    for k in ("pred_logits", "pred_embds", "pred_masks"):
+        assert rel_err(out[k].float(), ref[k]) < 0.15, (k, rel_err(out[k].float(), ref[k]))   # thresholded bf16 attention masks
