@@ -56,40 +56,51 @@ __global__ void __launch_bounds__(256) class_scores_kernel(const float *cls, con
                     threadIdx.x & 31);
 }
 
-// One CTA: class scores, then max_num rounds of a block-wide arg-max over the Q x (K1 - 1) object scores
-// (larger score first, lower flat index on ties), each winner removed before the next round (py:831-835).
+// Ordering of the top-k: larger score first, NaN above everything (torch.topk's convention), lower flat index on ties.
+__device__ __forceinline__ bool topk_before(float a, int ia, float b, int ib) {
+  const bool na = a != a, nb = b != b;
+  if (na != nb) return na;
+  if (!na && a != b) return a > b;
+  return ia < ib;
+}
+
+// One CTA: class scores, then max_num rounds of a block-wide arg-max over the Q x (K1 - 1) object scores, each winner
+// removed before the next round (py:831-835).  Entries that were taken hold -inf and a sentinel index that loses every
+// comparison, so NaN / inf logits can neither stall the selection nor produce an out-of-range index.
 __global__ void __launch_bounds__(1024) vis_topk_kernel(const float *cls, const float *aux, int Q, int K1, int max_num,
                                                         float *scores, float *out_scores, int64_t *out_labels,
                                                         int64_t *out_query) {
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
+  constexpr int kNone = 0x7fffffff;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   class_scores_rows(cls, aux, Q, K1, scores, warp, blockDim.x >> 5, lane);
   __syncthreads();
   const int K = K1 - 1, n = Q * K;
   for (int r = 0; r < max_num; ++r) {
     float best = -INFINITY;
-    int arg = 0x7fffffff;
+    int arg = kNone;
     for (int j = tid; j < n; j += blockDim.x) {
       const float v = scores[(size_t)(j / K) * K1 + (j % K)];
-      if (v > best) { best = v; arg = j; }                       // ascending j per thread: first maximum kept
+      if (arg == kNone || topk_before(v, j, best, arg)) { best = v; arg = j; }
     }
     for (int o = 16; o; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, best, o);
       const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+      if (oi != kNone && (arg == kNone || topk_before(ov, oi, best, arg))) { best = ov; arg = oi; }
     }
     if (lane == 0) { s_val[warp] = best; s_idx[warp] = arg; }
     __syncthreads();
     if (warp == 0) {
       best = lane < (blockDim.x >> 5) ? s_val[lane] : -INFINITY;
-      arg = lane < (blockDim.x >> 5) ? s_idx[lane] : 0x7fffffff;
+      arg = lane < (blockDim.x >> 5) ? s_idx[lane] : kNone;
       for (int o = 16; o; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-        if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+        if (oi != kNone && (arg == kNone || topk_before(ov, oi, best, arg))) { best = ov; arg = oi; }
       }
       if (lane == 0) {
+        if (arg == kNone) arg = 0;                                // cannot happen for max_num <= n; never index out of range
         out_scores[r] = best;
         out_labels[r] = arg % K;
         out_query[r] = arg / K;

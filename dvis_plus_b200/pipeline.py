@@ -104,7 +104,7 @@ class OfflineClipRunner:
                 "online_pred_logits": payload[None, :, :, Cm + K1:Cm + 2 * K1]}
 
     @torch.no_grad()
-    def vis_from_block(self, block, mask_features, C, post, img_size, output_size, first_resize_size=None):
+    def vis_from_block(self, block, mask_features, C, post, img_size, output_size, first_resize_size=None, packed=False):
         """Tracker + refiner + the video-instance post-processing of DVIS_Plus_offline.forward's eval branch
         (P/dvis_Plus/meta_architecture.py:1377-1396 -> post_processing py:758-772 -> inference_video_vis py:818-868), fused
         around the final mask GEMM: the `max_num` instances are selected from the time-averaged class logits FIRST, so the
@@ -115,9 +115,16 @@ class OfflineClipRunner:
         block: the gathered (T, Q, 2C+K+1) query block; mask_features: THIS rank's (t_local, C_m, h, w) features;
         post: modules.postprocess.VideoPostProcessor (task "vis").  Nothing here synchronises with the host.
         -> dict of DEVICE tensors: pred_scores (n,), pred_labels (n,), pred_ids (n,) -- identical on all ranks -- and
-        pred_masks (n, t_local, H_out, W_out) bool for this rank's frames."""
-        from . import ops
-        t_local = mask_features.shape[0]
+        pred_masks (n, t_local, H_out, W_out) bool for this rank's frames (`packed`: one bit per pixel, uint8
+        (n, t_local, H_out, ceil(W_out / 8)), see ops.unpack_masks)."""
+        payload = self.vis_payload(block, C, post)
+        return self.vis_from_payload(payload, mask_features, post.max_num, img_size, output_size, first_resize_size, packed)
+
+    @torch.no_grad()
+    def vis_payload(self, block, C, post):
+        """First half of vis_from_block (tracker + refiner + instance selection): one flat fp32 tensor
+        [mask embeddings of the n selected instances for every frame (T, n, Cm) | scores (n) | labels (n) | query ids (n)] --
+        T*n*Cm + 3n floats (164 KB at T=16, n=10): what RoundRobinClipRunner broadcasts from the clip's owner rank."""
         frame_embds, frame_embds_no_norm, _ = self.unpack_queries(block, C)
         track = self.tracker(frame_embds, None, resume=False, frame_embeds_no_norm=frame_embds_no_norm, with_masks=False)
         outputs = self.refiner.refine(track["pred_embds"], frame_embds_no_norm)           # (T, l, q, 1, c)
@@ -126,14 +133,23 @@ class OfflineClipRunner:
         mean_logits = logits[0].float().mean(0)                                           # post_processing, py:763-767
         aux_logits = track["pred_logits"][0].float().mean(0)
         scores, labels, query = post.select_vis(mean_logits, aux_logits)
+        emb = self.refiner.mask_embed(dec[0, 0].index_select(1, query)).float()           # (T, n, Cm)
+        return torch.cat([emb.flatten(), scores.float(), labels.float(), query.float()])  # ints < 2^24: exact in fp32
+
+    @torch.no_grad()
+    def vis_from_payload(self, payload, mask_features, n, img_size, output_size, first_resize_size=None, packed=False):
+        """Second half: this rank's final masks from the payload and its local mask features."""
+        from . import ops
+        t_local = mask_features.shape[0]
+        T = (payload.numel() - 3 * n) // (n * self.refiner.mask_embed.layers[-1].out_features)
+        emb = payload[:payload.numel() - 3 * n].view(T, n, -1)
+        tail = payload[payload.numel() - 3 * n:].view(3, n)
         t0 = self.rank * t_local
-        sel = dec[0, 0, t0:t0 + t_local].index_select(1, query)                           # (t_local, n, c)
-        emb = self.refiner.mask_embed(sel).float()
-        low = self.refiner._masks(emb[None, None], mask_features[None])[0, 0]             # (n, t_local, h, w), frame-major storage
+        low = self.refiner._masks(emb[t0:t0 + t_local][None, None], mask_features[None])[0, 0]   # (n, t_local, h, w), frame-major
         h, w = low.shape[-2:]
         first = first_resize_size if first_resize_size is not None else (4 * h, 4 * w)    # stride-4 mask features
-        masks = ops.vis_masks(low, None, first, img_size, output_size)
-        return {"pred_scores": scores, "pred_labels": labels, "pred_ids": query, "pred_masks": masks}
+        masks = ops.vis_masks(low, None, first, img_size, output_size, packed=packed)
+        return {"pred_scores": tail[0], "pred_labels": tail[1].long(), "pred_ids": tail[2].long(), "pred_masks": masks}
 
     @torch.no_grad()
     def temporal_stage(self, seg, mask_features):
@@ -274,9 +290,13 @@ class GraphedClipRunner:
     overlaps stage A of clip i+1 (bandwidth / tensor bound) on a second stream.
     """
 
-    def __init__(self, runner: OfflineClipRunner, example_features, depth=2):
+    def __init__(self, runner: OfflineClipRunner, example_features, depth=2, vis=None):
+        """vis: None -> stage B ends with all Q mask logits (temporal_from_block); or a dict(post=VideoPostProcessor,
+        img_size=, output_size=, first_resize_size=None, packed=False) -> stage B is vis_from_block: instances selected before
+        the final mask GEMM, fused resize / threshold, outputs = final (optionally bit-packed) masks + scores / labels / ids."""
         self.r = runner
         self.depth = depth
+        self.vis = vis
         self.slots = []
         self.stream_a = torch.cuda.Stream()
         self.stream_b = torch.cuda.Stream(priority=-1)           # latency-bound stage: its tiny kernels go first
@@ -287,7 +307,7 @@ class GraphedClipRunner:
         with torch.no_grad():
             for _ in range(2):                                   # populate caches / autotune outside capture
                 blk, mf = runner.segment_stage(example_features)
-                runner.temporal_from_block(runner.gather_queries(blk), mf, self._C(blk))
+                self._stage_b(runner.gather_queries(blk), mf, self._C(blk))
         torch.cuda.synchronize(dev)
         from . import _lib
         for _ in range(depth):
@@ -301,7 +321,7 @@ class GraphedClipRunner:
                                            dtype=slot["block"].dtype, device=dev)
             gb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gb, stream=self.stream_b), torch.no_grad():
-                slot["out"] = runner.temporal_from_block(slot["gathered"], slot["mf"], self._C(slot["block"]))
+                slot["out"] = self._stage_b(slot["gathered"], slot["mf"], self._C(slot["block"]))
             slot["gb"] = gb
             slot["ev_a"] = torch.cuda.Event()
             slot["ev_b"] = torch.cuda.Event()
@@ -313,6 +333,11 @@ class GraphedClipRunner:
     def _C(self, block):
         K1 = self.r.refiner.class_embed.out_features
         return (block.shape[-1] - K1) // 2
+
+    def _stage_b(self, gathered, mask_features, C):
+        if self.vis is None:
+            return self.r.temporal_from_block(gathered, mask_features, C)
+        return self.r.vis_from_block(gathered, mask_features, C, **self.vis)
 
     def submit(self, features=None, d2h=None):
         """Enqueue one clip.  `features`: optional host (pinned) tensors copied into the slot's input buffers on the
@@ -372,8 +397,11 @@ class RoundRobinClipRunner:
     GraphedClipRunner); on CPU tensors (gloo, tests) everything runs eagerly and synchronously.  Results are identical to
     the replicated runners' (tests/test_pipeline_dist.py, world size 2)."""
 
-    def __init__(self, runner: OfflineClipRunner, example_features, depth=None, graphs=True):
+    def __init__(self, runner: OfflineClipRunner, example_features, depth=None, graphs=True, vis=None):
+        """vis: as in GraphedClipRunner -- the owner selects the instances, the payload shrinks to the selected instances'
+        mask embeddings (T*n*Cm + 3n floats), every rank finishes fused-post-processed masks of its own frames."""
         self.r = runner
+        self.vis = vis
         self.world, self.rank = runner.world, runner.rank
         self.depth = depth or self.world + 2
         self.n = 0
@@ -388,7 +416,7 @@ class RoundRobinClipRunner:
             with torch.no_grad():
                 for _ in range(2):                                   # populate caches / autotune outside capture
                     blk, mf = runner.segment_stage(example_features)
-                    runner.outputs_from_payload(runner.temporal_payload(runner.gather_queries(blk), self._C(blk)), mf, self._C(blk))
+                    self._finish(self._payload(runner.gather_queries(blk), self._C(blk)), mf, self._C(blk))
             torch.cuda.synchronize()
         for _ in range(self.depth):
             self.slots.append(self._make_slot(example_features))
@@ -398,9 +426,24 @@ class RoundRobinClipRunner:
     def _C(self, block):
         return (block.shape[-1] - self.r.refiner.class_embed.out_features) // 2
 
+    def _payload(self, gathered, C):
+        if self.vis is None:
+            return self.r.temporal_payload(gathered, C)
+        return self.r.vis_payload(gathered, C, self.vis["post"])
+
+    def _finish(self, payload, mask_features, C):
+        if self.vis is None:
+            return self.r.outputs_from_payload(payload, mask_features, C)
+        v = self.vis
+        return self.r.vis_from_payload(payload, mask_features, v["post"].max_num, v["img_size"], v["output_size"],
+                                       v.get("first_resize_size"), v.get("packed", False))
+
     def _payload_shape(self, gathered):
         K1 = self.r.refiner.class_embed.out_features
         Cm = self.r.refiner.mask_embed.layers[-1].out_features
+        if self.vis is not None:
+            n = self.vis["post"].max_num
+            return (gathered.shape[0] * n * Cm + 3 * n,)
         return (gathered.shape[0], gathered.shape[1], Cm + 2 * K1 + self._C(gathered))
 
     def _make_slot(self, example_features):
@@ -424,10 +467,10 @@ class RoundRobinClipRunner:
                                        dtype=slot["block"].dtype, device=slot["block"].device)
         gt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gt, stream=self.stream_b), torch.no_grad():
-            slot["payload"] = r.temporal_payload(slot["gathered"], C)
+            slot["payload"] = self._payload(slot["gathered"], C)
         gm = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gm, stream=self.stream_b), torch.no_grad():
-            slot["out"] = r.outputs_from_payload(slot["payload"], slot["mf"], C)
+            slot["out"] = self._finish(slot["payload"], slot["mf"], C)
         slot.update(ga=ga, gt=gt, gm=gm, ev_a=torch.cuda.Event(), ev_b=torch.cuda.Event(), ev_c=torch.cuda.Event())
         self.captured_launches = _lib.launch_count - n0      # one clip's kernels if this rank owned every temporal stage
         return slot
@@ -449,10 +492,10 @@ class RoundRobinClipRunner:
             slot["block"], slot["mf"] = r.segment_stage(feats)
             C = self._C(slot["block"])
             slot["gathered"] = r.gather_queries(slot["block"])
-            slot["payload"] = r.temporal_payload(slot["gathered"], C) if owner == self.rank else \
+            slot["payload"] = self._payload(slot["gathered"], C) if owner == self.rank else \
                 slot["gathered"].new_empty(self._payload_shape(slot["gathered"]))
             self._exchange(slot, owner)
-            slot["out"] = r.outputs_from_payload(slot["payload"], slot["mf"], C)
+            slot["out"] = self._finish(slot["payload"], slot["mf"], C)
             return slot
         cur = torch.cuda.current_stream()
         if features is not None:
@@ -482,12 +525,12 @@ class RoundRobinClipRunner:
                 if self.graphs:
                     slot["gt"].replay()
                 else:
-                    slot["payload"].copy_(r.temporal_payload(slot["gathered"], C))
+                    slot["payload"].copy_(self._payload(slot["gathered"], C))
             self._exchange(slot, owner)
             if self.graphs:
                 slot["gm"].replay()
             else:
-                slot["out"] = r.outputs_from_payload(slot["payload"], slot["mf"], C)
+                slot["out"] = self._finish(slot["payload"], slot["mf"], C)
             if d2h is not None:
                 for k, v in d2h.items():
                     v.copy_(slot["out"][k], non_blocking=True)

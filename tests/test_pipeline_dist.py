@@ -183,6 +183,20 @@ def _rr_worker(rank, world, port, out_dir):
             outs.append({k: v.clone() for k, v in rr.submit(local(i))["out"].items()})
         rr.wait_all()
         torch.save(outs, os.path.join(out_dir, f"rr_rank{rank}.pt"))
+        # the same with the fused VIS post-processing as the last stage: the owner selects the instances and broadcasts only
+        # their mask embeddings (kernels on the SIMT emulator)
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+        from emulated_device import emulated_b200
+        from dvis_plus_b200.modules.postprocess import VideoPostProcessor
+        from dvis_plus_b200.modules.precision import precision
+        trk.use_cuda_graph = False
+        vis = dict(post=VideoPostProcessor(K, num_queries=Q, max_num=3), img_size=(30, 45), output_size=(40, 57))
+        with emulated_b200(), precision("fp32"):
+            rv = RoundRobinClipRunner(runner, local(0), graphs=False, vis=vis)
+            rv.cuda = False                                           # tensors claim to be on the device; keep the gloo path
+            vouts = [{k: v.clone() for k, v in rv.submit(local(i))["out"].items()} for i in range(3)]
+        torch.save(vouts, os.path.join(out_dir, f"rrvis_rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -197,6 +211,8 @@ def test_round_robin_temporal_ownership_world2_matches_replicated():
         mp.spawn(_rr_worker, args=(2, port, d), nprocs=2, join=True)
         r0 = torch.load(os.path.join(d, "rr_rank0.pt"))
         r1 = torch.load(os.path.join(d, "rr_rank1.pt"))
+        v0 = torch.load(os.path.join(d, "rrvis_rank0.pt"))
+        v1 = torch.load(os.path.join(d, "rrvis_rank1.pt"))
     trk, rfn = _models()
     single = OfflineClipRunner(None, None, trk, rfn)
     for i in range(5):
@@ -207,3 +223,19 @@ def test_round_robin_temporal_ownership_world2_matches_replicated():
             assert torch.allclose(r0[i][k], ref[k], atol=1e-6), (i, k)
         masks = torch.cat([r0[i]["pred_masks"], r1[i]["pred_masks"]], dim=2)
         assert torch.allclose(masks, ref["pred_masks"], atol=1e-5), i
+    # fused VIS variant: both ranks report the owner's selection; masks = the two frame blocks side by side == single process
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+    from emulated_device import emulated_b200
+    from dvis_plus_b200.modules.postprocess import VideoPostProcessor
+    from dvis_plus_b200.modules.precision import precision
+    trk.use_cuda_graph = False
+    post = VideoPostProcessor(K, num_queries=Q, max_num=3)
+    for i in range(3):
+        seg, mf = _clip(i)
+        with emulated_b200(), precision("fp32"), torch.no_grad():
+            ref = single.vis_from_block(single.pack_queries(seg), mf, C, post, (30, 45), (40, 57))
+        for k in ("pred_scores", "pred_labels", "pred_ids"):
+            assert torch.equal(v0[i][k], v1[i][k]) and torch.allclose(v0[i][k].float(), ref[k].float(), atol=1e-6), (i, k)
+        masks = torch.cat([v0[i]["pred_masks"], v1[i]["pred_masks"]], dim=1)
+        assert (masks != ref["pred_masks"]).float().mean().item() < 1e-3, i

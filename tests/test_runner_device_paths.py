@@ -148,3 +148,47 @@ def test_device_branches_of_the_clip_runners(cls, monkeypatch):
                 rr.wait_all()
                 for k in ("pred_logits", "pred_masks"):
                     assert torch.allclose(slot["out"][k].float(), eager[i][k].float(), atol=1e-5), ("graphs", i, k)
+
+
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize("cls", [GraphedClipRunner, RoundRobinClipRunner])
+@torch.no_grad()
+def test_device_branches_with_fused_vis_postprocessing(cls, monkeypatch):
+    """`vis=`: stage B of the runners is vis_from_block (instances selected before the final mask GEMM, fused resize /
+    threshold, bit-packed masks): equal to the eager call on every clip."""
+    from emulated_device import emulated_b200
+    from dvis_plus_b200 import ops
+    from dvis_plus_b200.modules.postprocess import VideoPostProcessor
+    runner, clip = _setup()
+    post = VideoPostProcessor(K, num_queries=Q, max_num=4)
+    vis = dict(post=post, img_size=(30, 45), output_size=(41, 61), packed=True)
+    with emulated_b200(), precision("bf16"), fake_cuda_runtime(monkeypatch):
+        @contextlib.contextmanager
+        def fake_graph(g, stream=None):
+            yield
+        monkeypatch.setattr(torch.cuda, "graph", fake_graph)
+
+        def eager(i):
+            blk, mf = runner.segment_stage(clip(i))
+            return runner.vis_from_block(blk, mf, C, **vis)
+        pipe = cls(runner, clip(0), depth=2, vis=vis) if cls is GraphedClipRunner else cls(runner, clip(0), graphs=False, vis=vis)
+        for i in range(3):
+            if cls is GraphedClipRunner:
+                slot = pipe.slots[i % pipe.depth]
+
+                def stage_a(slot=slot):
+                    blk, mf = runner.segment_stage(slot["in"])
+                    slot["block"].copy_(blk)
+                    slot["mf"].copy_(mf)
+
+                def stage_b(slot=slot):
+                    out = pipe._stage_b(slot["gathered"], slot["mf"], pipe._C(slot["block"]))
+                    for k in out:
+                        slot["out"][k].copy_(out[k])
+                slot["ga"].body, slot["gb"].body = stage_a, stage_b
+            out, ref = pipe.submit(clip(i))["out"], eager(i)
+            pipe.wait_all()
+            assert out["pred_masks"].dtype == torch.uint8 and out["pred_masks"].shape == (4, T, 41, 8)
+            for k in ref:
+                assert torch.equal(out[k], ref[k]), (cls.__name__, i, k)
+            assert ops.unpack_masks(out["pred_masks"], 61).shape == (4, T, 41, 61)

@@ -52,6 +52,17 @@ def test_class_scores_and_topk():
     assert (q * 2 + l).tolist() == [0, 1, 2, 3, 4]
     with pytest.raises(RuntimeError, match="out of range"):
         simt.vis_topk(torch.randn(3, 4), 10)
+    # non-finite logits: NaN scores rank above everything (torch.topk's convention), indices always stay in range
+    cls = torch.randn(6, 4, generator=g)
+    cls[2, 1] = float("nan")                                            # the whole softmax row 2 becomes NaN
+    s, l, q = simt.vis_topk(cls, 7)
+    assert (q[:3] == 2).all() and l[:3].tolist() == [0, 1, 2] and torch.isnan(s[:3]).all()
+    rest = pp.vis_scores(cls).flatten()
+    rest[torch.isnan(rest)] = -1
+    rs, ri = rest.topk(4, sorted=True)
+    assert torch.equal(q[3:] * 3 + l[3:], ri) and torch.allclose(s[3:], rs)
+    s, l, q = simt.vis_topk(torch.full((5, 3), float("nan")), 10)        # everything NaN: first 10 flat indices, in order
+    assert (q * 2 + l).tolist() == list(range(10))
 
 
 @pytest.mark.parametrize("geom", GEOMS)
