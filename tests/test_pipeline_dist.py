@@ -192,9 +192,9 @@ def _rr_worker(rank, world, port, out_dir):
         from dvis_plus_b200.modules.precision import precision
         trk.use_cuda_graph = False
         vis = dict(post=VideoPostProcessor(K, num_queries=Q, max_num=3), img_size=(30, 45), output_size=(40, 57))
+        rv = RoundRobinClipRunner(runner, local(0), graphs=False, vis=vis)    # built on CPU tensors: the synchronous gloo path
+        assert not rv.cuda
         with emulated_b200(), precision("fp32"):
-            rv = RoundRobinClipRunner(runner, local(0), graphs=False, vis=vis)
-            rv.cuda = False                                           # tensors claim to be on the device; keep the gloo path
             vouts = [{k: v.clone() for k, v in rv.submit(local(i))["out"].items()} for i in range(3)]
         torch.save(vouts, os.path.join(out_dir, f"rrvis_rank{rank}.pt"))
     finally:
