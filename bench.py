@@ -169,6 +169,10 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=8)   # ~10 s of host work on the GPU box (16 cores)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs / no pipelining across clips (debug)")
+    ap.add_argument("--postprocess", default="none", choices=["none", "vis"],
+                    help="vis: end the clip with the fused video-instance post-processing (top-10 instances selected before "
+                         "the final mask GEMM, 720p bit-packed masks) instead of all Q stride-4 mask logits -- a different, "
+                         "smaller result; not the default metric's workload and not yet timed on a B200")
     ap.add_argument("--temporal", default="replicated", choices=["replicated", "round_robin"],
                     help="N > 1: tracker + refiner replicated on every rank (default, measured) or owned round-robin per clip "
                          "with one broadcast (pipeline.RoundRobinClipRunner; not yet timed on a multi-GPU box)")
@@ -228,24 +232,33 @@ def main():
 
     from dvis_plus_b200.pipeline import GraphedClipRunner
 
+    vis = None
+    if args.postprocess == "vis":
+        from dvis_plus_b200.modules.postprocess import VideoPostProcessor
+        vis = dict(post=VideoPostProcessor(NUM_CLASSES, num_queries=Q, max_num=10), img_size=(720, IMG_W), output_size=(720, IMG_W),
+                   packed=True)
+        config["workload"] += " + fused VIS post-processing (10 instances selected before the final mask GEMM, 720p bit-packed masks)"
+
     def step_eager():
-        return runner(resident)
+        if vis is None:
+            return runner(resident)
+        blk, mf = runner.segment_stage(resident)
+        return runner.vis_from_block(runner.gather_queries(blk), mf, (blk.shape[-1] - (NUM_CLASSES + 1)) // 2, **vis)
 
     out0 = step_eager()
-    masks_host = torch.empty(out0["pred_masks"].shape, dtype=out0["pred_masks"].dtype).pin_memory()
-    logits_host = torch.empty(out0["pred_logits"].shape, dtype=out0["pred_logits"].dtype).pin_memory()
-    d2h = {"pred_masks": masks_host, "pred_logits": logits_host}
+    d2h_keys = ("pred_masks", "pred_logits") if vis is None else ("pred_masks", "pred_scores", "pred_labels", "pred_ids")
+    d2h = {k: torch.empty(out0[k].shape, dtype=out0[k].dtype).pin_memory() for k in d2h_keys}
     d2h_bytes = sum(v.numel() * v.element_size() for v in d2h.values())
 
     if args.eager:
         graphed = None
     elif args.temporal == "round_robin":
         from dvis_plus_b200.pipeline import RoundRobinClipRunner
-        graphed = RoundRobinClipRunner(runner, resident)
+        graphed = RoundRobinClipRunner(runner, resident, vis=vis)
         config["parallelism"] += "; temporal stage owned round-robin per clip + 1 broadcast"
         config["execution"] = "3 CUDA graphs per clip (per-frame, temporal on the owner rank, masks), %d clips in flight" % graphed.depth
     else:
-        graphed = GraphedClipRunner(runner, resident, depth=2)
+        graphed = GraphedClipRunner(runner, resident, depth=2, vis=vis)
 
     def run_steps(n, mode):
         """n clips back to back; every clip's results are complete when this returns (after the closing barrier)."""
@@ -253,7 +266,11 @@ def main():
             for _ in range(n):
                 if mode == "e2e":
                     feats = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-                    out = runner(feats)
+                    if vis is None:
+                        out = runner(feats)
+                    else:
+                        blk, mf = runner.segment_stage(feats)
+                        out = runner.vis_from_block(runner.gather_queries(blk), mf, (blk.shape[-1] - (NUM_CLASSES + 1)) // 2, **vis)
                     for k, v in d2h.items():
                         v.copy_(out[k], non_blocking=True)
                 else:
