@@ -20,6 +20,9 @@ timeout 200 python tests/perf/postproc_microbench.py > gpurun_out/postproc_micro
 tail -8 gpurun_out/postproc_microbench.log
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 cat gpurun_out/bench_n1.json
+# the clip ending in fused VIS post-processing (different, smaller result: 18 MB of packed masks instead of 377 MB of logits)
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --postprocess vis > gpurun_out/bench_n1_vis.json 2> gpurun_out/bench_n1_vis.err
+cat gpurun_out/bench_n1_vis.json
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_final.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --eager > gpurun_out/bench_under_ncu.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:vis_masks -c 6 -o gpurun_out/ncu_vis_masks \
