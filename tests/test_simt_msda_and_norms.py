@@ -61,7 +61,9 @@ def test_msda_forward_reference_golden(golden):
     assert torch.allclose(out64, g["out64"])                                                    # OPS/test.py:43
 
 
-@pytest.mark.parametrize("D,dtype", [(32, torch.float32), (8, torch.float32), (6, torch.float64)])
+# 30, 32, 64, 71: the small members of the gradcheck channel list of OPS/test.py:88 (odd widths take the scalar kernel)
+@pytest.mark.parametrize("D,dtype", [(32, torch.float32), (8, torch.float32), (6, torch.float64), (30, torch.float64), (64, torch.float32),
+                                     (71, torch.float32)])
 def test_msda_backward_kernels(D, dtype):
     value, sh, lsi, loc, attn = msda_case(dtype, 1, 4, D, 21, ((8, 12), (4, 6)), 4, seed=3)
     go = torch.randn(1, 21, 4 * D, generator=torch.Generator().manual_seed(5), dtype=dtype)
