@@ -22,6 +22,29 @@ import torch
 from .. import ops
 
 
+def minvis_link_indices(embds):
+    """MinVIS.match_from_embds chained over the frames (py:255-264, 284-290): embds (t, q, c) -> (t, q) int64 indices such
+    that frame i's queries re-ordered by indices[i] line up with frame i-1's re-ordered queries (frame 0: identity).
+    The optimum of a row-permuted assignment problem is the permuted optimum, so indices_t = sigma_t[indices_{t-1}] with
+    sigma_t solved against the UN-permuted previous frame: on the device all T-1 problems run as one batched launch of the
+    GPU Hungarian kernel (ops.lap_chain), no host sync; CPU tensors (training-time / test use) go through SciPy."""
+    T, Q = embds.shape[:2]
+    ident = torch.arange(Q, device=embds.device)[None]
+    if T == 1:
+        return ident
+    n = embds / embds.norm(dim=2, keepdim=True)                                  # py:256-257 (no epsilon)
+    cost = 1 - torch.bmm(n[:-1], n[1:].transpose(1, 2))                          # (t-1, q_prev, q_cur) == C.T of py:259-262
+    if cost.is_cuda:
+        return torch.cat([ident, ops.lap_chain(cost)[1]], 0)
+    from scipy.optimize import linear_sum_assignment
+    idx, rows = ident[0], [ident[0]]
+    for t in range(T - 1):
+        sigma = torch.as_tensor(linear_sum_assignment(cost[t].numpy())[1], dtype=torch.int64)
+        idx = sigma[idx]
+        rows.append(idx)
+    return torch.stack(rows, 0)
+
+
 class VideoPostProcessor:
     def __init__(self, num_classes, num_queries=None, max_num=20, object_mask_threshold=0.8, overlap_threshold=0.8,
                  num_thing_classes=0, task="vis"):
@@ -56,13 +79,7 @@ class VideoPostProcessor:
         launch of the GPU Hungarian kernel (ops.lap_chain), no host sync."""
         pred_logits, pred_masks, pred_embds = outputs["pred_logits"][0], outputs["pred_masks"][0], outputs["pred_embds"][0]
         T = pred_logits.shape[0]
-        embds = pred_embds.permute(1, 2, 0).float()                              # (t, q, c)
-        if T > 1:
-            n = embds / embds.norm(dim=2, keepdim=True)                          # py:256-257 (no epsilon)
-            cost = 1 - torch.bmm(n[:-1], n[1:].transpose(1, 2))                  # (t-1, q_prev, q_cur) == C.T of py:259-262
-            idx = torch.cat([torch.arange(embds.shape[1], device=embds.device)[None], ops.lap_chain(cost)[1]], 0)
-        else:
-            idx = torch.arange(embds.shape[1], device=embds.device)[None]
+        idx = minvis_link_indices(pred_embds.permute(1, 2, 0).float())
         t_ar = torch.arange(T, device=idx.device)[:, None]
         out_logits = pred_logits[t_ar, idx].sum(0) / T                           # sum(out_logits) / len(out_logits)
         out_masks = pred_masks.permute(1, 0, 2, 3)[t_ar, idx].permute(1, 0, 2, 3)  # (q, t, h, w)

@@ -279,6 +279,121 @@ class DAQOnlineRunner:
         return outputs
 
 
+class DAQOfflineRunner:
+    """DVIS_DAQ_offline.run_window_inference (D/dvis_daq/meta_architecture.py:1332-1365, with common_inference py:1169-1330
+    and minvis_post_processing py:1400-1437) between the backbone and the post-processing:
+
+      1. the segmenter head over all windows of the clip, results concatenated (py:1139-1167);
+      2. the VideoInstanceCutter over the same windows, fed with the confident segmenter queries (py:1186-1221);
+      3. every instance sequence that survived (>= `noise_frame_num` frames, or still alive at the clip end) becomes a row:
+         time-averaged logits, per-frame masks (-1e4 outside its life span), its per-frame track queries padded with its
+         position embedding at both ends, a padding mask, its id (py:1229-1270);
+      4. the `offline_topk_ins` best rows by class score (py:1285-1296); if fewer than the cutter's `num_new_ins` remain, the
+         free slots are filled with MinVIS-linked segmenter queries ranked by score (py:1298-1311);
+      5. the DAQ TemporalRefiner over (instances x frames) gives the final logits and masks (py:1353-1356).
+
+    `segment(window_features)` defaults to pixel decoder + predictor.  Mask logits of the online stage live on `to_store`
+    ("cpu" parks them on the host like the reference, None keeps them on the device)."""
+
+    def __init__(self, pixel_decoder, predictor, cutter, refiner, num_classes, aux_inference_select_thr, noise_frame_num=2,
+                 offline_topk_ins=20, window_size=30, segment=None, to_store=None):
+        self.pixel_decoder, self.predictor, self.cutter, self.refiner = pixel_decoder, predictor, cutter, refiner
+        self.num_classes, self.select_thr, self.noise_frame_num = num_classes, aux_inference_select_thr, noise_frame_num
+        self.offline_topk_ins, self.window_size = offline_topk_ins, window_size
+        self.segment = segment if segment is not None else self._segment
+        self.to_store = to_store
+
+    def _segment(self, window):
+        mask_features, _, multi_scale = self.pixel_decoder.forward_features(window)
+        return self.predictor(multi_scale, mask_features)
+
+    @torch.no_grad()
+    def __call__(self, features, keep=False, long_video_start_fidx=-1):
+        """-> {"pred_logits": (1, n, K+1), "pred_masks": (1, n, T, h, w), "pred_ids": (1, n), "shape": (h, w)}
+        (empty lists when exactly one instance slot is left, like the reference's `instance_embeds.shape[-1] == 1` case)."""
+        from .modules.postprocess import minvis_link_indices
+        video_start = max(long_video_start_fidx, 0)
+        num_frames = next(iter(features.values())).shape[0]
+        windows = [(s, min(s + self.window_size, num_frames)) for s in range(0, num_frames, self.window_size)]
+        outs = [self.segment({k: v[s:e] for k, v in features.items()}) for s, e in windows]
+        frame_embeds = torch.cat([o["pred_embds"] for o in outs], dim=2)                       # (1, c, T, q)
+        mask_features = torch.cat([o["mask_features"] for o in outs], dim=0).unsqueeze(0)      # (1, T, cm, h, w)
+        seg_logits = torch.cat([o["pred_logits"] for o in outs], dim=1).float()                # (1, T, q, K+1)
+        seg_masks = torch.cat([o["pred_masks"] for o in outs], dim=2)                          # (1, q, T, h, w)
+        dev = frame_embeds.device
+        store = self.to_store if self.to_store is not None else dev
+        C, T = frame_embeds.shape[1], frame_embeds.shape[2]
+        H, W = mask_features.shape[-2:]
+        logits_t, masks_t = seg_logits[0], seg_masks[0].transpose(0, 1)                        # (T, q, K+1), (T, q, h, w)
+        valid = logits_t.softmax(dim=-1)[..., :-1].max(dim=-1)[0] > self.select_thr
+        for i, (s, e) in enumerate(windows):
+            info = {"valid": [[v] for v in valid[s:e]], "pred_logits": [[l] for l in logits_t[s:e]],
+                    "pred_masks": [[m] for m in masks_t[s:e]], "seg_query_feat": self.predictor.query_feat,
+                    "seg_query_embed": self.predictor.query_embed}
+            self.cutter.inference(frame_embeds[:, :, s:e], mask_features[:, s:e], info, video_start + s,
+                                  resume=(i != 0 or keep), to_store=store)
+        rows, dead = [], []
+        for seq_id, seq in self.cutter.video_ins_hub.items():
+            n = len(seq.pred_masks)
+            if n < self.noise_frame_num and seq.sT + n < video_start + num_frames:
+                continue
+            first = max(video_start - seq.sT, 0)
+            if first >= n:
+                continue
+            t0 = seq.sT + first - video_start
+            full_masks = torch.full((num_frames, H, W), -1e4, dtype=torch.float32, device=store)
+            full_masks[t0:t0 + n - first] = torch.stack(seq.pred_masks[first:]).to(full_masks)
+            mean_logits = torch.stack(seq.pred_logits[first:]).float().mean(0)
+            front = seq.sT - video_start                                                        # py:1249 (long videos)
+            tail = num_frames - len(seq.embeds) - front
+            pad = self.refiner.padding_embed(seq.similarity_guided_pos_embed)
+            queries = torch.cat([pad[None].repeat(front, 1), torch.stack(seq.embeds), pad[None].repeat(tail, 1)])
+            padding = torch.tensor([True] * front + [False] * len(seq.embeds) + [True] * tail, device=dev)
+            rows.append((mean_logits, full_masks, queries, padding, seq_id))
+            if seq.dead:
+                dead.append(seq_id)
+        if rows:
+            online_logits = torch.stack([r[0] for r in rows])[None]                             # (1, n, K+1)
+            online_masks = torch.stack([r[1] for r in rows])[None]                              # (1, n, T, h, w)
+            trc_queries = torch.stack([r[2] for r in rows])[None]                               # (1, n, T, c)
+            padding_masks = torch.stack([r[3] for r in rows])[None]                             # (1, n, T)
+            seq_ids = torch.as_tensor([r[4] for r in rows], dtype=torch.int64, device=dev)
+        else:
+            online_logits = seg_logits.new_zeros((1, 0, seg_logits.shape[-1]))
+            online_masks = torch.zeros((1, 0, T, H, W), dtype=torch.float32, device=store)
+            trc_queries = seg_logits.new_zeros((1, 0, T, C))
+            padding_masks = torch.zeros((1, 0, T), dtype=torch.bool, device=dev)
+            seq_ids = torch.zeros(0, dtype=torch.int64, device=dev)
+        scores = online_logits[0].softmax(dim=-1)[:, :-1].max(dim=-1)[0]
+        top = torch.arange(scores.shape[0], device=dev) if self.offline_topk_ins > scores.shape[0] else \
+            scores.topk(self.offline_topk_ins, sorted=False)[1]
+        online_logits, trc_queries, padding_masks = online_logits[:, top], trc_queries[:, top], padding_masks[:, top]
+        online_masks = online_masks[:, top.to(online_masks.device)]
+        seq_id_list = seq_ids[top].tolist()
+        num_left = self.cutter.num_new_ins - online_logits.shape[1]
+        if num_left > 0:                                                                        # fill with naively linked queries
+            idx = minvis_link_indices(frame_embeds[0].permute(1, 2, 0).float())                 # (T, q)
+            t_ar = torch.arange(T, device=idx.device)[:, None]
+            link_logits = logits_t[t_ar, idx].sum(0) / T                                        # (q, K+1)
+            link_masks = masks_t[t_ar.to(masks_t.device), idx.to(masks_t.device)].transpose(0, 1)   # (q, T, h, w)
+            link_embds = frame_embeds[0].permute(1, 2, 0).float()[t_ar, idx].transpose(0, 1)    # (q, T, c)
+            best = link_logits.softmax(dim=-1)[:, :-1].max(dim=-1)[0].topk(num_left, sorted=False)[1]
+            online_logits = torch.cat([online_logits, link_logits[best][None]], dim=1)
+            online_masks = torch.cat([online_masks, link_masks[best.to(link_masks.device)][None].to(online_masks)], dim=1)
+            trc_queries = torch.cat([trc_queries, link_embds[best][None]], dim=1)
+            padding_masks = torch.cat([padding_masks, torch.zeros((1, num_left, num_frames), dtype=torch.bool, device=dev)], dim=1)
+            seq_id_list += [(10000 + video_start) * 10000 + ii * 1000 for ii in range(1, num_left + 1)]
+        for seq_id in dead:                                                                     # long videos: free finished objects
+            self.cutter.video_ins_hub.pop(seq_id)
+        instance_embeds = trc_queries.permute(0, 3, 2, 1)                                       # (1, c, T, n)
+        if instance_embeds.shape[-1] == 1:                                                      # py:1348-1351
+            return {"pred_logits": [], "pred_masks": [], "pred_ids": [], "shape": (H, W), "online_out": None}
+        out = self.refiner(instance_embeds, padding_masks, frame_embeds, mask_features, None)
+        return {"pred_logits": out["pred_logits"][:, 0], "pred_masks": out["pred_masks"],
+                "pred_ids": torch.as_tensor(seq_id_list, dtype=torch.int64)[None], "shape": (H, W),
+                "online_out": {"pred_logits": online_logits, "pred_masks": online_masks}}
+
+
 class GraphedClipRunner:
     """The clip pipeline as CUDA graphs, software-pipelined across clips.
 

@@ -133,3 +133,45 @@ def test_daq_online_window_loop_matches_reference(golden):
     close(out["full_logits"], ref["full_logits"])
     close(out["pred_masks"], ref["pred_masks"])
     assert all(not s.dead for s in cut.video_ins_hub.values())
+
+
+@pytest.mark.parametrize("case", ["topk5_filled", "topk_all"])
+@torch.no_grad()
+def test_daq_offline_window_loop_matches_reference(golden, case):
+    """pipeline.DAQOfflineRunner against the unmodified DVIS_DAQ_offline.run_window_inference (fixture:
+    tests/golden/make_golden_daq_runner.py offline): the cutter's surviving sequences, top-k, the MinVIS-linked fill-in
+    queries and the DAQ refiner on top -- same instance ids, logits and masks (instances compared in id order: the
+    reference's topk(sorted=False) leaves their order open)."""
+    import types
+    from dvis_plus_b200.pipeline import DAQOfflineRunner
+    g = golden("daq_offline_runner_small.pt")
+    seg, K = g["seg"], g["num_classes"]
+    C, fQ = seg["pred_embds"].shape[1], seg["pred_embds"].shape[3]
+    cut = M.VideoInstanceCutter(hidden_dim=C, feedforward_dim=128, num_head=8, decoder_layer_num=2, mask_dim=C, num_classes=K,
+                                num_new_ins=fQ, inference_select_threshold=0.1, kick_out_frame_num=2, num_slots=3,
+                                keep_threshold=0.01, ovis_infer=True).eval()
+    assert not any(cut.load_state_dict(g["cutter"]))
+    rf = M.DAQTemporalRefiner(hidden_channel=C, feedforward_channel=128, num_head=8, decoder_layer_num=2, mask_dim=C, class_num=K,
+                              windows=3, use_local_attn=False).eval()
+    assert not any(rf.load_state_dict(g["refiner"]))
+    emb = torch.nn.Embedding(fQ, C)
+    emb.weight.data.copy_(g["query_feat"])
+    predictor = types.SimpleNamespace(query_feat=emb, query_embed=emb)
+
+    def segment(window):
+        idx = window["frames"]
+        return {"pred_embds": seg["pred_embds"][:, :, idx], "mask_features": seg["mask_features"][idx],
+                "pred_logits": seg["pred_logits"][:, idx], "pred_masks": seg["pred_masks"][:, :, idx]}
+
+    c = g["cases"][case]
+    random.seed(g["seed"])
+    torch.manual_seed(24)
+    runner = DAQOfflineRunner(None, predictor, cut, rf, K, g["aux_inference_select_thr"], g["noise_frame_num"],
+                              offline_topk_ins=c["offline_topk_ins"], window_size=g["window_size"], segment=segment, to_store="cpu")
+    out, ref = runner({"frames": torch.arange(seg["pred_embds"].shape[2])}), c["out"]
+    assert out["shape"] == ref["shape"]
+    order, ref_order = out["pred_ids"][0].argsort(), ref["pred_ids"][0].argsort()
+    assert torch.equal(out["pred_ids"][0][order], ref["pred_ids"][0][ref_order])
+    # the refiner attends across instances, so logits / masks are compared after aligning the instance order
+    close(out["pred_logits"][0][order], ref["pred_logits"][0][ref_order])
+    close(out["pred_masks"][0][order], ref["pred_masks"][0][ref_order])
