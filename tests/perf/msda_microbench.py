@@ -23,7 +23,7 @@ PEAK_GBS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 
-def timeit(fn, iters=30, warmup=5, flush=None):
+def timeit(fn, iters=50, warmup=10, flush=None):   # 10 warm-up + >= 50 timed iterations, median and min
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
