@@ -209,3 +209,59 @@ def test_daq_track_query_matching_device_path_equals_host(device):
         calls = _lib.launch_count
         assert torch.equal(cutter.match_with_embeds(trc, seg), host)
         assert _lib.launch_count == calls + 1
+
+
+def test_predictor_fast_path_production_width(device):
+    """hidden_dim 128 (multiple of 128 -> the batch-first fused inference path: fused LayerNorm kernels, resized mask
+    features, attention-bias GEMM epilogue) against the oracle port."""
+    from oracle import torch_port as tp
+    torch.manual_seed(0)
+    d = M.VideoMultiScaleMaskedTransformerDecoder_dvisPlus(
+        128, True, num_classes=7, hidden_dim=128, num_queries=12, nheads=8, dim_feedforward=256, dec_layers=3,
+        pre_norm=False, mask_dim=128, enforce_input_project=False, num_frames=1, num_reid_head_layers=3,
+        reid_hidden_dim=128).eval()
+    ms = [torch.randn(2, 128, 2, 3), torch.randn(2, 128, 4, 6), torch.randn(2, 128, 8, 12)]
+    mf = torch.randn(2, 128, 16, 24)
+    ref = tp.predictor_forward({k: v.detach() for k, v in d.state_dict().items()}, ms, mf, num_layers=3)
+    calls = _lib.launch_count
+    with precision("fp32"):
+        out = d(ms, mf)
+    assert _lib.launch_count - calls > 10, "fused LayerNorm / mask kernels did not run"
+    for k in ("pred_logits", "pred_masks", "pred_embds", "pred_embds_without_norm"):
+        assert rel_err(out[k].float(), ref[k]) < 8e-2, (k, rel_err(out[k].float(), ref[k]))
+    with precision("bf16"):
+        out = d(ms, mf)
+    for k in ("pred_logits", "pred_masks", "pred_embds"):
+        assert rel_err(out[k].float(), ref[k]) < 0.12, (k, rel_err(out[k].float(), ref[k]))
+
+
+def test_predictor_prenorm_variant_golden(golden, device):
+    """pre_norm=True + enforce_input_project + no ReID head: the generic loop (the fused path is post-norm only)."""
+    g, base = golden("predictor_prenorm_small.pt"), golden("predictor_small.pt")
+    d = M.VideoMultiScaleMaskedTransformerDecoder_dvisPlus(
+        64, True, num_classes=5, hidden_dim=64, num_queries=12, nheads=8, dim_feedforward=128, dec_layers=2, pre_norm=True,
+        mask_dim=64, enforce_input_project=True, num_frames=2, num_reid_head_layers=0, reid_hidden_dim=64).eval()
+    d.load_state_dict(g["state_dict"])
+    with precision("fp32"):
+        out = d(list(base["multi_scale"]), base["mask_features"])
+    for k in ("pred_logits", "pred_masks", "pred_embds", "pred_embds_without_norm"):
+        assert rel_err(out[k].float(), g[k]) < 8e-2, (k, rel_err(out[k].float(), g[k]))
+
+
+def test_mask_logits_query_slices_beyond_256(device):
+    """Q = 300 (the DAQ stress size): ops.mask_logits splits the queries into in-place slices of <= 256 and
+    ops.mask_attn_bias takes its two-kernel route; both against plain torch."""
+    from dvis_plus_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    emb = torch.randn(2, 300, 64, generator=g)
+    feat = torch.randn(2, 64, 5, 7, generator=g)
+    eb, fb = emb.bfloat16().float(), feat.bfloat16().float()
+    ref = torch.einsum("bqc,bchw->bqhw", eb, fb)
+    calls = _lib.launch_count
+    out = ops.mask_logits(emb, feat.to(torch.bfloat16, memory_format=torch.channels_last), torch.float32)
+    assert _lib.launch_count == calls + 2                                       # two strided launches
+    assert rel_err(out, ref) < 1e-5
+    bias = ops.mask_attn_bias(emb, feat.to(torch.bfloat16, memory_format=torch.channels_last), torch.float32)
+    masked = ref.flatten(2) < 0
+    masked[masked.all(-1)] = False
+    assert torch.equal(torch.isinf(bias) & (bias < 0), masked)
