@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=8)   # ~10 s of host work on the GPU box (16 cores)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs / no pipelining across clips (debug)")
+    ap.add_argument("--d2h-stream", action="store_true",
+                    help="end-to-end mode: device->host copies on their own stream (GraphedClipRunner d2h_stream; not yet timed)")
     ap.add_argument("--postprocess", default="none", choices=["none", "vis"],
                     help="vis: end the clip with the fused video-instance post-processing (top-10 instances selected before "
                          "the final mask GEMM, 720p bit-packed masks) instead of all Q stride-4 mask logits -- a different, "
@@ -258,7 +260,7 @@ def main():
         config["parallelism"] += "; temporal stage owned round-robin per clip + 1 broadcast"
         config["execution"] = "3 CUDA graphs per clip (per-frame, temporal on the owner rank, masks), %d clips in flight" % graphed.depth
     else:
-        graphed = GraphedClipRunner(runner, resident, depth=2, vis=vis)
+        graphed = GraphedClipRunner(runner, resident, depth=2, vis=vis, d2h_stream=args.d2h_stream)
 
     def run_steps(n, mode):
         """n clips back to back; every clip's results are complete when this returns (after the closing barrier)."""

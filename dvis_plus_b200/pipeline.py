@@ -405,8 +405,10 @@ class GraphedClipRunner:
     overlaps stage A of clip i+1 (bandwidth / tensor bound) on a second stream.
     """
 
-    def __init__(self, runner: OfflineClipRunner, example_features, depth=2, vis=None):
-        """vis: None -> stage B ends with all Q mask logits (temporal_from_block); or a dict(post=VideoPostProcessor,
+    def __init__(self, runner: OfflineClipRunner, example_features, depth=2, vis=None, d2h_stream=False):
+        """d2h_stream: copy the results to the host on a stream of their own instead of the temporal stage's stream, so a
+        clip's device->host copy no longer delays the NEXT clip's temporal stage (opt-in until timed on a B200).
+        vis: None -> stage B ends with all Q mask logits (temporal_from_block); or a dict(post=VideoPostProcessor,
         img_size=, output_size=, first_resize_size=None, packed=False) -> stage B is vis_from_block: instances selected before
         the final mask GEMM, fused resize / threshold, outputs = final (optionally bit-packed) masks + scores / labels / ids."""
         self.r = runner
@@ -416,6 +418,7 @@ class GraphedClipRunner:
         self.stream_a = torch.cuda.Stream()
         self.stream_b = torch.cuda.Stream(priority=-1)           # latency-bound stage: its tiny kernels go first
         self.stream_c = torch.cuda.Stream()                      # host -> device copies of the next clip's inputs
+        self.stream_d = torch.cuda.Stream() if d2h_stream else None   # device -> host copies of the results
         self.n = 0
         self.captured_launches = 0
         dev = next(iter(example_features.values())).device
@@ -441,6 +444,7 @@ class GraphedClipRunner:
             slot["ev_a"] = torch.cuda.Event()
             slot["ev_b"] = torch.cuda.Event()
             slot["ev_c"] = torch.cuda.Event()
+            slot["ev_o"] = torch.cuda.Event()                         # stage B done (results ready to be copied out)
             self.captured_launches = _lib.launch_count - n0       # libdvis_b200 kernels inside one clip's two graphs
             self.slots.append(slot)
         torch.cuda.synchronize(dev)
@@ -481,10 +485,19 @@ class GraphedClipRunner:
             else:
                 slot["gathered"].copy_(slot["block"])
             slot["gb"].replay()
-            if d2h is not None:
+            if d2h is not None and self.stream_d is None:
                 for k, v in d2h.items():
                     v.copy_(slot["out"][k], non_blocking=True)
-            slot["ev_b"].record(self.stream_b)
+            if d2h is None or self.stream_d is None:
+                slot["ev_b"].record(self.stream_b)
+            else:
+                slot["ev_o"].record(self.stream_b)
+        if d2h is not None and self.stream_d is not None:
+            self.stream_d.wait_event(slot["ev_o"])
+            with torch.cuda.stream(self.stream_d):                    # one copy stream: copies of successive clips stay ordered
+                for k, v in d2h.items():
+                    v.copy_(slot["out"][k], non_blocking=True)
+                slot["ev_b"].record(self.stream_d)                    # the slot is free once its results have left
         return slot
 
     def wait_all(self):
@@ -492,6 +505,8 @@ class GraphedClipRunner:
         cur.wait_stream(self.stream_a)
         cur.wait_stream(self.stream_b)
         cur.wait_stream(self.stream_c)
+        if self.stream_d is not None:
+            cur.wait_stream(self.stream_d)
 
 
 class RoundRobinClipRunner:

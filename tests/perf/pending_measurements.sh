@@ -21,7 +21,9 @@ tail -8 gpurun_out/postproc_microbench.log
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 cat gpurun_out/bench_n1.json
 # the clip ending in fused VIS post-processing (different, smaller result: 18 MB of packed masks instead of 377 MB of logits)
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --postprocess vis > gpurun_out/bench_n1_vis.json 2> gpurun_out/bench_n1_vis.err
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --d2h-stream > gpurun_out/bench_n1_d2hstream.json 2> gpurun_out/bench_n1_d2hstream.err
+cat gpurun_out/bench_n1_d2hstream.json
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --d2h-stream --postprocess vis > gpurun_out/bench_n1_vis.json 2> gpurun_out/bench_n1_vis.err
 cat gpurun_out/bench_n1_vis.json
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_final.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --eager > gpurun_out/bench_under_ncu.log 2>&1

@@ -98,7 +98,7 @@ def test_device_branches_of_the_clip_runners(cls, monkeypatch):
             yield
         monkeypatch.setattr(torch.cuda, "graph", fake_graph)
         eager = [runner(clip(i)) for i in range(3)]
-        kwargs = dict(depth=2) if cls is GraphedClipRunner else dict(graphs=False)
+        kwargs = dict(depth=2, d2h_stream=True) if cls is GraphedClipRunner else dict(graphs=False)
         pipe = cls(runner, clip(0), **kwargs)
         assert getattr(pipe, "cuda", True)
         host = {k: torch.empty_like(v) for k, v in eager[0].items() if k in ("pred_masks", "pred_logits")}
