@@ -81,7 +81,7 @@ def test_vis_module_vs_reference_golden(golden):
         aux = g["aux_cls"].to(DEV) if c["use_aux"] else None
         out = post.inference_video_task(g["pred_cls"].to(DEV), g["pred_masks"].to(DEV), g["img_size"], Ho, Wo,
                                         g["first_resize_size"], g["pred_id"], aux_pred_cls=aux)
-        assert all(not m.is_cuda and m.dtype == torch.bool for m in out["pred_masks"])
+        assert all(m.device.type == "cpu" and m.dtype == torch.bool for m in out["pred_masks"])
         s, l, i, m = sort_instances(out["pred_scores"], out["pred_labels"], out["pred_ids"], torch.stack(out["pred_masks"]))
         rs, rl, ri, rm = sort_instances(c["pred_scores"], c["pred_labels"], c["pred_ids"], c["pred_masks"])
         torch.testing.assert_close(s, rs, rtol=1e-5, atol=1e-7)
@@ -174,7 +174,7 @@ def test_vps_module_vs_reference_golden(golden):
                                         g["first_resize_size"], g["pred_id"], aux_pred_cls=g["aux_cls"].to(DEV) if c["use_aux"] else None)
         assert out["segments_infos"] == c["segments_infos"], name
         assert [int(i) for i in out["pred_ids"]] == c["pred_ids"], name
-        assert out["pred_masks"].dtype == torch.int32 and not out["pred_masks"].is_cuda
+        assert out["pred_masks"].dtype == torch.int32 and out["pred_masks"].device.type == "cpu"
         assert (out["pred_masks"] != c["pred_masks"]).float().mean().item() < 1e-3, name
 
 
