@@ -3,7 +3,7 @@ dvis_plus_b200.ops front ends and module fast paths, every CUDA-core kernel on t
 tcgen05 mask GEMM) -- emulated_device.emulated_b200 plus a few shims so the tests' own `.cuda()` / `device="cuda"` calls
 stay on the host and the tracker runs its frame body without CUDA-graph capture.
 
-    python tests/simt/rehearse_gpu_tests.py [test_module ...]     (default: the four files below; ~15 min)
+    python tests/simt/rehearse_gpu_tests.py [-k substring] [test_module ...]     (default: the four files below; ~15 min)
 
 Expected artefacts of the rehearsal, not failures of the code: tests asserting that CPU tensors are REJECTED (every tensor
 claims to be on the device here), tests that need the reference's own CUDA kernel, and the full-size cases skipped below.
@@ -103,7 +103,7 @@ def cases_of(fn):
         yield kwargs
 
 
-def main(mods):
+def main(mods, only=None):
     install_host_shims()
     golden = lambda name: torch.load(os.path.join(ROOT, "tests", "golden", name), map_location="cpu", weights_only=False)  # noqa: E731
     ran = failed = 0
@@ -112,6 +112,8 @@ def main(mods):
             T = __import__(modname)
             for name, fn in inspect.getmembers(T, inspect.isfunction):
                 if not name.startswith("test_") or fn.__module__ != modname:
+                    continue
+                if only is not None and only not in name:
                     continue
                 if name in SKIP:
                     print(f"{modname}::{name} skipped ({SKIP[name]})", flush=True)
@@ -140,4 +142,9 @@ def main(mods):
 
 
 if __name__ == "__main__":
-    sys.exit(1 if main(sys.argv[1:] or DEFAULT) else 0)
+    argv, only = sys.argv[1:], None
+    if "-k" in argv:
+        i = argv.index("-k")
+        only = argv[i + 1]
+        del argv[i:i + 2]
+    sys.exit(1 if main(argv or DEFAULT, only) else 0)
