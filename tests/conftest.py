@@ -14,9 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+# GPU tests written after round 1's last B200 run (checked on the SIMT emulator only): they run after every
+# device-verified test, so a first-run surprise in one of them cannot hide the verified results behind `-x`.
+FIRST_DEVICE_RUN_PENDING = ("test_vis_masks_tiled_variant_is_bit_identical", "test_zz_config5_gpu")
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        items.sort(key=lambda it: any(s in it.nodeid for s in FIRST_DEVICE_RUN_PENDING))   # stable: order kept otherwise
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
