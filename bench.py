@@ -158,6 +158,19 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
+def merge_e2e_legs(e2e, frames, ms_first, ms_overlapped, rel_diff, tol=1e-2):
+    """Fold the second end-to-end leg (3 clips in flight, result copies on their own stream) into the `e2e` object: both
+    legs' times are always reported; the headline value switches to the second leg only if it is faster AND its results
+    agree with the first leg's within `tol` (north_star's bf16 tolerance, relative to the largest magnitude)."""
+    e2e["legs_ms_per_step"] = {"2 in flight, copies on the temporal stream": round(ms_first, 3),
+                               "3 in flight, copies on their own stream": round(ms_overlapped, 3)}
+    e2e["overlapped_leg_rel_max_diff_vs_first_leg"] = round(rel_diff, 6)
+    if rel_diff <= tol and ms_overlapped < ms_first:
+        e2e.update(value=round(frames / ms_overlapped * 1e3, 2), ms_per_step=round(ms_overlapped, 3),
+                   pipeline="3 clips in flight, result copies on their own stream")
+    return e2e
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,7 +341,37 @@ def main():
             torch.cuda.synchronize()
             os._exit(0)
 
+    # End-to-end, second configuration (timed after everything above; see e2e_overlapped_leg): 3 clips in flight and the
+    # result copies on a stream of their own.  Every rank takes part (the clip's all-gather is a collective).
+    d2h_ref = {k: v.clone() for k, v in d2h.items()} if graphed is not None else None
+
+    def e2e_overlapped_leg():
+        """-> (ms per clip, relative max difference of its results to the first end-to-end leg's) or None.  In the first leg a clip's 377 MB
+        device->host copy sits on the temporal stage's stream and its slot is one of two, so nothing else runs while it
+        drains (27.1 vs 20.2 ms per clip in round 1's run).  Same public API (GraphedClipRunner.submit with host buffers),
+        same per-step copies inside the timed region."""
+        nonlocal graphed
+        first = graphed
+        try:
+            graphed = GraphedClipRunner(runner, resident, depth=3, vis=vis, d2h_stream=True)
+            ms = timed("e2e", args.steps, 3)
+            torch.cuda.synchronize()
+            # same inputs -> same results, up to the GEMM algorithms a second capture may pick: relative max difference
+            diff = max(float((d2h[k].float() - d2h_ref[k].float()).abs().max() / d2h_ref[k].float().abs().max().clamp_min(1e-6))
+                       for k in d2h)
+            return ms, diff
+        except Exception as exc:                                  # keep the measured first leg; say why
+            sys.stderr.write("bench: overlapped end-to-end leg failed: %r\n" % (exc,))
+            return None
+        finally:
+            graphed = first
+
     if rank != 0:
+        if graphed is not None and not args.d2h_stream and args.temporal == "replicated":
+            watchdog = threading.Timer(120.0, lambda: os._exit(0))
+            watchdog.daemon = True
+            watchdog.start()
+            e2e_overlapped_leg()                                 # the timer stays armed: rank 0 may leave without the barrier
         finish()
         return
 
@@ -368,6 +411,26 @@ def main():
             "e2e": {"value": round(T / ms_e2e * 1e3, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": round(ms_e2e, 3)},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+    line["e2e"]["pipeline"] = ("eager, one clip at a time" if graphed is None else
+                               "result copies on their own stream" if args.d2h_stream else
+                               "2 clips in flight, result copies on the temporal stage's stream")
+    if graphed is not None and not args.d2h_stream and args.temporal == "replicated":
+        # The line above is complete and measured: if the extra leg hangs (it is new on a device), print it and leave.
+        def bail():
+            line["e2e"]["overlapped_leg"] = "timed out"
+            print(json.dumps(line), flush=True)
+            os._exit(0)
+        watchdog = threading.Timer(120.0, bail)
+        watchdog.daemon = True
+        watchdog.start()
+        res = e2e_overlapped_leg()
+        watchdog.cancel()
+        if res is None:
+            line["e2e"]["overlapped_leg"] = "failed (see stderr)"
+            print(json.dumps(line), flush=True)
+            sys.stdout.flush()
+            os._exit(0)                                           # the CUDA context may be unusable: no teardown
+        merge_e2e_legs(line["e2e"], T, ms_e2e, *res)
     print(json.dumps(line), flush=True)
     finish()
 

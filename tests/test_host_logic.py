@@ -48,3 +48,16 @@ def test_bench_helpers():
         "0, 1950, 1965, 500.0, 0x0, Not Active, Not Active, Not Active, Not Active"]
     out = s.stop()
     assert out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["samples"] == 3
+
+
+def test_bench_e2e_leg_merge():
+    """bench.merge_e2e_legs: both legs reported; the headline switches only to a faster leg with agreeing results."""
+    import bench
+    base = {"value": 590.04, "unit": "frames/s", "ms_per_step": 27.117, "pipeline": "first"}
+    e = bench.merge_e2e_legs(dict(base), 16, 27.117, 20.5, 0.0)
+    assert e["ms_per_step"] == 20.5 and abs(e["value"] - 16 / 20.5e-3) < 0.01 and "3 clips" in e["pipeline"]
+    assert list(e["legs_ms_per_step"].values()) == [27.117, 20.5]
+    slower = bench.merge_e2e_legs(dict(base), 16, 27.117, 30.0, 0.0)
+    assert slower["value"] == 590.04 and slower["pipeline"] == "first" and slower["legs_ms_per_step"]
+    wrong = bench.merge_e2e_legs(dict(base), 16, 27.117, 20.5, 0.5)
+    assert wrong["value"] == 590.04 and wrong["overlapped_leg_rel_max_diff_vs_first_leg"] == 0.5
