@@ -61,3 +61,22 @@ def test_bench_e2e_leg_merge():
     assert slower["value"] == 590.04 and slower["pipeline"] == "first" and slower["legs_ms_per_step"]
     wrong = bench.merge_e2e_legs(dict(base), 16, 27.117, 20.5, 0.5)
     assert wrong["value"] == 590.04 and wrong["overlapped_leg_rel_max_diff_vs_first_leg"] == 0.5
+
+
+def test_bench_round_robin_leg_merge():
+    """bench.merge_round_robin_leg: times always reported; value / e2e switch only where faster and results agree."""
+    import bench
+
+    def base():
+        return {"value": 1833.0, "ms_per_step": 8.73, "config": {"parallelism": "8 GPUs", "execution": "2 graphs"},
+                "e2e": {"value": 1500.0, "ms_per_step": 10.67, "pipeline": "first", "legs_ms_per_step": {"a": 10.67}}}
+    ln = bench.merge_round_robin_leg(base(), 16, 3.2, 4.0, 1e-4)
+    assert ln["ms_per_step"] == 3.2 and ln["value"] == 5000.0 and "round-robin" in ln["config"]["parallelism"]
+    assert ln["e2e"]["ms_per_step"] == 4.0 and ln["e2e"]["value"] == 4000.0 and len(ln["e2e"]["legs_ms_per_step"]) == 2
+    assert ln["temporal_stage_legs_ms_per_step"]["replicated on every rank"] == 8.73
+    mixed = bench.merge_round_robin_leg(base(), 16, 3.2, 12.0, 0.0)
+    assert mixed["value"] == 5000.0 and mixed["e2e"]["value"] == 1500.0 and mixed["e2e"]["pipeline"] == "first"
+    for bad in (0.3, float("nan")):
+        ln = bench.merge_round_robin_leg(base(), 16, 3.2, 4.0, bad)
+        assert ln["value"] == 1833.0 and ln["e2e"]["value"] == 1500.0 and ln["config"]["parallelism"] == "8 GPUs"
+        assert ln["temporal_stage_legs_ms_per_step"]["owned round-robin per clip + 1 broadcast"] == 3.2
