@@ -1,0 +1,150 @@
+"""TEST INFRASTRUCTURE ONLY.  Rehearse bench.py's `main()` WITHOUT a GPU: the real control flow of the measured legs and of
+the guarded extra legs (overlapped end-to-end leg; with --world 2 semantics the round-robin leg is forced on one rank), the
+real runners and module fast paths, every CUDA-core kernel on the SIMT emulator, a fake CUDA runtime (streams / events are
+no-ops, a graph replay re-runs the region the runner captured).  Sizes are cut down (32x64 frames, 2 frames, 10 queries, 1-2
+layers per stack).  Times printed by this run mean nothing; what it checks is that the line is assembled, the extra legs
+run, their results agree with the first leg's and the merge logic sees them.
+
+    python tests/simt/rehearse_bench.py [--force-round-robin] [--break-leg]
+"""
+import contextlib
+import functools
+import io
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "simt")]
+from emulated_device import emulated_b200  # noqa: E402
+from rehearse_gpu_tests import install_host_shims  # noqa: E402
+
+import bench  # noqa: E402
+
+
+class _Stream:
+    def __init__(self, priority=0):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, event):
+        pass
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def elapsed_time(self, other):
+        return 1.0
+
+
+class _Graph:
+    """No capture on CPU: the runner constructors are wrapped (give_graphs_bodies) so that every graph of a slot gets a body
+    recomputing what the captured region computes, from the slot's buffers into the slot's buffers."""
+    body = None
+
+    def replay(self):
+        self.body()
+
+
+def give_graphs_bodies():
+    import dvis_plus_b200.pipeline as P
+    g_init, r_init = P.GraphedClipRunner.__init__, P.RoundRobinClipRunner.__init__
+
+    def graphed_init(self, runner, *a, **k):
+        g_init(self, runner, *a, **k)
+        for slot in self.slots:
+            def stage_a(slot=slot):
+                blk, mf = runner.segment_stage(slot["in"])
+                slot["block"].copy_(blk)
+                slot["mf"].copy_(mf)
+
+            def stage_b(slot=slot):
+                out = self._stage_b(slot["gathered"], slot["mf"], self._C(slot["block"]))
+                for key in out:
+                    slot["out"][key].copy_(out[key])
+            slot["ga"].body, slot["gb"].body = stage_a, stage_b
+
+    def rr_init(self, runner, *a, **k):
+        r_init(self, runner, *a, **k)
+        for slot in self.slots:
+            def stage_a(slot=slot):
+                blk, mf = runner.segment_stage(slot["in"])
+                slot["block"].copy_(blk)
+                slot["mf"].copy_(mf)
+
+            def temporal(slot=slot):
+                slot["payload"].copy_(self._payload(slot["gathered"], self._C(slot["block"])))
+
+            def masks(slot=slot):
+                out = self._finish(slot["payload"], slot["mf"], self._C(slot["block"]))
+                for key in out:
+                    slot["out"][key].copy_(out[key])
+            slot["ga"].body, slot["gt"].body, slot["gm"].body = stage_a, temporal, masks
+    P.GraphedClipRunner.__init__, P.RoundRobinClipRunner.__init__ = graphed_init, rr_init
+
+
+def run(argv, force_round_robin=False, break_leg=False):
+    install_host_shims()
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+    torch.cuda.is_available = lambda: True
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.Stream, torch.cuda.Event, torch.cuda.CUDAGraph = _Stream, _Event, _Graph
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    torch.cuda.graph = lambda g, stream=None: contextlib.nullcontext()
+    torch.cuda.is_current_stream_capturing = lambda: False
+    bench.synthetic_features = functools.partial(bench.synthetic_features, hw=(32, 64))
+    bench.build_models = functools.partial(bench.build_models, enc_layers=1, dec_layers=2, trk_layers=1, ref_layers=1)
+    give_graphs_bodies()
+    if break_leg:
+        import dvis_plus_b200.pipeline as P
+        orig = P.GraphedClipRunner.__init__
+
+        def init(self, *a, **k):
+            if k.get("depth") == 3:
+                raise RuntimeError("injected failure of the overlapped leg")
+            orig(self, *a, **k)
+        P.GraphedClipRunner.__init__ = init
+    exits = []
+    os._exit = lambda code: (_ for _ in ()).throw(SystemExit(code)) if not exits.append(code) else None
+    sys.argv = ["bench.py"] + argv
+    out = io.StringIO()
+    with emulated_b200(), contextlib.redirect_stdout(out):
+        try:
+            if force_round_robin:
+                _force_round_robin(bench)
+            bench.main()
+        except SystemExit:
+            pass
+    lines = [ln for ln in out.getvalue().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.getvalue()
+    return json.loads(lines[0])
+
+
+def _force_round_robin(bench_mod):
+    """Single process: make main() believe N > 1 only where it decides to run the round-robin leg (RoundRobinClipRunner
+    itself sees world 1 and skips the collectives)."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count("if world > 1:\n            res = round_robin_leg()") == 1
+    src = src.replace("if world > 1:\n            res = round_robin_leg()", "if True:\n            res = round_robin_leg()")
+    code = compile(src, os.path.join(ROOT, "bench.py"), "exec")
+    keep = {k: getattr(bench_mod, k) for k in ("synthetic_features", "build_models")}
+    exec(code, bench_mod.__dict__)
+    for k, v in keep.items():
+        setattr(bench_mod, k, v)
+
+
+if __name__ == "__main__":
+    flags = set(sys.argv[1:])
+    line = run(["--frames", "2", "--queries", "10", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"],
+               force_round_robin="--force-round-robin" in flags, break_leg="--break-leg" in flags)
+    print(json.dumps(line, indent=1))

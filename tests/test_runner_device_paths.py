@@ -192,3 +192,21 @@ def test_device_branches_with_fused_vis_postprocessing(cls, monkeypatch):
             for k in ref:
                 assert torch.equal(out[k], ref[k]), (cls.__name__, i, k)
             assert ops.unpack_masks(out["pred_masks"], 61).shape == (4, T, 41, 61)
+
+
+@pytest.mark.timeout(900)
+def test_bench_main_rehearsal_including_the_guarded_extra_legs():
+    """bench.py's main() end to end on the emulated device + fake runtime (tests/simt/rehearse_bench.py, own process because
+    it patches torch globally): the line is assembled, both guarded extra legs (overlapped end-to-end, round-robin temporal
+    stage) run through the real runners, and their results agree with the first leg's."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tests", "simt", "rehearse_bench.py"), "--force-round-robin"],
+                       capture_output=True, text=True, timeout=850, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout[p.stdout.index("{"):])
+    assert "extra_legs" not in line and line["gpu_launches"] > 0 and line["roofline"]["kernel"].startswith("msda")
+    assert len(line["e2e"]["legs_ms_per_step"]) == 3 and len(line["temporal_stage_legs_ms_per_step"]) == 2
+    assert line["e2e"]["overlapped_leg_rel_max_diff_vs_first_leg"] <= 1e-2
+    assert line["round_robin_leg_rel_max_diff_vs_replicated"] <= 1e-2
