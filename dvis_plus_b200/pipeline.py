@@ -519,8 +519,13 @@ class RoundRobinClipRunner:
     own frames.  Per clip and rank that is 1/G of a temporal stage, overlapped with the other ranks' per-frame work:
 
         stream A   seg(n)  gather(n)  seg(n+1)  gather(n+1) ...                  (all ranks, every clip)
-        stream B   [temporal(n) if n mod G == rank]  broadcast(n)  masks(n) ...  (2nd communicator: broadcasts never
+        stream T   temporal(n) for the clips this rank owns (n mod G == rank)
+        stream B   broadcast(n)  masks(n)  broadcast(n+1) ...                    (2nd communicator: broadcasts never
                                                                                    queue behind the all-gathers)
+
+    The temporal stage has a stream of its own: broadcast(n) completes only when clip n's owner has finished temporal(n), so
+    on one in-order stream the owner of clip n+1 could not start temporal(n+1) before temporal(n) had finished on ANOTHER
+    rank -- the temporal stages of the G ranks would run one after the other and nothing would be gained.
 
     Every rank issues the same collectives in the same order on each communicator.  `depth` slots (default G + 2) bound
     the clips in flight.  With CUDA tensors the three stages are captured into CUDA graphs per slot (like
@@ -543,6 +548,7 @@ class RoundRobinClipRunner:
         self.slots = []
         if self.cuda:
             self.stream_a, self.stream_b, self.stream_c = torch.cuda.Stream(), torch.cuda.Stream(priority=-1), torch.cuda.Stream()
+            self.stream_t = torch.cuda.Stream(priority=-1)           # the owner's temporal stage (see the class docstring)
             with torch.no_grad():
                 for _ in range(2):                                   # populate caches / autotune outside capture
                     blk, mf = runner.segment_stage(example_features)
@@ -585,7 +591,7 @@ class RoundRobinClipRunner:
                     blk, _ = r.segment_stage(slot["in"])
                 slot["gathered"] = blk.new_zeros((self.world * blk.shape[0],) + tuple(blk.shape[1:]))
                 slot["payload"] = blk.new_zeros(self._payload_shape(slot["gathered"]))
-                slot.update(ev_a=torch.cuda.Event(), ev_b=torch.cuda.Event(), ev_c=torch.cuda.Event())
+                slot.update(ev_a=torch.cuda.Event(), ev_b=torch.cuda.Event(), ev_c=torch.cuda.Event(), ev_t=torch.cuda.Event())
             return slot
         from . import _lib
         n0 = _lib.launch_count
@@ -596,12 +602,13 @@ class RoundRobinClipRunner:
         slot["gathered"] = torch.zeros((self.world * slot["block"].shape[0],) + tuple(slot["block"].shape[1:]),
                                        dtype=slot["block"].dtype, device=slot["block"].device)
         gt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gt, stream=self.stream_b), torch.no_grad():
+        with torch.cuda.graph(gt, stream=self.stream_t), torch.no_grad():   # captured where it replays: own cuBLAS workspace
             slot["payload"] = self._payload(slot["gathered"], C)
         gm = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gm, stream=self.stream_b), torch.no_grad():
             slot["out"] = self._finish(slot["payload"], slot["mf"], C)
-        slot.update(ga=ga, gt=gt, gm=gm, ev_a=torch.cuda.Event(), ev_b=torch.cuda.Event(), ev_c=torch.cuda.Event())
+        slot.update(ga=ga, gt=gt, gm=gm, ev_a=torch.cuda.Event(), ev_b=torch.cuda.Event(), ev_c=torch.cuda.Event(),
+                    ev_t=torch.cuda.Event())
         self.captured_launches = _lib.launch_count - n0      # one clip's kernels if this rank owned every temporal stage
         return slot
 
@@ -648,14 +655,18 @@ class RoundRobinClipRunner:
             else:
                 slot["gathered"].copy_(slot["block"])
             slot["ev_a"].record(self.stream_a)
-        self.stream_b.wait_event(slot["ev_a"])
-        with torch.cuda.stream(self.stream_b):
-            C = self._C(slot["block"])
-            if owner == self.rank:
+        C = self._C(slot["block"])
+        if owner == self.rank:
+            self.stream_t.wait_event(slot["ev_a"])
+            with torch.cuda.stream(self.stream_t):
                 if self.graphs:
                     slot["gt"].replay()
                 else:
                     slot["payload"].copy_(self._payload(slot["gathered"], C))
+                slot["ev_t"].record(self.stream_t)
+            self.stream_b.wait_event(slot["ev_t"])
+        self.stream_b.wait_event(slot["ev_a"])
+        with torch.cuda.stream(self.stream_b):
             self._exchange(slot, owner)
             if self.graphs:
                 slot["gm"].replay()
@@ -674,3 +685,4 @@ class RoundRobinClipRunner:
         cur.wait_stream(self.stream_a)
         cur.wait_stream(self.stream_b)
         cur.wait_stream(self.stream_c)
+        cur.wait_stream(self.stream_t)
