@@ -190,6 +190,17 @@ def merge_round_robin_leg(line, frames, ms_resident, ms_e2e, rel_diff, tol=1e-2)
     return line
 
 
+def merge_sm_carveout_leg(line, frames, sms, ms_resident, rel_diff, tol=1e-2):
+    """Fold the leg captured with cuBLASLt leaving `sms` SMs to the temporal stage (1 GPU) into the line: always reported,
+    adopted as `value` only if faster and in agreement with the first leg."""
+    line["sm_carveout_leg"] = {"sms_left_free_by_cublaslt": sms, "ms_per_step": round(ms_resident, 3),
+                               "rel_max_diff_vs_first_leg": round(rel_diff, 6) if rel_diff < float("inf") else None}
+    if rel_diff <= tol and ms_resident < line["ms_per_step"]:
+        line.update(value=round(frames / ms_resident * 1e3, 2), ms_per_step=round(ms_resident, 3))
+        line["config"]["execution"] += "; cuBLASLt kernels leave %d SMs free for the temporal stage's stream" % sms
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -412,6 +423,29 @@ def main():
         finally:
             graphed = first
 
+    def sm_carveout_leg(sms=8):
+        """1 GPU -> (resident ms per clip, relative max difference to the first leg) or None.  The temporal stage is a chain
+        of ~900 tiny dependent kernels on a high-priority stream; while a persistent cuBLASLt kernel of the next clip's
+        per-frame stage owns every SM, the chain's next kernel has nowhere to run (pipelined 20.2 ms per clip against
+        16.2 ms of per-frame work in round 1's run).  Here the graphs are captured with cuBLASLt told to leave `sms` SMs
+        free (torch's SM carve-out -> CUBLASLT_MATMUL_DESC_SM_COUNT_TARGET)."""
+        nonlocal graphed
+        first = graphed
+        prev = torch._C._get_sm_carveout_experimental()
+        try:
+            torch._C._set_sm_carveout_experimental(sms)
+            graphed = GraphedClipRunner(runner, resident, depth=2, vis=vis)
+            ms = timed("resident", args.steps, 3)
+            graphed.submit(None, d2h)                             # one clip's results for the comparison
+            graphed.wait_all()
+            return ms, rel_diff_to_first_leg()
+        except Exception as exc:
+            sys.stderr.write("bench: SM carve-out leg failed: %r\n" % (exc,))
+            return None
+        finally:
+            torch._C._set_sm_carveout_experimental(prev)
+            graphed = first
+
     if rank != 0:
         if extra_legs:
             watchdog = threading.Timer(150.0, lambda: os._exit(0))   # stays armed: rank 0 may leave without the barrier
@@ -480,6 +514,11 @@ def main():
             if res is None:
                 leave("round-robin leg failed (see stderr)")
             merge_round_robin_leg(line, T, *res)
+        else:
+            res = sm_carveout_leg()
+            if res is None:
+                leave("SM carve-out leg failed (see stderr)")
+            merge_sm_carveout_leg(line, T, 8, *res)
         watchdog.cancel()
     print(json.dumps(line), flush=True)
     finish()

@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE ONLY.  Rehearse bench.py's `main()` WITHOUT a GPU: the real control flow of the measured legs and of
-the guarded extra legs (overlapped end-to-end leg; with --world 2 semantics the round-robin leg is forced on one rank), the
+the guarded extra legs (overlapped end-to-end leg, SM carve-out leg; --force-round-robin also runs the N > 1 round-robin leg on
+the single rank), the
 real runners and module fast paths, every CUDA-core kernel on the SIMT emulator, a fake CUDA runtime (streams / events are
 no-ops, a graph replay re-runs the region the runner captured).  Sizes are cut down (32x64 frames, 2 frames, 10 queries, 1-2
 layers per stack).  Times printed by this run mean nothing; what it checks is that the line is assembled, the extra legs
@@ -136,6 +137,8 @@ def _force_round_robin(bench_mod):
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert src.count("if world > 1:\n            res = round_robin_leg()") == 1
     src = src.replace("if world > 1:\n            res = round_robin_leg()", "if True:\n            res = round_robin_leg()")
+    assert src.count("        else:\n            res = sm_carveout_leg()") == 1       # ... and run the 1-GPU leg as well
+    src = src.replace("        else:\n            res = sm_carveout_leg()", "        if True:\n            res = sm_carveout_leg()")
     code = compile(src, os.path.join(ROOT, "bench.py"), "exec")
     keep = {k: getattr(bench_mod, k) for k in ("synthetic_features", "build_models")}
     exec(code, bench_mod.__dict__)

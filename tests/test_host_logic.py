@@ -80,3 +80,15 @@ def test_bench_round_robin_leg_merge():
         ln = bench.merge_round_robin_leg(base(), 16, 3.2, 4.0, bad)
         assert ln["value"] == 1833.0 and ln["e2e"]["value"] == 1500.0 and ln["config"]["parallelism"] == "8 GPUs"
         assert ln["temporal_stage_legs_ms_per_step"]["owned round-robin per clip + 1 broadcast"] == 3.2
+
+
+def test_bench_sm_carveout_leg_merge():
+    import bench
+
+    def base():
+        return {"value": 792.0, "ms_per_step": 20.2, "config": {"execution": "2 graphs"}}
+    ln = bench.merge_sm_carveout_leg(base(), 16, 8, 18.0, 1e-3)
+    assert ln["ms_per_step"] == 18.0 and abs(ln["value"] - 888.89) < 0.01 and "8 SMs" in ln["config"]["execution"]
+    for ms, diff in ((21.0, 0.0), (18.0, 0.5), (18.0, float("inf"))):
+        ln = bench.merge_sm_carveout_leg(base(), 16, 8, ms, diff)
+        assert ln["value"] == 792.0 and ln["config"]["execution"] == "2 graphs" and ln["sm_carveout_leg"]["ms_per_step"] == ms

@@ -197,8 +197,8 @@ def test_device_branches_with_fused_vis_postprocessing(cls, monkeypatch):
 @pytest.mark.timeout(900)
 def test_bench_main_rehearsal_including_the_guarded_extra_legs():
     """bench.py's main() end to end on the emulated device + fake runtime (tests/simt/rehearse_bench.py, own process because
-    it patches torch globally): the line is assembled, both guarded extra legs (overlapped end-to-end, round-robin temporal
-    stage) run through the real runners, and their results agree with the first leg's."""
+    it patches torch globally): the line is assembled, the guarded extra legs (overlapped end-to-end, round-robin temporal
+    stage, SM carve-out) run through the real runners, and their results agree with the first leg's."""
     import json
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -210,3 +210,4 @@ def test_bench_main_rehearsal_including_the_guarded_extra_legs():
     assert len(line["e2e"]["legs_ms_per_step"]) == 3 and len(line["temporal_stage_legs_ms_per_step"]) == 2
     assert line["e2e"]["overlapped_leg_rel_max_diff_vs_first_leg"] <= 1e-2
     assert line["round_robin_leg_rel_max_diff_vs_replicated"] <= 1e-2
+    assert line["sm_carveout_leg"]["rel_max_diff_vs_first_leg"] <= 1e-2
