@@ -520,6 +520,7 @@ def main():
                 leave("SM carve-out leg failed (see stderr)")
             merge_sm_carveout_leg(line, T, 8, *res)
         watchdog.cancel()
+        line["extra_legs"] = "completed"
     print(json.dumps(line), flush=True)
     finish()
 
