@@ -193,11 +193,13 @@ def merge_round_robin_leg(line, frames, ms_resident, ms_e2e, rel_diff, tol=1e-2)
 def merge_sm_carveout_leg(line, frames, sms, ms_resident, rel_diff, tol=1e-2):
     """Fold the leg captured with cuBLASLt leaving `sms` SMs to the temporal stage (1 GPU) into the line: always reported,
     adopted as `value` only if faster and in agreement with the first leg."""
-    line["sm_carveout_leg"] = {"sms_left_free_by_cublaslt": sms, "ms_per_step": round(ms_resident, 3),
-                               "rel_max_diff_vs_first_leg": round(rel_diff, 6) if rel_diff < float("inf") else None}
+    line.setdefault("sm_carveout_legs", []).append(
+        {"sms_left_free_by_cublaslt": sms, "ms_per_step": round(ms_resident, 3),
+         "rel_max_diff_vs_first_leg": round(rel_diff, 6) if rel_diff < float("inf") else None})
     if rel_diff <= tol and ms_resident < line["ms_per_step"]:
         line.update(value=round(frames / ms_resident * 1e3, 2), ms_per_step=round(ms_resident, 3))
-        line["config"]["execution"] += "; cuBLASLt kernels leave %d SMs free for the temporal stage's stream" % sms
+        line["config"]["execution"] = line["config"]["execution"].split("; cuBLASLt kernels leave")[0] + \
+            "; cuBLASLt kernels leave %d SMs free for the temporal stage's stream" % sms
     return line
 
 
@@ -515,10 +517,11 @@ def main():
                 leave("round-robin leg failed (see stderr)")
             merge_round_robin_leg(line, T, *res)
         else:
-            res = sm_carveout_leg()
-            if res is None:
-                leave("SM carve-out leg failed (see stderr)")
-            merge_sm_carveout_leg(line, T, 8, *res)
+            for sms in (8, 16):
+                res = sm_carveout_leg(sms)
+                if res is None:
+                    leave("SM carve-out leg failed (see stderr)")
+                merge_sm_carveout_leg(line, T, sms, *res)
         watchdog.cancel()
         line["extra_legs"] = "completed"
     print(json.dumps(line), flush=True)

@@ -137,8 +137,8 @@ def _force_round_robin(bench_mod):
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert src.count("if world > 1:\n            res = round_robin_leg()") == 1
     src = src.replace("if world > 1:\n            res = round_robin_leg()", "if True:\n            res = round_robin_leg()")
-    assert src.count("        else:\n            res = sm_carveout_leg()") == 1       # ... and run the 1-GPU leg as well
-    src = src.replace("        else:\n            res = sm_carveout_leg()", "        if True:\n            res = sm_carveout_leg()")
+    assert src.count("        else:\n            for sms in (8, 16):") == 1              # ... and run the 1-GPU legs as well
+    src = src.replace("        else:\n            for sms in (8, 16):", "        if True:\n            for sms in (8, 16):")
     code = compile(src, os.path.join(ROOT, "bench.py"), "exec")
     keep = {k: getattr(bench_mod, k) for k in ("synthetic_features", "build_models")}
     exec(code, bench_mod.__dict__)

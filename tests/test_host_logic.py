@@ -91,4 +91,7 @@ def test_bench_sm_carveout_leg_merge():
     assert ln["ms_per_step"] == 18.0 and abs(ln["value"] - 888.89) < 0.01 and "8 SMs" in ln["config"]["execution"]
     for ms, diff in ((21.0, 0.0), (18.0, 0.5), (18.0, float("inf"))):
         ln = bench.merge_sm_carveout_leg(base(), 16, 8, ms, diff)
-        assert ln["value"] == 792.0 and ln["config"]["execution"] == "2 graphs" and ln["sm_carveout_leg"]["ms_per_step"] == ms
+        assert ln["value"] == 792.0 and ln["config"]["execution"] == "2 graphs" and ln["sm_carveout_legs"][0]["ms_per_step"] == ms
+    ln = bench.merge_sm_carveout_leg(bench.merge_sm_carveout_leg(base(), 16, 8, 18.0, 0.0), 16, 16, 17.0, 0.0)
+    assert ln["ms_per_step"] == 17.0 and ln["config"]["execution"].count("cuBLASLt") == 1 and "16 SMs" in ln["config"]["execution"]
+    assert [l["sms_left_free_by_cublaslt"] for l in ln["sm_carveout_legs"]] == [8, 16]

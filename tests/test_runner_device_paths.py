@@ -210,4 +210,5 @@ def test_bench_main_rehearsal_including_the_guarded_extra_legs():
     assert len(line["e2e"]["legs_ms_per_step"]) == 3 and len(line["temporal_stage_legs_ms_per_step"]) == 2
     assert line["e2e"]["overlapped_leg_rel_max_diff_vs_first_leg"] <= 1e-2
     assert line["round_robin_leg_rel_max_diff_vs_replicated"] <= 1e-2
-    assert line["sm_carveout_leg"]["rel_max_diff_vs_first_leg"] <= 1e-2
+    assert [l["sms_left_free_by_cublaslt"] for l in line["sm_carveout_legs"]] == [8, 16]
+    assert all(l["rel_max_diff_vs_first_leg"] <= 1e-2 for l in line["sm_carveout_legs"])
