@@ -104,7 +104,7 @@ def run(argv, force_round_robin=False, break_leg=False):
     torch.cuda.graph = lambda g, stream=None: contextlib.nullcontext()
     torch.cuda.is_current_stream_capturing = lambda: False
     bench.synthetic_features = functools.partial(bench.synthetic_features, hw=(32, 64))
-    bench.build_models = functools.partial(bench.build_models, enc_layers=1, dec_layers=2, trk_layers=1, ref_layers=1)
+    bench.build_models = functools.partial(bench.build_models, enc_layers=1, dec_layers=1, trk_layers=1, ref_layers=1)
     give_graphs_bodies()
     if break_leg:
         import dvis_plus_b200.pipeline as P
@@ -148,6 +148,6 @@ def _force_round_robin(bench_mod):
 
 if __name__ == "__main__":
     flags = set(sys.argv[1:])
-    line = run(["--frames", "2", "--queries", "10", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"],
+    line = run(["--frames", "2", "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"],
                force_round_robin="--force-round-robin" in flags, break_leg="--break-leg" in flags)
     print(json.dumps(line, indent=1))
