@@ -6,7 +6,7 @@ no-ops, a graph replay re-runs the region the runner captured).  Sizes are cut d
 layers per stack).  Times printed by this run mean nothing; what it checks is that the line is assembled, the extra legs
 run, their results agree with the first leg's and the merge logic sees them.
 
-    python tests/simt/rehearse_bench.py [--force-round-robin] [--break-leg]
+    python tests/simt/rehearse_bench.py [--force-round-robin] [--break-leg] [--world2]
 """
 import contextlib
 import functools
@@ -115,6 +115,10 @@ def run(argv, force_round_robin=False, break_leg=False):
                 raise RuntimeError("injected failure of the overlapped leg")
             orig(self, *a, **k)
         P.GraphedClipRunner.__init__ = init
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:                    # --world 2: the ranks talk over gloo
+        import torch.distributed as dist
+        orig_init = dist.init_process_group
+        dist.init_process_group = lambda backend=None, device_id=None, **k: orig_init("gloo", **k)
     exits = []
     os._exit = lambda code: (_ for _ in ()).throw(SystemExit(code)) if not exits.append(code) else None
     sys.argv = ["bench.py"] + argv
@@ -127,8 +131,27 @@ def run(argv, force_round_robin=False, break_leg=False):
         except SystemExit:
             pass
     lines = [ln for ln in out.getvalue().splitlines() if ln.startswith("{")]
+    if int(os.environ.get("RANK", "0")) != 0:
+        assert not lines, out.getvalue()                              # only rank 0 prints
+        return None
     assert len(lines) == 1, out.getvalue()
     return json.loads(lines[0])
+
+
+def run_world(world, port=29631):
+    """bench.py on `world` ranks (one process each, gloo): frames sharded, the real all-gather / broadcast / barriers, and
+    the non-zero ranks' side of the guarded extra legs.  -> rank 0's line."""
+    import subprocess
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="4")
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--as-rank"], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=1500) for p in procs]
+    for rank, (p, (o, e)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d: %s" % (rank, e[-3000:])
+    return json.loads(outs[0][0][outs[0][0].index("{"):])
 
 
 def _force_round_robin(bench_mod):
@@ -148,6 +171,15 @@ def _force_round_robin(bench_mod):
 
 if __name__ == "__main__":
     flags = set(sys.argv[1:])
+    if "--world2" in flags:
+        print(json.dumps(run_world(2), indent=1))
+        sys.exit(0)
+    if "--as-rank" in flags:
+        w = os.environ["WORLD_SIZE"]
+        line = run(["--gpus", w, "--frames", w, "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"])
+        if line is not None:
+            print(json.dumps(line))
+        sys.exit(0)
     line = run(["--frames", "2", "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"],
                force_round_robin="--force-round-robin" in flags, break_leg="--break-leg" in flags)
     print(json.dumps(line, indent=1))

@@ -195,20 +195,26 @@ def test_device_branches_with_fused_vis_postprocessing(cls, monkeypatch):
 
 
 @pytest.mark.timeout(900)
-def test_bench_main_rehearsal_including_the_guarded_extra_legs():
-    """bench.py's main() end to end on the emulated device + fake runtime (tests/simt/rehearse_bench.py, own process because
-    it patches torch globally): the line is assembled, the guarded extra legs (overlapped end-to-end, round-robin temporal
-    stage, SM carve-out) run through the real runners, and their results agree with the first leg's."""
+@pytest.mark.parametrize("mode", ["one_rank", "two_ranks_gloo"])
+def test_bench_main_rehearsal_including_the_guarded_extra_legs(mode):
+    """bench.py's main() end to end on the emulated device + fake runtime (tests/simt/rehearse_bench.py, own processes
+    because it patches torch globally): the line is assembled and the guarded extra legs run through the real runners with
+    results that agree with the first leg's -- on one rank the overlapped end-to-end leg and the SM carve-out legs, on two
+    ranks (gloo: real all-gather / broadcast / barriers, both ranks' sides of the protocol) the round-robin leg."""
     import json
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, os.path.join(root, "tests", "simt", "rehearse_bench.py"), "--force-round-robin"],
+    flag = [] if mode == "one_rank" else ["--world2"]
+    p = subprocess.run([sys.executable, os.path.join(root, "tests", "simt", "rehearse_bench.py")] + flag,
                        capture_output=True, text=True, timeout=850, cwd=root)
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout[p.stdout.index("{"):])
     assert line["extra_legs"] == "completed" and line["gpu_launches"] > 0 and line["roofline"]["kernel"].startswith("msda")
-    assert len(line["e2e"]["legs_ms_per_step"]) == 3 and len(line["temporal_stage_legs_ms_per_step"]) == 2
     assert line["e2e"]["overlapped_leg_rel_max_diff_vs_first_leg"] <= 1e-2
-    assert line["round_robin_leg_rel_max_diff_vs_replicated"] <= 1e-2
-    assert [l["sms_left_free_by_cublaslt"] for l in line["sm_carveout_legs"]] == [8, 16]
-    assert all(l["rel_max_diff_vs_first_leg"] <= 1e-2 for l in line["sm_carveout_legs"])
+    if mode == "one_rank":
+        assert line["n_gpus"] == 1 and len(line["e2e"]["legs_ms_per_step"]) == 2
+        assert [l["sms_left_free_by_cublaslt"] for l in line["sm_carveout_legs"]] == [8, 16]
+        assert all(l["rel_max_diff_vs_first_leg"] <= 1e-2 for l in line["sm_carveout_legs"])
+    else:
+        assert line["n_gpus"] == 2 and len(line["e2e"]["legs_ms_per_step"]) == 3
+        assert len(line["temporal_stage_legs_ms_per_step"]) == 2 and line["round_robin_leg_rel_max_diff_vs_replicated"] <= 1e-2
