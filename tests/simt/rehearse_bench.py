@@ -172,11 +172,14 @@ def _force_round_robin(bench_mod):
 if __name__ == "__main__":
     flags = set(sys.argv[1:])
     if "--world2" in flags:
+        if "--break-leg" in flags:
+            os.environ["REHEARSE_BREAK_LEG"] = "1"
         print(json.dumps(run_world(2), indent=1))
         sys.exit(0)
     if "--as-rank" in flags:
         w = os.environ["WORLD_SIZE"]
-        line = run(["--gpus", w, "--frames", w, "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"])
+        line = run(["--gpus", w, "--frames", w, "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"],
+                   break_leg=os.environ.get("REHEARSE_BREAK_LEG") == "1")
         if line is not None:
             print(json.dumps(line))
         sys.exit(0)
