@@ -16,7 +16,9 @@ def pytest_configure(config):
 
 # GPU tests written after round 1's last B200 run (checked on the SIMT emulator only): they run after every
 # device-verified test, so a first-run surprise in one of them cannot hide the verified results behind `-x`.
-FIRST_DEVICE_RUN_PENDING = ("test_vis_masks_tiled_variant_is_bit_identical", "test_zz_config5_gpu")
+FIRST_DEVICE_RUN_PENDING = ("test_pipeline_vis_from_block_equals_postprocessing_all_masks", "test_vis_masks_packed",
+                            "test_vis_module_packed_transfer_equals_plain", "test_vis_masks_tiled_variant_is_bit_identical",
+                            "test_zz_config5_gpu")
 
 
 def pytest_collection_modifyitems(config, items):
