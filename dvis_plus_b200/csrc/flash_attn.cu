@@ -1,0 +1,269 @@
+// Multi-head attention core on the warp tensor cores, built for the SHORT-query attentions of the temporal stage:
+//   out[b, i, h, :] = softmax_j(scale * <q[b,i,h,:], k[b,j,h,:]> [masked]) @ v[b,j,h,:]
+// i.e. what nn.MultiheadAttention computes between its in- and out-projections in SelfAttentionLayer / CrossAttentionLayer
+// (P/mask2former_video/modeling/transformer_decoder/video_mask2former_transformer_decoder.py:46,104),
+// ReferringCrossAttentionLayer (P/dvis_Plus/tracker.py:45) and, with the bit mask, the segmenter decoder's masked
+// cross-attention (P/dvis_Plus/video_mask2former_transformer_decoder.py:295-315).
+//
+// Q = 200 rows is a LATENCY problem (one cuDNN flash call costs ~7 us here, 150 of them per clip), so the work is cut
+// for the shortest dependent chain instead of for reuse: a CTA owns 16 query rows of one (batch, head) -- 13 x 8 = 104
+// CTAs for one 200-query layer -- and its 4 warps split the KEYS (flash-decoding): warp w walks key blocks w, w+4, ...
+// of 64 keys with an online softmax in registers (mma.sync m16n8k16, bf16 operands, fp32 accumulate), K / V blocks
+// arrive through a warp-private cp.async ring (1 or 2 stages), and the 4 partial (max, sum, O) states are merged
+// through shared memory at the end.  Strides are explicit so q / k / v can be slices of a packed projection output.
+#include "mma.cuh"
+
+namespace dvis {
+namespace {
+
+constexpr int kFaWarps = 4;
+constexpr int kFaKeys = 64;    // keys per block
+constexpr int kFaRows = 16;    // query rows per CTA
+
+struct FlashParams {
+  const __nv_bfloat16 *q, *k, *v;
+  __nv_bfloat16 *o;
+  int64_t q_row, q_batch, q_head, k_row, k_batch, k_head, v_row, v_batch, v_head, o_row, o_batch;   // element strides
+  const uint8_t *mask;          // optional bits: (key j of row i) set -> j may NOT be attended; shared by the heads
+  int64_t mask_row, mask_batch; // bytes; mask_row % 8 == 0
+  int B, Lq, Lk, H;
+  float scale_log2e;
+  int stages;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashParams p) {
+  constexpr int RS = DH + 8;                       // padded row stride (bf16): 16-byte aligned, ldmatrix conflict-free
+  constexpr int TILE = kFaKeys * RS;               // elements of one K (or V) block
+  constexpr int KSTEPS = DH / 16, DT = DH / 8;
+  extern __shared__ uint4 fa_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, row0 = blockIdx.x * kFaRows;
+  __nv_bfloat16 *wbase = reinterpret_cast<__nv_bfloat16 *>(fa_smem) + (size_t)warp * p.stages * 2 * TILE;
+  const __nv_bfloat16 *kb = p.k + (size_t)b * p.k_batch + (size_t)h * p.k_head;
+  const __nv_bfloat16 *vb = p.v + (size_t)b * p.v_batch + (size_t)h * p.v_head;
+  const int nblocks = (p.Lk + kFaKeys - 1) / kFaKeys;
+
+  auto issue = [&](int blk, int stage) {           // this warp's copy of key block `blk` into ring slot `stage`
+    __nv_bfloat16 *sk = wbase + (size_t)stage * 2 * TILE, *sv = sk + TILE;
+    const int key0 = blk * kFaKeys;
+    constexpr int CH = DH / 8;                     // 16-byte chunks per row
+    // rows the MMAs below touch: whole 16-key steps that hold at least one valid key (the rest of the slot is never read);
+    // rows past Lk are zero-filled so that 0-probability x V stays 0
+    const int rows = min(kFaKeys, ((p.Lk - key0 + 15) >> 4) << 4);
+    for (int c = lane; c < rows * CH; c += 32) {
+      const int r = c / CH, cc = c - r * CH, key = key0 + r;
+      const bool ok = key < p.Lk;
+      const size_t kr = ok ? (size_t)key : 0;
+      cp_async_16(sk + r * RS + cc * 8, kb + kr * p.k_row + cc * 8, ok ? 16 : 0);
+      cp_async_16(sv + r * RS + cc * 8, vb + kr * p.v_row + cc * 8, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  pdl_wait();
+  if (warp < nblocks) issue(warp, 0);
+
+  // Q fragments of rows (g, g+8) straight from global memory
+  uint32_t qa[KSTEPS][4];
+  {
+    const int r0 = row0 + g, r1 = row0 + g + 8;
+    const __nv_bfloat16 *q0 = p.q + (size_t)b * p.q_batch + (size_t)h * p.q_head + (size_t)min(r0, p.Lq - 1) * p.q_row;
+    const __nv_bfloat16 *q1 = p.q + (size_t)b * p.q_batch + (size_t)h * p.q_head + (size_t)min(r1, p.Lq - 1) * p.q_row;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      qa[ks][0] = *reinterpret_cast<const uint32_t *>(q0 + ks * 16 + 2 * t);
+      qa[ks][1] = *reinterpret_cast<const uint32_t *>(q1 + ks * 16 + 2 * t);
+      qa[ks][2] = *reinterpret_cast<const uint32_t *>(q0 + ks * 16 + 2 * t + 8);
+      qa[ks][3] = *reinterpret_cast<const uint32_t *>(q1 + ks * 16 + 2 * t + 8);
+    }
+  }
+
+  float o[DT][4];
+#pragma unroll
+  for (int i = 0; i < DT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const uint8_t *mk0 = nullptr, *mk1 = nullptr;
+  if (p.mask) {
+    mk0 = p.mask + (size_t)b * p.mask_batch + (size_t)min(row0 + g, p.Lq - 1) * p.mask_row;
+    mk1 = p.mask + (size_t)b * p.mask_batch + (size_t)min(row0 + g + 8, p.Lq - 1) * p.mask_row;
+  }
+
+  int it = 0;
+  for (int blk = warp; blk < nblocks; blk += kFaWarps, ++it) {
+    const int stage = p.stages == 2 ? (it & 1) : 0;
+    const bool more = blk + kFaWarps < nblocks;
+    if (p.stages == 2 && more) {
+      issue(blk + kFaWarps, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    const __nv_bfloat16 *sk = wbase + (size_t)stage * 2 * TILE, *sv = sk + TILE;
+    const int key0 = blk * kFaKeys;
+    const int nkeys = min(kFaKeys, p.Lk - key0);
+    const int nkt = (nkeys + 7) >> 3;              // 8-key tiles that hold at least one valid key
+
+    // ---- S = Q K^T ----
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {               // pairs of 8-key tiles
+      if (2 * np < nkt) {
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          uint32_t bf[4];
+          const int key = (2 * np + (lane >> 4)) * 8 + (lane & 7), d = ks * 16 + ((lane >> 3) & 1) * 8;
+          ldmatrix_x4(bf, sk + key * RS + d);
+          mma_bf16_16816(s[2 * np], qa[ks], bf[0], bf[1]);
+          mma_bf16_16816(s[2 * np + 1], qa[ks], bf[2], bf[3]);
+        }
+      }
+    }
+    // ---- scale, mask, online softmax ----
+    uint64_t bits0 = 0, bits1 = 0;
+    if (p.mask) {
+      bits0 = *reinterpret_cast<const uint64_t *>(mk0 + (key0 >> 3));
+      bits1 = *reinterpret_cast<const uint64_t *>(mk1 + (key0 >> 3));
+    }
+    float mx0 = mrow[0], mx1 = mrow[1];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + 2 * t + (e & 1);
+        const bool dead = col >= nkeys || (((e < 2 ? bits0 : bits1) >> col) & 1);
+        s[nt][e] = dead ? -INFINITY : s[nt][e] * p.scale_log2e;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float use0 = mx0 == -INFINITY ? 0.f : mx0, use1 = mx1 == -INFINITY ? 0.f : mx1;   // rows with nothing open yet
+    const float al0 = exp2f(mrow[0] - use0), al1 = exp2f(mrow[1] - use1);
+    mrow[0] = mx0;
+    mrow[1] = mx1;
+    lrow[0] *= al0;
+    lrow[1] *= al1;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1;
+    }
+    uint32_t pa[4][4];                             // P as A fragments: k-step kk covers keys kk*16 .. kk*16+15
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] - use0), p1 = exp2f(s[nt][1] - use0);
+      const float p2 = exp2f(s[nt][2] - use1), p3 = exp2f(s[nt][3] - use1);
+      lrow[0] += p0 + p1;
+      lrow[1] += p2 + p3;
+      pa[nt >> 1][(nt & 1) * 2] = pack_bf16x2(p0, p1);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (2 * kk < nkt) {
+#pragma unroll
+        for (int dp = 0; dp < DT / 2; ++dp) {      // pairs of 8-wide output column tiles
+          uint32_t bf[4];
+          const int key = kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), d = (2 * dp + (lane >> 4)) * 8;
+          ldmatrix_x4_trans(bf, sv + key * RS + d);
+          mma_bf16_16816(o[2 * dp], pa[kk], bf[0], bf[1]);
+          mma_bf16_16816(o[2 * dp + 1], pa[kk], bf[2], bf[3]);
+        }
+      }
+    }
+    __syncwarp();                                  // every lane is done with this ring slot before it is refilled
+  }
+  pdl_launch_dependents();
+
+  // ---- merge the 4 warps' partial states ----
+  lrow[0] += __shfl_xor_sync(0xffffffffu, lrow[0], 1);
+  lrow[0] += __shfl_xor_sync(0xffffffffu, lrow[0], 2);
+  lrow[1] += __shfl_xor_sync(0xffffffffu, lrow[1], 1);
+  lrow[1] += __shfl_xor_sync(0xffffffffu, lrow[1], 2);
+  constexpr int OS = DH + 4;                       // fp32 row stride of the merge buffer
+  float *mo = reinterpret_cast<float *>(wbase);    // this warp's own ring memory: [16][OS] then m[16], l[16]
+  float *mm = mo + kFaRows * OS, *ml = mm + kFaRows;
+#pragma unroll
+  for (int i = 0; i < DT; ++i) {
+    *reinterpret_cast<float2 *>(mo + g * OS + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
+    *reinterpret_cast<float2 *>(mo + (g + 8) * OS + i * 8 + 2 * t) = make_float2(o[i][2], o[i][3]);
+  }
+  if (t == 0) {
+    mm[g] = mrow[0]; mm[g + 8] = mrow[1];
+    ml[g] = lrow[0]; ml[g + 8] = lrow[1];
+  }
+  __syncthreads();
+  const size_t wstride = (size_t)p.stages * 2 * TILE * sizeof(__nv_bfloat16) / sizeof(float);   // floats between warps' regions
+  const float *base = reinterpret_cast<const float *>(fa_smem);
+  for (int e = threadIdx.x; e < kFaRows * (DH / 2); e += kFaWarps * 32) {
+    const int r = e / (DH / 2), c = (e - r * (DH / 2)) * 2;
+    if (row0 + r >= p.Lq) continue;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kFaWarps; ++w) M = fmaxf(M, base[w * wstride + kFaRows * OS + r]);
+    float L = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kFaWarps; ++w) {
+      const float *wb = base + w * wstride;
+      const float mw = wb[kFaRows * OS + r];
+      const float f = mw == -INFINITY ? 0.f : exp2f(mw - M);
+      L += wb[kFaRows * OS + kFaRows + r] * f;
+      a0 += wb[r * OS + c] * f;
+      a1 += wb[r * OS + c + 1] * f;
+    }
+    const float inv = L > 0.f ? 1.f / L : 0.f;   // a row with every key masked (the mask producer never emits one) -> 0
+    __nv_bfloat16 *op = p.o + (size_t)b * p.o_batch + (size_t)(row0 + r) * p.o_row + (size_t)h * DH + c;
+    *reinterpret_cast<uint32_t *>(op) = pack_bf16x2(a0 * inv, a1 * inv);
+  }
+}
+
+template <int DH>
+int launch_flash(const FlashParams &p, cudaStream_t s) {
+  const size_t ring = (size_t)kFaWarps * p.stages * 2 * kFaKeys * (DH + 8) * sizeof(__nv_bfloat16);
+  cudaFuncSetAttribute(flash_attn_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring));
+  dim3 grid((p.Lq + kFaRows - 1) / kFaRows, p.H, p.B);
+  flash_attn_kernel<DH><<<grid, kFaWarps * 32, ring, s>>>(p);
+  return check_launch("flash_attn_kernel");
+}
+
+}  // namespace
+}  // namespace dvis
+
+using namespace dvis;
+
+extern "C" int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, int64_t q_head, const void *k, int64_t k_row,
+                               int64_t k_batch, int64_t k_head, const void *v, int64_t v_row, int64_t v_batch, int64_t v_head,
+                               void *out, int64_t o_row, int64_t o_batch, const void *mask_bits, int64_t mask_row_bytes,
+                               int64_t mask_batch_bytes, int B, int Lq, int Lk, int H, int Dh, float scale, void *stream) {
+  DVIS_REQUIRE(q && k && v && out, "flash_attn: null pointer argument");
+  DVIS_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && H > 0, "flash_attn: sizes must be positive");
+  DVIS_REQUIRE(B <= 65535 && H <= 65535, "flash_attn: batch / heads too large for the grid");
+  if (Dh != 32 && Dh != 64) return fail(DVIS_ERR_UNSUPPORTED, "flash_attn: head dim %d (built: 32, 64)", Dh);
+  const auto m8 = [](int64_t s) { return (s & 7) == 0; };
+  DVIS_REQUIRE(aligned16(k) && aligned16(v) && m8(k_row) && m8(k_batch) && m8(k_head) && m8(v_row) && m8(v_batch) && m8(v_head),
+               "flash_attn: k / v rows must be 16-byte aligned (pointer and strides multiples of 8 elements)");
+  const auto even = [](int64_t s) { return (s & 1) == 0; };
+  DVIS_REQUIRE((reinterpret_cast<uintptr_t>(q) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0 && even(q_row) &&
+                   even(q_batch) && even(q_head) && even(o_row) && even(o_batch),
+               "flash_attn: q / out must be 4-byte aligned (pointer and strides even)");
+  if (mask_bits) {
+    DVIS_REQUIRE((reinterpret_cast<uintptr_t>(mask_bits) & 7) == 0 && m8(mask_row_bytes) && m8(mask_batch_bytes) &&
+                     mask_row_bytes >= ((int64_t)(Lk + 63) / 64) * 8,
+                 "flash_attn: mask rows must be 8-byte aligned and hold ceil(Lk / 64) * 8 bytes");
+  }
+  FlashParams p{static_cast<const __nv_bfloat16 *>(q), static_cast<const __nv_bfloat16 *>(k), static_cast<const __nv_bfloat16 *>(v),
+                static_cast<__nv_bfloat16 *>(out), q_row, q_batch, q_head, k_row, k_batch, k_head, v_row, v_batch, v_head, o_row,
+                o_batch, static_cast<const uint8_t *>(mask_bits), mask_row_bytes, mask_batch_bytes, B, Lq, Lk, H,
+                scale * 1.4426950408889634f, 1};
+  const int nblocks = (Lk + kFaKeys - 1) / kFaKeys;
+  p.stages = nblocks > kFaWarps ? 2 : 1;           // a warp with more than one key block prefetches the next one
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return Dh == 32 ? launch_flash<32>(p, s) : launch_flash<64>(p, s);
+}

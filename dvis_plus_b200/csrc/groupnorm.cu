@@ -34,33 +34,59 @@ __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p, float4 v) {
 
 constexpr int kMaxGroups = 64;
 
-// ---- pass 1: per (n, group) sum and sum of squares, accumulated in double -----------------------------------
+// ---- pass 1: per (n, group) shifted sum and sum of squares ------------------------------------------------------
+// One CTA reduces one (sample, group) in a FIXED order -- no atomics, so the statistics (and everything downstream: bf16
+// roundings, thresholded attention masks, Hungarian decisions) are bit-identical from run to run; the first version
+// combined the threads' partial sums with shared-memory float atomics, whose arrival order made two runs of the same clip
+// differ by one bf16 ulp (profiles/r2_determinism.md).  Values are accumulated relative to a pivot K = x[n, pixel 0, first
+// channel of the group] (shifted-data variance: no cancellation when |mean| >> std), fp32 over runs of 16 pixels, double
+// across runs.  The 32 groups of a sample read interleaved 16-byte pieces of the same lines at the same time (L2 hits).
+template <typename T>
+__device__ __forceinline__ float gn_pivot(const T *x, int64_t batch_stride, int n, int g, int cpg) {
+  return float(ld4<T>(x + (size_t)n * batch_stride + (size_t)g * cpg).x);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const T *__restrict__ x, int64_t batch_stride, int HW, int C, int G,
-                                                       int pix_per_cta, double *__restrict__ sums) {
-  __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
-  const int n = blockIdx.y;
-  const int quads = C / 4, cpg = C / G;
-  const int cq = threadIdx.x % quads, pl = threadIdx.x / quads, prow = blockDim.x / quads;
-  if (threadIdx.x < G) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
-  const int p0 = blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, HW);
-  const T *xn = x + (size_t)n * batch_stride + cq * 4;
-  float s = 0.f, q = 0.f;
+                                                       double *__restrict__ sums) {
+  __shared__ double s_part[2][8];
+  const int g = blockIdx.x, n = blockIdx.y, cpg = C / G;
+  const int quads = min(cpg / 4, 256);
+  const int cq = threadIdx.x % quads, pl = threadIdx.x / quads, prow = 256 / quads;
+  const float K = gn_pivot<T>(x, batch_stride, n, g, cpg);
+  const T *xg = x + (size_t)n * batch_stride + (size_t)g * cpg;
+  double S = 0.0, Q = 0.0;
   if (pl < prow) {
-    for (int p = p0 + pl; p < p1; p += prow) {
-      const float4 v = ld4<T>(xn + (size_t)p * C);
-      s += v.x + v.y + v.z + v.w;
-      q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    for (int c = cq * 4; c < cpg; c += quads * 4) {
+      for (int pb = pl; pb < HW; pb += prow * 16) {
+        float s = 0.f, q = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int p = pb + i * prow;
+          if (p < HW) {
+            const float4 v = ld4<T>(xg + (size_t)p * C + c);
+            const float a = v.x - K, b = v.y - K, cc = v.z - K, d = v.w - K;
+            s += (a + b) + (cc + d);
+            q += (a * a + b * b) + (cc * cc + d * d);
+          }
+        }
+        S += double(s);
+        Q += double(q);
+      }
     }
-    const int g = (cq * 4) / cpg;
-    atomicAdd(&s_sum[g], s);
-    atomicAdd(&s_sq[g], q);
   }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {                       // fixed pairing: deterministic
+    S += __shfl_xor_sync(0xffffffffu, S, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_part[0][threadIdx.x >> 5] = S; s_part[1][threadIdx.x >> 5] = Q; }
   __syncthreads();
-  if (threadIdx.x < G) {
-    atomicAdd(&sums[((size_t)n * G + threadIdx.x) * 2], double(s_sum[threadIdx.x]));
-    atomicAdd(&sums[((size_t)n * G + threadIdx.x) * 2 + 1], double(s_sq[threadIdx.x]));
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < 8; ++w) { ts += s_part[0][w]; tq += s_part[1][w]; }
+    sums[((size_t)n * G + g) * 2] = ts;
+    sums[((size_t)n * G + g) * 2 + 1] = tq;
   }
 }
 
@@ -92,7 +118,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, in
   const int c = cq * 4, g = c / (p.C / p.G);
   const double inv_cnt = 1.0 / (double(p.HW) * double(p.C / p.G));
   const double su = p.sums[((size_t)n * p.G + g) * 2] * inv_cnt, sq = p.sums[((size_t)n * p.G + g) * 2 + 1] * inv_cnt;
-  const float mean = float(su);
+  const float mean = gn_pivot<T>(static_cast<const T *>(p.x), p.x_batch_stride, n, g, p.C / p.G) + float(su);   // sums are pivot-shifted
   const float rstd = rsqrtf(fmaxf(float(sq - su * su), 0.f) + p.eps);
   const float4 ga = *reinterpret_cast<const float4 *>(p.gamma + c), be = *reinterpret_cast<const float4 *>(p.beta + c);
   const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
@@ -152,13 +178,11 @@ extern "C" int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_s
   if ((x_dtype != DVIS_F32 && x_dtype != DVIS_BF16) || (lp_dtype != DVIS_F32 && lp_dtype != DVIS_BF16))
     return fail(DVIS_ERR_UNSUPPORTED, "groupnorm_nhwc: dtypes must be f32 or bf16");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(sums_workspace, 0, sizeof(double) * 2 * N * G, s);
-  const int pix_per_cta = 256;
-  dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
+  dim3 grid(G, N);
   if (x_dtype == DVIS_F32)
-    gn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(x), x_batch_stride, HW, C, G, pix_per_cta, sums_workspace);
+    gn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(x), x_batch_stride, HW, C, G, sums_workspace);
   else
-    gn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(x), x_batch_stride, HW, C, G, pix_per_cta, sums_workspace);
+    gn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(x), x_batch_stride, HW, C, G, sums_workspace);
   if (int rc = check_launch("gn_stats_kernel")) return rc;
   GnApplyParams p{x, x_batch_stride, sums_workspace, gamma, beta, N, HW, C, G, eps, relu, up, up_batch_stride, up_h, up_w,
                   H, W, pos, out_f32, out_lp, out_lp_pos, out_batch_stride};

@@ -1,0 +1,328 @@
+// Linear layers of the temporal stage (tracker / refiner blocks) as ONE kernel per dependent step:
+//     Y = act( A @ W^T + bias ) [+ residual]            W (N, K) bf16 row-major (nn.Linear layout), fp32 accumulate
+// where the A operand is either a bf16 matrix (optionally gathered over `taps` time-shifted rows: Conv1d with replicate
+// padding as a GEMM, P/dvis_Plus/refiner.py:44-52,116-119) or is BUILT IN THE PROLOGUE from the fp32 residual stream:
+//     A = LN1( LN0(src0) + src1 )                        (each step optional)
+// The post-norm blocks of the reference (SelfAttentionLayer / CrossAttentionLayer / FFNLayer.forward_post,
+// P/mask2former_video/modeling/transformer_decoder/video_mask2former_transformer_decoder.py:40-50,98-108,160-164;
+// ReferringCrossAttentionLayer, P/dvis_Plus/tracker.py:37-50) are  x <- LN(x + f(x)).  Here every producer writes the
+// PRE-norm sum (x + f(x), fp32) and every consumer normalises its own rows while its weight tiles are already in flight,
+// so LayerNorm never is a kernel (or a dependent step) of its own: a tracker layer is 5 launches (QKV, attention, out-proj,
+// FFN1, FFN2) instead of ~9 library kernels + 3 add_layernorm.  The normalised rows are also the next residual, so the
+// kernel can store them as a side output (each CTA of a row block stores a different column slice).
+//
+// M = 200 rows x K = 512 is latency-bound: 32-row x 64-column CTA tiles (7 x N/64 CTAs), 4 warps of mma.sync m16n8k16,
+// W (and bf16 A) tiles through a 4-stage cp.async ring; for the refiner's 3 200 rows the 64-row variant halves the
+// weight re-reads.  Weight tiles never depend on the previous kernel, so with programmatic dependent launch their
+// prefetch overlaps the predecessor's tail (griddepcontrol.wait sits between the W and the A loads).
+#include "mma.cuh"
+
+namespace dvis {
+namespace {
+
+constexpr int kLsThreads = 128;
+constexpr int kLsBN = 64, kLsBK = 64, kLsStages = 4;
+constexpr int kLsRS = kLsBK + 8;            // ring row stride (bf16): 144 bytes, ldmatrix conflict-free
+constexpr int kLsMaxProK = 512;             // widest LayerNorm the prologue handles (hidden size of tracker / refiner)
+
+struct LsParams {
+  // A operand, plain / conv mode
+  const __nv_bfloat16 *x;
+  int64_t ldx, x_batch;
+  int taps, tap_pad, tap_period, tap_len;   // row r = t * period + q reads rows clamp(t + d - pad, 0, len - 1) * period + q
+  // A operand, prologue mode (x == nullptr): A = LN1(LN0(src0) + src1), K <= 512, K % 128 == 0
+  const float *src0;
+  const float *ln0_g, *ln0_b;
+  const void *src1;
+  int src1_bf16;
+  const float *ln1_g, *ln1_b;
+  float eps;
+  float *side0;                              // optional (M, K) fp32: LN0(src0)
+  float *side1;                              // optional (M, K) fp32: the A rows before rounding to bf16
+  // B operand and epilogue
+  const __nv_bfloat16 *w;
+  int64_t w_batch;
+  const float *bias;
+  int64_t bias_batch;
+  const float *residual;                     // optional fp32 (M, N), row stride ldr
+  int64_t ldr;
+  int relu;
+  float *y_f32;
+  __nv_bfloat16 *y_bf16;
+  int64_t ldy, y_batch;
+  int M, N, K;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one LayerNorm over a row held as NV float4 per lane (columns lane*4 + 128*i), two-pass like csrc/layernorm.cu
+template <int NV>
+__device__ __forceinline__ void ln_row(float4 (&v)[NV], int nv, int K, const float *g, const float *b, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / float(K);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + c * c) + (d * d + e * e);
+    }
+  const float rstd = rsqrtf(warp_sum(q) / float(K) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (i < nv) {
+      const float4 ga = *reinterpret_cast<const float4 *>(g + lane * 4 + 128 * i);
+      const float4 be = *reinterpret_cast<const float4 *>(b + lane * 4 + 128 * i);
+      v[i] = make_float4((v[i].x - mean) * rstd * ga.x + be.x, (v[i].y - mean) * rstd * ga.y + be.y,
+                         (v[i].z - mean) * rstd * ga.z + be.z, (v[i].w - mean) * rstd * ga.w + be.w);
+    }
+}
+
+// BM = 32: warps 1 x 4 (warp tile 32 x 16);  BM = 64: warps 2 x 2 (warp tile 32 x 32)
+template <int BM, bool PRO>
+__global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams p) {
+  constexpr int WM = BM / 32, WN = 4 / WM, WCOLS = kLsBN / WN, NT = WCOLS / 8;
+  constexpr int A_TILE = BM * kLsRS, W_TILE = kLsBN * kLsRS;
+  extern __shared__ uint4 ls_smem[];
+  __nv_bfloat16 *sw = reinterpret_cast<__nv_bfloat16 *>(ls_smem);                  // [stages][64][RS]
+  __nv_bfloat16 *sa = sw + kLsStages * W_TILE;                                     // plain: [stages][BM][RS]; PRO: [BM][K + 8]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp / WN, wn = warp % WN;
+  const int n0 = blockIdx.x * kLsBN, m0 = blockIdx.y * BM, bz = blockIdx.z;
+  const int nk = p.K / kLsBK;
+  const __nv_bfloat16 *wsrc = p.w + (size_t)bz * p.w_batch;
+  const int ars = PRO ? p.K + 8 : kLsRS;                                           // A row stride in smem
+
+  auto issue_w = [&](int kc, int slot) {
+    __nv_bfloat16 *dst = sw + slot * W_TILE;
+    for (int c = tid; c < kLsBN * 8; c += kLsThreads) {
+      const int r = c >> 3, cc = c & 7, n = n0 + r;
+      const bool ok = n < p.N;
+      cp_async_16(dst + r * kLsRS + cc * 8, wsrc + (size_t)(ok ? n : 0) * p.K + kc * kLsBK + cc * 8, ok ? 16 : 0);
+    }
+  };
+  auto issue_a = [&](int kc, int slot) {
+    if constexpr (!PRO) {
+      __nv_bfloat16 *dst = sa + slot * A_TILE;
+      const int cin = p.K / p.taps, k0 = kc * kLsBK, tap = k0 / cin, col = k0 - tap * cin;
+      for (int c = tid; c < BM * 8; c += kLsThreads) {
+        const int r = c >> 3, cc = c & 7, m = m0 + r;
+        const bool ok = m < p.M;
+        int srow = ok ? m : 0;
+        if (p.taps > 1) {
+          const int tt = srow / p.tap_period, q = srow - tt * p.tap_period;
+          const int ts = min(max(tt + tap - p.tap_pad, 0), p.tap_len - 1);
+          srow = ts * p.tap_period + q;
+        }
+        cp_async_16(dst + r * kLsRS + cc * 8, p.x + (size_t)bz * p.x_batch + (size_t)srow * p.ldx + col + cc * 8, ok ? 16 : 0);
+      }
+    }
+  };
+
+  // weights first: they do not depend on the kernel before this one
+  for (int s = 0; s < kLsStages - 1; ++s)
+    if (s < nk) issue_w(s, s);
+  pdl_wait();
+  for (int s = 0; s < kLsStages - 1; ++s) {
+    if (s < nk) issue_a(s, s);
+    cp_async_commit();
+  }
+
+  if constexpr (PRO) {
+    // ---- prologue: A rows = LN1(LN0(src0) + src1) -> bf16 in shared memory; warp w owns rows w, w+4, ... ----
+    constexpr int NV = kLsMaxProK / 128;
+    const int nv = p.K / 128;
+    const int nseg = p.K / 64, gx = gridDim.x;
+    for (int r = warp; r < BM; r += 4) {
+      const int m = m0 + r;
+      float4 v[NV];
+      if (m < p.M) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i < nv) v[i] = *reinterpret_cast<const float4 *>(p.src0 + (size_t)m * p.K + lane * 4 + 128 * i);
+        if (p.ln0_g) ln_row<NV>(v, nv, p.K, p.ln0_g, p.ln0_b, p.eps, lane);
+        if (p.side0) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == (int)blockIdx.x % min(gx, nseg))
+              *reinterpret_cast<float4 *>(p.side0 + (size_t)m * p.K + lane * 4 + 128 * i) = v[i];
+        }
+        if (p.src1) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (i < nv) {
+              const size_t o = (size_t)m * p.K + lane * 4 + 128 * i;
+              if (p.src1_bf16) {
+                const uint2 u = *reinterpret_cast<const uint2 *>(static_cast<const __nv_bfloat16 *>(p.src1) + o);
+                v[i].x += __uint_as_float(u.x << 16); v[i].y += __uint_as_float(u.x & 0xffff0000u);
+                v[i].z += __uint_as_float(u.y << 16); v[i].w += __uint_as_float(u.y & 0xffff0000u);
+              } else {
+                const float4 u = *reinterpret_cast<const float4 *>(static_cast<const float *>(p.src1) + o);
+                v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+              }
+            }
+        }
+        if (p.ln1_g) ln_row<NV>(v, nv, p.K, p.ln1_g, p.ln1_b, p.eps, lane);
+        if (p.side1) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == (int)blockIdx.x % min(gx, nseg))
+              *reinterpret_cast<float4 *>(p.side1 + (size_t)m * p.K + lane * 4 + 128 * i) = v[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (i < nv)
+          *reinterpret_cast<uint2 *>(sa + r * ars + lane * 4 + 128 * i) =
+              make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+    }
+  }
+
+  float acc[2][NT][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+
+  for (int kc = 0; kc < nk; ++kc) {
+    cp_async_wait<kLsStages - 2>();
+    __syncthreads();                           // chunk kc has landed for everyone; slot (kc-1) % stages is free again
+    {
+      const int nx = kc + kLsStages - 1;
+      if (nx < nk) { issue_w(nx, nx % kLsStages); issue_a(nx, nx % kLsStages); }
+      cp_async_commit();
+    }
+    const __nv_bfloat16 *cw = sw + (kc % kLsStages) * W_TILE;
+    const __nv_bfloat16 *ca = PRO ? sa + kc * kLsBK : sa + (kc % kLsStages) * A_TILE;
+#pragma unroll
+    for (int ks = 0; ks < kLsBK / 16; ++ks) {
+      uint32_t af[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row = wm * 32 + mt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), col = ks * 16 + (lane >> 4) * 8;
+        ldmatrix_x4(af[mt], ca + row * ars + col);
+      }
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t bf[4];
+        const int n = wn * WCOLS + (2 * np + (lane >> 4)) * 8 + (lane & 7), col = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(bf, cw + n * kLsRS + col);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_bf16_16816(acc[mt][2 * np], af[mt], bf[0], bf[1]);
+          mma_bf16_16816(acc[mt][2 * np + 1], af[mt], bf[2], bf[3]);
+        }
+      }
+    }
+  }
+  pdl_launch_dependents();
+
+  // ---- epilogue: bias, ReLU, residual, stores ----
+  const float *bias = p.bias ? p.bias + (size_t)bz * p.bias_batch : nullptr;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m = m0 + wm * 32 + mt * 16 + g + half * 8;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n = n0 + wn * WCOLS + nt * 8 + 2 * t;
+        if (n >= p.N) continue;
+        float v0 = acc[mt][nt][half * 2], v1 = acc[mt][nt][half * 2 + 1];
+        if (bias) { v0 += __ldg(bias + n); v1 += __ldg(bias + n + 1); }
+        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        if (p.residual) {
+          const float2 r = *reinterpret_cast<const float2 *>(p.residual + (size_t)m * p.ldr + n);
+          v0 += r.x; v1 += r.y;
+        }
+        const size_t o = (size_t)bz * p.y_batch + (size_t)m * p.ldy + n;
+        if (p.y_f32) *reinterpret_cast<float2 *>(p.y_f32 + o) = make_float2(v0, v1);
+        if (p.y_bf16) *reinterpret_cast<uint32_t *>(p.y_bf16 + o) = pack_bf16x2(v0, v1);
+      }
+    }
+}
+
+bool g_pdl = false;   // programmatic dependent launch for the temporal-stage kernels (dvis_set_pdl)
+
+template <int BM, bool PRO>
+int launch_small_linear(const LsParams &p, int batch, cudaStream_t s) {
+  const size_t smem = (size_t)kLsStages * kLsBN * kLsRS * 2 +
+                      (PRO ? (size_t)BM * (p.K + 8) * 2 : (size_t)kLsStages * BM * kLsRS * 2);
+  auto kern = small_linear_kernel<BM, PRO>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  dim3 grid((p.N + kLsBN - 1) / kLsBN, (p.M + BM - 1) / BM, batch);
+#ifdef DVIS_SIMT_EMULATION
+  kern<<<grid, kLsThreads, smem, s>>>(p);
+#else
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kLsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, p);
+#endif
+  return check_launch("small_linear_kernel");
+}
+
+}  // namespace
+}  // namespace dvis
+
+using namespace dvis;
+
+extern "C" int dvis_set_pdl(int enabled) {
+  g_pdl = enabled != 0;
+  return DVIS_OK;
+}
+
+extern "C" int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, int taps, int tap_pad, int tap_period, int tap_len,
+                                 const float *src0, const float *ln0_gamma, const float *ln0_beta, const void *src1,
+                                 int src1_dtype, const float *ln1_gamma, const float *ln1_beta, float eps, float *side0,
+                                 float *side1, const void *w, int64_t w_batch, const float *bias, int64_t bias_batch,
+                                 const float *residual, int64_t ldr, int relu, float *y_f32, void *y_bf16, int64_t ldy,
+                                 int64_t y_batch, int batch, int M, int N, int K, void *stream) {
+  DVIS_REQUIRE(w && (y_f32 || y_bf16), "linear_small: null pointer argument");
+  DVIS_REQUIRE((x != nullptr) != (src0 != nullptr), "linear_small: exactly one of x (bf16 operand) and src0 (prologue) must be given");
+  DVIS_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0, "linear_small: sizes must be positive");
+  DVIS_REQUIRE(K % kLsBK == 0 && N % 8 == 0, "linear_small: need K %% 64 == 0 and N %% 8 == 0 (K=%d N=%d)", K, N);
+  DVIS_REQUIRE(aligned16(w) && w_batch % 8 == 0, "linear_small: weights must be 16-byte aligned");
+  DVIS_REQUIRE(ldy % 2 == 0 && y_batch % 2 == 0 && (!residual || ldr % 2 == 0), "linear_small: output / residual strides must be even");
+  LsParams p{};
+  p.w = static_cast<const __nv_bfloat16 *>(w); p.w_batch = w_batch; p.bias = bias; p.bias_batch = bias_batch;
+  p.residual = residual; p.ldr = ldr; p.relu = relu; p.y_f32 = y_f32; p.y_bf16 = static_cast<__nv_bfloat16 *>(y_bf16);
+  p.ldy = ldy; p.y_batch = y_batch; p.M = M; p.N = N; p.K = K;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool big = M > 512;                      // the refiner's T*Q rows: 64-row tiles halve the weight re-reads
+  if (x) {
+    DVIS_REQUIRE(taps >= 1 && K % taps == 0 && (K / taps) % kLsBK == 0, "linear_small: K must split into taps x (multiple of 64)");
+    DVIS_REQUIRE(taps == 1 || (tap_period > 0 && tap_len > 0 && M == tap_period * tap_len && batch == 1),
+                 "linear_small: conv mode needs M == tap_period * tap_len and batch == 1");
+    DVIS_REQUIRE(aligned16(x) && ldx % 8 == 0 && x_batch % 8 == 0, "linear_small: x rows must be 16-byte aligned");
+    p.x = static_cast<const __nv_bfloat16 *>(x); p.ldx = ldx; p.x_batch = x_batch;
+    p.taps = taps; p.tap_pad = tap_pad; p.tap_period = tap_period; p.tap_len = tap_len;
+    return big ? launch_small_linear<64, false>(p, batch, s) : launch_small_linear<32, false>(p, batch, s);
+  }
+  DVIS_REQUIRE(batch == 1, "linear_small: the LayerNorm prologue is not batched");
+  DVIS_REQUIRE(K <= kLsMaxProK && K % 128 == 0, "linear_small: prologue needs K <= 512 and K %% 128 == 0 (K=%d)", K);
+  DVIS_REQUIRE(!ln0_gamma == !ln0_beta && !ln1_gamma == !ln1_beta, "linear_small: LayerNorm needs both gamma and beta");
+  DVIS_REQUIRE(!src1 || src1_dtype == DVIS_F32 || src1_dtype == DVIS_BF16, "linear_small: src1 must be f32 or bf16");
+  DVIS_REQUIRE(!side0 || ln0_gamma, "linear_small: side0 is the output of LN0");
+  p.src0 = src0; p.ln0_g = ln0_gamma; p.ln0_b = ln0_beta; p.src1 = src1; p.src1_bf16 = src1_dtype == DVIS_BF16;
+  p.ln1_g = ln1_gamma; p.ln1_b = ln1_beta; p.eps = eps; p.side0 = side0; p.side1 = side1;
+  return big ? launch_small_linear<64, true>(p, batch, s) : launch_small_linear<32, true>(p, batch, s);
+}

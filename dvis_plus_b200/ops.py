@@ -331,6 +331,86 @@ def mha_core(q, k, v, scale):
     return out
 
 
+def flash_attn(q, k, v, scale, mask_bits=None):
+    """softmax(scale * q k^T [masked]) v on the warp tensor cores (dvis_flash_attn).
+
+    q (B, Lq, H, Dh), k / v (B, Lk, H, Dh): bf16 views with a contiguous head dim (any row / batch / head stride, e.g.
+    slices of a packed QKV projection).  mask_bits: optional uint8 (B, Lq, row_bytes) with row_bytes % 8 == 0 and
+    row_bytes >= ceil(Lk / 64) * 8: bit j set = key j masked for that query (all heads), see `ops.mask_attn_bits`.
+    Returns a contiguous (B, Lq, H*Dh) bf16 tensor."""
+    B, Lq, H, Dh = q.shape
+    Lk = k.shape[1]
+    for t in (q, k, v):
+        if not t.is_cuda:
+            raise RuntimeError("flash_attn: CUDA tensors required (there is no CPU path)")
+        assert t.dtype == torch.bfloat16 and t.stride(3) == 1, "bf16 with a contiguous head dim"
+    assert k.shape == (B, Lk, H, Dh) and v.shape == (B, Lk, H, Dh)
+    out = torch.empty((B, Lq, H * Dh), dtype=torch.bfloat16, device=q.device)
+    mrow = mbatch = 0
+    if mask_bits is not None:
+        assert mask_bits.dtype == torch.uint8 and mask_bits.is_cuda and mask_bits.dim() == 3 and mask_bits.stride(2) == 1
+        assert mask_bits.shape[0] == B and mask_bits.shape[1] == Lq
+        mrow, mbatch = mask_bits.stride(1), mask_bits.stride(0)
+    with torch.cuda.device(q.device):
+        _lib.call("dvis_flash_attn", q.data_ptr(), q.stride(1), q.stride(0), q.stride(2), k.data_ptr(), k.stride(1), k.stride(0),
+                  k.stride(2), v.data_ptr(), v.stride(1), v.stride(0), v.stride(2), out.data_ptr(), H * Dh, Lq * H * Dh,
+                  mask_bits.data_ptr() if mask_bits is not None else None, mrow, mbatch, B, Lq, Lk, H, Dh, float(scale), _stream())
+    return out
+
+
+def set_pdl(enabled):
+    """Programmatic dependent launch for the temporal-stage kernels (dvis_set_pdl)."""
+    _lib.lib().dvis_set_pdl(int(bool(enabled)))
+
+
+def linear_small(w, bias=None, *, x=None, src0=None, ln0=None, src1=None, ln1=None, eps=1e-5, want_side0=False,
+                 want_side1=False, residual=None, relu=False, out_f32=False, out_bf16=True, taps=1, tap_pad=0,
+                 tap_period=0, tap_len=0):
+    """One dependent step of a tracker / refiner block (dvis_linear_small):  Y = act(A @ w^T + bias) [+ residual].
+
+    w (N, K) or (B, N, K) bf16; bias (N,) / (B, N) f32 or None.
+    A = x: bf16 (M, K/taps) or (B, M, K/taps), last dim contiguous (taps > 1: Conv1d over time as a GEMM, see the header), or
+    A = LN1(LN0(src0) + src1) built in the kernel: src0 (M, K) f32, ln0 / ln1 = (gamma, beta, ...) f32 or None, src1 (M, K)
+    f32 | bf16 or None.  residual (M, N) f32.  -> (y_f32 | None, y_bf16 | None, side0 | None, side1 | None)."""
+    assert w.is_cuda and w.dtype == torch.bfloat16 and w.is_contiguous()
+    batched = w.dim() == 3
+    B = w.shape[0] if batched else 1
+    N, K = w.shape[-2], w.shape[-1]
+    dev = w.device
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape[-1] == N
+    if x is not None:
+        if not x.is_cuda:
+            raise RuntimeError("linear_small: CUDA tensors required (there is no CPU path)")
+        assert x.dtype == torch.bfloat16 and x.stride(-1) == 1 and x.shape[-1] * taps == K
+        M = x.shape[-2]
+        ldx, xb = x.stride(-2), (x.stride(0) if batched else 0)
+    else:
+        assert not batched and src0.dtype == torch.float32 and src0.is_contiguous() and src0.shape[-1] == K
+        M = src0.numel() // K
+        ldx = xb = 0
+        if src1 is not None:
+            assert src1.is_contiguous() and src1.numel() == src0.numel() and src1.dtype in (torch.float32, torch.bfloat16)
+    for ln in (ln0, ln1):
+        assert ln is None or (ln[0].dtype == torch.float32 and ln[1].dtype == torch.float32 and ln[0].numel() == K)
+    shape = (B, M, N) if batched else (M, N)
+    y32 = torch.empty(shape, dtype=torch.float32, device=dev) if out_f32 else None
+    y16 = torch.empty(shape, dtype=torch.bfloat16, device=dev) if out_bf16 else None
+    side0 = torch.empty((M, K), dtype=torch.float32, device=dev) if want_side0 else None
+    side1 = torch.empty((M, K), dtype=torch.float32, device=dev) if want_side1 else None
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(-1) == 1 and residual.numel() == M * N and not batched
+    with torch.cuda.device(dev):
+        _lib.call("dvis_linear_small", ptr(x), ldx, xb, taps, tap_pad, tap_period, tap_len, ptr(src0),
+                  ptr(ln0[0]) if ln0 else None, ptr(ln0[1]) if ln0 else None, ptr(src1),
+                  _DTYPE[src1.dtype] if src1 is not None else DVIS_F32, ptr(ln1[0]) if ln1 else None,
+                  ptr(ln1[1]) if ln1 else None, float(eps), ptr(side0), ptr(side1), w.data_ptr(), N * K if batched else 0,
+                  ptr(bias), N if (batched and bias is not None and bias.dim() == 2) else 0, ptr(residual),
+                  residual.stride(-2) if residual is not None else 0, int(relu), ptr(y32), ptr(y16), N, M * N, B, M, N, K, _stream())
+    return y32, y16, side0, side1
+
+
 # ---- video post-processing (csrc/postproc.cu; P/dvis_Plus/meta_architecture.py:818-979) --------------------------------
 
 def _mask_view(pred_masks):

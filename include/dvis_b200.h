@@ -123,6 +123,48 @@ int dvis_mha_core(const void *q, int64_t q_row, int64_t q_batch, const void *k, 
                   int Lq, int Lk, int H, int Dh, float scale, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The same attention core on the warp tensor cores (mma.sync bf16, fp32 accumulate, online softmax): the kernel the
+ * temporal stage runs (tracker / refiner self- and cross-attention, P/dvis_Plus/tracker.py:8-92,
+ * P/dvis_Plus/refiner.py:105-137) and, with `mask_bits`, the segmenter decoder's masked cross-attention
+ * (P/dvis_Plus/video_mask2former_transformer_decoder.py:295-315: `memory_mask=attn_mask`).
+ * q (B, Lq, H, Dh), k / v (B, Lk, H, Dh), out (B, Lq, H*Dh) bf16; *_row / *_batch / *_head = elements between consecutive
+ * sequence positions / batch items / heads.  k / v rows 16-byte aligned, q / out 4-byte aligned.  Dh in {32, 64}; any Lk.
+ * mask_bits (optional, NULL = none): B x Lq rows of bits, bit (j % 8) of byte (j / 8) set = key j may NOT be attended by
+ * that query (all heads); rows are mask_row_bytes apart (multiple of 8, >= ceil(Lk / 64) * 8), batches mask_batch_bytes.
+ * A row with every key masked yields zeros (torch would give NaN); the reference never produces one (:370-371).
+ */
+int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, int64_t q_head, const void *k, int64_t k_row,
+                    int64_t k_batch, int64_t k_head, const void *v, int64_t v_row, int64_t v_batch, int64_t v_head,
+                    void *out, int64_t o_row, int64_t o_batch, const void *mask_bits, int64_t mask_row_bytes,
+                    int64_t mask_batch_bytes, int B, int Lq, int Lk, int H, int Dh, float scale, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One dependent step of a tracker / refiner block as one kernel (warp tensor cores, bf16 operands, fp32 accumulate):
+ *     Y = act(A @ W^T + bias) [+ residual]
+ * W (N, K) bf16 row-major = nn.Linear.weight (nn.MultiheadAttention.in_proj_weight / out_proj.weight, FFNLayer.linear1/2,
+ * MLP.layers[i], P/mask2former_video/modeling/transformer_decoder/video_mask2former_transformer_decoder.py:18-205;
+ * Conv1d weights of P/dvis_Plus/refiner.py:44-52 re-laid as (C_out, k*C_in)); `batch` independent problems (x_batch /
+ * w_batch / bias_batch / y_batch elements apart).
+ * A is either
+ *   x != NULL: a bf16 matrix (M, K / taps), rows ldx apart; taps > 1 = Conv1d over time with replicate padding as a GEMM:
+ *              row r = t * tap_period + q reads, for tap d, row clamp(t + d - tap_pad, 0, tap_len - 1) * tap_period + q;
+ *   src0 != NULL: built in the kernel's prologue from the fp32 residual stream (post-norm blocks, :40-50,98-108,160-164;
+ *              P/dvis_Plus/tracker.py:37-50):  A = LN1(LN0(src0) + src1), src0 (M, K) f32, src1 (M, K) f32|bf16, each LN /
+ *              src1 optional (NULL); K <= 512, K % 128 == 0, batch == 1.  side0 / side1 (optional, (M, K) f32) receive
+ *              LN0(src0) and the final A rows (the next residual).
+ * residual (optional): f32 (M, N), rows ldr apart, added after the activation.  Outputs: y_f32 and / or y_bf16 (M, N), rows
+ * ldy apart.  K % 64 == 0, N % 8 == 0.
+ * dvis_set_pdl(1) launches these kernels (and dvis_flash_attn) with programmatic dependent launch: weight tiles are
+ * prefetched while the previous kernel of the stream drains.
+ */
+int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, int taps, int tap_pad, int tap_period, int tap_len,
+                      const float *src0, const float *ln0_gamma, const float *ln0_beta, const void *src1, int src1_dtype,
+                      const float *ln1_gamma, const float *ln1_beta, float eps, float *side0, float *side1, const void *w,
+                      int64_t w_batch, const float *bias, int64_t bias_batch, const float *residual, int64_t ldr, int relu,
+                      float *y_f32, void *y_bf16, int64_t ldy, int64_t y_batch, int batch, int M, int N, int K, void *stream);
+int dvis_set_pdl(int enabled);
+
+/* ------------------------------------------------------------------------------------------------
  * y = LayerNorm(x + residual) * gamma + beta over the last dim C, one pass.
  * The post-norm residual blocks of the path: MSDeformAttnTransformerEncoderLayer.forward
  * (P/mask2former/modeling/pixel_decoder/msdeformattn.py:118-119,125-126) and SelfAttentionLayer / CrossAttentionLayer /

@@ -15,7 +15,7 @@ from dvis_plus_b200 import _lib as product_binding  # noqa: E402  (signatures on
 _DT = {torch.float32: 0, torch.bfloat16: 2}
 _lib = None
 ENTRY_POINTS = ("dvis_class_scores", "dvis_vis_topk", "dvis_vis_masks", "dvis_vis_masks_packed", "dvis_vps_argmax", "dvis_vps_paint",
-                "dvis_vss_argmax", "dvis_lap_chain")
+                "dvis_vss_argmax", "dvis_lap_chain", "dvis_flash_attn")
 
 
 def lib():
@@ -210,6 +210,25 @@ def mha_core(q, k, v, scale):
     call("dvis_mha_core", _p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1), v.stride(0), _p(out),
          H * Dh, Lq * H * Dh, B, Lq, Lk, H, Dh, float(scale), None)
     return out
+
+
+def flash_attn(q, k, v, scale, mask_bits=None):
+    B, Lq, H, Dh = q.shape
+    Lk = k.shape[1]
+    out = torch.full((B, Lq, H * Dh), float("nan"), dtype=torch.bfloat16)
+    call("dvis_flash_attn", _p(q), q.stride(1), q.stride(0), q.stride(2), _p(k), k.stride(1), k.stride(0), k.stride(2), _p(v),
+         v.stride(1), v.stride(0), v.stride(2), _p(out), H * Dh, Lq * H * Dh, _p(mask_bits),
+         mask_bits.stride(1) if mask_bits is not None else 0, mask_bits.stride(0) if mask_bits is not None else 0,
+         B, Lq, Lk, H, Dh, float(scale), None)
+    return out
+
+
+def linear_small(w, bias=None, **kw):
+    """the product's own front end (dvis_plus_b200.ops.linear_small) on the emulated library"""
+    import emulated_device
+    from dvis_plus_b200 import ops
+    with emulated_device.emulated_b200():
+        return ops.linear_small(w, bias, **kw)
 
 
 def lap_rect(cost):

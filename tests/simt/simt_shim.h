@@ -102,6 +102,7 @@ struct Block {
   std::unique_ptr<std::barrier<>> bar;                   // __syncthreads
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar; // warp collectives
   std::vector<uint64_t> slot;                            // one 8-byte exchange slot per thread
+  std::vector<uint64_t> gather;                          // 64 bytes per thread: warp_gather (mma / ldmatrix emulation)
   std::vector<char> smem;                                // dynamic shared memory
 };
 inline Block *g_block = nullptr;
@@ -138,6 +139,18 @@ inline T exchange(T v, int src_lane) {
   return out;
 }
 
+// every lane of a (full) warp publishes N values and receives all 32 lanes' values: the building block of the
+// mma.sync / ldmatrix emulation in csrc/mma.cuh
+template <typename T, int N>
+inline void warp_gather(const T (&mine)[N], T (&all)[32][N]) {
+  static_assert(sizeof(T) * N <= 64, "gather slot");
+  std::memcpy(&g_block->gather[size_t(t_linear) * 8], mine, sizeof(T) * N);
+  warp_barrier().arrive_and_wait();
+  const int base = t_linear & ~31;
+  for (int l = 0; l < 32; ++l) std::memcpy(all[l], &g_block->gather[size_t(base + l) * 8], sizeof(T) * N);
+  warp_barrier().arrive_and_wait();
+}
+
 template <typename F>
 inline void launch(dim3 grid, dim3 block, size_t smem, F &&body) {
   const int nthr = int(block.x * block.y * block.z);
@@ -149,6 +162,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F &&body) {
         b.bar = std::make_unique<std::barrier<>>(nthr);
         for (int w = 0; w < (nthr + 31) / 32; ++w) b.warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32, nthr - 32 * w)));
         b.slot.assign(nthr, 0);
+        b.gather.assign(size_t(nthr) * 8, 0);
         b.smem.assign(smem + 16, 0);
         g_block = &b;
         std::vector<std::thread> pool;
