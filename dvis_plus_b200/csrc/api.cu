@@ -8,6 +8,13 @@ char *last_error_buffer() {
 }
 }  // namespace dvis
 
+namespace dvis {
+bool g_pdl = false;   // programmatic dependent launch for the temporal-stage kernels (dvis_set_pdl)
+}
+extern "C" int dvis_set_pdl(int enabled) {
+  dvis::g_pdl = enabled != 0;
+  return DVIS_OK;
+}
 extern "C" int dvis_abi_version(void) { return DVIS_B200_ABI_VERSION; }
 extern "C" const char *dvis_last_error(void) { return dvis::last_error_buffer(); }
 

@@ -229,7 +229,11 @@ int launch_flash(const FlashParams &p, cudaStream_t s) {
   const size_t ring = (size_t)kFaWarps * p.stages * 2 * kFaKeys * (DH + 8) * sizeof(__nv_bfloat16);
   cudaFuncSetAttribute(flash_attn_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring));
   dim3 grid((p.Lq + kFaRows - 1) / kFaRows, p.H, p.B);
+#ifdef DVIS_SIMT_EMULATION
   flash_attn_kernel<DH><<<grid, kFaWarps * 32, ring, s>>>(p);
+#else
+  launch_pdl<FlashParams>(flash_attn_kernel<DH>, grid, dim3(kFaWarps * 32), ring, s, p);
+#endif
   return check_launch("flash_attn_kernel");
 }
 

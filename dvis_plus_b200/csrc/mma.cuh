@@ -50,6 +50,23 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// launch with (or, when dvis_set_pdl(0), without) the programmatic-stream-serialization attribute
+extern bool g_pdl;
+template <typename P>
+inline void launch_pdl(void (*kern)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const P &params) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, params);
+}
+
 #else  // ---------------- CPU emulation (tests/simt/simt_shim.h) ----------------
 
 inline void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {

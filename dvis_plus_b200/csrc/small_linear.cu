@@ -253,8 +253,6 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
     }
 }
 
-bool g_pdl = false;   // programmatic dependent launch for the temporal-stage kernels (dvis_set_pdl)
-
 template <int BM, bool PRO>
 int launch_small_linear(const LsParams &p, int batch, cudaStream_t s) {
   const size_t smem = (size_t)kLsStages * kLsBN * kLsRS * 2 +
@@ -265,17 +263,7 @@ int launch_small_linear(const LsParams &p, int batch, cudaStream_t s) {
 #ifdef DVIS_SIMT_EMULATION
   kern<<<grid, kLsThreads, smem, s>>>(p);
 #else
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(kLsThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, p);
+  launch_pdl<LsParams>(kern, grid, dim3(kLsThreads), smem, s, p);
 #endif
   return check_launch("small_linear_kernel");
 }
@@ -284,11 +272,6 @@ int launch_small_linear(const LsParams &p, int batch, cudaStream_t s) {
 }  // namespace dvis
 
 using namespace dvis;
-
-extern "C" int dvis_set_pdl(int enabled) {
-  g_pdl = enabled != 0;
-  return DVIS_OK;
-}
 
 extern "C" int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, int taps, int tap_pad, int tap_period, int tap_len,
                                  const float *src0, const float *ln0_gamma, const float *ln0_beta, const void *src1,

@@ -49,9 +49,95 @@ class TemporalRefiner(nn.Module):
         y = F.conv1d(rep(F.relu(y), 1), c3.weight.to(dt), c3.bias.to(dt))
         return y
 
+    use_fused_kernels = True   # bf16 mode, batch 1: the layers run on csrc/small_linear.cu + csrc/flash_attn.cu (14 launches each)
+    _fast = None
+
+    def _stacked(self):
+        """bf16 weights (nn.Linear layout; Conv1d as (C_out, k*C_in), tap-major), fp32 biases / LayerNorm parameters."""
+        params = list(self.parameters())
+        key = (tuple(p._version for p in params), params[0].data_ptr())
+        if self._fast is None or self._fast["key"] != key:
+            w = lambda t: t.detach().to(torch.bfloat16).contiguous()
+            v = lambda t: t.detach().float().contiguous()
+            ln = lambda n: (v(n.weight), v(n.bias))
+            conv = lambda c: (w(c.weight.permute(0, 2, 1).reshape(c.weight.shape[0], -1)), v(c.bias))
+            C = self.decoder_norm.normalized_shape[0]
+            ta, oa, ca, ff = (self.transformer_time_self_attention_layers, self.transformer_obj_self_attention_layers,
+                              self.transformer_cross_attention_layers, self.transformer_ffn_layers)
+            L = self.num_layers
+            f = dict(key=key, C=C)
+            f["w_kv"] = w(torch.cat([ca[i].multihead_attn.in_proj_weight[C:] for i in range(L)], 0))      # (L*2C, C)
+            f["b_kv"] = v(torch.cat([ca[i].multihead_attn.in_proj_bias[C:] for i in range(L)], 0))
+            f["layers"] = [dict(
+                t_qkv=(w(ta[i].self_attn.in_proj_weight), v(ta[i].self_attn.in_proj_bias)),
+                t_o=(w(ta[i].self_attn.out_proj.weight), v(ta[i].self_attn.out_proj.bias)), ln_t=ln(ta[i].norm),
+                c5=conv(self.conv_short_aggregate_layers[i][0]), c3=conv(self.conv_short_aggregate_layers[i][2]),
+                ln_c=ln(self.conv_norms[i]),
+                o_qkv=(w(oa[i].self_attn.in_proj_weight), v(oa[i].self_attn.in_proj_bias)),
+                o_o=(w(oa[i].self_attn.out_proj.weight), v(oa[i].self_attn.out_proj.bias)), ln_o=ln(oa[i].norm),
+                x_q=(w(ca[i].multihead_attn.in_proj_weight[:C]), v(ca[i].multihead_attn.in_proj_bias[:C])),
+                x_o=(w(ca[i].multihead_attn.out_proj.weight), v(ca[i].multihead_attn.out_proj.bias)), ln_x=ln(ca[i].norm),
+                f1=(w(ff[i].linear1.weight), v(ff[i].linear1.bias)), f2=(w(ff[i].linear2.weight), v(ff[i].linear2.bias)),
+                ln_f=ln(ff[i].norm)) for i in range(L)]
+            self._fast = f
+        return self._fast
+
+    def _refine_fused(self, instance_embeds, frame_embeds):
+        """py:104-145 for batch 1 on libdvis_b200 kernels only, tokens kept as (t, q, c) rows throughout (no permutes): per
+        layer QKV / attention-over-time / out-proj, LayerNorm, Conv1d k5 + ReLU and k3 as tap-gather GEMMs, QKV /
+        attention-over-objects / out-proj, Q-proj / cross-attention to the frame queries / out-proj, FFN1, FFN2 -- 14
+        launches.  LayerNorms are folded into the consumers' prologues (csrc/small_linear.cu) except the one the
+        convolution reads through its time taps."""
+        f = self._stacked()
+        L, C, H = self.num_layers, f["C"], self.num_heads
+        dh = C // H
+        _, _, T, Q = instance_embeds.shape
+        scale = 1.0 / (dh ** 0.5)
+        eps = self.decoder_norm.eps
+        x0 = instance_embeds[0].permute(1, 2, 0).float().contiguous().view(T * Q, C)              # rows t*Q + q
+        mem = frame_embeds[0].permute(1, 2, 0).to(torch.bfloat16).contiguous().view(T * Q, C)
+        kv = ops.linear_small(f["w_kv"], f["b_kv"], x=mem)[1].view(T, Q, L, 2, H, dh)              # cross-attention keys / values
+        src, pending, outs = x0, None, []
+        for i in range(L):
+            p = f["layers"][i]
+            # time self-attention: every query attends over its own T frames (py:105-113)
+            _, qkv, _, x = ops.linear_small(*p["t_qkv"], src0=src, ln1=pending, eps=eps, want_side1=pending is not None)
+            if pending is None:
+                x = src
+            else:
+                outs.append(x)                                                                   # layer i-1's output
+            qkv = qkv.view(T, Q, 3, H, dh).permute(1, 0, 2, 3, 4)                                  # (q, t, 3, H, dh) view
+            o = torch.empty((T, Q, C), dtype=torch.bfloat16, device=x0.device)
+            ops.flash_attn(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, out=o.permute(1, 0, 2))
+            pre, _, _, _ = ops.linear_small(*p["t_o"], x=o.view(T * Q, C), residual=x, out_f32=True, out_bf16=False)
+            # short-term convolution over time (py:116-119): the taps read neighbouring frames, so this LN is materialised
+            x32, x16, _ = ops.add_layernorm(pre, None, *p["ln_t"], eps, lp_dtype=torch.bfloat16)
+            _, h, _, _ = ops.linear_small(*p["c5"], x=x16, taps=5, tap_pad=2, tap_period=Q, tap_len=T, relu=True)
+            pre, _, _, _ = ops.linear_small(*p["c3"], x=h, taps=3, tap_pad=1, tap_period=Q, tap_len=T, residual=x32, out_f32=True,
+                                            out_bf16=False)
+            # object self-attention within each frame (py:125-129)
+            _, qkv, _, x = ops.linear_small(*p["o_qkv"], src0=pre, ln1=p["ln_c"], eps=eps, want_side1=True)
+            qkv = qkv.view(T, Q, 3, H, dh)
+            o = ops.flash_attn(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale)
+            pre, _, _, _ = ops.linear_small(*p["o_o"], x=o.view(T * Q, C), residual=x, out_f32=True, out_bf16=False)
+            # cross-attention to the same frame's segmenter queries (py:132-137)
+            _, q, _, x = ops.linear_small(*p["x_q"], src0=pre, ln1=p["ln_o"], eps=eps, want_side1=True)
+            o = ops.flash_attn(q.view(T, Q, H, dh), kv[:, :, i, 0], kv[:, :, i, 1], scale)
+            pre, _, _, _ = ops.linear_small(*p["x_o"], x=o.view(T * Q, C), residual=x, out_f32=True, out_bf16=False)
+            # FFN (py:140-142)
+            _, h, _, x = ops.linear_small(*p["f1"], src0=pre, ln1=p["ln_x"], eps=eps, want_side1=True, relu=True)
+            src, _, _, _ = ops.linear_small(*p["f2"], x=h, residual=x, out_f32=True, out_bf16=False)
+            pending = p["ln_f"]
+        outs.append(ops.add_layernorm(src, None, *pending, eps)[0])
+        return torch.stack(outs, 0).view(L, T, Q, 1, C).permute(1, 0, 2, 3, 4)                     # (t, l, q, b, c)
+
     def refine(self, instance_embeds, frame_embeds):
         """The 6 refinement layers (py:104-145).  (b, c, t, q) x2 -> stacked per-layer outputs (t, l, q, b, c), fp32."""
         n_batch, n_channel, n_frames, n_instance = instance_embeds.size()
+        if (self.use_fused_kernels and not self.training and _fast_path(instance_embeds) and n_batch == 1
+                and gemm_dtype() == torch.bfloat16 and n_channel % 128 == 0 and n_channel <= 512
+                and n_channel // self.num_heads in (32, 64)):
+            return self._refine_fused(instance_embeds, frame_embeds)
         outputs = []
         output = instance_embeds.float()
         frame_embeds = frame_embeds.float().permute(3, 0, 2, 1).flatten(1, 2)        # (q, bt, c)

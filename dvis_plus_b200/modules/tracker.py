@@ -117,6 +117,9 @@ class ReferringTracker_noiser(nn.Module):
         # dvis_mha_core instead of the library SDPA (bf16 GEMM dtype, head dim 32 / 64).  Off by default: measured on B200
         # at Q=200, 8 heads x 64 it is ~3x slower per call than cuDNN's flash kernel (tracker 7.6 ms vs 5.1 ms per T=16 clip).
         self.use_custom_attention = False
+        # bf16 mode: frames after the first run on the fused temporal-stage kernels (csrc/small_linear.cu, csrc/flash_attn.cu):
+        # 36 launches per frame, no library GEMM / SDPA / LayerNorm kernel in the sequential chain
+        self.use_fused_kernels = True
         self._fast = None
 
     def _clear_memory(self):
@@ -247,6 +250,21 @@ class ReferringTracker_noiser(nn.Module):
             f["bkv"] = d(torch.cat([ca[j].multihead_attn.in_proj_bias[C:] for j in range(L)], 0))
             f["wo"] = d(torch.stack([ca[j].multihead_attn.out_proj.weight.t() for j in range(L)], 0))       # (L, C, C) = W^T
             f["bo"] = d(torch.stack([ca[j].multihead_attn.out_proj.bias for j in range(L)], 0))[:, None, :]
+            if dt == torch.bfloat16:
+                # operands of the fused temporal-stage kernels (ops.linear_small / ops.flash_attn): bf16 weights in
+                # nn.Linear layout, fp32 biases and LayerNorm parameters
+                w = lambda t: t.detach().to(torch.bfloat16).contiguous()
+                v = lambda t: t.detach().float().contiguous()
+                ln = lambda n: (v(n.weight), v(n.bias))
+                f["k_ref"] = [(w(l.weight), v(l.bias)) for l in self.ref_proj.layers]
+                f["k_wq"], f["k_bq"] = f["wq"], v(f["bq"])
+                f["k_wo"] = w(torch.stack([ca[j].multihead_attn.out_proj.weight for j in range(L)], 0))       # (L, C_out, C_in)
+                f["k_bo"] = v(torch.stack([ca[j].multihead_attn.out_proj.bias for j in range(L)], 0))
+                f["k_layers"] = [dict(ln_ca=ln(ca[j].norm), ln_sa=ln(sa[j].norm), ln_ff=ln(ff[j].norm),
+                                      w_qkv=w(sa[j].self_attn.in_proj_weight), b_qkv=v(sa[j].self_attn.in_proj_bias),
+                                      w_o=w(sa[j].self_attn.out_proj.weight), b_o=v(sa[j].self_attn.out_proj.bias),
+                                      w_1=w(ff[j].linear1.weight), b_1=v(ff[j].linear1.bias),
+                                      w_2=w(ff[j].linear2.weight), b_2=v(ff[j].linear2.bias)) for j in range(L)]
             self._fast = f
             self._graphs = {}
         return self._fast
@@ -338,27 +356,114 @@ class ReferringTracker_noiser(nn.Module):
             outs.append(x32)
         return torch.stack(outs, 0), reference.float()
 
-    def _graph_step(self, f, first, Q, dev):
-        """Capture `_frame_body` for (first / later) frames once; returns (graph, static inputs, static output)."""
-        key = (first, Q, str(dev), gemm_dtype())
+    def _fused_ok(self, f):
+        """The hand-written temporal-stage kernels cover bf16 mode, post-norm layers, hidden sizes 256 / 384 / 512 and
+        head dims 32 / 64 (every DVIS++ / DVIS-DAQ config).  fp32 mode keeps the library GEMMs (CUDA-core fp32)."""
+        C = f["C"]
+        return self.use_fused_kernels and "k_layers" in f and C % 128 == 0 and C <= 512 and (C // self.num_heads) in (32, 64)
+
+    def _frame_body_fused(self, f, prev, prev_is_pre, identity, kv, first):
+        """One frame of py:236-329 on libdvis_b200 kernels only -- 36 launches (3 + 1 + 1 + 1 + 6 x 5) for a frame after the
+        first, 66 for the first frame of a video (its referring query is re-derived per layer, py:244-251) -- and no
+        LayerNorm kernel: every producer writes the pre-norm sum and every consumer normalises its own rows in its prologue
+        (csrc/small_linear.cu).
+        prev (Q, C) fp32: the previous frame's last-layer output -- PRE-norm when `prev_is_pre` (then this frame's first
+        kernel also materialises the normalised output) -- or, for the first frame, the frame key; identity (Q, C) fp32;
+        kv (Q, L, 2, H, dh) bf16.
+        -> (pre (Q, C) fp32: this frame's last-layer PRE-norm output, prev_out: the previous frame's normalised last-layer
+        output (None unless prev_is_pre), reference (Q, C) fp32, inner: the L-1 inner layer outputs, fp32)."""
+        L, C, H = self.num_layers, f["C"], self.num_heads
+        dh = C // H
+        Q = identity.shape[0]
+        scale = 1.0 / (dh ** 0.5)
+        lay = f["k_layers"]
+        eps = self.transformer_ffn_layers[0].norm.eps
+        (w1, b1), (w2, b2), (w3, b3) = f["k_ref"]
+        kvl = kv.permute(1, 0, 2, 3, 4)                                                              # (L, Q, 2, H, dh) view
+
+        def ref_mlp(src, ln, want_side):
+            """ref_proj(LN(src)) -> (fp32, bf16, LN(src) | None)"""
+            _, h, _, side = ops.linear_small(w1, b1, src0=src, ln1=ln, eps=eps, want_side1=want_side, relu=True)
+            _, h, _, _ = ops.linear_small(w2, b2, x=h, relu=True)
+            r32, r16, _, _ = ops.linear_small(w3, b3, x=h, out_f32=True)
+            return r32, r16, side
+
+        prev_out = None
+        if not first:
+            # reference = ref_proj(last_outputs[-1]) (py:278); the 6 layers' referring cross-attention shares it (py:293,313)
+            ref32, ref16, prev_out = ref_mlp(prev, lay[L - 1]["ln_ff"] if prev_is_pre else None, prev_is_pre)
+            _, q_all, _, _ = ops.linear_small(f["k_wq"], f["k_bq"], x=ref16)                          # (Q, L*C)
+            o = ops.flash_attn(q_all.view(Q, L, H, dh).permute(1, 0, 2, 3), kvl[:, :, 0], kvl[:, :, 1], scale)   # (L, Q, C)
+            _, o_all, _, _ = ops.linear_small(f["k_wo"], f["k_bo"], x=o)                              # (L, Q, C) bf16
+        src, ln0 = identity, None
+        inner = []
+        for j in range(L):
+            p = lay[j]
+            if first:
+                # tgt = ref_proj(frame key) for layer 0, ref_proj(previous layer's output) afterwards (py:244-251)
+                r32, r16, _ = ref_mlp(prev if j == 0 else src, None if j == 0 else ln0, False)
+                if j == 0:
+                    ref32 = r32
+                _, q, _, _ = ops.linear_small(f["k_wq"][j * C:(j + 1) * C], f["k_bq"][j * C:(j + 1) * C], x=r16)
+                o = ops.flash_attn(q.view(1, Q, H, dh), kvl[j:j + 1, :, 0], kvl[j:j + 1, :, 1], scale)[0]
+                _, o_j, _, _ = ops.linear_small(f["k_wo"][j], f["k_bo"][j], x=o)
+            else:
+                o_j = o_all[j]
+            # x1 = LN_ca(x + o_j) (tracker.py:47-48), x = identity or LN_ffn of the previous layer's pre-norm sum
+            _, qkv, x_prev, x1 = ops.linear_small(p["w_qkv"], p["b_qkv"], src0=src, ln0=ln0, src1=o_j, ln1=p["ln_ca"], eps=eps,
+                                                  want_side0=ln0 is not None, want_side1=True)
+            if x_prev is not None:
+                inner.append(x_prev)
+            qkv = qkv.view(1, Q, 3, H, dh)
+            o = ops.flash_attn(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale)[0]
+            pre_sa, _, _, _ = ops.linear_small(p["w_o"], p["b_o"], x=o, residual=x1, out_f32=True, out_bf16=False)
+            _, hid, _, x2 = ops.linear_small(p["w_1"], p["b_1"], src0=pre_sa, ln1=p["ln_sa"], eps=eps, want_side1=True, relu=True)
+            pre_ff, _, _, _ = ops.linear_small(p["w_2"], p["b_2"], x=hid, residual=x2, out_f32=True, out_bf16=False)
+            src, ln0 = pre_ff, p["ln_ff"]
+        return src, prev_out, ref32, inner
+
+    def _graph_step(self, f, first, Q, dev, prev_is_pre=False):
+        """Capture one frame step (first / later frame; fused or library body) once per configuration; returns
+        (graph, static inputs (prev, identity, kv), static outputs).  The static buffers are shared by every replay of a
+        configuration: replays must stay on ONE stream (the tracker's callers do)."""
+        fused = self._fused_ok(f)
+        key = (first, prev_is_pre, fused, self.use_custom_attention, Q, str(dev), gemm_dtype())
         g = self._graphs.get(key)
         if g is None:
             C, L, H = f["C"], self.num_layers, self.num_heads
             s_ref = torch.zeros(Q, C, device=dev)
             s_id = torch.zeros(Q, C, device=dev)
             s_kv = torch.zeros(Q, L, 2, H, C // H, device=dev, dtype=gemm_dtype())
+            if fused:
+                body = lambda: self._frame_body_fused(f, s_ref, prev_is_pre, s_id, s_kv, first)
+            else:
+                body = lambda: self._frame_body(f, s_ref, s_id, s_kv, first)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self._frame_body(f, s_ref, s_id, s_kv, first)
+                    body()
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                s_out, s_refout = self._frame_body(f, s_ref, s_id, s_kv, first)
-            g = (graph, s_ref, s_id, s_kv, s_out, s_refout)
+                s_out = body()
+            g = (graph, s_ref, s_id, s_kv, s_out)
             self._graphs[key] = g
         return g
+
+    def _run_frame(self, f, prev, prev_is_pre, identity, kv, first, fused):
+        """One frame step, through its CUDA graph unless an outer capture is running; returns fresh tensors."""
+        if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
+            graph, s_ref, s_id, s_kv, s_out = self._graph_step(f, first, identity.shape[0], identity.device, prev_is_pre)
+            s_ref.copy_(prev)
+            s_id.copy_(identity)
+            s_kv.copy_(kv)
+            graph.replay()
+            clone = lambda o: None if o is None else [x.clone() for x in o] if isinstance(o, list) else o.clone()
+            return tuple(clone(o) for o in s_out)
+        if fused:
+            return self._frame_body_fused(f, prev, prev_is_pre, identity, kv, first)
+        return self._frame_body(f, prev, identity, kv, first)
 
     def _forward_fast(self, frame_embeds, mask_features, resume, return_indices, frame_embeds_no_norm, with_masks):
         dt = gemm_dtype()
@@ -375,29 +480,37 @@ class ReferringTracker_noiser(nn.Module):
         idx_dev = self._match_all(cur, ref0)                                               # (T, Q) on the device
         init = torch.gather(cur_nn, 1, idx_dev[..., None].expand(-1, -1, C))               # cur_nn[t][idx_t]
         self.last_frame_embeds = torch.gather(cur[-1], 0, idx_dev[-1][:, None].expand(-1, C))[:, None, :]
-        # keys / values of all frames and layers: one GEMM
-        kv = F.linear(cur_nn.to(dt), f["wkv"], f["bkv"]).view(T, Q, L, 2, H, C // H)           # per frame: (Q, L, 2, H, dh)
-        outs, refs = [], []
+        refs = []
         prev_last = None if start_of_video else self.last_outputs[-1][:, 0, :]
-        for t in range(T):
-            first = prev_last is None
-            ref_src = cur_nn[t] if first else prev_last
-            if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
-                graph, s_ref, s_id, s_kv, s_out, s_refout = self._graph_step(f, first, Q, dev)
-                s_ref.copy_(ref_src)
-                s_id.copy_(init[t])
-                s_kv.copy_(kv[t])
-                graph.replay()
-                layer_out, reference = s_out.clone(), s_refout.clone()
-            else:
-                layer_out, reference = self._frame_body(f, ref_src, init[t], kv[t], first)
-            refs.append(reference)
-            prev_last = layer_out[-1]
-            outs.append(layer_out)
-            last_stack = torch.cat([init[t][None], layer_out], 0)
+        if self._fused_ok(f):
+            # keys / values of all frames and layers: one launch (T*Q rows x L*2C columns)
+            kv = ops.linear_small(f["wkv"], f["bkv"].float(), x=cur_nn.to(dt).view(T * Q, C))[1].view(T, Q, L, 2, H, C // H)
+            lasts, prev, is_pre = [], prev_last, False                                      # normalised last-layer outputs
+            for t in range(T):
+                first = prev is None
+                pre, prev_out, reference, inner = self._run_frame(f, cur_nn[t] if first else prev, is_pre, init[t], kv[t], first, True)
+                if prev_out is not None:
+                    lasts.append(prev_out)                                                  # frame t-1, materialised by frame t
+                refs.append(reference)
+                prev, is_pre = pre, True
+            n_last = self.transformer_ffn_layers[L - 1].norm
+            lasts.append(ops.add_layernorm(prev, None, n_last.weight, n_last.bias, n_last.eps)[0])
+            last_stack = torch.stack([init[T - 1]] + inner + [lasts[-1]], 0)
+            outputs = torch.stack(lasts, 0)[:, None, :, None, :]                            # (t, 1, q, b, c)  eval: last layer
+        else:
+            # keys / values of all frames and layers: one GEMM
+            kv = F.linear(cur_nn.to(dt), f["wkv"], f["bkv"]).view(T, Q, L, 2, H, C // H)       # per frame: (Q, L, 2, H, dh)
+            outs = []
+            for t in range(T):
+                first = prev_last is None
+                layer_out, reference = self._run_frame(f, cur_nn[t] if first else prev_last, False, init[t], kv[t], first, False)
+                refs.append(reference)
+                prev_last = layer_out[-1]
+                outs.append(layer_out)
+                last_stack = torch.cat([init[t][None], layer_out], 0)
+            outputs = torch.stack([o[-1:] for o in outs], 0)[:, :, :, None, :]              # (t, 1, q, b, c)  eval: last layer
         self.last_outputs = last_stack[:, :, None, :]                                       # (1+L, q, b, c)
         self.last_reference = refs[-1][:, None, :]
-        outputs = torch.stack([o[-1:] for o in outs], 0)[:, :, :, None, :]                  # (t, 1, q, b, c)  eval: last layer
         all_refs = torch.stack(refs, 0)[:, :, None, :]                                      # (t, q, b, c)
         outputs_class, outputs_masks = self.prediction(outputs, mask_features, all_refs, with_masks=with_masks)
         out = {

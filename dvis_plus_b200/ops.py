@@ -331,13 +331,14 @@ def mha_core(q, k, v, scale):
     return out
 
 
-def flash_attn(q, k, v, scale, mask_bits=None):
+def flash_attn(q, k, v, scale, mask_bits=None, out=None):
     """softmax(scale * q k^T [masked]) v on the warp tensor cores (dvis_flash_attn).
 
     q (B, Lq, H, Dh), k / v (B, Lk, H, Dh): bf16 views with a contiguous head dim (any row / batch / head stride, e.g.
     slices of a packed QKV projection).  mask_bits: optional uint8 (B, Lq, row_bytes) with row_bytes % 8 == 0 and
     row_bytes >= ceil(Lk / 64) * 8: bit j set = key j masked for that query (all heads), see `ops.mask_attn_bits`.
-    Returns a contiguous (B, Lq, H*Dh) bf16 tensor."""
+    out: optional (B, Lq, H*Dh) bf16 view to write into (any batch / row stride, e.g. a transposed buffer).
+    Returns `out` or a new contiguous (B, Lq, H*Dh) bf16 tensor."""
     B, Lq, H, Dh = q.shape
     Lk = k.shape[1]
     for t in (q, k, v):
@@ -345,7 +346,9 @@ def flash_attn(q, k, v, scale, mask_bits=None):
             raise RuntimeError("flash_attn: CUDA tensors required (there is no CPU path)")
         assert t.dtype == torch.bfloat16 and t.stride(3) == 1, "bf16 with a contiguous head dim"
     assert k.shape == (B, Lk, H, Dh) and v.shape == (B, Lk, H, Dh)
-    out = torch.empty((B, Lq, H * Dh), dtype=torch.bfloat16, device=q.device)
+    if out is None:
+        out = torch.empty((B, Lq, H * Dh), dtype=torch.bfloat16, device=q.device)
+    assert out.shape == (B, Lq, H * Dh) and out.dtype == torch.bfloat16 and out.stride(2) == 1
     mrow = mbatch = 0
     if mask_bits is not None:
         assert mask_bits.dtype == torch.uint8 and mask_bits.is_cuda and mask_bits.dim() == 3 and mask_bits.stride(2) == 1
@@ -353,7 +356,7 @@ def flash_attn(q, k, v, scale, mask_bits=None):
         mrow, mbatch = mask_bits.stride(1), mask_bits.stride(0)
     with torch.cuda.device(q.device):
         _lib.call("dvis_flash_attn", q.data_ptr(), q.stride(1), q.stride(0), q.stride(2), k.data_ptr(), k.stride(1), k.stride(0),
-                  k.stride(2), v.data_ptr(), v.stride(1), v.stride(0), v.stride(2), out.data_ptr(), H * Dh, Lq * H * Dh,
+                  k.stride(2), v.data_ptr(), v.stride(1), v.stride(0), v.stride(2), out.data_ptr(), out.stride(1), out.stride(0),
                   mask_bits.data_ptr() if mask_bits is not None else None, mrow, mbatch, B, Lq, Lk, H, Dh, float(scale), _stream())
     return out
 

@@ -1,0 +1,129 @@
+"""Micro-benchmarks of the round-2 temporal-stage kernels on one B200 (CUDA events, L2-resident by nature: these are
+latency-bound 200-row problems).  Writes gpurun_out/r2_temporal_microbench.json.
+
+  * dvis_flash_attn vs cuDNN / flash SDPA (F.scaled_dot_product_attention) at the tracker / refiner / predictor shapes
+  * dvis_linear_small vs torch.addmm (cuBLASLt) at the tracker shapes
+  * tracker (T=16, Q=200, hidden 512) and refiner: fused kernels vs the library path, with and without programmatic
+    dependent launch, eager per-frame graphs and one whole-stage CUDA graph
+"""
+import json
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from dvis_plus_b200 import ops  # noqa: E402
+from dvis_plus_b200.modules.precision import set_precision  # noqa: E402
+
+
+def timeit(fn, iters=50, warmup=10):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e3          # us
+
+
+def graphed(fn):
+    """capture fn once; returns a callable replaying it (removes host launch overhead from the comparison)"""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g.replay
+
+
+@torch.no_grad()
+def main():
+    set_precision("bf16")
+    dev = "cuda"
+    out = {"attention_us": {}, "linear_us": {}, "stage_ms": {}}
+    for name, (B, Lq, Lk, H, Dh) in {"tracker_self (1,200,200,8x64)": (1, 200, 200, 8, 64),
+                                     "tracker_cross_6_layers (6,200,200,8x64)": (6, 200, 200, 8, 64),
+                                     "refiner_objects (16,200,200,8x64)": (16, 200, 200, 8, 64),
+                                     "refiner_time (200,16,16,8x64)": (200, 16, 16, 8, 64),
+                                     "predictor_self (16,200,200,8x32)": (16, 200, 200, 8, 32)}.items():
+        q = torch.randn(B, Lq, H, Dh, device=dev).to(torch.bfloat16)
+        k = torch.randn(B, Lk, H, Dh, device=dev).to(torch.bfloat16)
+        v = torch.randn(B, Lk, H, Dh, device=dev).to(torch.bfloat16)
+        scale = 1 / math.sqrt(Dh)
+        ours = graphed(lambda: ops.flash_attn(q, k, v, scale))
+        lib = graphed(lambda: F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), scale=scale))
+        out["attention_us"][name] = {"dvis_flash_attn": round(timeit(ours), 2), "torch_sdpa": round(timeit(lib), 2)}
+    for name, (M, N, K) in {"qkv (200,1536,512)": (200, 1536, 512), "out_proj (200,512,512)": (200, 512, 512),
+                            "ffn1 (200,2048,512)": (200, 2048, 512), "ffn2 (200,512,2048)": (200, 512, 2048),
+                            "refiner_qkv (3200,1536,512)": (3200, 1536, 512), "refiner_ffn2 (3200,512,2048)": (3200, 512, 2048)}.items():
+        x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+        b = torch.randn(N, device=dev)
+        b16 = b.to(torch.bfloat16)
+        ours = graphed(lambda: ops.linear_small(w, b, x=x))
+        lib = graphed(lambda: torch.addmm(b16, x, w.t()))
+        out["linear_us"][name] = {"dvis_linear_small": round(timeit(ours), 2), "torch_addmm": round(timeit(lib), 2)}
+    # LayerNorm-prologue form vs library GEMM + the separate add_layernorm it replaces
+    M, N, K = 200, 1536, 512
+    src0, src1 = torch.randn(M, K, device=dev), torch.randn(M, K, device=dev).to(torch.bfloat16)
+    g, b0 = torch.ones(K, device=dev), torch.zeros(K, device=dev)
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    ours = graphed(lambda: ops.linear_small(w, bias, src0=src0, ln0=(g, b0), src1=src1, ln1=(g, b0), want_side0=True, want_side1=True))
+    b16 = bias.to(torch.bfloat16)
+
+    def lib_fn():
+        y32, y16, _ = ops.add_layernorm(src1, src0, g, b0, 1e-5, lp_dtype=torch.bfloat16)
+        return torch.addmm(b16, y16, w.t())
+    out["linear_us"]["ln_prologue_qkv (200,1536,512)"] = {"dvis_linear_small (2 LN in prologue)": round(timeit(ours), 2),
+                                                         "add_layernorm + addmm": round(timeit(graphed(lib_fn)), 2)}
+
+    runner = bench.build_models(dev, queries=200)
+    T, Q = 16, 200
+    base = torch.randn(1, 512, 1, Q, device=dev)
+    fe = base + 0.3 * torch.randn(1, 512, T, Q, device=dev)
+    fn = fe + 0.1 * torch.randn(1, 512, T, Q, device=dev)
+    trk, rfn = runner.tracker, runner.refiner
+
+    def tracker():
+        return trk(fe, None, resume=False, frame_embeds_no_norm=fn, with_masks=False)
+    emb = tracker()["pred_embds"]
+
+    def refiner():
+        return rfn.refine(emb, fn)
+    for fused in (False, True):
+        for pdl in ((False, True) if fused else (False,)):
+            ops.set_pdl(pdl)
+            trk.use_fused_kernels = rfn.use_fused_kernels = fused
+            trk._graphs = {}
+            tag = ("fused" if fused else "library") + (" +pdl" if pdl else "")
+            res = {}
+            trk.use_cuda_graph = True
+            res["tracker_eager_per_frame_graphs"] = round(timeit(tracker, 10, 3) / 1e3, 3)
+            res["refiner_eager"] = round(timeit(refiner, 10, 3) / 1e3, 3)
+            try:
+                res["tracker_one_graph"] = round(timeit(graphed(tracker), 20, 3) / 1e3, 3)
+                res["refiner_one_graph"] = round(timeit(graphed(refiner), 20, 3) / 1e3, 3)
+            except Exception as exc:                      # PDL inside stream capture is the open question
+                res["one_graph_error"] = repr(exc)[:300]
+            out["stage_ms"][tag] = res
+    ops.set_pdl(False)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r2_temporal_microbench.json"), "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,7 @@ namespace dvis { char *last_error_buffer() { static thread_local char buf[512] =
 extern "C" const char *dvis_last_error(void) { return dvis::last_error_buffer(); }
 extern "C" int dvis_abi_version(void) { return DVIS_B200_ABI_VERSION; }
 extern "C" void simt_set_jitter(int one_in) { simt::g_jitter = one_in; }
+extern "C" int dvis_set_pdl(int) { return 0; }
 
 namespace {
 template <typename TO>

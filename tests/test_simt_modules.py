@@ -265,3 +265,74 @@ def test_mask_logits_query_slices_beyond_256(device):
     masked = ref.flatten(2) < 0
     masked[masked.all(-1)] = False
     assert torch.equal(torch.isinf(bias) & (bias < 0), masked)
+
+
+# ---- round 2: the fused temporal-stage kernels (csrc/small_linear.cu, csrc/flash_attn.cu) under the module fast paths ----
+
+def build_tracker_w128(g):
+    t = M.ReferringTracker_noiser(hidden_channel=128, feedforward_channel=256, num_head=4, decoder_layer_num=2,
+                                  mask_dim=64, class_num=5, noise_mode="none").eval()
+    assert not any(t.load_state_dict(g["state_dict"]))
+    return t
+
+
+def build_refiner_w128(g):
+    r = M.TemporalRefiner(hidden_channel=128, feedforward_channel=256, num_head=4, decoder_layer_num=2, mask_dim=64,
+                          class_num=5, windows=3).eval()
+    assert not any(r.load_state_dict(g["state_dict"]))
+    return r
+
+
+def test_tracker_fused_kernels_vs_reference_golden(golden, device):
+    """hidden 128 (4 heads x 32): first frame, later frames and a resumed window all run on dvis_linear_small /
+    dvis_flash_attn only -- against the unmodified reference's outputs (tests/golden/make_golden_r2.py)."""
+    g = golden("tracker_w128.pt")
+    t = build_tracker_w128(g)
+    t.use_cuda_graph = False
+    fe, fn, mf = g["frame_embeds"], g["frame_embeds_no_norm"], g["mask_features"]
+    calls = _lib.launch_count
+    with precision("bf16"):
+        assert t._fused_ok(t._stacked(torch.bfloat16))
+        o1, i1 = t(fe[:, :, :3], mf[:, :3], resume=False, return_indices=True, frame_embeds_no_norm=fn[:, :, :3])
+        o2, i2 = t(fe[:, :, 3:], mf[:, 3:], resume=True, return_indices=True, frame_embeds_no_norm=fn[:, :, 3:])
+    # window 1: kv + first frame (2 layers x 11) + 2 later frames (6 + 2 x 5) + final LN; window 2: kv + 1 frame + final LN (+ LAP, masks)
+    assert _lib.launch_count - calls >= (1 + 22 + 2 * 16 + 1) + (1 + 16 + 1)
+    for a, b in zip(i1 + i2, g["indices"]):
+        assert np.array_equal(np.asarray(a), b.numpy())
+    assert rel_err(torch.cat([o1["pred_embds"], o2["pred_embds"]], 2).float(), g["pred_embds"]) < 3e-2
+    assert rel_err(torch.cat([o1["pred_references"], o2["pred_references"]], 2).float(), g["pred_references"]) < 3e-2
+    assert rel_err(torch.cat([o1["pred_logits"], o2["pred_logits"]], 1).float(), g["pred_logits"]) < 3e-2
+    assert rel_err(torch.cat([o1["pred_masks"], o2["pred_masks"]], 2).float(), g["pred_masks"]) < 3e-2
+    # the recurrent state keeps the reference's layout: (1 + layers, q, b, c)
+    assert t.last_outputs.shape == (3, 10, 1, 128) and t.last_reference.shape == (10, 1, 128)
+
+
+def test_tracker_fused_equals_library_path(golden, device):
+    g = golden("tracker_w128.pt")
+    fe, fn = g["frame_embeds"], g["frame_embeds_no_norm"]
+    outs = []
+    for fused in (True, False):
+        t = build_tracker_w128(g)
+        t.use_cuda_graph = False
+        t.use_fused_kernels = fused
+        with precision("bf16"):
+            outs.append(t(fe, None, resume=False, frame_embeds_no_norm=fn, with_masks=False))
+    assert rel_err(outs[0]["pred_embds"].float(), outs[1]["pred_embds"].float()) < 2e-2
+    assert rel_err(outs[0]["pred_logits"].float(), outs[1]["pred_logits"].float()) < 2e-2
+
+
+def test_refiner_fused_kernels_vs_reference_golden(golden, device):
+    """hidden 128, T=7: time attention through strided views, Conv1d k5 / k3 as tap GEMMs with replicate padding, object
+    and cross attention -- all on dvis_linear_small / dvis_flash_attn -- against the unmodified reference."""
+    g = golden("refiner_w128.pt")
+    r = build_refiner_w128(g)
+    calls = _lib.launch_count
+    with precision("bf16"):
+        o = r(g["instance_embeds"], g["frame_embeds"], g["mask_features"])
+    assert _lib.launch_count - calls >= 1 + 2 * 14 + 1
+    for k in ("pred_embds", "pred_logits", "pred_masks"):
+        assert rel_err(o[k].float(), g[k]) < 3e-2, (k, rel_err(o[k].float(), g[k]))
+    r.use_fused_kernels = False
+    with precision("bf16"):
+        o_lib = r(g["instance_embeds"], g["frame_embeds"], g["mask_features"])
+    assert rel_err(o["pred_embds"].float(), o_lib["pred_embds"].float()) < 2e-2

@@ -1,0 +1,167 @@
+"""Round-2 temporal-stage kernels on the B200 through the C ABI (ops front ends): dvis_flash_attn and dvis_linear_small
+against fp32 torch references on the same bf16 inputs, at the sizes the tracker / refiner / predictor use them, and the
+fused tracker / refiner module paths against the unmodified reference's golden outputs (hidden 128) and against the
+library path at production width (hidden 512, Q = 200)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from dvis_plus_b200 import _lib, ops
+from dvis_plus_b200.modules.precision import precision
+from test_simt_temporal_kernels import _bf, _ln, pack_bits, ref_attention
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return (a.double() - b.double()).abs().max().item() / max(1e-6, b.double().abs().max().item())
+
+
+@pytest.mark.parametrize("B,Lq,Lk,H,Dh", [(1, 200, 200, 8, 64), (6, 200, 200, 8, 64), (16, 200, 200, 8, 64), (200, 16, 16, 8, 64),
+                                          (2, 300, 300, 8, 32), (1, 100, 920, 8, 32), (1, 7, 1, 1, 64), (3, 33, 1000, 2, 32)])
+def test_flash_attn_vs_fp32_reference(B, Lq, Lk, H, Dh):
+    torch.manual_seed(Lq + Lk)
+    scale = 1 / math.sqrt(Dh)
+    qp = torch.randn(B, Lq, 3, H, Dh, device="cuda").to(torch.bfloat16)       # slices of packed projections
+    kvp = torch.randn(B, Lk, 2, H, Dh, device="cuda").to(torch.bfloat16)
+    q, k, v = qp[:, :, 0], kvp[:, :, 0], kvp[:, :, 1]
+    n0 = _lib.launch_count
+    out = ops.flash_attn(q, k, v, scale)
+    assert _lib.launch_count == n0 + 1
+    ref = ref_attention(q, k, v, scale)
+    assert rel_err(out.float(), ref) < 1e-2                                    # north star: 1e-2 bf16
+
+
+def test_flash_attn_time_attention_layout():
+    """the refiner's attention over time: batch = queries, rows = frames, output written transposed (t, q, c)"""
+    T, Q, H, Dh = 16, 200, 8, 64
+    qkv = torch.randn(T, Q, 3, H, Dh, device="cuda").to(torch.bfloat16)
+    v = qkv.permute(1, 0, 2, 3, 4)
+    o = torch.empty(T, Q, H * Dh, device="cuda", dtype=torch.bfloat16)
+    ops.flash_attn(v[:, :, 0], v[:, :, 1], v[:, :, 2], 0.125, out=o.permute(1, 0, 2))
+    ref = ref_attention(v[:, :, 0], v[:, :, 1], v[:, :, 2], 0.125).permute(1, 0, 2)
+    assert rel_err(o.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("Lk", [920, 3680, 14720])
+def test_flash_attn_bit_mask_predictor_levels(Lk):
+    """masked cross-attention at the predictor's three memory lengths (720p levels), 8 heads x 32"""
+    torch.manual_seed(Lk)
+    B, Lq, H, Dh = 2, 200, 8, 32
+    q = torch.randn(B, Lq, H, Dh, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, Lk, H, Dh, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, Lk, H, Dh, device="cuda").to(torch.bfloat16)
+    mask = torch.rand(B, Lq, Lk) < 0.8
+    mask[:, :, 5] = False
+    out = ops.flash_attn(q, k, v, 1 / math.sqrt(Dh), pack_bits(mask).cuda())
+    ref = ref_attention(q, k, v, 1 / math.sqrt(Dh), mask.cuda())
+    assert rel_err(out.float(), ref) < 1e-2
+
+
+def test_flash_attn_rejects_cpu_tensors():
+    q = torch.zeros(1, 4, 1, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.flash_attn(q, q, q, 1.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 512, 512), (200, 1536, 512), (200, 2048, 512), (200, 512, 2048), (200, 3072, 512),
+                                   (3200, 512, 512), (3200, 2048, 512), (3200, 512, 2048), (45, 72, 128)])
+def test_linear_small_plain(M, N, K):
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    b, res = torch.randn(N, device="cuda"), torch.randn(M, N, device="cuda")
+    y32, y16, _, _ = ops.linear_small(w, b, x=x, relu=True, residual=res, out_f32=True)
+    ref = torch.relu(x.float() @ w.float().t() + b) + res
+    assert rel_err(y32, ref) < 1e-3                                            # north star: 1e-3 fp32 (same bf16 operands)
+    assert rel_err(y16.float(), ref) < 1e-2
+
+
+def test_linear_small_batched_out_projections():
+    L, Q, C = 6, 200, 512
+    x = torch.randn(L, Q, C, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(L, C, C, device="cuda") / C ** 0.5).to(torch.bfloat16)
+    b = torch.randn(L, C, device="cuda")
+    y32, _, _, _ = ops.linear_small(w, b, x=x, out_f32=True, out_bf16=False)
+    assert rel_err(y32, torch.einsum("bmk,bnk->bmn", x.float(), w.float()) + b[:, None]) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 1536, 512), (3200, 512, 512), (200, 768, 256), (37, 192, 384)])
+def test_linear_small_layernorm_prologue(M, N, K):
+    torch.manual_seed(N)
+    dev = "cuda"
+    src0, src1 = torch.randn(M, K, device=dev) * 2 + 0.5, torch.randn(M, K, device=dev).to(torch.bfloat16)
+    g0, b0, g1, b1 = (torch.rand(K, device=dev) + 0.5, torch.randn(K, device=dev) * 0.1, torch.rand(K, device=dev) + 0.5,
+                      torch.randn(K, device=dev) * 0.1)
+    w, b = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16), torch.randn(N, device=dev)
+    y32, _, s0, s1 = ops.linear_small(w, b, src0=src0, ln0=(g0, b0), src1=src1, ln1=(g1, b1), want_side0=True, want_side1=True,
+                                     out_f32=True, out_bf16=False)
+    r0 = _ln(src0, g0, b0)
+    r1 = _ln(r0 + src1.float(), g1, b1)
+    assert (s0 - r0).abs().max() < 2e-5 and (s1 - r1).abs().max() < 2e-5       # every element of both side outputs written
+    assert rel_err(y32, _bf(r1) @ w.float().t() + b) < 2e-3
+
+
+@pytest.mark.parametrize("k", [5, 3])
+def test_linear_small_conv1d_over_time(k):
+    T, Q, C = 16, 200, 512
+    x = torch.randn(T, Q, C, device="cuda").to(torch.bfloat16)
+    conv = torch.nn.Conv1d(C, C, k, padding="same", padding_mode="replicate").cuda()
+    conv.weight.data = conv.weight.data.to(torch.bfloat16).float()
+    wk = conv.weight.detach().permute(0, 2, 1).reshape(C, k * C).to(torch.bfloat16).contiguous()
+    y32, _, _, _ = ops.linear_small(wk, conv.bias.detach().float(), x=x.view(T * Q, C), taps=k, tap_pad=k // 2, tap_period=Q,
+                                    tap_len=T, out_f32=True, out_bf16=False)
+    with torch.no_grad():
+        ref = conv(x.float().permute(1, 2, 0)).permute(2, 0, 1).reshape(T * Q, C)
+    assert rel_err(y32, ref) < 1e-3
+
+
+@torch.no_grad()
+def test_tracker_and_refiner_fused_paths_vs_reference_golden(golden):
+    from test_simt_modules import build_refiner_w128, build_tracker_w128
+    g = golden("tracker_w128.pt")
+    t = build_tracker_w128(g).cuda()
+    fe, fn, mf = g["frame_embeds"].cuda(), g["frame_embeds_no_norm"].cuda(), g["mask_features"].cuda()
+    with precision("bf16"):
+        o1, i1 = t(fe[:, :, :3], mf[:, :3], resume=False, return_indices=True, frame_embeds_no_norm=fn[:, :, :3])
+        o2, i2 = t(fe[:, :, 3:], mf[:, 3:], resume=True, return_indices=True, frame_embeds_no_norm=fn[:, :, 3:])
+    for a, b in zip(i1 + i2, g["indices"]):
+        assert np.array_equal(np.asarray(a), b.numpy())
+    assert rel_err(torch.cat([o1["pred_embds"], o2["pred_embds"]], 2).float().cpu(), g["pred_embds"]) < 1e-2
+    assert rel_err(torch.cat([o1["pred_logits"], o2["pred_logits"]], 1).float().cpu(), g["pred_logits"]) < 1e-2
+    assert rel_err(torch.cat([o1["pred_masks"], o2["pred_masks"]], 2).float().cpu(), g["pred_masks"]) < 1e-2
+    g = golden("refiner_w128.pt")
+    r = build_refiner_w128(g).cuda()
+    n0 = _lib.launch_count
+    with precision("bf16"):
+        o = r(g["instance_embeds"].cuda(), g["frame_embeds"].cuda(), g["mask_features"].cuda())
+    assert _lib.launch_count - n0 >= 30
+    for k in ("pred_embds", "pred_logits", "pred_masks"):
+        assert rel_err(o[k].float().cpu(), g[k]) < 1e-2, k
+
+
+@torch.no_grad()
+def test_fused_temporal_stage_equals_library_path_at_production_width():
+    """hidden 512, Q = 200, T = 16 (BASELINE config 4): fused kernels vs the cuBLAS / cuDNN path of round 1, and the
+    per-frame CUDA graph vs the plain loop (bit-identical: same kernels, same order)."""
+    import bench
+    torch.manual_seed(1)
+    runner = bench.build_models("cuda", queries=200)
+    T, Q = 16, 200
+    base = torch.randn(1, 512, 1, Q, device="cuda")
+    fe = base + 0.3 * torch.randn(1, 512, T, Q, device="cuda")
+    fn = fe + 0.1 * torch.randn(1, 512, T, Q, device="cuda")
+    trk, rfn = runner.tracker, runner.refiner
+    res = {}
+    for name, fused, graph in (("fused", True, True), ("fused_nograph", True, False), ("library", False, True)):
+        trk.use_fused_kernels = rfn.use_fused_kernels = fused
+        trk.use_cuda_graph = graph
+        with precision("bf16"):
+            o = trk(fe, None, resume=False, frame_embeds_no_norm=fn, with_masks=False)
+            res[name] = (o["pred_embds"].float(), o["pred_logits"].float(), rfn.refine(o["pred_embds"], fn).float())
+    for a, b in zip(res["fused"], res["fused_nograph"]):
+        assert torch.equal(a, b)
+    for a, b in zip(res["fused"], res["library"]):
+        assert rel_err(a, b) < 1e-2, rel_err(a, b)
