@@ -31,6 +31,7 @@ SIGNATURES = {
     "dvis_lap_rect": [_vp, _i, _i, _i, _vp, _vp],
     "dvis_mask_logits_strided": [_vp, _i64, _vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp],
     "dvis_mask_attn_bias": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp, _vp],
+    "dvis_mask_attn_bits": [_vp, _vp, _i, _i, _i, _i64, _vp, _i64, _vp, _vp],
     "dvis_mha_core": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp],
     "dvis_flash_attn": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                         _i, _i, _i, _i, _i, _f, _vp],

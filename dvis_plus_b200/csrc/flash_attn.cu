@@ -31,27 +31,33 @@ struct FlashParams {
   int stages;
 };
 
-template <int DH>
+// SPLIT = true  (short key sequences): 16 query rows per CTA, the 4 warps split the KEY blocks, states merged at the end;
+// SPLIT = false (long key sequences, the predictor's 920 .. 14 720-pixel memories): 64 query rows per CTA, one m16 tile per
+//                warp, all warps walk every key block through a CTA-wide 2-stage ring -- K / V are streamed 4x less often.
+template <int DH, bool SPLIT>
 __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashParams p) {
   constexpr int RS = DH + 8;                       // padded row stride (bf16): 16-byte aligned, ldmatrix conflict-free
   constexpr int TILE = kFaKeys * RS;               // elements of one K (or V) block
   constexpr int KSTEPS = DH / 16, DT = DH / 8;
   extern __shared__ uint4 fa_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.z, h = blockIdx.y, row0 = blockIdx.x * kFaRows;
-  __nv_bfloat16 *wbase = reinterpret_cast<__nv_bfloat16 *>(fa_smem) + (size_t)warp * p.stages * 2 * TILE;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int row0 = SPLIT ? blockIdx.x * kFaRows : (blockIdx.x * kFaWarps + warp) * kFaRows;   // this WARP's first query row
+  __nv_bfloat16 *wbase = reinterpret_cast<__nv_bfloat16 *>(fa_smem) + (SPLIT ? (size_t)warp * p.stages * 2 * TILE : 0);
+  const int ld0 = SPLIT ? lane : (int)threadIdx.x, ldn = SPLIT ? 32 : kFaWarps * 32;          // who copies a key block
+  const int blk0 = SPLIT ? warp : 0, blk_step = SPLIT ? kFaWarps : 1;
   const __nv_bfloat16 *kb = p.k + (size_t)b * p.k_batch + (size_t)h * p.k_head;
   const __nv_bfloat16 *vb = p.v + (size_t)b * p.v_batch + (size_t)h * p.v_head;
   const int nblocks = (p.Lk + kFaKeys - 1) / kFaKeys;
 
-  auto issue = [&](int blk, int stage) {           // this warp's copy of key block `blk` into ring slot `stage`
+  auto issue = [&](int blk, int stage) {           // this warp's (SPLIT) / CTA's copy of key block `blk` into ring slot `stage`
     __nv_bfloat16 *sk = wbase + (size_t)stage * 2 * TILE, *sv = sk + TILE;
     const int key0 = blk * kFaKeys;
     constexpr int CH = DH / 8;                     // 16-byte chunks per row
     // rows the MMAs below touch: whole 16-key steps that hold at least one valid key (the rest of the slot is never read);
     // rows past Lk are zero-filled so that 0-probability x V stays 0
     const int rows = min(kFaKeys, ((p.Lk - key0 + 15) >> 4) << 4);
-    for (int c = lane; c < rows * CH; c += 32) {
+    for (int c = ld0; c < rows * CH; c += ldn) {
       const int r = c / CH, cc = c - r * CH, key = key0 + r;
       const bool ok = key < p.Lk;
       const size_t kr = ok ? (size_t)key : 0;
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
   };
 
   pdl_wait();
-  if (warp < nblocks) issue(warp, 0);
+  if (blk0 < nblocks) issue(blk0, 0);
 
   // Q fragments of rows (g, g+8) straight from global memory
   uint32_t qa[KSTEPS][4];
@@ -90,16 +96,16 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
   }
 
   int it = 0;
-  for (int blk = warp; blk < nblocks; blk += kFaWarps, ++it) {
+  for (int blk = blk0; blk < nblocks; blk += blk_step, ++it) {
     const int stage = p.stages == 2 ? (it & 1) : 0;
-    const bool more = blk + kFaWarps < nblocks;
+    const bool more = blk + blk_step < nblocks;
     if (p.stages == 2 && more) {
-      issue(blk + kFaWarps, stage ^ 1);
+      issue(blk + blk_step, stage ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    __syncwarp();
+    if constexpr (SPLIT) __syncwarp(); else __syncthreads();
     const __nv_bfloat16 *sk = wbase + (size_t)stage * 2 * TILE, *sv = sk + TILE;
     const int key0 = blk * kFaKeys;
     const int nkeys = min(kFaKeys, p.Lk - key0);
@@ -178,15 +184,27 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
         }
       }
     }
-    __syncwarp();                                  // every lane is done with this ring slot before it is refilled
+    if constexpr (SPLIT) __syncwarp(); else __syncthreads();   // everyone is done with this ring slot before it is refilled
   }
   pdl_launch_dependents();
 
-  // ---- merge the 4 warps' partial states ----
   lrow[0] += __shfl_xor_sync(0xffffffffu, lrow[0], 1);
   lrow[0] += __shfl_xor_sync(0xffffffffu, lrow[0], 2);
   lrow[1] += __shfl_xor_sync(0xffffffffu, lrow[1], 1);
   lrow[1] += __shfl_xor_sync(0xffffffffu, lrow[1], 2);
+  if constexpr (!SPLIT) {
+    // each warp owns its 16 rows outright: normalise and store from the fragments
+    const float i0 = lrow[0] > 0.f ? 1.f / lrow[0] : 0.f, i1 = lrow[1] > 0.f ? 1.f / lrow[1] : 0.f;
+    __nv_bfloat16 *ob = p.o + (size_t)b * p.o_batch + (size_t)h * DH + 2 * t;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      if (row0 + g < p.Lq) *reinterpret_cast<uint32_t *>(ob + (size_t)(row0 + g) * p.o_row + i * 8) = pack_bf16x2(o[i][0] * i0, o[i][1] * i0);
+      if (row0 + g + 8 < p.Lq)
+        *reinterpret_cast<uint32_t *>(ob + (size_t)(row0 + g + 8) * p.o_row + i * 8) = pack_bf16x2(o[i][2] * i1, o[i][3] * i1);
+    }
+    return;
+  }
+  // ---- SPLIT: merge the 4 warps' partial states ----
   constexpr int OS = DH + 4;                       // fp32 row stride of the merge buffer
   float *mo = reinterpret_cast<float *>(wbase);    // this warp's own ring memory: [16][OS] then m[16], l[16]
   float *mm = mo + kFaRows * OS, *ml = mm + kFaRows;
@@ -224,15 +242,16 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
   }
 }
 
-template <int DH>
+template <int DH, bool SPLIT>
 int launch_flash(const FlashParams &p, cudaStream_t s) {
-  const size_t ring = (size_t)kFaWarps * p.stages * 2 * kFaKeys * (DH + 8) * sizeof(__nv_bfloat16);
-  cudaFuncSetAttribute(flash_attn_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring));
-  dim3 grid((p.Lq + kFaRows - 1) / kFaRows, p.H, p.B);
+  const size_t ring = (size_t)(SPLIT ? kFaWarps : 1) * p.stages * 2 * kFaKeys * (DH + 8) * sizeof(__nv_bfloat16);
+  cudaFuncSetAttribute(flash_attn_kernel<DH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring));
+  const int rows = SPLIT ? kFaRows : kFaRows * kFaWarps;
+  dim3 grid((p.Lq + rows - 1) / rows, p.H, p.B);
 #ifdef DVIS_SIMT_EMULATION
-  flash_attn_kernel<DH><<<grid, kFaWarps * 32, ring, s>>>(p);
+  flash_attn_kernel<DH, SPLIT><<<grid, kFaWarps * 32, ring, s>>>(p);
 #else
-  launch_pdl<FlashParams>(flash_attn_kernel<DH>, grid, dim3(kFaWarps * 32), ring, s, p);
+  launch_pdl<FlashParams>(flash_attn_kernel<DH, SPLIT>, grid, dim3(kFaWarps * 32), ring, s, p);
 #endif
   return check_launch("flash_attn_kernel");
 }
@@ -267,7 +286,11 @@ extern "C" int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, in
                 o_batch, static_cast<const uint8_t *>(mask_bits), mask_row_bytes, mask_batch_bytes, B, Lq, Lk, H,
                 scale * 1.4426950408889634f, 1};
   const int nblocks = (Lk + kFaKeys - 1) / kFaKeys;
-  p.stages = nblocks > kFaWarps ? 2 : 1;           // a warp with more than one key block prefetches the next one
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return Dh == 32 ? launch_flash<32>(p, s) : launch_flash<64>(p, s);
+  if (Lk > 512) {                                   // long memories: 64-row tiles, every warp walks every key block
+    p.stages = 2;
+    return Dh == 32 ? launch_flash<32, false>(p, s) : launch_flash<64, false>(p, s);
+  }
+  p.stages = nblocks > kFaWarps ? 2 : 1;           // a warp with more than one key block prefetches the next one
+  return Dh == 32 ? launch_flash<32, true>(p, s) : launch_flash<64, true>(p, s);
 }

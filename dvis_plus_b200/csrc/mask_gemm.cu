@@ -41,6 +41,9 @@ struct MaskGemmParams {
   int *row_open;        // kBias epilogue: row_open[b*Q + q] = 1 if some pixel of the row has logit >= 0
   int64_t out_batch;    // elements between batch items of `out` (Q*HW when dense; larger for a query slice)
   int epi_bufs;         // output staging tiles in flight (2..4): depth of the TMA-store pipeline
+  uint8_t *bits;        // kBits epilogue: (B*Q) rows of bits_row bytes, bit (p % 8) of byte (p / 8) set <=> logit[p] < 0
+  int64_t bits_row;
+  int row_batch;        // rows (queries) per batch item in row_open / bits (= Q unless this launch covers a query slice)
 };
 
 struct __align__(8) Barriers {
@@ -63,7 +66,11 @@ __device__ __forceinline__ __nv_bfloat16 cvt_logit<__nv_bfloat16>(uint32_t bits)
 // kBias = true: the epilogue writes the additive attention bias of the masked-attention decoder instead of the logits:
 // -inf where sigmoid(logit) < 0.5 <=> logit < 0, else 0 (decoder.py:370-371), and records per (b, q) row whether any pixel
 // stays open so that fully masked rows can be reset afterwards (decoder.py:297).
-template <typename TO, bool kTmaStore, bool kBias = false>
+// kBits = true: the epilogue writes ONE BIT per (query, pixel) -- set where the query may NOT attend the pixel -- instead of
+// a 16- or 32-bit bias: what csrc/flash_attn.cu consumes (16x fewer bytes than the bf16 bias, L2-resident; nothing else of the
+// 9 intermediate mask-head calls ever reaches HBM).  A warp's 32 lanes are 32 consecutive pixels, so one ballot per query
+// column is the packed word; lane i keeps column i's word and the 32 words of a chunk go out as 32 4-byte stores.
+template <typename TO, bool kTmaStore, bool kBias = false, bool kBits = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_emb,
                  const __grid_constant__ CUtensorMap tmap_out, const MaskGemmParams p) {
@@ -171,13 +178,28 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
         uint32_t r[32];
         tmem_ld_32x32(taddr + c0, r);
         tmem_ld_wait();
+        if constexpr (kBits) {
+          const bool pix_ok = (int64_t)tile * kTileM + px < p.HW;
+          uint32_t mine = 0;
+#pragma unroll
+          for (int i = 0; i < kEpiCols; ++i) {
+            const bool open = pix_ok && !(__uint_as_float(r[i]) < 0.f);
+            const unsigned any = __ballot_sync(0xffffffffu, open);
+            if (any && lane == 0 && c0 + i < p.Q) p.row_open[b * p.row_batch + c0 + i] = 1;
+            if (lane == i) mine = ~any;
+          }
+          const int64_t off = (int64_t)tile * (kTileM / 8) + quarter * 4;
+          if (c0 + lane < p.Q && off + 4 <= p.bits_row)
+            *reinterpret_cast<uint32_t *>(p.bits + ((int64_t)b * p.row_batch + c0 + lane) * p.bits_row + off) = mine;
+          continue;
+        }
         if constexpr (kBias) {
           const bool pix_ok = (int64_t)tile * kTileM + px < p.HW;
 #pragma unroll
           for (int i = 0; i < kEpiCols; ++i) {
             const bool open = pix_ok && !(__uint_as_float(r[i]) < 0.f);
             const unsigned any = __ballot_sync(0xffffffffu, open);
-            if (any && lane == 0 && c0 + i < p.Q) p.row_open[b * p.Q + c0 + i] = 1;
+            if (any && lane == 0 && c0 + i < p.Q) p.row_open[b * p.row_batch + c0 + i] = 1;
             r[i] = open ? 0u : 0xff800000u;                 // 0.0f / -inf
           }
         }
@@ -249,9 +271,17 @@ __global__ void __launch_bounds__(256) reset_closed_rows_kernel(const int *__res
   TB *b = bias + row * HW;
   for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) b[i] = TB(0.f);
 }
+__global__ void __launch_bounds__(128) reset_closed_bit_rows_kernel(const int *__restrict__ row_open, uint8_t *__restrict__ bits,
+                                                                   int64_t row_bytes) {
+  const int64_t row = blockIdx.x;
+  if (row_open[row]) return;
+  uint32_t *w = reinterpret_cast<uint32_t *>(bits + row * row_bytes);
+  for (int64_t i = threadIdx.x; i < row_bytes / 4; i += blockDim.x) w[i] = 0u;
+}
 }  // namespace
 int mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
-                     int *row_open, void *stream, int64_t emb_batch = 0, int64_t out_batch = 0);
+                     int *row_open, void *stream, int64_t emb_batch = 0, int64_t out_batch = 0, int64_t bits_row = 0,
+                     int row_batch = 0);
 }  // namespace dvis
 
 extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out,
@@ -279,8 +309,26 @@ extern "C" int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int
   return check_launch("reset_closed_rows_kernel");
 }
 
+extern "C" int dvis_mask_attn_bits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bits,
+                                   int64_t bits_row_bytes, int *row_open_workspace, void *stream) {
+  DVIS_REQUIRE(row_open_workspace && bits, "mask_attn_bits: null pointer argument");
+  DVIS_REQUIRE(bits_row_bytes % 8 == 0 && bits_row_bytes >= ((HW + 63) / 64) * 8 && (reinterpret_cast<uintptr_t>(bits) & 7) == 0,
+               "mask_attn_bits: rows must be 8-byte aligned and hold ceil(HW / 64) * 8 bytes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(row_open_workspace, 0, sizeof(int) * size_t(B) * Q, s);
+  for (int q0 = 0; q0 < Q; q0 += 256) {             // the GEMM holds at most 256 queries in TMEM: slices of the query dim
+    const int nq = std::min(256, Q - q0);
+    if (int rc = mask_gemm_launch(static_cast<const __nv_bfloat16 *>(emb) + (size_t)q0 * C, feat, B, nq, C, HW,
+                                  static_cast<uint8_t *>(bits) + (size_t)q0 * bits_row_bytes, DVIS_F32, row_open_workspace + q0,
+                                  stream, (int64_t)Q * C, 0, bits_row_bytes, Q))
+      return rc;
+  }
+  reset_closed_bit_rows_kernel<<<B * Q, 128, 0, s>>>(row_open_workspace, static_cast<uint8_t *>(bits), bits_row_bytes);
+  return check_launch("reset_closed_bit_rows_kernel");
+}
+
 int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
-                           int *row_open, void *stream, int64_t emb_batch, int64_t out_batch) {
+                           int *row_open, void *stream, int64_t emb_batch, int64_t out_batch, int64_t bits_row, int row_batch) {
   DVIS_REQUIRE(emb && feat && out, "mask_logits: null pointer argument");
   DVIS_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_logits: sizes must be positive");
   DVIS_REQUIRE(C % kBlockK == 0 && C <= 512, "mask_logits: C must be a multiple of 64 and <= 512 (got %d)", C);
@@ -293,12 +341,15 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
   MaskGemmParams p{};
   p.out = out; p.B = B; p.Q = Q; p.Qpad = (Q + 15) & ~15; p.KB = C / kBlockK; p.HW = HW;
   p.row_open = row_open;
+  p.bits = bits_row ? static_cast<uint8_t *>(out) : nullptr;
+  p.bits_row = bits_row;
+  p.row_batch = row_batch ? row_batch : Q;
   p.out_batch = out_batch ? out_batch : (int64_t)Q * HW;
   p.tiles_per_batch = int((HW + kTileM - 1) / kTileM);
   p.total_tiles = p.tiles_per_batch * B;
   const int b_bytes = p.KB * p.Qpad * 128;
   const int esize = out_dtype == DVIS_F32 ? 4 : 2;
-  const bool tma_store = aligned16(out) && (HW * esize) % 16 == 0 && (p.out_batch * esize) % 16 == 0;   // TMA: 16-byte pitches
+  const bool tma_store = !bits_row && aligned16(out) && (HW * esize) % 16 == 0 && (p.out_batch * esize) % 16 == 0;   // TMA: 16-byte pitches
   // deepest store pipeline (up to 4 staging tiles) that still leaves >= 4 A stages
   int stage_out_bytes = 0, budget = 0;
   for (p.epi_bufs = 4; p.epi_bufs >= 2; --p.epi_bufs) {
@@ -333,7 +384,10 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
     if (row_open) { if (tma_store) DVIS_LAUNCH(TO, true, true); else DVIS_LAUNCH(TO, false, true); } \
     else { if (tma_store) DVIS_LAUNCH(TO, true, false); else DVIS_LAUNCH(TO, false, false); }        \
   } while (0)
-  if (out_dtype == DVIS_F32) DVIS_LAUNCH_T(float); else DVIS_LAUNCH_T(__nv_bfloat16);
+  if (bits_row) {
+    cudaFuncSetAttribute(mask_gemm_kernel<float, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    mask_gemm_kernel<float, false, false, true><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);
+  } else if (out_dtype == DVIS_F32) DVIS_LAUNCH_T(float); else DVIS_LAUNCH_T(__nv_bfloat16);
 #undef DVIS_LAUNCH_T
 #undef DVIS_LAUNCH
   return check_launch("mask_gemm_kernel");

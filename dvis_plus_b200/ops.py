@@ -314,6 +314,26 @@ def mask_attn_bias(mask_embed, level_features, dtype=torch.bfloat16):
     return bias
 
 
+def mask_attn_bits(mask_embed, level_features):
+    """The masked-attention decoder's attention mask as packed bits, straight from the tcgen05 mask GEMM
+    (dvis_mask_attn_bits): mask_embed (B,Q,C); level_features (B,C,h,w) bf16 channels_last.
+    -> uint8 (B, Q, ceil(h*w / 64) * 8): bit (p % 8) of byte (p / 8) set where sigmoid(E @ F)[p] < 0.5 (query may not attend
+    pixel p); rows that would be fully masked are cleared.  Feed to `flash_attn(..., mask_bits=)`."""
+    B, Q, C = mask_embed.shape
+    _, _, h, w = level_features.shape
+    if not level_features.is_cuda:
+        raise RuntimeError("mask_attn_bits: CUDA tensors required (there is no CPU path)")
+    assert level_features.dtype == torch.bfloat16 and level_features.is_contiguous(memory_format=torch.channels_last)
+    emb = mask_embed.to(torch.bfloat16).contiguous()
+    row = (h * w + 63) // 64 * 8
+    bits = torch.empty((B, Q, row), dtype=torch.uint8, device=emb.device)
+    ws = torch.empty(B * Q, dtype=torch.int32, device=emb.device)
+    with torch.cuda.device(emb.device):
+        _lib.call("dvis_mask_attn_bits", emb.data_ptr(), level_features.data_ptr(), B, Q, C, h * w, bits.data_ptr(), row,
+                  ws.data_ptr(), _stream())
+    return bits
+
+
 def mha_core(q, k, v, scale):
     """softmax(scale * q k^T) v for short sequences (dvis_mha_core).
 

@@ -233,6 +233,14 @@ int dvis_mask_logits_strided(const void *emb, int64_t emb_batch_stride, const vo
 int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias, int bias_dtype,
                         int *row_open_workspace, void *stream);
 
+/* The same threshold as ONE BIT per (query, pixel) -- the form dvis_flash_attn's `mask_bits` consumes: bit (p % 8) of byte
+ * (p / 8) of row (b*Q + q) is set where sigmoid(logit) < 0.5, i.e. the query may NOT attend pixel p
+ * (P/dvis_Plus/video_mask2former_transformer_decoder.py:370-371); rows that would be fully masked are cleared (:297).
+ * bits: B*Q rows of bits_row_bytes bytes (multiple of 8, >= ceil(HW / 64) * 8; bytes past ceil(HW / 8) are unspecified).
+ * row_open_workspace: B*Q ints. */
+int dvis_mask_attn_bits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bits, int64_t bits_row_bytes,
+                        int *row_open_workspace, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Helpers of the masked-attention decoder's mask head (P/dvis_Plus/video_mask2former_transformer_decoder.py:358-374).
  * dvis_resize_bilinear_nhwc: F.interpolate(mode="bilinear", align_corners=False) (py:367) of a channels-last bf16 map

@@ -63,6 +63,26 @@ extern "C" int dvis_mask_logits_strided(const void *emb, int64_t emb_batch_strid
 extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype, void *s) {
   return dvis_mask_logits_strided(emb, (int64_t)Q * C, feat, B, Q, C, HW, out, (int64_t)Q * HW, out_dtype, s);
 }
+extern "C" int dvis_mask_attn_bits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bits, int64_t row_bytes,
+                                   int *, void *) {
+  const auto *e = static_cast<const __nv_bfloat16 *>(emb), *f = static_cast<const __nv_bfloat16 *>(feat);
+  auto *out = static_cast<uint8_t *>(bits);
+  for (int b = 0; b < B; ++b)
+    for (int q = 0; q < Q; ++q) {
+      uint8_t *row = out + ((int64_t)b * Q + q) * row_bytes;
+      std::memset(row, 0xff, row_bytes);                         // bytes past the row's pixels are unspecified in the product
+      bool any_open = false;
+      for (int64_t p = 0; p < HW; ++p) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc += float(e[((int64_t)b * Q + q) * C + c]) * float(f[((int64_t)b * HW + p) * C + c]);
+        const bool open = !(acc < 0.f);
+        any_open |= open;
+        if (open) row[p >> 3] &= uint8_t(~(1u << (p & 7)));
+      }
+      if (!any_open) std::memset(row, 0, row_bytes);
+    }
+  return 0;
+}
 extern "C" int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias, int bias_dtype, int *,
                                    void *) {
   const auto *e = static_cast<const __nv_bfloat16 *>(emb), *f = static_cast<const __nv_bfloat16 *>(feat);

@@ -32,7 +32,8 @@ def pack_bits(mask):
     return (m.view(B, Lq, nbytes, 8).int() * w).sum(-1).to(torch.uint8).contiguous()
 
 
-@pytest.mark.parametrize("B,Lq,Lk,H,Dh", [(1, 20, 40, 2, 64), (2, 16, 7, 1, 32), (1, 33, 200, 1, 64), (1, 5, 330, 2, 32)])
+@pytest.mark.parametrize("B,Lq,Lk,H,Dh", [(1, 20, 40, 2, 64), (2, 16, 7, 1, 32), (1, 33, 200, 1, 64), (1, 5, 330, 2, 32),
+                                          (1, 70, 530, 1, 32), (1, 9, 577, 1, 64)])      # Lk > 512: the 64-row variant
 def test_flash_attn_matches_fp32_reference(B, Lq, Lk, H, Dh):
     torch.manual_seed(B * 1000 + Lq * 10 + Lk)
     scale = 1 / math.sqrt(Dh)
