@@ -7,18 +7,17 @@
 //
 // Q = 200 rows is a LATENCY problem (one cuDNN flash call costs ~7 us here, 150 of them per clip), so the work is cut
 // for the shortest dependent chain instead of for reuse: a CTA owns 16 query rows of one (batch, head) -- 13 x 8 = 104
-// CTAs for one 200-query layer -- and its 4 warps split the KEYS (flash-decoding): warp w walks key blocks w, w+4, ...
-// of 64 keys with an online softmax in registers (mma.sync m16n8k16, bf16 operands, fp32 accumulate), K / V blocks
-// arrive through a warp-private cp.async ring (1 or 2 stages), and the 4 partial (max, sum, O) states are merged
+// CTAs for one 200-query layer -- and its 8 warps split the KEYS (flash-decoding): warp w walks key blocks w, w+8, ...
+// of 32 keys with an online softmax in registers (mma.sync m16n8k16, bf16 operands, fp32 accumulate), K / V blocks
+// arrive through a warp-private cp.async ring (1 or 2 stages), and the 8 partial (max, sum, O) states are merged
 // through shared memory at the end.  Strides are explicit so q / k / v can be slices of a packed projection output.
 #include "mma.cuh"
 
 namespace dvis {
 namespace {
 
-constexpr int kFaWarps = 4;
-constexpr int kFaKeys = 64;    // keys per block
-constexpr int kFaRows = 16;    // query rows per CTA
+constexpr int kFaWarps = 8;    // 2 warps per scheduler: with 1 the kernel is bound by dependent-issue latency
+constexpr int kFaRows = 16;    // query rows per warp tile
 
 struct FlashParams {
   const __nv_bfloat16 *q, *k, *v;
@@ -31,38 +30,42 @@ struct FlashParams {
   int stages;
 };
 
-// SPLIT = true  (short key sequences): 16 query rows per CTA, the 4 warps split the KEY blocks, states merged at the end;
-// SPLIT = false (long key sequences, the predictor's 920 .. 14 720-pixel memories): 64 query rows per CTA, one m16 tile per
-//                warp, all warps walk every key block through a CTA-wide 2-stage ring -- K / V are streamed 4x less often.
+// SPLIT = true  (short key sequences): 16 query rows per CTA, the 8 warps split the keys in blocks of 32 (flash-decoding),
+//                warp-private cp.async ring, the 8 partial (max, sum, O) states merged through shared memory;
+// SPLIT = false (long key sequences, the predictor's 920 .. 14 720-pixel memories): 128 query rows per CTA, one m16 tile per
+//                warp, all warps walk every 64-key block through a CTA-wide 2-stage ring -- K / V are streamed 8x less often.
 template <int DH, bool SPLIT>
 __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashParams p) {
+  constexpr int KB = SPLIT ? 32 : 64;              // keys per block
   constexpr int RS = DH + 8;                       // padded row stride (bf16): 16-byte aligned, ldmatrix conflict-free
-  constexpr int TILE = kFaKeys * RS;               // elements of one K (or V) block
-  constexpr int KSTEPS = DH / 16, DT = DH / 8;
+  constexpr int TILE = KB * RS;                    // elements of one K (or V) block
+  constexpr int KSTEPS = DH / 16, DT = DH / 8, NKT = KB / 8;
+  constexpr int CH = DH / 8;                       // 16-byte pieces per row
+  constexpr int LDT = SPLIT ? 32 : kFaWarps * 32;  // threads copying one block
+  constexpr int RPP = LDT / CH, PASSES = KB / RPP; // rows per pass, passes per block
   extern __shared__ uint4 fa_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y;
   const int row0 = SPLIT ? blockIdx.x * kFaRows : (blockIdx.x * kFaWarps + warp) * kFaRows;   // this WARP's first query row
-  __nv_bfloat16 *wbase = reinterpret_cast<__nv_bfloat16 *>(fa_smem) + (SPLIT ? (size_t)warp * p.stages * 2 * TILE : 0);
-  const int ld0 = SPLIT ? lane : (int)threadIdx.x, ldn = SPLIT ? 32 : kFaWarps * 32;          // who copies a key block
-  const int blk0 = SPLIT ? warp : 0, blk_step = SPLIT ? kFaWarps : 1;
+  __nv_bfloat16 *ring = reinterpret_cast<__nv_bfloat16 *>(fa_smem) + (SPLIT ? (size_t)warp * p.stages * 2 * TILE : 0);
   const __nv_bfloat16 *kb = p.k + (size_t)b * p.k_batch + (size_t)h * p.k_head;
   const __nv_bfloat16 *vb = p.v + (size_t)b * p.v_batch + (size_t)h * p.v_head;
-  const int nblocks = (p.Lk + kFaKeys - 1) / kFaKeys;
+  const int nblocks = (p.Lk + KB - 1) / KB;
+  const int blk0 = SPLIT ? warp : 0, blk_step = SPLIT ? kFaWarps : 1;
 
+  // per-thread copy assignment, computed once: row (ld / CH) + RPP * pass, piece (ld % CH)
+  const int ld = SPLIT ? lane : (int)threadIdx.x, lr = ld / CH, lc = (ld % CH) * 8;
+  const saddr_t k_dst = saddr(ring) + (lr * RS + lc) * 2;
   auto issue = [&](int blk, int stage) {           // this warp's (SPLIT) / CTA's copy of key block `blk` into ring slot `stage`
-    __nv_bfloat16 *sk = wbase + (size_t)stage * 2 * TILE, *sv = sk + TILE;
-    const int key0 = blk * kFaKeys;
-    constexpr int CH = DH / 8;                     // 16-byte chunks per row
-    // rows the MMAs below touch: whole 16-key steps that hold at least one valid key (the rest of the slot is never read);
-    // rows past Lk are zero-filled so that 0-probability x V stays 0
-    const int rows = min(kFaKeys, ((p.Lk - key0 + 15) >> 4) << 4);
-    for (int c = ld0; c < rows * CH; c += ldn) {
-      const int r = c / CH, cc = c - r * CH, key = key0 + r;
-      const bool ok = key < p.Lk;
+    const int key0 = blk * KB + lr;
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      const int key = key0 + i * RPP;
+      const bool ok = key < p.Lk;                  // rows past Lk are zero-filled so that 0-probability x V stays 0
       const size_t kr = ok ? (size_t)key : 0;
-      cp_async_16(sk + r * RS + cc * 8, kb + kr * p.k_row + cc * 8, ok ? 16 : 0);
-      cp_async_16(sv + r * RS + cc * 8, vb + kr * p.v_row + cc * 8, ok ? 16 : 0);
+      const saddr_t d = k_dst + (stage * 2 * TILE + i * RPP * RS) * 2;
+      cp_async_16(d, kb + kr * p.k_row + lc, ok ? 16 : 0);
+      cp_async_16(d + TILE * 2, vb + kr * p.v_row + lc, ok ? 16 : 0);
     }
     cp_async_commit();
   };
@@ -74,14 +77,14 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
   uint32_t qa[KSTEPS][4];
   {
     const int r0 = row0 + g, r1 = row0 + g + 8;
-    const __nv_bfloat16 *q0 = p.q + (size_t)b * p.q_batch + (size_t)h * p.q_head + (size_t)min(r0, p.Lq - 1) * p.q_row;
-    const __nv_bfloat16 *q1 = p.q + (size_t)b * p.q_batch + (size_t)h * p.q_head + (size_t)min(r1, p.Lq - 1) * p.q_row;
+    const __nv_bfloat16 *q0 = p.q + (size_t)b * p.q_batch + (size_t)h * p.q_head + (size_t)min(r0, p.Lq - 1) * p.q_row + 2 * t;
+    const __nv_bfloat16 *q1 = p.q + (size_t)b * p.q_batch + (size_t)h * p.q_head + (size_t)min(r1, p.Lq - 1) * p.q_row + 2 * t;
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks) {
-      qa[ks][0] = *reinterpret_cast<const uint32_t *>(q0 + ks * 16 + 2 * t);
-      qa[ks][1] = *reinterpret_cast<const uint32_t *>(q1 + ks * 16 + 2 * t);
-      qa[ks][2] = *reinterpret_cast<const uint32_t *>(q0 + ks * 16 + 2 * t + 8);
-      qa[ks][3] = *reinterpret_cast<const uint32_t *>(q1 + ks * 16 + 2 * t + 8);
+      qa[ks][0] = *reinterpret_cast<const uint32_t *>(q0 + ks * 16);
+      qa[ks][1] = *reinterpret_cast<const uint32_t *>(q1 + ks * 16);
+      qa[ks][2] = *reinterpret_cast<const uint32_t *>(q0 + ks * 16 + 8);
+      qa[ks][3] = *reinterpret_cast<const uint32_t *>(q1 + ks * 16 + 8);
     }
   }
 
@@ -94,6 +97,9 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
     mk0 = p.mask + (size_t)b * p.mask_batch + (size_t)min(row0 + g, p.Lq - 1) * p.mask_row;
     mk1 = p.mask + (size_t)b * p.mask_batch + (size_t)min(row0 + g + 8, p.Lq - 1) * p.mask_row;
   }
+  // this lane's ldmatrix addresses inside a ring slot: K as the col-major B operand of S = Q K^T, V (transposed load) of O = P V
+  const saddr_t k_lds = saddr(ring) + (((lane >> 4) * 8 + (lane & 7)) * RS + ((lane >> 3) & 1) * 8) * 2;
+  const saddr_t v_lds = saddr(ring) + (TILE + (((lane >> 3) & 1) * 8 + (lane & 7)) * RS + (lane >> 4) * 8) * 2;
 
   int it = 0;
   for (int blk = blk0; blk < nblocks; blk += blk_step, ++it) {
@@ -106,23 +112,22 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
       cp_async_wait<0>();
     }
     if constexpr (SPLIT) __syncwarp(); else __syncthreads();
-    const __nv_bfloat16 *sk = wbase + (size_t)stage * 2 * TILE, *sv = sk + TILE;
-    const int key0 = blk * kFaKeys;
-    const int nkeys = min(kFaKeys, p.Lk - key0);
+    const saddr_t sk = k_lds + stage * (2 * TILE * 2), sv = v_lds + stage * (2 * TILE * 2);
+    const int key0 = blk * KB;
+    const int nkeys = min(KB, p.Lk - key0);
     const int nkt = (nkeys + 7) >> 3;              // 8-key tiles that hold at least one valid key
 
     // ---- S = Q K^T ----
-    float s[8][4];
+    float s[NKT][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    for (int nt = 0; nt < NKT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {               // pairs of 8-key tiles
+    for (int np = 0; np < NKT / 2; ++np) {         // pairs of 8-key tiles
       if (2 * np < nkt) {
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
           uint32_t bf[4];
-          const int key = (2 * np + (lane >> 4)) * 8 + (lane & 7), d = ks * 16 + ((lane >> 3) & 1) * 8;
-          ldmatrix_x4(bf, sk + key * RS + d);
+          ldmatrix_x4(bf, sk + (np * 16 * RS) * 2 + ks * 32);
           mma_bf16_16816(s[2 * np], qa[ks], bf[0], bf[1]);
           mma_bf16_16816(s[2 * np + 1], qa[ks], bf[2], bf[3]);
         }
@@ -130,13 +135,13 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
     }
     // ---- scale, mask, online softmax ----
     uint64_t bits0 = 0, bits1 = 0;
-    if (p.mask) {
-      bits0 = *reinterpret_cast<const uint64_t *>(mk0 + (key0 >> 3));
-      bits1 = *reinterpret_cast<const uint64_t *>(mk1 + (key0 >> 3));
+    if (p.mask) {                                  // 64-bit words hold 64 keys; a 32-key block reads its half
+      bits0 = *reinterpret_cast<const uint64_t *>(mk0 + ((key0 >> 6) << 3)) >> (key0 & 63);
+      bits1 = *reinterpret_cast<const uint64_t *>(mk1 + ((key0 >> 6) << 3)) >> (key0 & 63);
     }
     float mx0 = mrow[0], mx1 = mrow[1];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NKT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = nt * 8 + 2 * t + (e & 1);
@@ -160,9 +165,9 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
     for (int i = 0; i < DT; ++i) {
       o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1;
     }
-    uint32_t pa[4][4];                             // P as A fragments: k-step kk covers keys kk*16 .. kk*16+15
+    uint32_t pa[NKT / 2][4];                       // P as A fragments: k-step kk covers keys kk*16 .. kk*16+15
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NKT; ++nt) {
       const float p0 = exp2f(s[nt][0] - use0), p1 = exp2f(s[nt][1] - use0);
       const float p2 = exp2f(s[nt][2] - use1), p3 = exp2f(s[nt][3] - use1);
       lrow[0] += p0 + p1;
@@ -172,13 +177,12 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
     }
     // ---- O += P V ----
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < NKT / 2; ++kk) {
       if (2 * kk < nkt) {
 #pragma unroll
         for (int dp = 0; dp < DT / 2; ++dp) {      // pairs of 8-wide output column tiles
           uint32_t bf[4];
-          const int key = kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), d = (2 * dp + (lane >> 4)) * 8;
-          ldmatrix_x4_trans(bf, sv + key * RS + d);
+          ldmatrix_x4_trans(bf, sv + (kk * 16 * RS) * 2 + dp * 32);
           mma_bf16_16816(o[2 * dp], pa[kk], bf[0], bf[1]);
           mma_bf16_16816(o[2 * dp + 1], pa[kk], bf[2], bf[3]);
         }
@@ -204,9 +208,9 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
     }
     return;
   }
-  // ---- SPLIT: merge the 4 warps' partial states ----
+  // ---- SPLIT: merge the 8 warps' partial states ----
   constexpr int OS = DH + 4;                       // fp32 row stride of the merge buffer
-  float *mo = reinterpret_cast<float *>(wbase);    // this warp's own ring memory: [16][OS] then m[16], l[16]
+  float *mo = reinterpret_cast<float *>(ring);     // this warp's own ring memory: [16][OS] then m[16], l[16]
   float *mm = mo + kFaRows * OS, *ml = mm + kFaRows;
 #pragma unroll
   for (int i = 0; i < DT; ++i) {
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
   const float *base = reinterpret_cast<const float *>(fa_smem);
   for (int e = threadIdx.x; e < kFaRows * (DH / 2); e += kFaWarps * 32) {
     const int r = e / (DH / 2), c = (e - r * (DH / 2)) * 2;
-    if (row0 + r >= p.Lq) continue;
+    if (blockIdx.x * kFaRows + r >= p.Lq) continue;
     float M = -INFINITY;
 #pragma unroll
     for (int w = 0; w < kFaWarps; ++w) M = fmaxf(M, base[w * wstride + kFaRows * OS + r]);
@@ -237,14 +241,15 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
       a1 += wb[r * OS + c + 1] * f;
     }
     const float inv = L > 0.f ? 1.f / L : 0.f;   // a row with every key masked (the mask producer never emits one) -> 0
-    __nv_bfloat16 *op = p.o + (size_t)b * p.o_batch + (size_t)(row0 + r) * p.o_row + (size_t)h * DH + c;
+    __nv_bfloat16 *op = p.o + (size_t)b * p.o_batch + (size_t)(blockIdx.x * kFaRows + r) * p.o_row + (size_t)h * DH + c;
     *reinterpret_cast<uint32_t *>(op) = pack_bf16x2(a0 * inv, a1 * inv);
   }
 }
 
 template <int DH, bool SPLIT>
 int launch_flash(const FlashParams &p, cudaStream_t s) {
-  const size_t ring = (size_t)(SPLIT ? kFaWarps : 1) * p.stages * 2 * kFaKeys * (DH + 8) * sizeof(__nv_bfloat16);
+  const int kb = SPLIT ? 32 : 64;
+  const size_t ring = (size_t)(SPLIT ? kFaWarps : 1) * p.stages * 2 * kb * (DH + 8) * sizeof(__nv_bfloat16);
   cudaFuncSetAttribute(flash_attn_kernel<DH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring));
   const int rows = SPLIT ? kFaRows : kFaRows * kFaWarps;
   dim3 grid((p.Lq + rows - 1) / rows, p.H, p.B);
@@ -285,12 +290,11 @@ extern "C" int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, in
                 static_cast<__nv_bfloat16 *>(out), q_row, q_batch, q_head, k_row, k_batch, k_head, v_row, v_batch, v_head, o_row,
                 o_batch, static_cast<const uint8_t *>(mask_bits), mask_row_bytes, mask_batch_bytes, B, Lq, Lk, H,
                 scale * 1.4426950408889634f, 1};
-  const int nblocks = (Lk + kFaKeys - 1) / kFaKeys;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (Lk > 512) {                                   // long memories: 64-row tiles, every warp walks every key block
+  if (Lk > 512) {                                   // long memories: 128-row tiles, every warp walks every key block
     p.stages = 2;
     return Dh == 32 ? launch_flash<32, false>(p, s) : launch_flash<64, false>(p, s);
   }
-  p.stages = nblocks > kFaWarps ? 2 : 1;           // a warp with more than one key block prefetches the next one
+  p.stages = (Lk + 31) / 32 > kFaWarps ? 2 : 1;    // a warp with more than one 32-key block prefetches the next one
   return Dh == 32 ? launch_flash<32, true>(p, s) : launch_flash<64, true>(p, s);
 }

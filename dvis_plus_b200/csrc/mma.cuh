@@ -36,6 +36,24 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void *
                : "r"(smem_addr_u32(row_ptr)));
 }
 
+// Shared-memory addresses as 32-bit values, computed once and advanced by byte offsets: with one warp per scheduler these
+// kernels are bound by INSTRUCTION COUNT (profiles/r2_temporal_kernels.md), so the hot loops must not re-derive
+// generic -> shared conversions or 64-bit addresses.
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t saddr(const void *p) { return smem_addr_u32(p); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], saddr_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], saddr_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void cp_async_16(saddr_t dst, const void *gmem_src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(saddr_t dst, const void *gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
 // 16-byte asynchronous global -> shared copy (L2 only: the operands are read once per CTA); src_bytes < 16 zero-fills
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, int src_bytes = 16) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
@@ -107,11 +125,21 @@ inline void ldmatrix_generic(uint32_t (&r)[4], const void *row_ptr, bool trans) 
 }
 inline void ldmatrix_x4(uint32_t (&r)[4], const void *row_ptr) { ldmatrix_generic(r, row_ptr, false); }
 inline void ldmatrix_x4_trans(uint32_t (&r)[4], const void *row_ptr) { ldmatrix_generic(r, row_ptr, true); }
+// "shared addresses" are plain host pointers with byte arithmetic
+struct saddr_t {
+  char *p;
+  saddr_t operator+(long o) const { return saddr_t{p + o}; }
+  saddr_t &operator+=(long o) { p += o; return *this; }
+};
+inline saddr_t saddr(const void *p) { return saddr_t{static_cast<char *>(const_cast<void *>(p))}; }
+inline void ldmatrix_x4(uint32_t (&r)[4], saddr_t a) { ldmatrix_generic(r, a.p, false); }
+inline void ldmatrix_x4_trans(uint32_t (&r)[4], saddr_t a) { ldmatrix_generic(r, a.p, true); }
 
 inline void cp_async_16(void *smem_dst, const void *gmem_src, int src_bytes = 16) {
   std::memset(smem_dst, 0, 16);
   std::memcpy(smem_dst, gmem_src, size_t(src_bytes));
 }
+inline void cp_async_16(saddr_t dst, const void *gmem_src, int src_bytes = 16) { cp_async_16(static_cast<void *>(dst.p), gmem_src, src_bytes); }
 inline void cp_async_commit() {}
 template <int N>
 inline void cp_async_wait() {}

@@ -15,13 +15,15 @@
 // W (and bf16 A) tiles through a 4-stage cp.async ring; for the refiner's 3 200 rows the 64-row variant halves the
 // weight re-reads.  Weight tiles never depend on the previous kernel, so with programmatic dependent launch their
 // prefetch overlaps the predecessor's tail (griddepcontrol.wait sits between the W and the A loads).
+#include <algorithm>
+
 #include "mma.cuh"
 
 namespace dvis {
 namespace {
 
-constexpr int kLsThreads = 128;
-constexpr int kLsBN = 64, kLsBK = 64, kLsStages = 4;
+constexpr int kLsThreads = 256;             // 8 warps = 2 per scheduler: with 1 the kernel is bound by dependent-issue latency
+constexpr int kLsBN = 64, kLsBK = 64, kLsMaxStages = 8;
 constexpr int kLsRS = kLsBK + 8;            // ring row stride (bf16): 144 bytes, ldmatrix conflict-free
 constexpr int kLsMaxProK = 512;             // widest LayerNorm the prologue handles (hidden size of tracker / refiner)
 
@@ -51,6 +53,7 @@ struct LsParams {
   __nv_bfloat16 *y_bf16;
   int64_t ldy, y_batch;
   int M, N, K;
+  int stages;                                // cp.async ring depth (2..8): bytes in flight cover the ~1 us L2 latency
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -85,62 +88,95 @@ __device__ __forceinline__ void ln_row(float4 (&v)[NV], int nv, int K, const flo
     }
 }
 
-// BM = 32: warps 1 x 4 (warp tile 32 x 16);  BM = 64: warps 2 x 2 (warp tile 32 x 32)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // cp.async.wait_group takes an immediate
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    default: cp_async_wait<6>(); break;
+  }
+}
+
+// 8 warps.  BM = 32: warps 2 x 4, warp tile 16 x 16;  BM = 64: warps 4 x 2, warp tile 16 x 32.
+// Every per-thread source pointer / shared address is computed once; a k-chunk costs each thread 3-4 cp.async, one wait, one
+// barrier, 8-12 ldmatrix and 8-16 mma.
 template <int BM, bool PRO>
 __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams p) {
-  constexpr int WM = BM / 32, WN = 4 / WM, WCOLS = kLsBN / WN, NT = WCOLS / 8;
+  constexpr int WM = BM / 16, WN = 8 / WM, WCOLS = kLsBN / WN, NT = WCOLS / 8;
   constexpr int A_TILE = BM * kLsRS, W_TILE = kLsBN * kLsRS;
+  constexpr int AI = BM / 32;                                                      // A rows per thread and chunk (plain mode)
   extern __shared__ uint4 ls_smem[];
   __nv_bfloat16 *sw = reinterpret_cast<__nv_bfloat16 *>(ls_smem);                  // [stages][64][RS]
-  __nv_bfloat16 *sa = sw + kLsStages * W_TILE;                                     // plain: [stages][BM][RS]; PRO: [BM][K + 8]
+  __nv_bfloat16 *sa = sw + p.stages * W_TILE;                                      // plain: [stages][BM][RS]; PRO: [BM][K + 8]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int wm = warp / WN, wn = warp % WN;
   const int n0 = blockIdx.x * kLsBN, m0 = blockIdx.y * BM, bz = blockIdx.z;
-  const int nk = p.K / kLsBK;
-  const __nv_bfloat16 *wsrc = p.w + (size_t)bz * p.w_batch;
-  const int ars = PRO ? p.K + 8 : kLsRS;                                           // A row stride in smem
+  const int nk = p.K / kLsBK, S = p.stages;
+  const int ars = PRO ? p.K + 8 : kLsRS;                                           // A row stride in smem (elements)
 
-  auto issue_w = [&](int kc, int slot) {
-    __nv_bfloat16 *dst = sw + slot * W_TILE;
-    for (int c = tid; c < kLsBN * 8; c += kLsThreads) {
-      const int r = c >> 3, cc = c & 7, n = n0 + r;
-      const bool ok = n < p.N;
-      cp_async_16(dst + r * kLsRS + cc * 8, wsrc + (size_t)(ok ? n : 0) * p.K + kc * kLsBK + cc * 8, ok ? 16 : 0);
+  // ---- per-thread copy assignments: row (tid / 8) + 32 i, 16-byte piece (tid % 8) ----
+  const int lr = tid >> 3, lc = (tid & 7) * 8;
+  const __nv_bfloat16 *w_src[2];
+  int w_bytes[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int n = n0 + lr + 32 * i;
+    w_bytes[i] = n < p.N ? 16 : 0;
+    w_src[i] = p.w + (size_t)bz * p.w_batch + (size_t)(n < p.N ? n : 0) * p.K + lc;
+  }
+  const saddr_t w_dst = saddr(sw) + (lr * kLsRS + lc) * 2, a_dst = saddr(sa) + (lr * kLsRS + lc) * 2;
+  const __nv_bfloat16 *a_src[AI];
+  int a_bytes[AI], a_t[AI], a_q[AI];
+  const int cin = PRO ? p.K : p.K / p.taps;
+  if constexpr (!PRO) {
+#pragma unroll
+    for (int i = 0; i < AI; ++i) {
+      const int m = m0 + lr + 32 * i, mm = m < p.M ? m : 0;
+      a_bytes[i] = m < p.M ? 16 : 0;
+      a_t[i] = p.taps > 1 ? mm / p.tap_period : 0;
+      a_q[i] = p.taps > 1 ? mm - a_t[i] * p.tap_period : mm;
+      a_src[i] = p.x + (size_t)bz * p.x_batch + (size_t)mm * p.ldx + lc;           // taps == 1; conv mode re-points per tap
     }
+  }
+  auto issue_w = [&](int kc, int slot) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) cp_async_16(w_dst + (slot * W_TILE + i * 32 * kLsRS) * 2, w_src[i] + kc * kLsBK, w_bytes[i]);
   };
   auto issue_a = [&](int kc, int slot) {
     if constexpr (!PRO) {
-      __nv_bfloat16 *dst = sa + slot * A_TILE;
-      const int cin = p.K / p.taps, k0 = kc * kLsBK, tap = k0 / cin, col = k0 - tap * cin;
-      for (int c = tid; c < BM * 8; c += kLsThreads) {
-        const int r = c >> 3, cc = c & 7, m = m0 + r;
-        const bool ok = m < p.M;
-        int srow = ok ? m : 0;
-        if (p.taps > 1) {
-          const int tt = srow / p.tap_period, q = srow - tt * p.tap_period;
-          const int ts = min(max(tt + tap - p.tap_pad, 0), p.tap_len - 1);
-          srow = ts * p.tap_period + q;
+      int col = kc * kLsBK;
+      if (p.taps > 1) {                                                            // Conv1d taps: chunk kc belongs to tap kc*64 / C_in
+        const int tap = col / cin;
+        col -= tap * cin;
+#pragma unroll
+        for (int i = 0; i < AI; ++i) {
+          const int ts = min(max(a_t[i] + tap - p.tap_pad, 0), p.tap_len - 1);
+          a_src[i] = p.x + (size_t)(ts * p.tap_period + a_q[i]) * p.ldx + lc;
         }
-        cp_async_16(dst + r * kLsRS + cc * 8, p.x + (size_t)bz * p.x_batch + (size_t)srow * p.ldx + col + cc * 8, ok ? 16 : 0);
       }
+#pragma unroll
+      for (int i = 0; i < AI; ++i) cp_async_16(a_dst + (slot * A_TILE + i * 32 * kLsRS) * 2, a_src[i] + col, a_bytes[i]);
     }
   };
 
   // weights first: they do not depend on the kernel before this one
-  for (int s = 0; s < kLsStages - 1; ++s)
+  for (int s = 0; s < S - 1; ++s)
     if (s < nk) issue_w(s, s);
   pdl_wait();
-  for (int s = 0; s < kLsStages - 1; ++s) {
+  for (int s = 0; s < S - 1; ++s) {
     if (s < nk) issue_a(s, s);
     cp_async_commit();
   }
 
   if constexpr (PRO) {
-    // ---- prologue: A rows = LN1(LN0(src0) + src1) -> bf16 in shared memory; warp w owns rows w, w+4, ... ----
+    // ---- prologue: A rows = LN1(LN0(src0) + src1) -> bf16 in shared memory; warp w owns rows w, w+8, ... ----
     constexpr int NV = kLsMaxProK / 128;
     const int nv = p.K / 128;
-    const int nseg = p.K / 64, gx = gridDim.x;
-    for (int r = warp; r < BM; r += 4) {
+    const int nseg = p.K / 64, gx = gridDim.x, my_seg = (int)blockIdx.x % min(gx, nseg);
+    for (int r = warp; r < BM; r += 8) {
       const int m = m0 + r;
       float4 v[NV];
       if (m < p.M) {
@@ -151,7 +187,7 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
         if (p.side0) {
 #pragma unroll
           for (int i = 0; i < NV; ++i)
-            if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == (int)blockIdx.x % min(gx, nseg))
+            if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg)
               *reinterpret_cast<float4 *>(p.side0 + (size_t)m * p.K + lane * 4 + 128 * i) = v[i];
         }
         if (p.src1) {
@@ -173,7 +209,7 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
         if (p.side1) {
 #pragma unroll
           for (int i = 0; i < NV; ++i)
-            if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == (int)blockIdx.x % min(gx, nseg))
+            if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg)
               *reinterpret_cast<float4 *>(p.side1 + (size_t)m * p.K + lane * 4 + 128 * i) = v[i];
         }
       } else {
@@ -188,40 +224,34 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
     }
   }
 
-  float acc[2][NT][4];
+  float acc[NT][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  // ldmatrix addresses of this lane inside a ring slot (A: 16 x 16 tile of the warp's rows; B: pairs of 8-column tiles)
+  const saddr_t a_lds = saddr(sa) + ((wm * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * ars + (lane >> 4) * 8) * 2;
+  const saddr_t b_lds = saddr(sw) + ((wn * WCOLS + (lane >> 4) * 8 + (lane & 7)) * kLsRS + ((lane >> 3) & 1) * 8) * 2;
 
   for (int kc = 0; kc < nk; ++kc) {
-    cp_async_wait<kLsStages - 2>();
-    __syncthreads();                           // chunk kc has landed for everyone; slot (kc-1) % stages is free again
+    cp_async_wait_dyn(S - 2);
+    __syncthreads();                           // chunk kc has landed for everyone; slot (kc-1) % S is free again
     {
-      const int nx = kc + kLsStages - 1;
-      if (nx < nk) { issue_w(nx, nx % kLsStages); issue_a(nx, nx % kLsStages); }
+      const int nx = kc + S - 1;
+      if (nx < nk) { issue_w(nx, nx % S); issue_a(nx, nx % S); }
       cp_async_commit();
     }
-    const __nv_bfloat16 *cw = sw + (kc % kLsStages) * W_TILE;
-    const __nv_bfloat16 *ca = PRO ? sa + kc * kLsBK : sa + (kc % kLsStages) * A_TILE;
+    const int slot = kc % S;
+    const saddr_t ca = PRO ? a_lds + kc * (kLsBK * 2) : a_lds + slot * (A_TILE * 2);
+    const saddr_t cw = b_lds + slot * (W_TILE * 2);
 #pragma unroll
     for (int ks = 0; ks < kLsBK / 16; ++ks) {
-      uint32_t af[2][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int row = wm * 32 + mt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), col = ks * 16 + (lane >> 4) * 8;
-        ldmatrix_x4(af[mt], ca + row * ars + col);
-      }
+      uint32_t af[4];
+      ldmatrix_x4(af, ca + ks * 32);
 #pragma unroll
       for (int np = 0; np < NT / 2; ++np) {
         uint32_t bf[4];
-        const int n = wn * WCOLS + (2 * np + (lane >> 4)) * 8 + (lane & 7), col = ks * 16 + ((lane >> 3) & 1) * 8;
-        ldmatrix_x4(bf, cw + n * kLsRS + col);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          mma_bf16_16816(acc[mt][2 * np], af[mt], bf[0], bf[1]);
-          mma_bf16_16816(acc[mt][2 * np + 1], af[mt], bf[2], bf[3]);
-        }
+        ldmatrix_x4(bf, cw + (np * 16 * kLsRS) * 2 + ks * 32);
+        mma_bf16_16816(acc[2 * np], af, bf[0], bf[1]);
+        mma_bf16_16816(acc[2 * np + 1], af, bf[2], bf[3]);
       }
     }
   }
@@ -230,33 +260,32 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
   // ---- epilogue: bias, ReLU, residual, stores ----
   const float *bias = p.bias ? p.bias + (size_t)bz * p.bias_batch : nullptr;
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int half = 0; half < 2; ++half) {
+    const int m = m0 + wm * 16 + g + half * 8;
+    if (m >= p.M) continue;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int m = m0 + wm * 32 + mt * 16 + g + half * 8;
-      if (m >= p.M) continue;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int n = n0 + wn * WCOLS + nt * 8 + 2 * t;
-        if (n >= p.N) continue;
-        float v0 = acc[mt][nt][half * 2], v1 = acc[mt][nt][half * 2 + 1];
-        if (bias) { v0 += __ldg(bias + n); v1 += __ldg(bias + n + 1); }
-        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-        if (p.residual) {
-          const float2 r = *reinterpret_cast<const float2 *>(p.residual + (size_t)m * p.ldr + n);
-          v0 += r.x; v1 += r.y;
-        }
-        const size_t o = (size_t)bz * p.y_batch + (size_t)m * p.ldy + n;
-        if (p.y_f32) *reinterpret_cast<float2 *>(p.y_f32 + o) = make_float2(v0, v1);
-        if (p.y_bf16) *reinterpret_cast<uint32_t *>(p.y_bf16 + o) = pack_bf16x2(v0, v1);
+    for (int nt = 0; nt < NT; ++nt) {
+      const int n = n0 + wn * WCOLS + nt * 8 + 2 * t;
+      if (n >= p.N) continue;
+      float v0 = acc[nt][half * 2], v1 = acc[nt][half * 2 + 1];
+      if (bias) { v0 += __ldg(bias + n); v1 += __ldg(bias + n + 1); }
+      if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+      if (p.residual) {
+        const float2 r = *reinterpret_cast<const float2 *>(p.residual + (size_t)m * p.ldr + n);
+        v0 += r.x; v1 += r.y;
       }
+      const size_t o = (size_t)bz * p.y_batch + (size_t)m * p.ldy + n;
+      if (p.y_f32) *reinterpret_cast<float2 *>(p.y_f32 + o) = make_float2(v0, v1);
+      if (p.y_bf16) *reinterpret_cast<uint32_t *>(p.y_bf16 + o) = pack_bf16x2(v0, v1);
     }
+  }
 }
 
 template <int BM, bool PRO>
-int launch_small_linear(const LsParams &p, int batch, cudaStream_t s) {
-  const size_t smem = (size_t)kLsStages * kLsBN * kLsRS * 2 +
-                      (PRO ? (size_t)BM * (p.K + 8) * 2 : (size_t)kLsStages * BM * kLsRS * 2);
+int launch_small_linear(LsParams p, int batch, cudaStream_t s) {
+  p.stages = std::max(2, std::min(p.K / kLsBK, BM == 32 ? kLsMaxStages : 6));
+  const size_t smem = (size_t)p.stages * kLsBN * kLsRS * 2 +
+                      (PRO ? (size_t)BM * (p.K + 8) * 2 : (size_t)p.stages * BM * kLsRS * 2);
   auto kern = small_linear_kernel<BM, PRO>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   dim3 grid((p.N + kLsBN - 1) / kLsBN, (p.M + BM - 1) / BM, batch);

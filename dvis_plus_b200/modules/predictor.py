@@ -72,6 +72,9 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         else:
             self.reid_embed = nn.Identity()
         self.materialize_aux_masks = False
+        # bf16 mode: masked cross-attention and query self-attention on csrc/flash_attn.cu; the attention mask is one BIT per
+        # (query, pixel) written by the tcgen05 mask GEMM's epilogue (ops.mask_attn_bits) instead of a dense additive bias
+        self.use_fused_attention = True
         self._pos_cache = {}
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
@@ -166,7 +169,8 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         dh = C // H
         scale = 1.0 / math.sqrt(dh)
         B = x[0].shape[0]
-        sizes, k_all, v_all, level_feats = [], [], [], []
+        sizes, k_all, v_all, level_feats, kv_rows = [], [], [], [], []
+        own_attn = self.use_fused_attention and dt == torch.bfloat16 and dh in (32, 64)
         mf_lp = mask_features
         if mf_lp.dtype != torch.bfloat16 or not mf_lp.is_contiguous(memory_format=torch.channels_last):
             mf_lp = mf_lp.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
@@ -182,9 +186,11 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
                 v = F.linear(tok.to(dt), f["wv"][l], f["bv"][l]).view(B, h * w, n_of, H, dh)
                 k_all.append(k.permute(2, 0, 3, 1, 4))                                                # (n_of, B, H, hw, dh) views
                 v_all.append(v.permute(2, 0, 3, 1, 4))
+                kv_rows.append((k, v))                                                                # (B, hw, n_of, H, dh)
             else:
                 k_all.append(None)
                 v_all.append(None)
+                kv_rows.append(None)
             # mask features resized once to this level's grid: interpolate(E @ F) == E @ interpolate(F)
             level_feats.append(ops.resize_bilinear_nhwc(mf_lp, (h, w)))
         query_embed = self.query_embed.weight.detach().float().contiguous()                            # (Q, C)
@@ -196,6 +202,8 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
 
         def attn_bias(level):
             normed_lp = ops.add_layernorm(out32, None, dn.weight, dn.bias, dn.eps, want_f32=False, lp_dtype=dt)[1]
+            if own_attn:
+                return ops.mask_attn_bits(self.mask_embed(normed_lp), level_feats[level])            # (B, Q, bytes): 1 bit / pixel
             return ops.mask_attn_bias(self.mask_embed(normed_lp), level_feats[level], dt)[:, None]   # (B, 1, Q, hw)
 
         def ln(norm, x, want_lp=True, want_q=True):
@@ -208,17 +216,25 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
             j = i // nl
             sa, ff, ca = self.transformer_self_attention_layers[i], self.transformer_ffn_layers[i], self.transformer_cross_attention_layers[i]
             # masked cross-attention to level l
-            q = F.linear(out_q, f["wq"][i], f["bq"][i]).view(B, Q, H, dh).transpose(1, 2)
-            o = F.scaled_dot_product_attention(q, k_all[l][j], v_all[l][j], attn_mask=bias, scale=scale)
-            o = linear(ca.multihead_attn.out_proj, o.transpose(1, 2).reshape(B, Q, C))
+            q = F.linear(out_q, f["wq"][i], f["bq"][i]).view(B, Q, H, dh)
+            if own_attn:
+                o = ops.flash_attn(q, kv_rows[l][0][:, :, j], kv_rows[l][1][:, :, j], scale, mask_bits=bias)
+            else:
+                o = F.scaled_dot_product_attention(q.transpose(1, 2), k_all[l][j], v_all[l][j], attn_mask=bias, scale=scale)
+                o = o.transpose(1, 2).reshape(B, Q, C)
+            o = linear(ca.multihead_attn.out_proj, o)
             out32, out_lp, out_q = ln(ca.norm, o)
             # self-attention over the queries
             m = sa.self_attn
             w, b = m._weights(dt)
             qk = F.linear(out_q, w[:2 * C], b[:2 * C]).view(B, Q, 2, H, dh)
             v = F.linear(out_lp, w[2 * C:], b[2 * C:]).view(B, Q, H, dh)
-            o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2), scale=scale)
-            o = linear(m.out_proj, o.transpose(1, 2).reshape(B, Q, C))
+            if own_attn:
+                o = ops.flash_attn(qk[:, :, 0], qk[:, :, 1], v, scale)
+            else:
+                o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2), scale=scale)
+                o = o.transpose(1, 2).reshape(B, Q, C)
+            o = linear(m.out_proj, o)
             out32, out_lp, _ = ln(sa.norm, o, want_q=False)
             # FFN
             out32, out_lp, out_q = ln(ff.norm, linear(ff.linear2, linear(ff.linear1, out_lp, relu=True)))

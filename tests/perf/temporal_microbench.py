@@ -65,6 +65,19 @@ def main():
         ours = graphed(lambda: ops.flash_attn(q, k, v, scale))
         lib = graphed(lambda: F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), scale=scale))
         out["attention_us"][name] = {"dvis_flash_attn": round(timeit(ours), 2), "torch_sdpa": round(timeit(lib), 2)}
+    # the predictor's masked cross-attention at its three memory lengths: bit mask + dvis_flash_attn vs dense bias + SDPA
+    for Lk in (920, 3680, 14720):
+        B, Lq, H, Dh = 16, 200, 8, 32
+        q = torch.randn(B, Lq, H, Dh, device=dev).to(torch.bfloat16)
+        k = torch.randn(B, Lk, H, Dh, device=dev).to(torch.bfloat16)
+        v = torch.randn(B, Lk, H, Dh, device=dev).to(torch.bfloat16)
+        bits = torch.randint(0, 255, (B, Lq, (Lk + 63) // 64 * 8), device=dev, dtype=torch.uint8)
+        bias = torch.zeros(B, 1, Lq, Lk, device=dev, dtype=torch.bfloat16)
+        scale = 1 / math.sqrt(Dh)
+        ours = graphed(lambda: ops.flash_attn(q, k, v, scale, mask_bits=bits))
+        lib = graphed(lambda: F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=bias, scale=scale))
+        out["attention_us"]["predictor_masked_cross (16,200,%d,8x32)" % Lk] = {"dvis_flash_attn + bits": round(timeit(ours), 2),
+                                                                              "torch_sdpa + dense bias": round(timeit(lib), 2)}
     for name, (M, N, K) in {"qkv (200,1536,512)": (200, 1536, 512), "out_proj (200,512,512)": (200, 512, 512),
                             "ffn1 (200,2048,512)": (200, 2048, 512), "ffn2 (200,512,2048)": (200, 512, 2048),
                             "refiner_qkv (3200,1536,512)": (3200, 1536, 512), "refiner_ffn2 (3200,512,2048)": (3200, 512, 2048)}.items():

@@ -165,3 +165,43 @@ def test_fused_temporal_stage_equals_library_path_at_production_width():
         assert torch.equal(a, b)
     for a, b in zip(res["fused"], res["library"]):
         assert rel_err(a, b) < 1e-2, rel_err(a, b)
+
+
+@pytest.mark.parametrize("B,Q,hw", [(2, 200, (23, 40)), (1, 100, (46, 80)), (2, 300, (34, 60)), (1, 7, (5, 13))])
+def test_mask_attn_bits_equal_thresholded_logits(B, Q, hw):
+    """the tcgen05 mask GEMM's bit epilogue == (E @ F < 0) packed, fully masked rows cleared (decoder.py:297,370-371)"""
+    torch.manual_seed(Q)
+    h, w = hw
+    C = 256
+    emb = torch.randn(B, Q, C, device="cuda").to(torch.bfloat16)
+    emb[0, 1] = -emb[0, 1].abs()                                     # a row that ends up fully masked ...
+    feat = torch.randn(B, C, h, w, device="cuda").abs().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    emb[0, 2] = emb[0, 2].abs()                                      # ... and one fully open
+    bits = ops.mask_attn_bits(emb, feat)
+    logits = ops.mask_logits(emb, feat, torch.float32).flatten(2)    # same GEMM, plain epilogue
+    masked = logits < 0
+    masked[masked.all(-1)] = False
+    HW = h * w
+    got = ((bits[..., None].int() >> torch.arange(8, device="cuda")) & 1).bool().flatten(2)[..., :HW]
+    assert bits.shape[-1] % 8 == 0 and bits.shape[-1] * 8 >= HW
+    assert torch.equal(got, masked)
+    assert not got[0, 1].any() and not got[0, 2].any()
+
+
+@torch.no_grad()
+def test_predictor_flash_attention_equals_library_attention(golden):
+    """production width (hidden 256, 8 heads x 32, Q = 200, 720p levels): bit-mask + dvis_flash_attn path vs the dense
+    additive bias + cuDNN SDPA path of round 1"""
+    import bench
+    runner = bench.build_models("cuda", queries=200)
+    dec = runner.predictor
+    torch.manual_seed(0)
+    ms = [torch.randn(2, 256, 23, 40, device="cuda"), torch.randn(2, 256, 46, 80, device="cuda"), torch.randn(2, 256, 92, 160, device="cuda")]
+    mf = torch.randn(2, 256, 184, 320, device="cuda")
+    outs = {}
+    for fused in (True, False):
+        dec.use_fused_attention = fused
+        with precision("bf16"):
+            outs[fused] = dec(ms, mf)
+    for k in ("pred_logits", "pred_embds", "pred_masks"):
+        assert rel_err(outs[True][k].float(), outs[False][k].float()) < 3e-2, (k, rel_err(outs[True][k].float(), outs[False][k].float()))
