@@ -158,49 +158,17 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-def merge_e2e_legs(e2e, frames, ms_first, ms_overlapped, rel_diff, tol=1e-2):
-    """Fold the second end-to-end leg (3 clips in flight, result copies on their own stream) into the `e2e` object: both
-    legs' times are always reported; the headline value switches to the second leg only if it is faster AND its results
-    agree with the first leg's within `tol` (north_star's bf16 tolerance, relative to the largest magnitude)."""
-    e2e["legs_ms_per_step"] = {"2 in flight, copies on the temporal stream": round(ms_first, 3),
-                               "3 in flight, copies on their own stream": round(ms_overlapped, 3)}
-    e2e["overlapped_leg_rel_max_diff_vs_first_leg"] = round(rel_diff, 6) if rel_diff < float("inf") else None   # no NaN / Infinity in JSON
-    if rel_diff <= tol and ms_overlapped < ms_first:
-        e2e.update(value=round(frames / ms_overlapped * 1e3, 2), ms_per_step=round(ms_overlapped, 3),
-                   pipeline="3 clips in flight, result copies on their own stream")
-    return e2e
+METRIC = "frames/sec (720p, T=16, Q=200) pixel-decoder+mask+refiner"
 
 
-def merge_round_robin_leg(line, frames, ms_resident, ms_e2e, rel_diff, tol=1e-2):
-    """Fold the leg with the temporal stage owned round-robin (N > 1) into the line: its times are always reported; `value`
-    and `e2e` switch to it only where it is faster AND its results agree with the replicated leg's within `tol`."""
-    line["temporal_stage_legs_ms_per_step"] = {"replicated on every rank": line["ms_per_step"],
-                                               "owned round-robin per clip + 1 broadcast": round(ms_resident, 3)}
-    line["round_robin_leg_rel_max_diff_vs_replicated"] = round(rel_diff, 6) if rel_diff < float("inf") else None
-    line["e2e"].setdefault("legs_ms_per_step", {})["round-robin temporal stage, copies on the masks stream"] = round(ms_e2e, 3)
-    if not rel_diff <= tol:
-        return line
-    if ms_resident < line["ms_per_step"]:
-        line.update(value=round(frames / ms_resident * 1e3, 2), ms_per_step=round(ms_resident, 3))
-        line["config"]["parallelism"] += "; temporal stage owned round-robin per clip + 1 broadcast"
-        line["config"]["execution"] = "3 CUDA graphs per clip (per-frame, temporal on the owner rank, masks), N + 2 clips in flight"
-    if ms_e2e < line["e2e"]["ms_per_step"]:
-        line["e2e"].update(value=round(frames / ms_e2e * 1e3, 2), ms_per_step=round(ms_e2e, 3),
-                           pipeline="temporal stage owned round-robin per clip, N + 2 clips in flight")
-    return line
-
-
-def merge_sm_carveout_leg(line, frames, sms, ms_resident, rel_diff, tol=1e-2):
-    """Fold the leg captured with cuBLASLt leaving `sms` SMs to the temporal stage (1 GPU) into the line: always reported,
-    adopted as `value` only if faster and in agreement with the first leg."""
-    line.setdefault("sm_carveout_legs", []).append(
-        {"sms_left_free_by_cublaslt": sms, "ms_per_step": round(ms_resident, 3),
-         "rel_max_diff_vs_first_leg": round(rel_diff, 6) if rel_diff < float("inf") else None})
-    if rel_diff <= tol and ms_resident < line["ms_per_step"]:
-        line.update(value=round(frames / ms_resident * 1e3, 2), ms_per_step=round(ms_resident, 3))
-        line["config"]["execution"] = line["config"]["execution"].split("; cuBLASLt kernels leave")[0] + \
-            "; cuBLASLt kernels leave %d SMs free for the temporal stage's stream" % sms
-    return line
+def rel_max_diff(a, b):
+    """max |a - b| / max |b| over a dict of tensors (NaN anywhere -> inf)."""
+    worst = 0.0
+    for k in b:
+        x, y = a[k].float(), b[k].float().to(a[k].device)
+        d = float((x - y).abs().max() / y.abs().max().clamp_min(1e-6))
+        worst = max(worst, d if d == d else float("inf"))
+    return worst
 
 
 def main():
@@ -209,41 +177,52 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=16)
-    ap.add_argument("--queries", type=int, default=200)
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4],
+                    help="BASELINE.json config: 4 = the headline metric's workload (default); 2 = R50 pixel decoder + predictor, "
+                         "single 720p frame, Q=100; 3 = R50 online clip T=5, Q=200 with the tracker (1 GPU each)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="fp32: every GEMM / conv in fp32 like the reference's forced-fp32 pixel decoder (msdeformattn.py:314)")
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--queries", type=int, default=None)
     ap.add_argument("--cpu-sample-frames", type=int, default=8)   # ~10 s of host work on the GPU box (16 cores)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs / no pipelining across clips (debug)")
-    ap.add_argument("--d2h-stream", action="store_true",
-                    help="end-to-end mode: device->host copies on their own stream (GraphedClipRunner d2h_stream; not yet timed)")
     ap.add_argument("--postprocess", default="none", choices=["none", "vis"],
                     help="vis: end the clip with the fused video-instance post-processing (top-10 instances selected before "
                          "the final mask GEMM, 720p bit-packed masks) instead of all Q stride-4 mask logits -- a different, "
-                         "smaller result; not the default metric's workload and not yet timed on a B200")
-    ap.add_argument("--temporal", default="replicated", choices=["replicated", "round_robin"],
-                    help="N > 1: tracker + refiner replicated on every rank (default, measured) or owned round-robin per clip "
-                         "with one broadcast (pipeline.RoundRobinClipRunner; not yet timed on a multi-GPU box)")
+                         "smaller result, not the default metric's workload")
+    ap.add_argument("--temporal", default="auto", choices=["auto", "replicated", "round_robin"],
+                    help="N > 1: tracker + refiner replicated on every rank, or owned round-robin per clip with one broadcast "
+                         "(pipeline.RoundRobinClipRunner); auto = round_robin when N > 1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    T, Q = args.frames, args.queries
-    config = {"workload": "DVIS++ Swin-L offline: T=16 clip 720p (736x1280 padded), Q=200, pixel decoder (6 MSDeformAttn "
-                          "encoder layers + FPN) + mask head (9-layer masked-attention predictor, 10 mask GEMMs/frame) + "
-                          "ReferringTracker (6 layers) + TemporalRefiner (6 layers) + final mask GEMM; backbone features synthetic",
-              "frames": T, "queries": Q, "backbone_channels": "swinl",
+    cfg = {4: dict(T=16, Q=200, backbone="swinl"), 3: dict(T=5, Q=200, backbone="r50"), 2: dict(T=1, Q=100, backbone="r50")}[args.config]
+    T = args.frames or cfg["T"]
+    Q = args.queries or cfg["Q"]
+    backbone = cfg["backbone"]
+    workloads = {
+        4: "DVIS++ Swin-L offline: T=16 clip 720p (736x1280 padded), Q=200, pixel decoder (6 MSDeformAttn encoder layers + FPN) + "
+           "mask head (9-layer masked-attention predictor, 10 mask GEMMs/frame) + ReferringTracker (6 layers) + TemporalRefiner "
+           "(6 layers) + final mask GEMM; backbone features synthetic",
+        3: "DVIS++ R50 online: T=5 clip 720p, Q=200: pixel decoder + mask head + ReferringTracker with its mask GEMM "
+           "(BASELINE config 3); backbone features synthetic",
+        2: "R50 MSDeformAttnPixelDecoder, 4 scales, 720p single frame + Q=100 predictor (10 mask-head calls) (BASELINE config 2); "
+           "backbone features synthetic"}
+    config = {"workload": workloads[args.config], "baseline_config": args.config, "frames": T, "queries": Q,
+              "backbone_channels": backbone, "precision": args.precision,
               "parallelism": f"frames sharded {world}x{T // max(world, 1)} + 1 NCCL all-gather of frame queries" if world > 1 else "1 GPU",
-              "l2": "inputs larger than L2 (0.68 GB of bf16 backbone features per step >> 126 MB)",
-              "execution": "2 CUDA graphs per clip (per-frame stage, temporal stage), software-pipelined across consecutive "
-                           "clips on 2 streams (depth 2); latency_ms_per_clip is one clip run alone, eagerly"}
+              "l2": "inputs larger than L2 (%.2f GB of backbone features per step >> 126 MB)" % (0.0424 * T) if T >= 4 else
+                    "L2 flushed between steps (256 MB write)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         sample = max(4, args.cpu_sample_frames)     # 4 frames per step: ~5-20 s of host work per step
         fps, dt = run_cpu_reference(sample, max(1, min(args.steps, 3)), min(args.warmup, 1), Q)
-        line = {"impl": "reference", "metric": "frames/sec (720p, T=16, Q=200) pixel-decoder+mask+refiner", "value": round(fps, 4),
+        line = {"impl": "reference", "metric": METRIC, "value": round(fps, 4),
                 "unit": "frames/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": min(args.warmup, 1),
                 "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
@@ -258,16 +237,17 @@ def main():
     from dvis_plus_b200 import _lib
     from dvis_plus_b200.modules.precision import set_precision
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (there is no CPU fallback)"
+    assert args.config == 4 or world == 1, "configs 2 and 3 are single-GPU workloads"
     assert T % world == 0, "frames must divide evenly across ranks"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    set_precision("bf16")
+    set_precision(args.precision)
     _lib.lib()
-    runner = build_models(dev, queries=Q)
+    runner = build_models(dev, queries=Q, backbone=backbone)
     t_local = T // world
-    host = synthetic_features(T, pin=False)
+    host = synthetic_features(T, backbone, pin=False)
     host = {k: v[rank * t_local:(rank + 1) * t_local].contiguous(memory_format=torch.channels_last).pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
@@ -277,47 +257,65 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    from dvis_plus_b200.pipeline import GraphedClipRunner
+    from dvis_plus_b200.pipeline import GraphedClipRunner, OnlineClipRunner, RoundRobinClipRunner
 
     vis = None
     if args.postprocess == "vis":
+        assert args.config == 4
         from dvis_plus_b200.modules.postprocess import VideoPostProcessor
         vis = dict(post=VideoPostProcessor(NUM_CLASSES, num_queries=Q, max_num=10), img_size=(720, IMG_W), output_size=(720, IMG_W),
                    packed=True)
         config["workload"] += " + fused VIS post-processing (10 instances selected before the final mask GEMM, 720p bit-packed masks)"
 
-    def step_eager():
+    online = OnlineClipRunner(runner.pixel_decoder, runner.predictor, runner.tracker, window_size=T) if args.config == 3 else None
+
+    def step_eager(feats=None):
+        """one clip through the public runner API, eagerly; -> dict of device tensors"""
+        feats = resident if feats is None else feats
+        if args.config == 2:
+            mf, _, ms = runner.pixel_decoder.forward_features(feats)
+            seg = runner.predictor(ms, mf)
+            return {"pred_masks": seg["pred_masks"], "pred_logits": seg["pred_logits"]}
+        if args.config == 3:
+            out = online(feats)
+            return {"pred_masks": out["pred_masks"], "pred_logits": out["pred_logits"]}
         if vis is None:
-            return runner(resident)
-        blk, mf = runner.segment_stage(resident)
+            return runner(feats)
+        blk, mf = runner.segment_stage(feats)
         return runner.vis_from_block(runner.gather_queries(blk), mf, (blk.shape[-1] - (NUM_CLASSES + 1)) // 2, **vis)
 
     out0 = step_eager()
     d2h_keys = ("pred_masks", "pred_logits") if vis is None else ("pred_masks", "pred_scores", "pred_labels", "pred_ids")
     d2h = {k: torch.empty(out0[k].shape, dtype=out0[k].dtype).pin_memory() for k in d2h_keys}
     d2h_bytes = sum(v.numel() * v.element_size() for v in d2h.values())
+    eager_ref = {k: out0[k].clone() for k in d2h_keys}
+    del out0
 
-    if args.eager:
-        graphed = None
-    elif args.temporal == "round_robin":
-        from dvis_plus_b200.pipeline import RoundRobinClipRunner
-        graphed = RoundRobinClipRunner(runner, resident, vis=vis)
-        config["parallelism"] += "; temporal stage owned round-robin per clip + 1 broadcast"
-        config["execution"] = "3 CUDA graphs per clip (per-frame, temporal on the owner rank, masks), %d clips in flight" % graphed.depth
+    temporal = args.temporal if args.temporal != "auto" else ("round_robin" if world > 1 else "replicated")
+    graphed = None
+    if args.config == 4 and not args.eager:
+        if temporal == "round_robin" and world > 1:
+            graphed = RoundRobinClipRunner(runner, resident, vis=vis)
+            config["parallelism"] += "; temporal stage owned round-robin per clip + 1 broadcast"
+            config["execution"] = ("3 CUDA graphs per clip (per-frame stage, temporal stage on the owner rank, masks), %d clips "
+                                   "in flight" % graphed.depth)
+        else:
+            graphed = GraphedClipRunner(runner, resident, depth=3, vis=vis, d2h_stream=True)
+            config["execution"] = ("2 CUDA graphs per clip (per-frame stage, temporal stage), software-pipelined across 3 clips "
+                                   "in flight on 2 streams; host<->device copies on streams of their own")
     else:
-        graphed = GraphedClipRunner(runner, resident, depth=2, vis=vis, d2h_stream=args.d2h_stream)
+        config["execution"] = "eager, one clip at a time (the tracker replays a CUDA graph per frame)"
+    if T < 4:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def run_steps(n, mode):
         """n clips back to back; every clip's results are complete when this returns (after the closing barrier)."""
         if graphed is None:
             for _ in range(n):
+                if T < 4:
+                    flush.zero_()                                   # inputs smaller than L2: flush it between steps
                 if mode == "e2e":
-                    feats = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-                    if vis is None:
-                        out = runner(feats)
-                    else:
-                        blk, mf = runner.segment_stage(feats)
-                        out = runner.vis_from_block(runner.gather_queries(blk), mf, (blk.shape[-1] - (NUM_CLASSES + 1)) // 2, **vis)
+                    out = step_eager({k: v.to(dev, non_blocking=True) for k, v in host.items()})
                     for k, v in d2h.items():
                         v.copy_(out[k], non_blocking=True)
                 else:
@@ -340,12 +338,23 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    warm = max(3, args.warmup, graphed.depth if graphed is not None else 0)     # every slot used once before timing
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed("resident", args.steps, max(3, args.warmup))
+    ms_dev = timed("resident", args.steps, warm)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed("e2e", args.steps, 2)
+    ms_e2e = timed("e2e", args.steps, warm)
+
+    # parity of the TIMED path: the result the end-to-end leg just delivered to the host buffers against the eager
+    # runner's result for the same clip (every rank's frames; bit-identical since round 2, profiles/r2_determinism.md)
+    torch.cuda.synchronize()
+    diff = torch.tensor([rel_max_diff({k: d2h[k].to(dev) for k in d2h}, eager_ref)], device=dev)
+    if world > 1:
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    parity = {"timed_e2e_output_vs_eager_runner_rel_max_diff": float(diff.item()), "bit_identical": float(diff.item()) == 0.0,
+              "what": "pred_masks + pred_logits delivered to the host by the last timed end-to-end step vs OfflineClipRunner run "
+                      "eagerly on the same clip, max over ranks; the eager runner vs the oracle port is tests/test_configs_gpu.py"}
 
     # single-clip latency and per-kernel CUDA-event timing: an instrumented EAGER pass of the same clip
     # (kernels inside CUDA graphs cannot be bracketed from the host)
@@ -362,100 +371,14 @@ def main():
     barrier()
     kern = _lib.stop_timing()
     ms_latency = s.elapsed_time(e) / n_lat
-    launches = (graphed.captured_launches if graphed is not None else sum(v[0] for v in kern.values()) // n_lat) * args.steps
+    eager_launches = sum(v[0] for v in kern.values()) // n_lat
+    launches = (graphed.captured_launches if graphed is not None else eager_launches) * args.steps
 
-    def finish():
-        """Leave without tearing NCCL down rank by rank (ProcessGroupNCCL teardown can wait on peers that already left):
-        one last barrier so rank 0 has printed, then a hard exit on every rank."""
-        sys.stdout.flush()
-        if world > 1:
+    if rank != 0:
+        if world > 1:                                               # leave together: rank 0 prints first
             dist.barrier()
             torch.cuda.synchronize()
             os._exit(0)
-
-    # Two more configurations of the SAME workload, timed after everything above on every rank (their collectives need all
-    # of them).  Both are new on a device this round, so each runs under a watchdog, its results are compared with the first
-    # leg's, and the line's headline numbers switch to it only if it is faster and agrees (merge_e2e_legs /
-    # merge_round_robin_leg); whatever happens, the numbers measured above are printed.
-    extra_legs = graphed is not None and not args.d2h_stream and args.temporal == "replicated"
-    d2h_ref = {k: v.clone() for k, v in d2h.items()} if extra_legs else None
-
-    def rel_diff_to_first_leg():
-        """same inputs -> same results, up to the GEMM algorithms a second capture may pick: relative max difference"""
-        torch.cuda.synchronize()
-        diff = max(float((d2h[k].float() - d2h_ref[k].float()).abs().max() / d2h_ref[k].float().abs().max().clamp_min(1e-6))
-                   for k in d2h)
-        t = torch.tensor([diff if diff == diff else float("inf")], device=dev)     # NaN anywhere counts as a mismatch
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)                               # every rank's frames must agree
-        return float(t.item())
-
-    def e2e_overlapped_leg():
-        """-> (ms per clip, relative max difference of its results to the first end-to-end leg's) or None.  In the first
-        leg a clip's 377 MB device->host copy sits on the temporal stage's stream and its slot is one of two, so nothing else
-        runs while it drains (27.1 vs 20.2 ms per clip in round 1's run).  Same public API (GraphedClipRunner.submit with
-        host buffers), same per-step copies inside the timed region."""
-        nonlocal graphed
-        first = graphed
-        try:
-            graphed = GraphedClipRunner(runner, resident, depth=3, vis=vis, d2h_stream=True)
-            ms = timed("e2e", args.steps, 3)
-            return ms, rel_diff_to_first_leg()
-        except Exception as exc:                                  # keep the measured first leg; say why
-            sys.stderr.write("bench: overlapped end-to-end leg failed: %r\n" % (exc,))
-            return None
-        finally:
-            graphed = first
-
-    def round_robin_leg():
-        """N > 1 -> (resident ms per clip, end-to-end ms per clip, relative max difference to the first leg) or None: the
-        temporal stage owned round-robin per clip + one broadcast (pipeline.RoundRobinClipRunner) instead of replicated on
-        every rank, which is the Amdahl term of the strong scaling."""
-        nonlocal graphed
-        first = graphed
-        try:
-            from dvis_plus_b200.pipeline import RoundRobinClipRunner
-            graphed = RoundRobinClipRunner(runner, resident, vis=vis)
-            ms_res = timed("resident", args.steps, max(3, args.warmup, graphed.depth))   # every slot used once before timing
-            ms_e2e_rr = timed("e2e", args.steps, 3)
-            return ms_res, ms_e2e_rr, rel_diff_to_first_leg()
-        except Exception as exc:
-            sys.stderr.write("bench: round-robin leg failed: %r\n" % (exc,))
-            return None
-        finally:
-            graphed = first
-
-    def sm_carveout_leg(sms=8):
-        """1 GPU -> (resident ms per clip, relative max difference to the first leg) or None.  The temporal stage is a chain
-        of ~900 tiny dependent kernels on a high-priority stream; while a persistent cuBLASLt kernel of the next clip's
-        per-frame stage owns every SM, the chain's next kernel has nowhere to run (pipelined 20.2 ms per clip against
-        16.2 ms of per-frame work in round 1's run).  Here the graphs are captured with cuBLASLt told to leave `sms` SMs
-        free (torch's SM carve-out -> CUBLASLT_MATMUL_DESC_SM_COUNT_TARGET)."""
-        nonlocal graphed
-        first = graphed
-        prev = torch._C._get_sm_carveout_experimental()
-        try:
-            torch._C._set_sm_carveout_experimental(sms)
-            graphed = GraphedClipRunner(runner, resident, depth=2, vis=vis)
-            ms = timed("resident", args.steps, 3)
-            graphed.submit(None, d2h)                             # one clip's results for the comparison
-            graphed.wait_all()
-            return ms, rel_diff_to_first_leg()
-        except Exception as exc:
-            sys.stderr.write("bench: SM carve-out leg failed: %r\n" % (exc,))
-            return None
-        finally:
-            torch._C._set_sm_carveout_experimental(prev)
-            graphed = first
-
-    if rank != 0:
-        if extra_legs:
-            watchdog = threading.Timer(150.0, lambda: os._exit(0))   # stays armed: rank 0 may leave without the barrier
-            watchdog.daemon = True
-            watchdog.start()
-            if e2e_overlapped_leg() is None or (world > 1 and round_robin_leg() is None):
-                os._exit(0)                                       # rank 0 prints what was measured before; no teardown
-        finish()
         return
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -465,67 +388,53 @@ def main():
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     # dominant kernel of this repo on the path: the fused MSDA forward (6 launches / step / rank)
     S, M_, D_, L_, P_ = 19320, 8, 32, 3, 4
-    msda_bytes = t_local * (S * M_ * D_ * 2 + S * M_ * L_ * P_ * 3 * 2 + S * L_ * 2 * 4 + S * M_ * D_ * 2)
+    esz = 2 if args.precision == "bf16" else 4
+    msda_bytes = t_local * (S * M_ * D_ * esz + S * M_ * L_ * P_ * 3 * esz + S * L_ * 2 * 4 + S * M_ * D_ * esz)
     roof = None
     if kern and "dvis_msda_fused_forward" in kern:
         n, tot = kern["dvis_msda_fused_forward"]
         us = tot / n * 1e3
         ach = msda_bytes / us / 1e3
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r1_ncu_msda_bf16_fused_and_pair_N8.txt
-        # (ncu --set full, 8 frames per launch: 173.1 + 62.3 MB) scaled to the frames of one launch here
-        traffic = int((173.107712e6 + 62.283008e6) / 8 * t_local)
         roof = {"kernel": "msda_fwd_staged_kernel (dvis_msda_fused_forward)", "bound": "hbm", "achieved": round(ach, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic, "us_per_launch": round(us, 1),
-                "algorithmic_bytes_per_launch": msda_bytes, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                # not measurable inside this run (needs ncu): imported from the committed ncu --set full capture, per launch,
+                # scaled by frames -- null for shapes that capture does not cover
+                "traffic": int(MSDA_NCU_DRAM_BYTES_PER_FRAME * t_local) if args.precision == "bf16" else None,
+                "traffic_source": MSDA_NCU_SOURCE if args.precision == "bf16" else None,
+                "us_per_launch": round(us, 1), "algorithmic_bytes_per_launch": msda_bytes, "peak_source": peak_src,
                 "share_of_clip_latency": round(tot / (ms_latency * n_lat), 4),
                 "measured": "CUDA events around each launch in an eager instrumented pass of the same clip",
-                "our_kernels_ms_per_clip": {k: round(v[1] / n_lat, 3) for k, v in kern.items()}}
+                "our_kernels_ms_per_clip": {k: round(v[1] / n_lat, 3) for k, v in kern.items()},
+                "our_kernel_launches_per_clip": {k: v[0] // n_lat for k, v in kern.items()}}
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == 4:
         fps, dt = run_cpu_reference(args.cpu_sample_frames, 1, 0, Q)
         cpu = {"value": round(fps, 4), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"{args.cpu_sample_frames} frame(s) of the same 720p Q={Q} workload, one pass of the oracle port "
                          f"(reference's pure-PyTorch CPU path), fp32, all host threads, {dt:.1f} s"}
-    line = {"metric": "frames/sec (720p, T=16, Q=200) pixel-decoder+mask+refiner", "value": round(T / ms_dev * 1e3, 2),
-            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+    metric = METRIC if args.config == 4 else "frames/sec, BASELINE config %d (%s)" % (args.config, workloads[args.config].split(":")[0])
+    line = {"metric": metric, "value": round(T / ms_dev * 1e3, 2),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": round(ms_dev, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic (random backbone features, random-init weights, perturbed MSDeformAttn offsets)",
+            "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic (random backbone features, random-init weights, perturbed MSDeformAttn offsets)",
             "config": config, "clocks": clocks, "latency_ms_per_clip": round(ms_latency, 3),
             "e2e": {"value": round(T / ms_e2e * 1e3, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": round(ms_e2e, 3)},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
-    line["e2e"]["pipeline"] = ("eager, one clip at a time" if graphed is None else
-                               "result copies on their own stream" if args.d2h_stream else
-                               "2 clips in flight, result copies on the temporal stage's stream")
-    if extra_legs:
-        # The line above is complete and measured: if an extra leg hangs or fails, print it as it stands and leave.
-        def leave(why):
-            line["extra_legs"] = why
-            print(json.dumps(line), flush=True)
-            sys.stdout.flush()
-            os._exit(0)                                           # the CUDA context / NCCL may be unusable: no teardown
-        watchdog = threading.Timer(150.0, leave, args=("timed out",))
-        watchdog.daemon = True
-        watchdog.start()
-        res = e2e_overlapped_leg()
-        if res is None:
-            leave("overlapped end-to-end leg failed (see stderr)")
-        merge_e2e_legs(line["e2e"], T, ms_e2e, *res)
-        if world > 1:
-            res = round_robin_leg()
-            if res is None:
-                leave("round-robin leg failed (see stderr)")
-            merge_round_robin_leg(line, T, *res)
-        else:
-            for sms in (8, 16):
-                res = sm_carveout_leg(sms)
-                if res is None:
-                    leave("SM carve-out leg failed (see stderr)")
-                merge_sm_carveout_leg(line, T, sms, *res)
-        watchdog.cancel()
-        line["extra_legs"] = "completed"
+            "gpu_launches": launches, "parity_check": parity, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    finish()
+    sys.stdout.flush()
+    if world > 1:
+        # leave without tearing NCCL down rank by rank (ProcessGroupNCCL teardown can wait on peers that already left)
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of msda_fwd_staged_kernel per 720p frame, bf16 fused variant, from the committed
+# `ncu --set full` capture (8 frames per launch: 173.1 + 62.3 MB); refreshed whenever the kernel changes
+MSDA_NCU_DRAM_BYTES_PER_FRAME = (173.107712e6 + 62.283008e6) / 8
+MSDA_NCU_SOURCE = "imported: profiles/r1_ncu_msda_bf16_fused_and_pair_N8.txt (ncu --set full, 8 frames per launch), scaled to this launch"
 
 
 if __name__ == "__main__":

@@ -291,7 +291,10 @@ extern "C" int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, in
                 o_batch, static_cast<const uint8_t *>(mask_bits), mask_row_bytes, mask_batch_bytes, B, Lq, Lk, H,
                 scale * 1.4426950408889634f, 1};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (Lk > 512) {                                   // long memories: 128-row tiles, every warp walks every key block
+  // 128-row tiles (every warp walks every key block) for long memories, and for big batches of 200-query problems, where
+  // 16-row CTAs would re-stream K / V 13x per head (refiner: 1 664 CTAs, 30 us; cuDNN 8 us)
+  const int64_t split_ctas = (int64_t)((Lq + kFaRows - 1) / kFaRows) * H * B;
+  if (Lk > 512 || (Lq > 64 && split_ctas > 2 * kNumSMs)) {
     p.stages = 2;
     return Dh == 32 ? launch_flash<32, false>(p, s) : launch_flash<64, false>(p, s);
   }

@@ -306,6 +306,17 @@ int log2_exact(int v) {
 }
 
 constexpr int kMaxStagedLP = 32;   // L*P beyond this goes to the generic kernel
+constexpr size_t kMaxStagedSmem = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+
+// dynamic shared memory the staged kernel needs (same formula as launch_staged): lets the plain op fall back to the generic
+// kernel for shapes whose staging does not fit (D = 8 fp32 with L*P >= 24 asks for > 100 KB)
+template <typename T, int D, bool FUSED>
+size_t staged_smem(int L, int P) {
+  constexpr int G = 32 / (D / Vec16<T>::N);
+  const int LP = L * P, LPs = LP | 1;
+  const int items = std::max(64, kWarps * G);
+  return (size_t)items * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
+}
 
 template <typename T, typename TO, int D, bool FUSED, typename TP = float>
 int launch_staged(MsdaParams p, cudaStream_t stream) {
@@ -320,6 +331,9 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
   while (lpc < LP) { lpc <<= 1; ++sh; }
   p.lpc_shift = sh;
   const size_t smem = (size_t)p.items_per_cta * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
+  if (smem > kMaxStagedSmem)
+    return fail(DVIS_ERR_UNSUPPORTED, "msda: %zu bytes of shared memory per CTA for D=%d, L*P=%d exceed the %d-byte opt-in limit", smem,
+                D, LP, int(kMaxStagedSmem));
   auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP>;
   {  // occupancy / unroll variants (DVIS_MSDA_VARIANT), kept for the micro-benchmark.  Default: 6 CTAs/SM, unroll 2
      // (40 registers): measured 23 % faster than 3 CTAs/SM x unroll 4 (80 registers) -- the gather is latency bound.
@@ -328,7 +342,8 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
     if (variant == 2) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 2>;
     if (variant == 3) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 1>;
   }
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 48 * 1024))) != cudaSuccess)
+    return check_launch("msda_fwd_staged_kernel (shared-memory opt-in)");
   dim3 grid((per_batch + p.items_per_cta - 1) / p.items_per_cta, p.N);
   kern<<<grid, kThreads, smem, stream>>>(p);
   return check_launch("msda_fwd_staged_kernel");
@@ -338,9 +353,9 @@ template <typename T>
 int launch_plain(const MsdaParams &p, int D, cudaStream_t stream) {
   const bool vec_ok = aligned16(p.value) && aligned16(p.out) && p.L * p.P <= kMaxStagedLP;
   if (vec_ok && std::is_same<T, float>::value) {
-    switch (D) {
-      case 8: return launch_staged<float, float, 8, false>(p, stream);
-      case 16: return launch_staged<float, float, 16, false>(p, stream);
+    switch (D) {   // shapes whose staging would not fit in shared memory take the generic kernel below
+      case 8: if (staged_smem<float, 8, false>(p.L, p.P) <= kMaxStagedSmem) return launch_staged<float, float, 8, false>(p, stream); break;
+      case 16: if (staged_smem<float, 16, false>(p.L, p.P) <= kMaxStagedSmem) return launch_staged<float, float, 16, false>(p, stream); break;
       case 32: return launch_staged<float, float, 32, false>(p, stream);
       case 64: return launch_staged<float, float, 64, false>(p, stream);
       case 128: return launch_staged<float, float, 128, false>(p, stream);

@@ -16,6 +16,7 @@
 // weight re-reads.  Weight tiles never depend on the previous kernel, so with programmatic dependent launch their
 // prefetch overlaps the predecessor's tail (griddepcontrol.wait sits between the W and the A loads).
 #include <algorithm>
+#include <cstdlib>
 
 #include "mma.cuh"
 
@@ -54,7 +55,8 @@ struct LsParams {
   int64_t ldy, y_batch;
   int M, N, K;
   int stages;                                // cp.async ring depth (2..8): bytes in flight cover the ~1 us L2 latency
-};
+  long long *prof;                           // debug (DVIS_LS_PROF=1): clock64 stamps of CTA (0,0,0): start, ring filled, first
+};                                           // chunk landed, k loop done, end
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -62,9 +64,10 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// one LayerNorm over a row held as NV float4 per lane (columns lane*4 + 128*i), two-pass like csrc/layernorm.cu
+// one LayerNorm over a row held as NV float4 per lane (columns lane*4 + 128*i), two-pass like csrc/layernorm.cu;
+// gamma / beta are already in registers (loaded once per warp, in the same L2 round trip as the rows)
 template <int NV>
-__device__ __forceinline__ void ln_row(float4 (&v)[NV], int nv, int K, const float *g, const float *b, float eps, int lane) {
+__device__ __forceinline__ void ln_row(float4 (&v)[NV], int nv, int K, const float4 (&ga)[NV], const float4 (&be)[NV], float eps) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i)
@@ -80,12 +83,9 @@ __device__ __forceinline__ void ln_row(float4 (&v)[NV], int nv, int K, const flo
   const float rstd = rsqrtf(warp_sum(q) / float(K) + eps);
 #pragma unroll
   for (int i = 0; i < NV; ++i)
-    if (i < nv) {
-      const float4 ga = *reinterpret_cast<const float4 *>(g + lane * 4 + 128 * i);
-      const float4 be = *reinterpret_cast<const float4 *>(b + lane * 4 + 128 * i);
-      v[i] = make_float4((v[i].x - mean) * rstd * ga.x + be.x, (v[i].y - mean) * rstd * ga.y + be.y,
-                         (v[i].z - mean) * rstd * ga.z + be.z, (v[i].w - mean) * rstd * ga.w + be.w);
-    }
+    if (i < nv)
+      v[i] = make_float4((v[i].x - mean) * rstd * ga[i].x + be[i].x, (v[i].y - mean) * rstd * ga[i].y + be[i].y,
+                         (v[i].z - mean) * rstd * ga[i].z + be[i].z, (v[i].w - mean) * rstd * ga[i].w + be[i].w);
 }
 
 __device__ __forceinline__ void cp_async_wait_dyn(int n) {   // cp.async.wait_group takes an immediate
@@ -145,101 +145,143 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
 #pragma unroll
     for (int i = 0; i < 2; ++i) cp_async_16(w_dst + (slot * W_TILE + i * 32 * kLsRS) * 2, w_src[i] + kc * kLsBK, w_bytes[i]);
   };
-  auto issue_a = [&](int kc, int slot) {
+  // chunks are issued in order 0, 1, 2, ...: the Conv1d tap / column of the next chunk is tracked incrementally (no division)
+  int a_col = 0, a_tap = 0;
+  auto issue_a = [&](int slot) {
     if constexpr (!PRO) {
-      int col = kc * kLsBK;
-      if (p.taps > 1) {                                                            // Conv1d taps: chunk kc belongs to tap kc*64 / C_in
-        const int tap = col / cin;
-        col -= tap * cin;
+      if (p.taps > 1 && a_col == 0) {                                              // first chunk of a tap: re-point the source rows
 #pragma unroll
         for (int i = 0; i < AI; ++i) {
-          const int ts = min(max(a_t[i] + tap - p.tap_pad, 0), p.tap_len - 1);
+          const int ts = min(max(a_t[i] + a_tap - p.tap_pad, 0), p.tap_len - 1);
           a_src[i] = p.x + (size_t)(ts * p.tap_period + a_q[i]) * p.ldx + lc;
         }
       }
 #pragma unroll
-      for (int i = 0; i < AI; ++i) cp_async_16(a_dst + (slot * A_TILE + i * 32 * kLsRS) * 2, a_src[i] + col, a_bytes[i]);
+      for (int i = 0; i < AI; ++i) cp_async_16(a_dst + (slot * A_TILE + i * 32 * kLsRS) * 2, a_src[i] + a_col, a_bytes[i]);
+      a_col += kLsBK;
+      if (a_col == cin) { a_col = 0; ++a_tap; }
     }
   };
 
+  const bool prof = p.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (prof) p.prof[0] = clock64();
   // weights first: they do not depend on the kernel before this one
   for (int s = 0; s < S - 1; ++s)
     if (s < nk) issue_w(s, s);
   pdl_wait();
   for (int s = 0; s < S - 1; ++s) {
-    if (s < nk) issue_a(s, s);
+    if (s < nk) issue_a(s);
     cp_async_commit();
   }
 
   if constexpr (PRO) {
     // ---- prologue: A rows = LN1(LN0(src0) + src1) -> bf16 in shared memory; warp w owns rows w, w+8, ... ----
-    constexpr int NV = kLsMaxProK / 128;
+    // All global loads of a group of 4 rows (both sources, gamma / beta) are issued before anything is computed: ONE L2
+    // round trip per group instead of one per row and source (the first version spent 14 600 of its 20 000 cycles here).
+    constexpr int NV = kLsMaxProK / 128, RG = 4;
     const int nv = p.K / 128;
     const int nseg = p.K / 64, gx = gridDim.x, my_seg = (int)blockIdx.x % min(gx, nseg);
-    for (int r = warp; r < BM; r += 8) {
-      const int m = m0 + r;
-      float4 v[NV];
-      if (m < p.M) {
+    float4 g0[NV], b0[NV], g1[NV], b1[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-          if (i < nv) v[i] = *reinterpret_cast<const float4 *>(p.src0 + (size_t)m * p.K + lane * 4 + 128 * i);
-        if (p.ln0_g) ln_row<NV>(v, nv, p.K, p.ln0_g, p.ln0_b, p.eps, lane);
-        if (p.side0) {
+    for (int i = 0; i < NV; ++i)
+      if (i < nv) {
+        const int c = lane * 4 + 128 * i;
+        if (p.ln0_g) { g0[i] = *reinterpret_cast<const float4 *>(p.ln0_g + c); b0[i] = *reinterpret_cast<const float4 *>(p.ln0_b + c); }
+        if (p.ln1_g) { g1[i] = *reinterpret_cast<const float4 *>(p.ln1_g + c); b1[i] = *reinterpret_cast<const float4 *>(p.ln1_b + c); }
+      }
+    for (int r0 = warp; r0 < BM; r0 += 8 * RG) {
+      float4 v[RG][NV], u[RG][NV];
 #pragma unroll
-          for (int i = 0; i < NV; ++i)
-            if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg)
-              *reinterpret_cast<float4 *>(p.side0 + (size_t)m * p.K + lane * 4 + 128 * i) = v[i];
-        }
-        if (p.src1) {
+      for (int j = 0; j < RG; ++j) {
+        const int m = m0 + r0 + 8 * j;
 #pragma unroll
-          for (int i = 0; i < NV; ++i)
-            if (i < nv) {
-              const size_t o = (size_t)m * p.K + lane * 4 + 128 * i;
+        for (int i = 0; i < NV; ++i) {
+          v[j][i] = u[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < nv && m < p.M) {
+            const size_t o = (size_t)m * p.K + lane * 4 + 128 * i;
+            v[j][i] = *reinterpret_cast<const float4 *>(p.src0 + o);
+            if (p.src1) {
               if (p.src1_bf16) {
-                const uint2 u = *reinterpret_cast<const uint2 *>(static_cast<const __nv_bfloat16 *>(p.src1) + o);
-                v[i].x += __uint_as_float(u.x << 16); v[i].y += __uint_as_float(u.x & 0xffff0000u);
-                v[i].z += __uint_as_float(u.y << 16); v[i].w += __uint_as_float(u.y & 0xffff0000u);
+                const uint2 w2 = *reinterpret_cast<const uint2 *>(static_cast<const __nv_bfloat16 *>(p.src1) + o);
+                u[j][i] = make_float4(__uint_as_float(w2.x << 16), __uint_as_float(w2.x & 0xffff0000u), __uint_as_float(w2.y << 16),
+                                      __uint_as_float(w2.y & 0xffff0000u));
               } else {
-                const float4 u = *reinterpret_cast<const float4 *>(static_cast<const float *>(p.src1) + o);
-                v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+                u[j][i] = *reinterpret_cast<const float4 *>(static_cast<const float *>(p.src1) + o);
               }
             }
+          }
         }
-        if (p.ln1_g) ln_row<NV>(v, nv, p.K, p.ln1_g, p.ln1_b, p.eps, lane);
-        if (p.side1) {
-#pragma unroll
-          for (int i = 0; i < NV; ++i)
-            if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg)
-              *reinterpret_cast<float4 *>(p.side1 + (size_t)m * p.K + lane * 4 + 128 * i) = v[i];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (i < nv)
-          *reinterpret_cast<uint2 *>(sa + r * ars + lane * 4 + 128 * i) =
-              make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+      for (int j = 0; j < RG; ++j) {
+        const int r = r0 + 8 * j, m = m0 + r;
+        if (m < p.M) {
+          if (p.ln0_g) ln_row<NV>(v[j], nv, p.K, g0, b0, p.eps);
+          if (p.side0) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+              if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg)
+                *reinterpret_cast<float4 *>(p.side0 + (size_t)m * p.K + lane * 4 + 128 * i) = v[j][i];
+          }
+#pragma unroll
+          for (int i = 0; i < NV; ++i) { v[j][i].x += u[j][i].x; v[j][i].y += u[j][i].y; v[j][i].z += u[j][i].z; v[j][i].w += u[j][i].w; }
+          if (p.ln1_g) ln_row<NV>(v[j], nv, p.K, g1, b1, p.eps);
+          if (p.side1) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+              if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg)
+                *reinterpret_cast<float4 *>(p.side1 + (size_t)m * p.K + lane * 4 + 128 * i) = v[j][i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i < nv)
+            *reinterpret_cast<uint2 *>(sa + r * ars + lane * 4 + 128 * i) =
+                make_uint2(pack_bf16x2(v[j][i].x, v[j][i].y), pack_bf16x2(v[j][i].z, v[j][i].w));
+      }
     }
   }
 
   float acc[NT][4];
 #pragma unroll
   for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  // epilogue operands (bias, residual) are fetched now, so their L2 round trip hides behind the k loop
+  const float *bias = p.bias ? p.bias + (size_t)bz * p.bias_batch : nullptr;
+  float2 e_bias[NT], e_res[2][NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int n = n0 + wn * WCOLS + nt * 8 + 2 * t;
+    e_bias[nt] = (bias && n < p.N) ? *reinterpret_cast<const float2 *>(bias + n) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m = m0 + wm * 16 + g + half * 8;
+      e_res[half][nt] = (p.residual && n < p.N && m < p.M) ? *reinterpret_cast<const float2 *>(p.residual + (size_t)m * p.ldr + n)
+                                                           : make_float2(0.f, 0.f);
+    }
+  }
   // ldmatrix addresses of this lane inside a ring slot (A: 16 x 16 tile of the warp's rows; B: pairs of 8-column tiles)
   const saddr_t a_lds = saddr(sa) + ((wm * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * ars + (lane >> 4) * 8) * 2;
   const saddr_t b_lds = saddr(sw) + ((wn * WCOLS + (lane >> 4) * 8 + (lane & 7)) * kLsRS + ((lane >> 3) & 1) * 8) * 2;
 
+  // resident: the ring holds ALL of K (S - 1 >= nk): everything is already in flight, one wait + one barrier, then a pure
+  // ldmatrix / mma loop -- the per-chunk wait + barrier of the streaming form cost 550 cycles a chunk with 8 warps
+  const bool resident = nk <= S - 1;
+  int slot = 0, fill = S - 1;                  // ring slots of chunk kc and of chunk kc + S - 1 (kept without % S)
+  if (prof) p.prof[1] = clock64();
+  if (resident) {
+    cp_async_wait<0>();
+    __syncthreads();
+    if (prof) p.prof[2] = clock64();
+  }
   for (int kc = 0; kc < nk; ++kc) {
-    cp_async_wait_dyn(S - 2);
-    __syncthreads();                           // chunk kc has landed for everyone; slot (kc-1) % S is free again
-    {
+    if (!resident) {
+      cp_async_wait_dyn(S - 2);
+      __syncthreads();                         // chunk kc has landed for everyone; the slot of chunk kc - 1 is free again
+      if (prof && kc == 0) p.prof[2] = clock64();
       const int nx = kc + S - 1;
-      if (nx < nk) { issue_w(nx, nx % S); issue_a(nx, nx % S); }
+      if (nx < nk) { issue_w(nx, fill); issue_a(fill); }
       cp_async_commit();
     }
-    const int slot = kc % S;
     const saddr_t ca = PRO ? a_lds + kc * (kLsBK * 2) : a_lds + slot * (A_TILE * 2);
     const saddr_t cw = b_lds + slot * (W_TILE * 2);
 #pragma unroll
@@ -254,11 +296,13 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
         mma_bf16_16816(acc[2 * np + 1], af, bf[2], bf[3]);
       }
     }
+    slot = slot + 1 == S ? 0 : slot + 1;
+    fill = fill + 1 == S ? 0 : fill + 1;
   }
   pdl_launch_dependents();
+  if (prof) p.prof[3] = clock64();
 
   // ---- epilogue: bias, ReLU, residual, stores ----
-  const float *bias = p.bias ? p.bias + (size_t)bz * p.bias_batch : nullptr;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int m = m0 + wm * 16 + g + half * 8;
@@ -267,23 +311,32 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
     for (int nt = 0; nt < NT; ++nt) {
       const int n = n0 + wn * WCOLS + nt * 8 + 2 * t;
       if (n >= p.N) continue;
-      float v0 = acc[nt][half * 2], v1 = acc[nt][half * 2 + 1];
-      if (bias) { v0 += __ldg(bias + n); v1 += __ldg(bias + n + 1); }
+      float v0 = acc[nt][half * 2] + e_bias[nt].x, v1 = acc[nt][half * 2 + 1] + e_bias[nt].y;
       if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-      if (p.residual) {
-        const float2 r = *reinterpret_cast<const float2 *>(p.residual + (size_t)m * p.ldr + n);
-        v0 += r.x; v1 += r.y;
-      }
+      v0 += e_res[half][nt].x;
+      v1 += e_res[half][nt].y;
       const size_t o = (size_t)bz * p.y_batch + (size_t)m * p.ldy + n;
       if (p.y_f32) *reinterpret_cast<float2 *>(p.y_f32 + o) = make_float2(v0, v1);
       if (p.y_bf16) *reinterpret_cast<uint32_t *>(p.y_bf16 + o) = pack_bf16x2(v0, v1);
     }
   }
+  if (prof) p.prof[4] = clock64();
 }
+
+#ifndef DVIS_SIMT_EMULATION
+long long *g_ls_prof = nullptr;                // device buffer of 8 stamps when DVIS_LS_PROF is set (tests/perf only)
+#endif
 
 template <int BM, bool PRO>
 int launch_small_linear(LsParams p, int batch, cudaStream_t s) {
-  p.stages = std::max(2, std::min(p.K / kLsBK, BM == 32 ? kLsMaxStages : 6));
+#ifndef DVIS_SIMT_EMULATION
+  static const bool want_prof = getenv("DVIS_LS_PROF") != nullptr;
+  if (want_prof && !g_ls_prof) cudaMalloc(&g_ls_prof, 8 * sizeof(long long));
+  p.prof = g_ls_prof;
+#endif
+  // K <= 512 (8 chunks; 6 for the 64-row tiles): the ring holds all of K (+1 slot: the loop's look-ahead index); else 6 deep
+  const int nk = p.K / kLsBK, cap = BM == 32 ? kLsMaxStages : 6;
+  p.stages = nk <= cap ? nk + 1 : 6;
   const size_t smem = (size_t)p.stages * kLsBN * kLsRS * 2 +
                       (PRO ? (size_t)BM * (p.K + 8) * 2 : (size_t)p.stages * BM * kLsRS * 2);
   auto kern = small_linear_kernel<BM, PRO>;
@@ -301,6 +354,16 @@ int launch_small_linear(LsParams p, int batch, cudaStream_t s) {
 }  // namespace dvis
 
 using namespace dvis;
+
+extern "C" int dvis_debug_linear_small_stamps(long long *host_out) {   // tests/perf: the stamps of the last profiled launch
+#ifndef DVIS_SIMT_EMULATION
+  if (!g_ls_prof) return fail(DVIS_ERR_INVALID, "set DVIS_LS_PROF=1 before the first dvis_linear_small call");
+  return cudaMemcpy(host_out, g_ls_prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? DVIS_OK : DVIS_ERR_CUDA;
+#else
+  (void)host_out;
+  return DVIS_OK;
+#endif
+}
 
 extern "C" int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, int taps, int tap_pad, int tap_period, int tap_len,
                                  const float *src0, const float *ln0_gamma, const float *ln0_beta, const void *src1,

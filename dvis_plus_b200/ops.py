@@ -39,6 +39,8 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     L = spatial_shapes.shape[0]
     Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
     step = min(N, int(im2col_step))
+    if step <= 0:
+        raise RuntimeError(f"im2col_step({im2col_step}) and batch({N}) must be positive")
     if N % step != 0:
         raise RuntimeError(f"batch({N}) must divide im2col_step({step})")
     if value.dtype not in (torch.float32, torch.float64):
@@ -131,6 +133,8 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     L = spatial_shapes.shape[0]
     Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
     step = min(N, int(im2col_step))
+    if step <= 0:
+        raise RuntimeError(f"im2col_step({im2col_step}) and batch({N}) must be positive")
     if N % step != 0:
         raise RuntimeError(f"batch({N}) must divide im2col_step({step})")
     if value.dtype not in (torch.float32, torch.float64):

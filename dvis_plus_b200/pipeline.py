@@ -543,7 +543,13 @@ class RoundRobinClipRunner:
         self.cuda = next(iter(example_features.values())).is_cuda
         self.graphs = graphs and self.cuda
         # a second communicator for the broadcasts (every rank must create it, in the same order)
-        self.group_bc = dist.new_group(ranks=list(range(self.world))) if self.world > 1 else None
+        # (built from the RUNNER's group, which may be a subgroup of the job -- e.g. one box of a multi-node run; new_group
+        # is collective over the default group, so every process of the job must construct its runner)
+        self.group_bc = None
+        if self.world > 1:
+            ranks = dist.get_process_group_ranks(runner.group) if runner.group is not None else list(range(dist.get_world_size()))
+            self.group_bc = dist.new_group(ranks=ranks)
+            self._global_rank_of = list(ranks)
         self.captured_launches = 0
         self.slots = []
         if self.cuda:
@@ -614,7 +620,7 @@ class RoundRobinClipRunner:
 
     def _exchange(self, slot, owner):
         if self.world > 1:
-            dist.broadcast(slot["payload"], src=owner, group=self.group_bc)
+            dist.broadcast(slot["payload"], src=self._global_rank_of[owner], group=self.group_bc)   # src is a GLOBAL rank
 
     @torch.no_grad()
     def submit(self, features=None, d2h=None):

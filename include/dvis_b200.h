@@ -163,6 +163,8 @@ int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, int taps, int
                       int64_t w_batch, const float *bias, int64_t bias_batch, const float *residual, int64_t ldr, int relu,
                       float *y_f32, void *y_bf16, int64_t ldy, int64_t y_batch, int batch, int M, int N, int K, void *stream);
 int dvis_set_pdl(int enabled);
+/* debug aid of tests/perf (DVIS_LS_PROF=1): clock64 stamps (8 values) of CTA 0 of the last dvis_linear_small launch */
+int dvis_debug_linear_small_stamps(long long *host_out);
 
 /* ------------------------------------------------------------------------------------------------
  * y = LayerNorm(x + residual) * gamma + beta over the last dim C, one pass.

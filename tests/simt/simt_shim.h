@@ -80,6 +80,7 @@ inline __half2 __floats2half2_rn(float a, float b) { return __half2{(_Float16)a,
 inline float __low2float(__half2 h) { return float(h.x); }
 inline float __high2float(__half2 h) { return float(h.y); }
 #define __align__(n) alignas(n)
+inline long long clock64() { return 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline int min(int a, int b) { return a < b ? a : b; }
