@@ -32,7 +32,6 @@ SIGNATURES = {
     "dvis_mask_logits_strided": [_vp, _i64, _vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp],
     "dvis_mask_attn_bias": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp, _vp],
     "dvis_mask_attn_bits": [_vp, _vp, _i, _i, _i, _i64, _vp, _i64, _vp, _vp],
-    "dvis_mha_core": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp],
     "dvis_flash_attn": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                         _i, _i, _i, _i, _i, _f, _vp],
     "dvis_linear_small": [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _i64, _vp, _i64,

@@ -35,59 +35,72 @@ __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p, float4 v) {
 constexpr int kMaxGroups = 64;
 
 // ---- pass 1: per (n, group) shifted sum and sum of squares ------------------------------------------------------
-// One CTA reduces one (sample, group) in a FIXED order -- no atomics, so the statistics (and everything downstream: bf16
-// roundings, thresholded attention masks, Hungarian decisions) are bit-identical from run to run; the first version
-// combined the threads' partial sums with shared-memory float atomics, whose arrival order made two runs of the same clip
-// differ by one bf16 ulp (profiles/r2_determinism.md).  Values are accumulated relative to a pivot K = x[n, pixel 0, first
-// channel of the group] (shifted-data variance: no cancellation when |mean| >> std), fp32 over runs of 16 pixels, double
-// across runs.  The 32 groups of a sample read interleaved 16-byte pieces of the same lines at the same time (L2 hits).
+// Deterministic (no atomics): the statistics -- and everything downstream: bf16 roundings, thresholded attention masks,
+// Hungarian decisions -- are bit-identical from run to run.  The first version combined partial sums with shared-memory
+// float atomics, whose arrival order made two runs of the same clip differ by one bf16 ulp (profiles/r2_determinism.md).
+//   gn_partial_kernel: a CTA reads a contiguous chunk of 256 pixels x all channels (fully coalesced, the map is read once
+//     at HBM speed), every thread reduces its pixels in a fixed order, threads of a group are combined in a fixed order
+//     -> one (sum, sumsq) double pair per (sample, chunk, group) in the workspace;
+//   gn_finalize_kernel: one thread per (sample, group) adds the chunks' partials in chunk order.
+// Values are accumulated relative to a pivot K = x[n, pixel 0, first channel of the group] (shifted-data variance: no
+// cancellation when |mean| >> std), fp32 within a thread's <= 64 pixels, double across threads and chunks.
+constexpr int kGnChunk = 256;   // pixels per CTA of the partial pass
+
 template <typename T>
 __device__ __forceinline__ float gn_pivot(const T *x, int64_t batch_stride, int n, int g, int cpg) {
   return float(ld4<T>(x + (size_t)n * batch_stride + (size_t)g * cpg).x);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T *__restrict__ x, int64_t batch_stride, int HW, int C, int G,
-                                                       double *__restrict__ sums) {
-  __shared__ double s_part[2][8];
-  const int g = blockIdx.x, n = blockIdx.y, cpg = C / G;
-  const int quads = min(cpg / 4, 256);
-  const int cq = threadIdx.x % quads, pl = threadIdx.x / quads, prow = 256 / quads;
-  const float K = gn_pivot<T>(x, batch_stride, n, g, cpg);
-  const T *xg = x + (size_t)n * batch_stride + (size_t)g * cpg;
-  double S = 0.0, Q = 0.0;
+__global__ void __launch_bounds__(256) gn_partial_kernel(const T *__restrict__ x, int64_t batch_stride, int HW, int C, int G,
+                                                         double *__restrict__ partials) {
+  __shared__ float s_s[256], s_q[256];
+  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int quads = C / 4, cpg = C / G;
+  const int cq = threadIdx.x % quads, pl = threadIdx.x / quads, prow = blockDim.x / quads;
+  const int p0 = chunk * kGnChunk, p1 = min(p0 + kGnChunk, HW);
+  const int g = (cq * 4) / cpg;
+  float s = 0.f, q = 0.f;
   if (pl < prow) {
-    for (int c = cq * 4; c < cpg; c += quads * 4) {
-      for (int pb = pl; pb < HW; pb += prow * 16) {
-        float s = 0.f, q = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int p = pb + i * prow;
-          if (p < HW) {
-            const float4 v = ld4<T>(xg + (size_t)p * C + c);
-            const float a = v.x - K, b = v.y - K, cc = v.z - K, d = v.w - K;
-            s += (a + b) + (cc + d);
-            q += (a * a + b * b) + (cc * cc + d * d);
-          }
-        }
-        S += double(s);
-        Q += double(q);
-      }
+    const float K = gn_pivot<T>(x, batch_stride, n, g, cpg);
+    const T *xn = x + (size_t)n * batch_stride + cq * 4;
+    for (int p = p0 + pl; p < p1; p += prow) {
+      const float4 v = ld4<T>(xn + (size_t)p * C);
+      const float a = v.x - K, b = v.y - K, c = v.z - K, d = v.w - K;
+      s += (a + b) + (c + d);
+      q += (a * a + b * b) + (c * c + d * d);
     }
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {                       // fixed pairing: deterministic
-    S += __shfl_xor_sync(0xffffffffu, S, o);
-    Q += __shfl_xor_sync(0xffffffffu, Q, o);
-  }
-  if ((threadIdx.x & 31) == 0) { s_part[0][threadIdx.x >> 5] = S; s_part[1][threadIdx.x >> 5] = Q; }
+  s_s[threadIdx.x] = s;
+  s_q[threadIdx.x] = q;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < G) {                       // thread g adds its group's threads in a fixed order: quads of the group, then rows
+    const int qpg = cpg / 4;
     double ts = 0.0, tq = 0.0;
-    for (int w = 0; w < 8; ++w) { ts += s_part[0][w]; tq += s_part[1][w]; }
-    sums[((size_t)n * G + g) * 2] = ts;
-    sums[((size_t)n * G + g) * 2 + 1] = tq;
+    for (int r = 0; r < prow; ++r)
+      for (int c = 0; c < qpg; ++c) {
+        const int t = r * quads + threadIdx.x * qpg + c;
+        ts += double(s_s[t]);
+        tq += double(s_q[t]);
+      }
+    double *dst = partials + (((size_t)n * nchunks + chunk) * G + threadIdx.x) * 2;
+    dst[0] = ts;
+    dst[1] = tq;
   }
+}
+
+__global__ void gn_finalize_kernel(const double *__restrict__ partials, int nchunks, int G, int total, double *__restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (n, g)
+  if (i >= total) return;
+  const int n = i / G, g = i - n * G;
+  double ts = 0.0, tq = 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    const double *src = partials + (((size_t)n * nchunks + c) * G + g) * 2;
+    ts += src[0];
+    tq += src[1];
+  }
+  sums[(size_t)i * 2] = ts;
+  sums[(size_t)i * 2 + 1] = tq;
 }
 
 struct GnApplyParams {
@@ -178,12 +191,16 @@ extern "C" int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_s
   if ((x_dtype != DVIS_F32 && x_dtype != DVIS_BF16) || (lp_dtype != DVIS_F32 && lp_dtype != DVIS_BF16))
     return fail(DVIS_ERR_UNSUPPORTED, "groupnorm_nhwc: dtypes must be f32 or bf16");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  dim3 grid(G, N);
+  const int nchunks = (HW + kGnChunk - 1) / kGnChunk;
+  double *partials = sums_workspace + (size_t)2 * N * G;      // workspace layout: [N*G*2 sums][N*nchunks*G*2 partials]
+  dim3 grid(nchunks, N);
   if (x_dtype == DVIS_F32)
-    gn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(x), x_batch_stride, HW, C, G, sums_workspace);
+    gn_partial_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(x), x_batch_stride, HW, C, G, partials);
   else
-    gn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(x), x_batch_stride, HW, C, G, sums_workspace);
-  if (int rc = check_launch("gn_stats_kernel")) return rc;
+    gn_partial_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(x), x_batch_stride, HW, C, G, partials);
+  if (int rc = check_launch("gn_partial_kernel")) return rc;
+  gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partials, nchunks, G, N * G, sums_workspace);
+  if (int rc = check_launch("gn_finalize_kernel")) return rc;
   GnApplyParams p{x, x_batch_stride, sums_workspace, gamma, beta, N, HW, C, G, eps, relu, up, up_batch_stride, up_h, up_w,
                   H, W, pos, out_f32, out_lp, out_lp_pos, out_batch_stride};
   const int apply_pix = 64;                                     // 16 pixels per thread row at C = 256

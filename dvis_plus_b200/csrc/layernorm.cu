@@ -44,7 +44,7 @@ struct LnParams {
   void *out_lp, *out_lp_pos;
 };
 
-// VPL = float4 vectors per lane (C = 128 * VPL)
+// VPL = float4 vectors per lane (C <= 128 * VPL, C % 4 == 0; vectors past C are predicated off)
 template <typename TX, typename TR, typename TL, int VPL>
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
@@ -58,10 +58,13 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const LnParams p) {
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = (i * 32 + lane) * 4;
-    v[i] = load4<TX>(x + c);
-    if (r) {
-      const float4 t = load4<TR>(r + c);
-      v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+      v[i] = load4<TX>(x + c);
+      if (r) {
+        const float4 t = load4<TR>(r + c);
+        v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+      }
     }
     sum += v[i].x + v[i].y + v[i].z + v[i].w;
   }
@@ -71,8 +74,10 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const LnParams p) {
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    sq += a * a + b * b + c * c + d * d;
+    if ((i * 32 + lane) * 4 < C) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += a * a + b * b + c * c + d * d;
+    }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -81,6 +86,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const LnParams p) {
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = (i * 32 + lane) * 4;
+    if (c >= C) continue;
     const float4 g = *reinterpret_cast<const float4 *>(p.gamma + c), b = *reinterpret_cast<const float4 *>(p.beta + c);
     float4 y;
     y.x = (v[i].x - mean) * rstd * g.x + b.x;
@@ -100,11 +106,15 @@ template <typename TX, typename TR, typename TL>
 int launch_ln(const LnParams &p, cudaStream_t s) {
   const int warps = 8;
   const unsigned grid = unsigned((p.rows + warps - 1) / warps);
-  switch (p.C / 128) {
+  int vpl = (p.C + 127) / 128;
+  if (vpl == 5) vpl = 6;                       // built: 1, 2, 3, 4, 6, 8, 16 vectors per lane (extra vectors are predicated off)
+  else if (vpl == 7) vpl = 8;
+  else if (vpl > 8) vpl = 16;
+  switch (vpl) {
 #define DVIS_LN(V) case V: add_layernorm_kernel<TX, TR, TL, V><<<grid, warps * 32, 0, s>>>(p); break;
     DVIS_LN(1) DVIS_LN(2) DVIS_LN(3) DVIS_LN(4) DVIS_LN(6) DVIS_LN(8) DVIS_LN(16)
 #undef DVIS_LN
-    default: return fail(DVIS_ERR_UNSUPPORTED, "add_layernorm: C=%d (built: 128,256,384,512,768,1024,2048)", p.C);
+    default: return fail(DVIS_ERR_UNSUPPORTED, "add_layernorm: C=%d", p.C);
   }
   return check_launch("add_layernorm_kernel");
 }
@@ -119,7 +129,7 @@ extern "C" int dvis_add_layernorm(const void *x, int x_dtype, const void *residu
                                   int C, float eps, float *out_f32, void *out_lp, void *out_lp_pos, int lp_dtype,
                                   void *stream) {
   DVIS_REQUIRE(x && gamma && beta, "add_layernorm: null pointer argument");
-  DVIS_REQUIRE(rows > 0 && C > 0 && C % 128 == 0, "add_layernorm: rows > 0 and C %% 128 == 0 required (C=%d)", C);
+  DVIS_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 2048, "add_layernorm: rows > 0, C %% 4 == 0 and C <= 2048 required (C=%d)", C);
   DVIS_REQUIRE(out_f32 || out_lp || out_lp_pos, "add_layernorm: no output requested");
   DVIS_REQUIRE(!out_lp_pos || (pos && pos_rows > 0), "add_layernorm: out_lp_pos needs pos");
   DVIS_REQUIRE((rows + 7) / 8 < (int64_t(1) << 31), "add_layernorm: too many rows");

@@ -22,9 +22,10 @@ def _fast_path(x):
 
 def add_norm(norm: nn.LayerNorm, x, residual):
     """LayerNorm(x + residual) -> fp32; fused kernel on the inference path."""
-    if _fast_path(x) and x.shape[-1] % 128 == 0 and x.dtype in (torch.float32, torch.bfloat16) and \
-            residual.dtype in (torch.float32, torch.bfloat16):
-        return ops.add_layernorm(x.contiguous(), residual.contiguous(), norm.weight, norm.bias, norm.eps)[0]
+    if _fast_path(x):
+        # device inference: the kernel or an error -- never a silent torch substitute (C % 4 == 0, C <= 2048: every DVIS width)
+        to = lambda t: t if t.dtype in (torch.float32, torch.bfloat16) else t.float()
+        return ops.add_layernorm(to(x).contiguous(), to(residual).contiguous(), norm.weight, norm.bias, norm.eps)[0]
     return F.layer_norm(x.float() + residual.float(), norm.normalized_shape, norm.weight, norm.bias, norm.eps)
 
 
@@ -50,6 +51,13 @@ def _cast_cached(layer, dt):
         c = (key, layer.weight.detach().to(dt), None if layer.bias is None else layer.bias.detach().to(dt))
         layer._dvis_cast = c
     return c[1], c[2]
+
+
+def flash_attn_wins(B, H, Lq):
+    """Where dvis_flash_attn measured faster than cuDNN SDPA on a B200 (profiles/r2_temporal_kernels.md): short query
+    sequences (<= 16 rows: attention over time) and small batches of 200-query problems; 16 frames x 8 heads x 200 queries
+    run 2x faster on the library kernel."""
+    return Lq <= 16 or B * H * ((Lq + 15) // 16) <= 296
 
 
 class MultiheadAttention(nn.Module):
@@ -106,6 +114,11 @@ class MultiheadAttention(nn.Module):
         mask = None
         if attn_mask is not None:
             mask = ~attn_mask.reshape(B, H, Lq, Lk) if attn_mask.dim() == 3 else ~attn_mask
+        if fast and attn_mask is None and dt == torch.bfloat16 and dh in (32, 64) and flash_attn_wins(B, H, Lq):
+            # latency-bound shapes (one 200-query problem, or the refiner's 200 x 8 attentions over 16 frames): the
+            # hand-written core (csrc/flash_attn.cu) beats the library kernel; big batches stay on cuDNN's flash kernel
+            o = ops.flash_attn(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), 1.0 / math.sqrt(dh))   # (B, Lq, E)
+            return linear(self.out_proj, o.transpose(0, 1))
         o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, scale=1.0 / math.sqrt(dh))
         o = o.permute(2, 0, 1, 3).reshape(Lq, B, E)
         return linear(self.out_proj, o)

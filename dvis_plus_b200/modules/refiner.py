@@ -49,7 +49,9 @@ class TemporalRefiner(nn.Module):
         y = F.conv1d(rep(F.relu(y), 1), c3.weight.to(dt), c3.bias.to(dt))
         return y
 
-    use_fused_kernels = True   # bf16 mode, batch 1: the layers run on csrc/small_linear.cu + csrc/flash_attn.cu (14 launches each)
+    # opt-in (bf16 mode, batch 1): the layers run on csrc/small_linear.cu + csrc/flash_attn.cu only (14 launches each).
+    # Parity-green but slower than the library GEMMs at T*Q = 3 200 rows (4.7 ms vs 1.8 ms per clip): off by default
+    use_fused_kernels = False
     _fast = None
 
     def _stacked(self):

@@ -114,12 +114,13 @@ class ReferringTracker_noiser(nn.Module):
         self.use_fast_path = True      # inference: batched matching + CUDA-graph frame steps (set False for the eager loop)
         self.use_cuda_graph = True
         self.match_on_host = False     # True: SciPy linear_sum_assignment on the host instead of the GPU LAP kernel
-        # dvis_mha_core instead of the library SDPA (bf16 GEMM dtype, head dim 32 / 64).  Off by default: measured on B200
-        # at Q=200, 8 heads x 64 it is ~3x slower per call than cuDNN's flash kernel (tracker 7.6 ms vs 5.1 ms per T=16 clip).
-        self.use_custom_attention = False
-        # bf16 mode: frames after the first run on the fused temporal-stage kernels (csrc/small_linear.cu, csrc/flash_attn.cu):
-        # 36 launches per frame, no library GEMM / SDPA / LayerNorm kernel in the sequential chain
-        self.use_fused_kernels = True
+        # bf16 mode: the attention cores run on csrc/flash_attn.cu (dvis_flash_attn) instead of the library SDPA: 4.2 us vs
+        # 6.5 us per call in the dependent chain at Q=200, 8 heads x 64 (profiles/r2_temporal_kernels.md)
+        self.use_custom_attention = True
+        # opt-in: every linear step on csrc/small_linear.cu as well (LayerNorm folded into the consumers' prologues: 36 launches
+        # per frame, no library kernel in the chain).  Parity-green, but a mma.sync + cp.async GEMM step costs 4.9 us against
+        # 3.3 us for cuBLAS's TMA / tcgen05 small-GEMM kernels, so the chain as a whole is slower (7.5 ms vs 4.3 ms per clip)
+        self.use_fused_kernels = False
         self._fast = None
 
     def _clear_memory(self):
@@ -300,15 +301,11 @@ class ReferringTracker_noiser(nn.Module):
         sa, ff = self.transformer_self_attention_layers, self.transformer_ffn_layers
         ca = self.transformer_cross_attention_layers
         scale = 1.0 / (dh ** 0.5)
-        fused_ln = C % 128 == 0
 
         def ln(norm, x, res32):
             """LayerNorm(x + res) -> (fp32 stream, GEMM-dtype copy) in one kernel."""
-            if fused_ln:
-                y32, ylp, _ = ops.add_layernorm(x.contiguous(), res32, norm.weight, norm.bias, norm.eps, lp_dtype=dt)
-                return y32, ylp
-            y32 = F.layer_norm(x.float() + res32, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
-            return y32, y32.to(dt)
+            y32, ylp, _ = ops.add_layernorm(x.contiguous(), res32, norm.weight, norm.bias, norm.eps, lp_dtype=dt)
+            return y32, ylp
 
         def lin(layer, x_lp, relu=False):
             w, b = _cast_cached(layer, dt) if layer.weight.dtype != dt else (layer.weight, layer.bias)
@@ -321,7 +318,7 @@ class ReferringTracker_noiser(nn.Module):
         def attend(q, k, v):
             """q (B, Lq, H, dh), k / v (B, Lk, H, dh) views with packed heads -> (B, Lq, C)."""
             if own_attn:
-                return ops.mha_core(q, k, v, scale)
+                return ops.flash_attn(q, k, v, scale)
             o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), scale=scale)
             return o.transpose(1, 2).reshape(q.shape[0], q.shape[1], C)
 

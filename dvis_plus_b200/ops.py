@@ -231,7 +231,7 @@ def groupnorm_nhwc(x, num_groups, weight, bias, eps=1e-5, *, relu=False, up=None
     lp_dtype = lp.dtype if lp is not None else torch.float32
     if out_lp is not None and out_lp_pos is not None:
         assert out_lp.dtype == out_lp_pos.dtype
-    ws = torch.empty(2 * N * num_groups, dtype=torch.float64, device=x.device)
+    ws = torch.empty(2 * N * num_groups * (1 + (HW + 255) // 256), dtype=torch.float64, device=x.device)
     uh = uw = H = W = 0
     if up is not None:
         (uh, uw), (H, W) = up_hw, hw
@@ -336,23 +336,6 @@ def mask_attn_bits(mask_embed, level_features):
         _lib.call("dvis_mask_attn_bits", emb.data_ptr(), level_features.data_ptr(), B, Q, C, h * w, bits.data_ptr(), row,
                   ws.data_ptr(), _stream())
     return bits
-
-
-def mha_core(q, k, v, scale):
-    """softmax(scale * q k^T) v for short sequences (dvis_mha_core).
-
-    q (B, Lq, H, Dh), k / v (B, Lk, H, Dh): bf16 views with contiguous (H, Dh) (any row / batch stride, e.g. slices of a
-    packed QKV projection).  Returns a contiguous (B, Lq, H*Dh) bf16 tensor."""
-    B, Lq, H, Dh = q.shape
-    Lk = k.shape[1]
-    for t in (q, k, v):
-        assert t.dtype == torch.bfloat16 and t.is_cuda and t.stride(3) == 1 and t.stride(2) == Dh, "heads must be packed (H, Dh)"
-    out = torch.empty((B, Lq, H * Dh), dtype=torch.bfloat16, device=q.device)
-    with torch.cuda.device(q.device):
-        _lib.call("dvis_mha_core", q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
-                  v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), H * Dh, Lq * H * Dh, B, Lq, Lk, H, Dh,
-                  float(scale), _stream())
-    return out
 
 
 def flash_attn(q, k, v, scale, mask_bits=None, out=None):

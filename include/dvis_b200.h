@@ -109,22 +109,9 @@ int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int
                      int out_dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Fused multi-head attention core for the short query sequences of tracker / refiner / predictor self-attention
- * (what nn.MultiheadAttention does between its projections inside SelfAttentionLayer / CrossAttentionLayer /
- * ReferringCrossAttentionLayer, P/mask2former_video/modeling/transformer_decoder/video_mask2former_transformer_decoder.py:46,104;
- * P/dvis_Plus/tracker.py:45):
+ * Multi-head attention core on the warp tensor cores (mma.sync bf16, fp32 accumulate, online softmax):
  *   out[b, i, h, :] = softmax_j(scale * q[b,i,h,:] . k[b,j,h,:]) @ v[b,j,h,:]
- * q (B, Lq, H, Dh), k / v (B, Lk, H, Dh), out (B, Lq, H, Dh), all bf16; *_row = elements between consecutive sequence
- * positions, *_batch = elements between batch items (heads are Dh apart), so q / k / v may be slices of one packed
- * projection.  Dh must be 32 or 64; K and V of one (batch, head) must fit in shared memory (Lk <= ~380 at Dh = 64).
- */
-int dvis_mha_core(const void *q, int64_t q_row, int64_t q_batch, const void *k, int64_t k_row, int64_t k_batch,
-                  const void *v, int64_t v_row, int64_t v_batch, void *out, int64_t o_row, int64_t o_batch, int B,
-                  int Lq, int Lk, int H, int Dh, float scale, void *stream);
-
-/* ------------------------------------------------------------------------------------------------
- * The same attention core on the warp tensor cores (mma.sync bf16, fp32 accumulate, online softmax): the kernel the
- * temporal stage runs (tracker / refiner self- and cross-attention, P/dvis_Plus/tracker.py:8-92,
+ * what nn.MultiheadAttention does between its projections; the kernel the temporal stage runs (tracker / refiner self- and cross-attention, P/dvis_Plus/tracker.py:8-92,
  * P/dvis_Plus/refiner.py:105-137) and, with `mask_bits`, the segmenter decoder's masked cross-attention
  * (P/dvis_Plus/video_mask2former_transformer_decoder.py:295-315: `memory_mask=attn_mask`).
  * q (B, Lq, H, Dh), k / v (B, Lk, H, Dh), out (B, Lq, H*Dh) bf16; *_row / *_batch / *_head = elements between consecutive
@@ -189,7 +176,7 @@ int dvis_add_layernorm(const void *x, int x_dtype, const void *residual, int res
  * the ReLU (P/mask2former/modeling/pixel_decoder/msdeformattn.py:213-226,262-286,321,346-351) and the flatten /
  * transpose / cat / with_pos_embed that build the encoder inputs (:70-80,112-114).
  *   x (N, HW, C) x_dtype, batch stride x_batch_stride elements; gamma, beta (C,) f32
- *   sums_workspace: 2*N*G doubles of scratch (zeroed and filled by the call)
+ *   sums_workspace: 2*N*G*(1 + ceil(HW / 256)) doubles of scratch (per-chunk partial sums, reduced in a fixed order)
  *   up: optional (N, up_h, up_w, C) f32 with batch stride up_batch_stride (needs H*W == HW), else NULL
  *   outputs, each optional: out_f32; out_lp (lp_dtype); out_lp_pos = y + pos[pixel] (pos (HW, C) f32); all laid out as
  *   (N, HW, C) with batch stride out_batch_stride elements (so a level can land in its slice of a token buffer).

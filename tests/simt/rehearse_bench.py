@@ -1,12 +1,11 @@
-"""TEST INFRASTRUCTURE ONLY.  Rehearse bench.py's `main()` WITHOUT a GPU: the real control flow of the measured legs and of
-the guarded extra legs (overlapped end-to-end leg, SM carve-out leg; --force-round-robin also runs the N > 1 round-robin leg on
-the single rank), the
+"""TEST INFRASTRUCTURE ONLY.  Rehearse bench.py's `main()` WITHOUT a GPU: the real control flow of the measured legs (resident,
+end to end, parity check, instrumented eager pass; --world2: two ranks over gloo with the round-robin temporal stage), the
 real runners and module fast paths, every CUDA-core kernel on the SIMT emulator, a fake CUDA runtime (streams / events are
 no-ops, a graph replay re-runs the region the runner captured).  Sizes are cut down (32x64 frames, 2 frames, 10 queries, 1-2
-layers per stack).  Times printed by this run mean nothing; what it checks is that the line is assembled, the extra legs
-run, their results agree with the first leg's and the merge logic sees them.
+layers per stack).  Times printed by this run mean nothing; what it checks is that the line is assembled and that the timed
+path's results equal the eager runner's.
 
-    python tests/simt/rehearse_bench.py [--force-round-robin] [--break-leg] [--world2]
+    python tests/simt/rehearse_bench.py [--world2]
 """
 import contextlib
 import functools
@@ -93,7 +92,7 @@ def give_graphs_bodies():
     P.GraphedClipRunner.__init__, P.RoundRobinClipRunner.__init__ = graphed_init, rr_init
 
 
-def run(argv, force_round_robin=False, break_leg=False):
+def run(argv):
     install_host_shims()
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     torch.cuda.is_available = lambda: True
@@ -106,15 +105,6 @@ def run(argv, force_round_robin=False, break_leg=False):
     bench.synthetic_features = functools.partial(bench.synthetic_features, hw=(32, 64))
     bench.build_models = functools.partial(bench.build_models, enc_layers=1, dec_layers=1, trk_layers=1, ref_layers=1)
     give_graphs_bodies()
-    if break_leg:
-        import dvis_plus_b200.pipeline as P
-        orig = P.GraphedClipRunner.__init__
-
-        def init(self, *a, **k):
-            if k.get("depth") == 3:
-                raise RuntimeError("injected failure of the overlapped leg")
-            orig(self, *a, **k)
-        P.GraphedClipRunner.__init__ = init
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:                    # --world 2: the ranks talk over gloo
         import torch.distributed as dist
         orig_init = dist.init_process_group
@@ -125,8 +115,6 @@ def run(argv, force_round_robin=False, break_leg=False):
     out = io.StringIO()
     with emulated_b200(), contextlib.redirect_stdout(out):
         try:
-            if force_round_robin:
-                _force_round_robin(bench)
             bench.main()
         except SystemExit:
             pass
@@ -154,35 +142,16 @@ def run_world(world, port=29631):
     return json.loads(outs[0][0][outs[0][0].index("{"):])
 
 
-def _force_round_robin(bench_mod):
-    """Single process: make main() believe N > 1 only where it decides to run the round-robin leg (RoundRobinClipRunner
-    itself sees world 1 and skips the collectives)."""
-    src = open(os.path.join(ROOT, "bench.py")).read()
-    assert src.count("if world > 1:\n            res = round_robin_leg()") == 1
-    src = src.replace("if world > 1:\n            res = round_robin_leg()", "if True:\n            res = round_robin_leg()")
-    assert src.count("        else:\n            for sms in (8, 16):") == 1              # ... and run the 1-GPU legs as well
-    src = src.replace("        else:\n            for sms in (8, 16):", "        if True:\n            for sms in (8, 16):")
-    code = compile(src, os.path.join(ROOT, "bench.py"), "exec")
-    keep = {k: getattr(bench_mod, k) for k in ("synthetic_features", "build_models")}
-    exec(code, bench_mod.__dict__)
-    for k, v in keep.items():
-        setattr(bench_mod, k, v)
-
-
 if __name__ == "__main__":
     flags = set(sys.argv[1:])
     if "--world2" in flags:
-        if "--break-leg" in flags:
-            os.environ["REHEARSE_BREAK_LEG"] = "1"
         print(json.dumps(run_world(2), indent=1))
         sys.exit(0)
     if "--as-rank" in flags:
         w = os.environ["WORLD_SIZE"]
-        line = run(["--gpus", w, "--frames", w, "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"],
-                   break_leg=os.environ.get("REHEARSE_BREAK_LEG") == "1")
+        line = run(["--gpus", w, "--frames", w, "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"])
         if line is not None:
             print(json.dumps(line))
         sys.exit(0)
-    line = run(["--frames", "2", "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"],
-               force_round_robin="--force-round-robin" in flags, break_leg="--break-leg" in flags)
+    line = run(["--frames", "2", "--queries", "10", "--steps", "1", "--warmup", "1", "--no-cpu-baseline"])
     print(json.dumps(line, indent=1))

@@ -122,7 +122,7 @@ def set_jitter(one_in):
 
 # ---- the remaining CUDA-core entry points (same argument order as dvis_plus_b200/ops.py) ------------------------------------
 ENTRY_POINTS += ("dvis_msda_forward", "dvis_msda_backward", "dvis_msda_fused_forward", "dvis_add_layernorm", "dvis_groupnorm_nhwc",
-                 "dvis_resize_bilinear_nhwc", "dvis_attn_bias_from_logits", "dvis_mha_core", "dvis_msda_pack_pairs",
+                 "dvis_resize_bilinear_nhwc", "dvis_attn_bias_from_logits", "dvis_msda_pack_pairs",
                  "dvis_msda_pair_forward", "dvis_lap_rect")
 _DT[torch.float64] = 1
 
@@ -177,7 +177,7 @@ def add_layernorm(x, residual, weight, bias, eps=1e-5, lp_dtype=None, pos=None):
 
 def groupnorm_nhwc(x, G, weight, bias, eps=1e-5, relu=False, up=None, up_hw=None, hw=None, pos=None, lp_dtype=torch.bfloat16):
     N, HW, C = x.shape
-    ws = torch.empty(2 * N * G, dtype=torch.float64)
+    ws = torch.empty(2 * N * G * (1 + (HW + 255) // 256), dtype=torch.float64)
     out32 = torch.full((N, HW, C), float("nan"), dtype=torch.float32)
     lp = torch.zeros((N, HW, C), dtype=lp_dtype)
     lpp = torch.zeros((N, HW, C), dtype=lp_dtype) if pos is not None else None
@@ -201,15 +201,6 @@ def attn_bias_from_logits(logits, dtype=torch.float32):
     bias = torch.full(logits.shape, 7.0, dtype=dtype)
     call("dvis_attn_bias_from_logits", _p(logits), logits.numel() // hw, hw, _p(bias), _DT[dtype], None)
     return bias
-
-
-def mha_core(q, k, v, scale):
-    B, Lq, H, Dh = q.shape
-    Lk = k.shape[1]
-    out = torch.zeros((B, Lq, H * Dh), dtype=torch.bfloat16)
-    call("dvis_mha_core", _p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1), v.stride(0), _p(out),
-         H * Dh, Lq * H * Dh, B, Lq, Lk, H, Dh, float(scale), None)
-    return out
 
 
 def flash_attn(q, k, v, scale, mask_bits=None):

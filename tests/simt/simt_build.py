@@ -20,7 +20,7 @@ OUT = os.path.join(OUT_DIR, "libdvis_simt_%s.so" % os.environ["SIMT_SANITIZE"] i
 # every CUDA-core kernel file of the library; csrc/mask_gemm.cu (tcgen05 / TMEM / TMA) and csrc/api.cu (driver entry
 # points) have no CPU meaning and stay out
 FILES = ["postproc.cu", "lap.cu", "msda_forward.cu", "msda_backward.cu", "layernorm.cu", "groupnorm.cu", "mask_aux.cu",
-         "attention.cu", "msda_pair.cu", "flash_attn.cu", "small_linear.cu"]
+         "msda_pair.cu", "flash_attn.cu", "small_linear.cu"]
 
 
 # What csrc/api.cu provides in the real library, plus TEST DOUBLES (plain loops, not emulation) for the entry points of

@@ -50,48 +50,12 @@ def test_bench_helpers():
     assert out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["samples"] == 3
 
 
-def test_bench_e2e_leg_merge():
-    """bench.merge_e2e_legs: both legs reported; the headline switches only to a faster leg with agreeing results."""
+def test_bench_rel_max_diff():
+    """bench.rel_max_diff (the line's parity_check): max over tensors of max|a-b| / max|b|; NaN counts as a mismatch."""
     import bench
-    base = {"value": 590.04, "unit": "frames/s", "ms_per_step": 27.117, "pipeline": "first"}
-    e = bench.merge_e2e_legs(dict(base), 16, 27.117, 20.5, 0.0)
-    assert e["ms_per_step"] == 20.5 and abs(e["value"] - 16 / 20.5e-3) < 0.01 and "3 clips" in e["pipeline"]
-    assert list(e["legs_ms_per_step"].values()) == [27.117, 20.5]
-    slower = bench.merge_e2e_legs(dict(base), 16, 27.117, 30.0, 0.0)
-    assert slower["value"] == 590.04 and slower["pipeline"] == "first" and slower["legs_ms_per_step"]
-    wrong = bench.merge_e2e_legs(dict(base), 16, 27.117, 20.5, 0.5)
-    assert wrong["value"] == 590.04 and wrong["overlapped_leg_rel_max_diff_vs_first_leg"] == 0.5
-
-
-def test_bench_round_robin_leg_merge():
-    """bench.merge_round_robin_leg: times always reported; value / e2e switch only where faster and results agree."""
-    import bench
-
-    def base():
-        return {"value": 1833.0, "ms_per_step": 8.73, "config": {"parallelism": "8 GPUs", "execution": "2 graphs"},
-                "e2e": {"value": 1500.0, "ms_per_step": 10.67, "pipeline": "first", "legs_ms_per_step": {"a": 10.67}}}
-    ln = bench.merge_round_robin_leg(base(), 16, 3.2, 4.0, 1e-4)
-    assert ln["ms_per_step"] == 3.2 and ln["value"] == 5000.0 and "round-robin" in ln["config"]["parallelism"]
-    assert ln["e2e"]["ms_per_step"] == 4.0 and ln["e2e"]["value"] == 4000.0 and len(ln["e2e"]["legs_ms_per_step"]) == 2
-    assert ln["temporal_stage_legs_ms_per_step"]["replicated on every rank"] == 8.73
-    mixed = bench.merge_round_robin_leg(base(), 16, 3.2, 12.0, 0.0)
-    assert mixed["value"] == 5000.0 and mixed["e2e"]["value"] == 1500.0 and mixed["e2e"]["pipeline"] == "first"
-    for bad in (0.3, float("nan")):
-        ln = bench.merge_round_robin_leg(base(), 16, 3.2, 4.0, bad)
-        assert ln["value"] == 1833.0 and ln["e2e"]["value"] == 1500.0 and ln["config"]["parallelism"] == "8 GPUs"
-        assert ln["temporal_stage_legs_ms_per_step"]["owned round-robin per clip + 1 broadcast"] == 3.2
-
-
-def test_bench_sm_carveout_leg_merge():
-    import bench
-
-    def base():
-        return {"value": 792.0, "ms_per_step": 20.2, "config": {"execution": "2 graphs"}}
-    ln = bench.merge_sm_carveout_leg(base(), 16, 8, 18.0, 1e-3)
-    assert ln["ms_per_step"] == 18.0 and abs(ln["value"] - 888.89) < 0.01 and "8 SMs" in ln["config"]["execution"]
-    for ms, diff in ((21.0, 0.0), (18.0, 0.5), (18.0, float("inf"))):
-        ln = bench.merge_sm_carveout_leg(base(), 16, 8, ms, diff)
-        assert ln["value"] == 792.0 and ln["config"]["execution"] == "2 graphs" and ln["sm_carveout_legs"][0]["ms_per_step"] == ms
-    ln = bench.merge_sm_carveout_leg(bench.merge_sm_carveout_leg(base(), 16, 8, 18.0, 0.0), 16, 16, 17.0, 0.0)
-    assert ln["ms_per_step"] == 17.0 and ln["config"]["execution"].count("cuBLASLt") == 1 and "16 SMs" in ln["config"]["execution"]
-    assert [l["sms_left_free_by_cublaslt"] for l in ln["sm_carveout_legs"]] == [8, 16]
+    a = {"x": torch.tensor([1.0, 2.0, 4.0]), "y": torch.tensor([10.0])}
+    assert bench.rel_max_diff(a, {k: v.clone() for k, v in a.items()}) == 0.0
+    b = {"x": torch.tensor([1.0, 2.0, 5.0]), "y": torch.tensor([10.0])}
+    assert abs(bench.rel_max_diff(a, b) - 0.2) < 1e-6
+    c = {"x": torch.tensor([1.0, float("nan"), 4.0]), "y": torch.tensor([10.0])}
+    assert bench.rel_max_diff(c, a) == float("inf")

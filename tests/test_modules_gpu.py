@@ -156,7 +156,6 @@ def test_mask_head_golden_and_lowres_equivalence(golden):
 def test_tracker_golden(golden, mode, tol):
     g = golden("tracker_small.pt")
     t = build_tracker(g).cuda()
-    t.use_custom_attention = mode == "bf16"      # also exercise the hand-written attention core (off by default)
     fe, fn, mf = g["frame_embeds"].cuda(), g["frame_embeds_no_norm"].cuda(), g["mask_features"].cuda()
     with precision(mode):
         o1, i1 = t(fe[:, :, :2], mf[:, :2], resume=False, return_indices=True, frame_embeds_no_norm=fn[:, :, :2])
@@ -328,8 +327,8 @@ def test_resize_and_attn_bias_kernels():
 @pytest.mark.parametrize("B,Lq,Lk,H,dh", [(1, 200, 200, 8, 64), (6, 200, 200, 8, 64), (3, 16, 16, 8, 64), (2, 37, 53, 4, 32),
                                          (16, 200, 200, 8, 32), (1, 1, 300, 8, 64)])
 @torch.no_grad()
-def test_mha_core_kernel(B, Lq, Lk, H, dh):
-    """dvis_mha_core vs an fp32 softmax(QK^T)V on the same bf16 inputs, with q / k / v as strided slices of packed
+def test_flash_attn_kernel_tracker_layouts(B, Lq, Lk, H, dh):
+    """dvis_flash_attn vs an fp32 softmax(QK^T)V on the same bf16 inputs, with q / k / v as strided slices of packed
     projections (the layouts the tracker uses)."""
     from dvis_plus_b200 import ops
     import torch.nn.functional as F
@@ -343,7 +342,7 @@ def test_mha_core_kernel(B, Lq, Lk, H, dh):
         kv = torch.randn(B, Lk, 2, H, dh, device="cuda").bfloat16()
         k, v = kv[:, :, 0], kv[:, :, 1]
     scale = dh ** -0.5
-    out = ops.mha_core(q, k, v, scale)
+    out = ops.flash_attn(q, k, v, scale)
     ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2), scale=scale)
     ref = ref.transpose(1, 2).reshape(B, Lq, C)
     assert out.shape == (B, Lq, C)

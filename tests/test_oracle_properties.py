@@ -83,7 +83,7 @@ def test_product_has_no_host_implementation_of_the_postprocessing_kernels():
 def test_gpu_tests_do_not_read_the_reference_tree():
     """/root/reference does not exist on the GPU box: only the fixture generators and the explicitly skipped drop-in test
     may mention it."""
-    allowed = {"reference_loader.py", "make_golden.py", "make_golden_postprocess.py", "make_golden_daq_runner.py", "test_dropin_reference.py", "test_oracle_properties.py"}
+    allowed = {"reference_loader.py", "make_golden.py", "make_golden_r2.py", "make_golden_postprocess.py", "make_golden_daq_runner.py", "test_dropin_reference.py", "test_oracle_properties.py"}
     bad = [p for p in _py_files("tests") if os.path.basename(p) not in allowed and "/root/reference" in open(p).read()]
     assert not bad, bad
 

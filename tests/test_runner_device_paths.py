@@ -196,11 +196,10 @@ def test_device_branches_with_fused_vis_postprocessing(cls, monkeypatch):
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("mode", ["one_rank", "two_ranks_gloo"])
-def test_bench_main_rehearsal_including_the_guarded_extra_legs(mode):
+def test_bench_main_rehearsal(mode):
     """bench.py's main() end to end on the emulated device + fake runtime (tests/simt/rehearse_bench.py, own processes
-    because it patches torch globally): the line is assembled and the guarded extra legs run through the real runners with
-    results that agree with the first leg's -- on one rank the overlapped end-to-end leg and the SM carve-out legs, on two
-    ranks (gloo: real all-gather / broadcast / barriers, both ranks' sides of the protocol) the round-robin leg."""
+    because it patches torch globally): the line is assembled and the timed path's results -- 3 clips in flight on one rank;
+    on two ranks (gloo: real all-gather / broadcast / barriers) the round-robin temporal stage -- equal the eager runner's."""
     import json
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -209,12 +208,10 @@ def test_bench_main_rehearsal_including_the_guarded_extra_legs(mode):
                        capture_output=True, text=True, timeout=850, cwd=root)
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout[p.stdout.index("{"):])
-    assert line["extra_legs"] == "completed" and line["gpu_launches"] > 0 and line["roofline"]["kernel"].startswith("msda")
-    assert line["e2e"]["overlapped_leg_rel_max_diff_vs_first_leg"] <= 1e-2
+    assert line["gpu_launches"] > 0 and line["roofline"]["kernel"].startswith("msda")
+    assert line["parity_check"]["bit_identical"], line["parity_check"]
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     if mode == "one_rank":
-        assert line["n_gpus"] == 1 and len(line["e2e"]["legs_ms_per_step"]) == 2
-        assert [l["sms_left_free_by_cublaslt"] for l in line["sm_carveout_legs"]] == [8, 16]
-        assert all(l["rel_max_diff_vs_first_leg"] <= 1e-2 for l in line["sm_carveout_legs"])
+        assert line["n_gpus"] == 1 and "3 clips in flight" in line["config"]["execution"]
     else:
-        assert line["n_gpus"] == 2 and len(line["e2e"]["legs_ms_per_step"]) == 3
-        assert len(line["temporal_stage_legs_ms_per_step"]) == 2 and line["round_robin_leg_rel_max_diff_vs_replicated"] <= 1e-2
+        assert line["n_gpus"] == 2 and "round-robin" in line["config"]["parallelism"]

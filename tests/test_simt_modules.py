@@ -289,6 +289,7 @@ def test_tracker_fused_kernels_vs_reference_golden(golden, device):
     g = golden("tracker_w128.pt")
     t = build_tracker_w128(g)
     t.use_cuda_graph = False
+    t.use_fused_kernels = True                    # opt-in: every linear step on csrc/small_linear.cu
     fe, fn, mf = g["frame_embeds"], g["frame_embeds_no_norm"], g["mask_features"]
     calls = _lib.launch_count
     with precision("bf16"):
@@ -305,6 +306,20 @@ def test_tracker_fused_kernels_vs_reference_golden(golden, device):
     assert rel_err(torch.cat([o1["pred_masks"], o2["pred_masks"]], 2).float(), g["pred_masks"]) < 3e-2
     # the recurrent state keeps the reference's layout: (1 + layers, q, b, c)
     assert t.last_outputs.shape == (3, 10, 1, 128) and t.last_reference.shape == (10, 1, 128)
+
+
+def test_tracker_default_path_with_flash_attention_vs_reference_golden(golden, device):
+    """the DEFAULT bf16 path at a width the attention kernel covers (4 heads x 32): library GEMMs + dvis_flash_attn"""
+    g = golden("tracker_w128.pt")
+    t = build_tracker_w128(g)
+    t.use_cuda_graph = False
+    assert t.use_custom_attention and not t.use_fused_kernels
+    fe, fn, mf = g["frame_embeds"], g["frame_embeds_no_norm"], g["mask_features"]
+    with precision("bf16"):
+        o1 = t(fe[:, :, :3], mf[:, :3], resume=False, frame_embeds_no_norm=fn[:, :, :3])
+        o2 = t(fe[:, :, 3:], mf[:, 3:], resume=True, frame_embeds_no_norm=fn[:, :, 3:])
+    assert rel_err(torch.cat([o1["pred_embds"], o2["pred_embds"]], 2).float(), g["pred_embds"]) < 3e-2
+    assert rel_err(torch.cat([o1["pred_masks"], o2["pred_masks"]], 2).float(), g["pred_masks"]) < 3e-2
 
 
 def test_tracker_fused_equals_library_path(golden, device):
@@ -326,6 +341,7 @@ def test_refiner_fused_kernels_vs_reference_golden(golden, device):
     and cross attention -- all on dvis_linear_small / dvis_flash_attn -- against the unmodified reference."""
     g = golden("refiner_w128.pt")
     r = build_refiner_w128(g)
+    r.use_fused_kernels = True
     calls = _lib.launch_count
     with precision("bf16"):
         o = r(g["instance_embeds"], g["frame_embeds"], g["mask_features"])

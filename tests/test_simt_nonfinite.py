@@ -53,7 +53,7 @@ def test_nonfinite_inputs_never_leave_the_buffers():
         simt.groupnorm_nhwc(poison(torch.randn(2, 24, 128, generator=g)), 32, torch.randn(128), torch.randn(128))
         simt.attn_bias_from_logits(poison(torch.randn(3, 4, 30, generator=g), 0.2))
         qkv = poison(torch.randn(1, 13, 3, 2, 32, generator=g)).bfloat16()
-        simt.mha_core(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 0.2)
+        simt.flash_attn(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 0.2)
     # the Hungarian kernels: NaN counts as 0 (reference semantics); inf / huge costs terminate with in-range assignments
     for bad in (float("nan"), 1e30, float("inf")):
         c = torch.rand(2, 9, 9, generator=g)

@@ -123,6 +123,7 @@ def test_tracker_and_refiner_fused_paths_vs_reference_golden(golden):
     from test_simt_modules import build_refiner_w128, build_tracker_w128
     g = golden("tracker_w128.pt")
     t = build_tracker_w128(g).cuda()
+    t.use_fused_kernels = True
     fe, fn, mf = g["frame_embeds"].cuda(), g["frame_embeds_no_norm"].cuda(), g["mask_features"].cuda()
     with precision("bf16"):
         o1, i1 = t(fe[:, :, :3], mf[:, :3], resume=False, return_indices=True, frame_embeds_no_norm=fn[:, :, :3])
@@ -134,6 +135,7 @@ def test_tracker_and_refiner_fused_paths_vs_reference_golden(golden):
     assert rel_err(torch.cat([o1["pred_masks"], o2["pred_masks"]], 2).float().cpu(), g["pred_masks"]) < 1e-2
     g = golden("refiner_w128.pt")
     r = build_refiner_w128(g).cuda()
+    r.use_fused_kernels = True
     n0 = _lib.launch_count
     with precision("bf16"):
         o = r(g["instance_embeds"].cuda(), g["frame_embeds"].cuda(), g["mask_features"].cuda())
@@ -157,6 +159,7 @@ def test_fused_temporal_stage_equals_library_path_at_production_width():
     res = {}
     for name, fused, graph in (("fused", True, True), ("fused_nograph", True, False), ("library", False, True)):
         trk.use_fused_kernels = rfn.use_fused_kernels = fused
+        trk.use_custom_attention = fused                  # "library": cuBLAS + cuDNN SDPA only (round 1's path)
         trk.use_cuda_graph = graph
         with precision("bf16"):
             o = trk(fe, None, resume=False, frame_embeds_no_norm=fn, with_masks=False)
