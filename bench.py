@@ -171,6 +171,39 @@ def rel_max_diff(a, b):
     return worst
 
 
+class GraphedStep:
+    """One whole step (configs 2 / 3: a single frame / a 5-frame online clip) captured into ONE CUDA graph with static input
+    buffers; same submit / wait_all surface as the clip runners."""
+    depth = 1
+
+    def __init__(self, fn, example):
+        self.inp = {k: v.clone() for k, v in example.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):
+                fn(self.inp)
+        torch.cuda.current_stream().wait_stream(side)
+        from dvis_plus_b200 import _lib
+        n0 = _lib.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = fn(self.inp)
+        self.captured_launches = _lib.launch_count - n0
+
+    def submit(self, features=None, d2h=None):
+        if features is not None:
+            for k, v in features.items():
+                self.inp[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        if d2h is not None:
+            for k, v in d2h.items():
+                v.copy_(self.out[k], non_blocking=True)
+
+    def wait_all(self):
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -303,6 +336,9 @@ def main():
             graphed = GraphedClipRunner(runner, resident, depth=3, vis=vis, d2h_stream=True)
             config["execution"] = ("2 CUDA graphs per clip (per-frame stage, temporal stage), software-pipelined across 3 clips "
                                    "in flight on 2 streams; host<->device copies on streams of their own")
+    elif not args.eager:
+        graphed = GraphedStep(step_eager, resident)
+        config["execution"] = "one CUDA graph per step, one step at a time; host<->device copies on the same stream"
     else:
         config["execution"] = "eager, one clip at a time (the tracker replays a CUDA graph per frame)"
     if T < 4:
@@ -322,6 +358,8 @@ def main():
                     step_eager()
         else:
             for _ in range(n):
+                if T < 4:
+                    flush.zero_()                                   # inputs smaller than L2: flush it between steps
                 graphed.submit(host if mode == "e2e" else None, d2h if mode == "e2e" else None)
             graphed.wait_all()
 

@@ -101,6 +101,12 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
   const saddr_t k_lds = saddr(ring) + (((lane >> 4) * 8 + (lane & 7)) * RS + ((lane >> 3) & 1) * 8) * 2;
   const saddr_t v_lds = saddr(ring) + (TILE + (((lane >> 3) & 1) * 8 + (lane & 7)) * RS + (lane >> 4) * 8) * 2;
 
+  // the mask words of a block are fetched one block ahead: their L2 round trip must not sit between S and the softmax
+  uint64_t nb0 = 0, nb1 = 0;
+  if (p.mask && blk0 < nblocks) {
+    nb0 = *reinterpret_cast<const uint64_t *>(mk0 + (((blk0 * KB) >> 6) << 3));
+    nb1 = *reinterpret_cast<const uint64_t *>(mk1 + (((blk0 * KB) >> 6) << 3));
+  }
   int it = 0;
   for (int blk = blk0; blk < nblocks; blk += blk_step, ++it) {
     const int stage = p.stages == 2 ? (it & 1) : 0;
@@ -134,20 +140,29 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
       }
     }
     // ---- scale, mask, online softmax ----
-    uint64_t bits0 = 0, bits1 = 0;
-    if (p.mask) {                                  // 64-bit words hold 64 keys; a 32-key block reads its half
-      bits0 = *reinterpret_cast<const uint64_t *>(mk0 + ((key0 >> 6) << 3)) >> (key0 & 63);
-      bits1 = *reinterpret_cast<const uint64_t *>(mk1 + ((key0 >> 6) << 3)) >> (key0 & 63);
+    // 64-bit words hold 64 keys; a 32-key block reads its half.  Keys past Lk count as masked: fold them into the words
+    // once per block instead of comparing every element
+    uint64_t bits0 = nb0 >> (key0 & 63), bits1 = nb1 >> (key0 & 63);
+    if (nkeys < KB) {
+      const uint64_t tail = ~uint64_t(0) << nkeys;
+      bits0 |= tail;
+      bits1 |= tail;
     }
+    if (p.mask && more) {
+      const int nk0 = (blk + blk_step) * KB;
+      nb0 = *reinterpret_cast<const uint64_t *>(mk0 + ((nk0 >> 6) << 3));
+      nb1 = *reinterpret_cast<const uint64_t *>(mk1 + ((nk0 >> 6) << 3));
+    }
+    const uint32_t lo0 = uint32_t(bits0 >> (2 * t)), hi0 = uint32_t(bits0 >> (32 + 2 * t));   // this lane's columns 2t, 2t+1 (+8 nt)
+    const uint32_t lo1 = uint32_t(bits1 >> (2 * t)), hi1 = uint32_t(bits1 >> (32 + 2 * t));
     float mx0 = mrow[0], mx1 = mrow[1];
 #pragma unroll
     for (int nt = 0; nt < NKT; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = nt * 8 + 2 * t + (e & 1);
-        const bool dead = col >= nkeys || (((e < 2 ? bits0 : bits1) >> col) & 1);
-        s[nt][e] = dead ? -INFINITY : s[nt][e] * p.scale_log2e;
-      }
+      const uint32_t w0 = (nt < 4 ? lo0 : hi0) >> ((nt & 3) * 8), w1 = (nt < 4 ? lo1 : hi1) >> ((nt & 3) * 8);
+      s[nt][0] = (w0 & 1) ? -INFINITY : s[nt][0] * p.scale_log2e;
+      s[nt][1] = (w0 & 2) ? -INFINITY : s[nt][1] * p.scale_log2e;
+      s[nt][2] = (w1 & 1) ? -INFINITY : s[nt][2] * p.scale_log2e;
+      s[nt][3] = (w1 & 2) ? -INFINITY : s[nt][3] * p.scale_log2e;
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }

@@ -24,6 +24,7 @@ namespace dvis {
 namespace {
 
 constexpr int kMaxLevels = 8;
+constexpr int kMaxStagedLP = 32;   // L*P beyond this goes to the generic kernel
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 
@@ -42,6 +43,7 @@ struct MsdaParams {
   int N, S, M, L, Lq, P;
   int items_per_cta;
   int m_shift, p_shift, lpc_shift;  // log2(M), log2(P) or -1 when not a power of two; log2(next_pow2(L*P))
+  unsigned lp_magic;                // ceil(2^20 / (L*P)): e / (L*P) == (e * lp_magic) >> 20 for e < 2^12
 };
 
 template <typename T>
@@ -110,6 +112,25 @@ __device__ __forceinline__ void point_params(A x, A y, A a, int H, int W, int st
   off.o11 = uint32_t(v11 ? o11 : safe) << 4;
 }
 
+// Blackwell mixed-precision FMA (PTX fma.rn.f32.bf16 -> SASS FHFMA.BF16 with .H0 / .H1 operand selectors): fp32 accumulator +=
+// bf16 x bf16 straight from the halves of packed registers -- no bf16 -> fp32 conversion instructions (they were 32 of the
+// 54 instructions per sampling point of the bf16 gather loop).  a0 += lo(v) * w, a1 += hi(v) * w with w = the HI-th half of wp.
+template <int HI>
+__device__ __forceinline__ void fhfma2(float &a0, float &a1, uint32_t v, uint32_t wp) {
+#ifndef DVIS_SIMT_EMULATION
+  if (HI)
+    asm("{\n .reg .b16 vl, vh, wl, wh;\n mov.b32 {vl, vh}, %2;\n mov.b32 {wl, wh}, %3;\n"
+        " fma.rn.f32.bf16 %0, vl, wh, %0;\n fma.rn.f32.bf16 %1, vh, wh, %1;\n}" : "+f"(a0), "+f"(a1) : "r"(v), "r"(wp));
+  else
+    asm("{\n .reg .b16 vl, vh, wl, wh;\n mov.b32 {vl, vh}, %2;\n mov.b32 {wl, wh}, %3;\n"
+        " fma.rn.f32.bf16 %0, vl, wl, %0;\n fma.rn.f32.bf16 %1, vh, wl, %1;\n}" : "+f"(a0), "+f"(a1) : "r"(v), "r"(wp));
+#else
+  const float w = __uint_as_float(HI ? (wp & 0xffff0000u) : (wp << 16));
+  a0 = fmaf(__uint_as_float(v << 16), w, a0);
+  a1 = fmaf(__uint_as_float(v & 0xffff0000u), w, a1);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // staged kernel: T = value type, TO = output type, D = channels per head.
 // A CTA owns `items_per_cta` (query, head) items.
@@ -136,11 +157,16 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
 
   extern __shared__ uint4 dyn_smem[];
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
+  __shared__ float sInvH[kMaxLevels], sInvW[kMaxLevels];
+  __shared__ unsigned char sLevelOf[kMaxStagedLP];          // level of sampling point pt (pt / P), looked up instead of divided
   if (threadIdx.x < p.L) {
     sH[threadIdx.x] = int(p.shapes[2 * threadIdx.x]);
     sW[threadIdx.x] = int(p.shapes[2 * threadIdx.x + 1]);
     sStart[threadIdx.x] = int(p.level_start[threadIdx.x]);
+    sInvH[threadIdx.x] = 1.f / float(int(p.shapes[2 * threadIdx.x]));
+    sInvW[threadIdx.x] = 1.f / float(int(p.shapes[2 * threadIdx.x + 1]));
   }
+  if (threadIdx.x < p.L * p.P) sLevelOf[threadIdx.x] = (unsigned char)(threadIdx.x / p.P);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.y, M = p.M, P = p.P, LP = p.L * p.P;
@@ -148,8 +174,11 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
   const int per_batch = p.Lq * M;
   const int chunk_begin = blockIdx.x * p.items_per_cta;
   const int nitems = min(p.items_per_cta, per_batch - chunk_begin);
+  // bf16 in AND out (the encoder's production path): the 4 corner weights are kept as packed bf16 and the gather loop runs on
+  // FHFMA (fhfma2 above); every other combination keeps exact fp32 weights (the plain op's 2e-5 contract)
+  constexpr bool kMixed = std::is_same<T, __nv_bfloat16>::value && std::is_same<TO, __nv_bfloat16>::value;
   PointOffsets *s_off = reinterpret_cast<PointOffsets *>(dyn_smem);
-  float4 *s_wt = reinterpret_cast<float4 *>(dyn_smem + p.items_per_cta * LPs);
+  float4 *s_wt = reinterpret_cast<float4 *>(dyn_smem + p.items_per_cta * LPs);   // kMixed: only .x / .y used (2 x bf16x2 bit patterns)
   float *s_prob = reinterpret_cast<float *>(dyn_smem + 2 * p.items_per_cta * LPs);
   int *s_item = reinterpret_cast<int *>(s_prob + (FUSED ? p.items_per_cta * LP : 0));
 
@@ -157,64 +186,75 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
   __syncthreads();
 
   if constexpr (FUSED) {
-    // phase 0: 4 threads per item; softmax over L*P logits (OPS/modules/ms_deform_attn.py:103-104)
-    for (int il = tid >> 2; il < ((nitems + 63) & ~63); il += kThreads >> 2) {
-      const int sub = tid & 3;
-      const bool act = il < nitems;
-      const int item = act ? s_item[il] : 0;
+    // phase 0: ONE thread per item: softmax over its L*P contiguous logits (OPS/modules/ms_deform_attn.py:103-104).  The row
+    // (24 bytes at L*P = 12, bf16) is read twice from L1 (max, then exp) -- the first version used 4 threads + shuffles per
+    // item and cost 13 % of the kernel's instructions (ncu source view, profiles/r2_msda.md); this form costs ~1.5 %.
+    for (int il = tid; il < nitems; il += kThreads) {
+      const int item = s_item[il];
       const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
       const TP *lg = static_cast<const TP *>(p.attn) + ((size_t)n * p.Lq + q) * p.attn_stride + (size_t)m * LP;
+      float *pr = s_prob + il * LP;
       float mx = -INFINITY;
-      for (int i = sub; i < LP; i += 4) mx = fmaxf(mx, act ? ldp<TP>(lg + i) : 0.f);
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      for (int i = 0; i < LP; ++i) mx = fmaxf(mx, ldp<TP>(lg + i));
       float sum = 0.f;
-      for (int i = sub; i < LP; i += 4) {
-        const float e = act ? __expf(ldp<TP>(lg + i) - mx) : 0.f;
-        if (act) s_prob[il * LP + i] = e;
+      for (int i = 0; i < LP; ++i) {
+        const float e = __expf(ldp<TP>(lg + i) - mx);
+        pr[i] = e;
         sum += e;
       }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       const float inv = 1.f / sum;
-      if (act)
-        for (int i = sub; i < LP; i += 4) s_prob[il * LP + i] *= inv;   // same thread wrote these
+      for (int i = 0; i < LP; ++i) pr[i] *= inv;
     }
     __syncthreads();
   }
 
-  // phase 1: thread -> (item il, point pt); LPc = LP rounded up to a power of two so the split is shifts only
+  // phase 1: one thread per (item, point), ALL lanes busy: the flat index e = il * LP + pt is split with a multiply-shift
+  // (magic = ceil(2^20 / LP), exact for e < 2^12), the point's level comes from a table, 1 / W and 1 / H from shared memory
   {
-    const int lpc_shift = p.lpc_shift, pt = tid & ((1 << lpc_shift) - 1);
-    if (pt < LP) {
-      const int l = p.p_shift >= 0 ? pt >> p.p_shift : pt / P;
+    const int total = nitems * LP;
+    const unsigned magic = p.lp_magic;
+    for (int e = tid; e < total; e += kThreads) {
+      const int il = int((unsigned(e) * magic) >> 20), pt = e - il * LP;
+      const int l = sLevelOf[pt];
       const int H = sH[l], W = sW[l], start = sStart[l];
-      for (int il = tid >> lpc_shift; il < nitems; il += kThreads >> lpc_shift) {
-        const int item = s_item[il];
-        const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
-        const size_t nq = (size_t)n * p.Lq + q;
-        PointOffsets off;
-        float4 wt;
-        if constexpr (FUSED) {
-          const TP *of = static_cast<const TP *>(p.loc) + nq * p.loc_stride + ((size_t)m * LP + pt) * 2;
-          const float *rf = p.ref + (nq * p.L + l) * p.ref_dim;
-          const float2 o = make_float2(ldp<TP>(of), ldp<TP>(of + 1));
-          // loc = ref + off / (W_l, H_l) for 2-d reference points (py:106-109);
-          // loc = ref_xy + off / P * ref_wh * 0.5 for boxes (py:110-112)
-          const float sx = p.ref_dim == 2 ? 1.f / float(W) : __ldg(rf + 2) * (0.5f / float(P));
-          const float sy = p.ref_dim == 2 ? 1.f / float(H) : __ldg(rf + 3) * (0.5f / float(P));
-          point_params<float>(fmaf(o.x, sx, __ldg(rf)), fmaf(o.y, sy, __ldg(rf + 1)), s_prob[il * LP + pt], H, W, start,
-                              M, m, LPR, off, wt);
+      const int item = s_item[il];
+      const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
+      const size_t nq = (size_t)n * p.Lq + q;
+      PointOffsets off;
+      float4 wt;
+      if constexpr (FUSED) {
+        const TP *of = static_cast<const TP *>(p.loc) + nq * p.loc_stride + ((size_t)m * LP + pt) * 2;
+        const float *rf = p.ref + (nq * p.L + l) * p.ref_dim;
+        float2 o;
+        if constexpr (std::is_same<TP, __nv_bfloat16>::value) {       // x and y offsets: one 32-bit load
+          const uint32_t u = __ldg(reinterpret_cast<const uint32_t *>(of));
+          o = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
         } else {
-          using TL = typename LocType<T>::type;   // plain op: loc / attn have the value's dtype
-          const size_t i = (nq * M + m) * (size_t)LP + pt;
-          const TL *lc = static_cast<const TL *>(p.loc) + 2 * i;
-          point_params<TL>(__ldg(lc), __ldg(lc + 1), __ldg(static_cast<const TL *>(p.attn) + i), H, W, start, M, m, LPR,
-                           off, wt);
+          o = __ldg(reinterpret_cast<const float2 *>(of));
         }
-        s_off[il * LPs + pt] = off;
-        s_wt[il * LPs + pt] = wt;
+        // loc = ref + off / (W_l, H_l) for 2-d reference points (py:106-109);
+        // loc = ref_xy + off / P * ref_wh * 0.5 for boxes (py:110-112)
+        float rx, ry, sx, sy;
+        if (p.ref_dim == 2) {
+          const float2 r2 = __ldg(reinterpret_cast<const float2 *>(rf));
+          rx = r2.x; ry = r2.y; sx = sInvW[l]; sy = sInvH[l];
+        } else {
+          const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rf));
+          rx = r4.x; ry = r4.y; sx = r4.z * (0.5f / float(P)); sy = r4.w * (0.5f / float(P));
+        }
+        point_params<float>(fmaf(o.x, sx, rx), fmaf(o.y, sy, ry), s_prob[e], H, W, start, M, m, LPR, off, wt);
+      } else {
+        using TL = typename LocType<T>::type;   // plain op: loc / attn have the value's dtype
+        const size_t i = (nq * M + m) * (size_t)LP + pt;
+        const TL *lc = static_cast<const TL *>(p.loc) + 2 * i;
+        point_params<TL>(__ldg(lc), __ldg(lc + 1), __ldg(static_cast<const TL *>(p.attn) + i), H, W, start, M, m, LPR,
+                         off, wt);
       }
+      s_off[il * LPs + pt] = off;
+      if constexpr (kMixed)
+        *reinterpret_cast<uint2 *>(&s_wt[il * LPs + pt]) = make_uint2(pack_bf16x2(wt.x, wt.y), pack_bf16x2(wt.z, wt.w));
+      else
+        s_wt[il * LPs + pt] = wt;
     }
   }
   __syncthreads();
@@ -224,6 +264,32 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
   using V = decltype(Vec16<T>::v);
   const char *vb = reinterpret_cast<const char *>(static_cast<const T *>(p.value) + (size_t)n * p.S * M * D) + j * 16;
   for (int il = warp * G + g; il < nitems; il += kWarps * G) {
+    if constexpr (kMixed) {
+      float acc[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      const uint4 *so = reinterpret_cast<const uint4 *>(s_off) + il * LPs;
+      const float4 *sw = s_wt + il * LPs;
+#pragma unroll UNROLL
+      for (int pt = 0; pt < LP; ++pt) {
+        const uint4 o = so[pt];
+        const uint2 w = *reinterpret_cast<const uint2 *>(&sw[pt]);
+        const uint4 v00 = __ldg(reinterpret_cast<const uint4 *>(vb + o.x)), v01 = __ldg(reinterpret_cast<const uint4 *>(vb + o.y));
+        const uint4 v10 = __ldg(reinterpret_cast<const uint4 *>(vb + o.z)), v11 = __ldg(reinterpret_cast<const uint4 *>(vb + o.w));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          fhfma2<0>(acc[2 * k], acc[2 * k + 1], (&v00.x)[k], w.x);
+          fhfma2<1>(acc[2 * k], acc[2 * k + 1], (&v01.x)[k], w.x);
+          fhfma2<0>(acc[2 * k], acc[2 * k + 1], (&v10.x)[k], w.y);
+          fhfma2<1>(acc[2 * k], acc[2 * k + 1], (&v11.x)[k], w.y);
+        }
+      }
+      const int item = s_item[il];
+      const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
+      TO *dst = static_cast<TO *>(p.out) + (((size_t)n * p.Lq + q) * M + m) * (size_t)D + j * VEC;
+      store_vec<TO, float, VEC>(dst, acc);
+      continue;
+    }
     // accumulators as f32x2 pairs: Blackwell's packed FFMA2 (fma.rn.f32x2) halves the FMA issue slots
     float2 acc2[VEC / 2];
 #pragma unroll
@@ -305,7 +371,6 @@ int log2_exact(int v) {
   return s;
 }
 
-constexpr int kMaxStagedLP = 32;   // L*P beyond this goes to the generic kernel
 constexpr size_t kMaxStagedSmem = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 
 // dynamic shared memory the staged kernel needs (same formula as launch_staged): lets the plain op fall back to the generic
@@ -330,6 +395,7 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
   int lpc = 1, sh = 0;
   while (lpc < LP) { lpc <<= 1; ++sh; }
   p.lpc_shift = sh;
+  p.lp_magic = ((1u << 20) + LP - 1) / LP;
   const size_t smem = (size_t)p.items_per_cta * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
   if (smem > kMaxStagedSmem)
     return fail(DVIS_ERR_UNSUPPORTED, "msda: %zu bytes of shared memory per CTA for D=%d, L*P=%d exceed the %d-byte opt-in limit", smem,
@@ -411,6 +477,8 @@ extern "C" int dvis_msda_fused_forward(const void *value, int value_dtype, const
     return rc;
   DVIS_REQUIRE(ref && (ref_dim == 2 || ref_dim == 4), "msda_fused: reference points must be 2-d or 4-d");
   DVIS_REQUIRE(aligned16(value) && aligned16(out), "msda_fused: value/out must be 16-byte aligned");
+  DVIS_REQUIRE(aligned16(ref) && (reinterpret_cast<uintptr_t>(offsets) & 7) == 0 && offsets_stride % 2 == 0,
+               "msda_fused: reference points must be 16-byte aligned, offsets 8-byte aligned with an even row stride");
   DVIS_REQUIRE(param_dtype == DVIS_F32 || param_dtype == DVIS_BF16, "msda_fused: offsets/logits must be f32 or bf16");
   MsdaParams p{};
   p.value = value; p.shapes = spatial_shapes; p.level_start = level_start; p.loc = offsets; p.attn = logits;

@@ -88,11 +88,14 @@ def main():
             offs_flat = offsets.view(N, S, -1)
             lg_flat = logits.view(N, S, -1)
             vb = value.bfloat16()
+            ob16, lb16 = offs_flat.bfloat16(), lg_flat.bfloat16()
             variants = {
                 "ours_plain": lambda: ops.ms_deform_attn_forward(value, sh_t, lsi, loc, attn, 128),
                 "ours_plain_tiled": lambda: ops.ms_deform_attn_forward(value, sh_t, lsi, loc, attn, 128, item_order=order),
                 "ours_fused_f32_tiled": lambda: ops.msda_fused_forward(value, sh_t, lsi, offs_flat, lg_flat, ref, M, L, P, item_order=order),
                 "ours_fused_bf16_tiled": lambda: ops.msda_fused_forward(vb, sh_t, lsi, offs_flat, lg_flat, ref, M, L, P, item_order=order),
+                # the encoder's production form: value, offsets, logits and output all bf16
+                "ours_fused_bf16_params_bf16_tiled": lambda: ops.msda_fused_forward(vb, sh_t, lsi, ob16, lb16, ref, M, L, P, item_order=order),
             }
             if refcuda.available():
                 variants["reference_cuda_sm100"] = lambda: refcuda.forward(value, sh_t, lsi, loc, attn)

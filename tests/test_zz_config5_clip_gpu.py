@@ -99,22 +99,35 @@ def test_config5_daq_clip_full_frame_size_T4_q300():
 
 
 @torch.no_grad()
-def test_config5_daq_clip_device_matches_host_modules():
+def test_config5_daq_temporal_stage_device_matches_host_modules():
+    """Cutter + refiner on the device (fp32 mode) vs the same modules on the host, both fed the SAME segmenter outputs (the
+    oracle port's, so that the comparison is not at the mercy of near-threshold anchor selections flipping with the
+    segmenter's bf16 mask GEMM; the per-frame stage at 1080p has its own parity tests in test_zz_config5_gpu.py)."""
     T, hw = 5, (160, 256)
     pd, dec, cut, rf = build(40, "cpu", layers=2, seed=3)
     feats = features(T, hw, 9, "cpu", torch.float32)
     kw = dict(aux_inference_select_thr=0.05, noise_frame_num=1, offline_topk_ins=8, window_size=3)
+    seg_host, cache = host_segment(pd, dec, 2), {}
+
+    def cached(device):
+        def segment(window):
+            key = (tuple(window["res2"].shape), float(window["res2"].flatten()[0]))
+            if key not in cache:
+                cache[key] = seg_host({k: v.cpu() for k, v in window.items()})
+            return {k: v.to(device) for k, v in cache[key].items()}
+        return segment
     random.seed(1)
-    ref = DAQOfflineRunner(pd, dec, cut, rf, K, to_store="cpu", segment=host_segment(pd, dec, 2), **kw)(feats)
+    ref = DAQOfflineRunner(pd, dec, cut, rf, K, to_store="cpu", segment=cached("cpu"), **kw)(feats)
     hub_ref = {sid: (s.sT, len(s.embeds), s.dead) for sid, s in cut.video_ins_hub.items()}
+    assert len(hub_ref) >= 40
     for m in (pd, dec, cut, rf):
         m.cuda()
     cut._clear_memory()
     random.seed(1)
     n0 = _lib.launch_count
     with precision("fp32"):
-        out = DAQOfflineRunner(pd, dec, cut, rf, K, segment=device_segment(pd, dec), **kw)({k: v.cuda() for k, v in feats.items()})
-    assert _lib.launch_count - n0 > 30
+        out = DAQOfflineRunner(pd, dec, cut, rf, K, segment=cached("cuda"), **kw)({k: v.cuda() for k, v in feats.items()})
+    assert _lib.launch_count - n0 > 10
     assert {sid: (s.sT, len(s.embeds), s.dead) for sid, s in cut.video_ins_hub.items()} == hub_ref   # same instances, same life spans
     assert out["pred_ids"].tolist() == ref["pred_ids"].tolist()
     for k in ("pred_logits", "pred_masks"):
