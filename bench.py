@@ -166,7 +166,7 @@ def rel_max_diff(a, b):
     worst = 0.0
     for k in b:
         x, y = a[k].float(), b[k].float().to(a[k].device)
-        d = float((x - y).abs().max() / y.abs().max().clamp_min(1e-6))
+        d = float((x.detach() - y.detach()).abs().max() / y.detach().abs().max().clamp_min(1e-6))
         worst = max(worst, d if d == d else float("inf"))
     return worst
 
@@ -302,6 +302,7 @@ def main():
 
     online = OnlineClipRunner(runner.pixel_decoder, runner.predictor, runner.tracker, window_size=T) if args.config == 3 else None
 
+    @torch.no_grad()
     def step_eager(feats=None):
         """one clip through the public runner API, eagerly; -> dict of device tensors"""
         feats = resident if feats is None else feats

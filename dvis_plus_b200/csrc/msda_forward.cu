@@ -178,9 +178,9 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
   // FHFMA (fhfma2 above); every other combination keeps exact fp32 weights (the plain op's 2e-5 contract)
   constexpr bool kMixed = std::is_same<T, __nv_bfloat16>::value && std::is_same<TO, __nv_bfloat16>::value;
   PointOffsets *s_off = reinterpret_cast<PointOffsets *>(dyn_smem);
-  float4 *s_wt = reinterpret_cast<float4 *>(dyn_smem + p.items_per_cta * LPs);   // kMixed: only .x / .y used (2 x bf16x2 bit patterns)
+  float4 *s_wt = reinterpret_cast<float4 *>(dyn_smem + p.items_per_cta * LPs);   // kMixed: a dense uint2 array (2 x bf16x2) in the same region
   float *s_prob = reinterpret_cast<float *>(dyn_smem + 2 * p.items_per_cta * LPs);
-  int *s_item = reinterpret_cast<int *>(s_prob + (FUSED ? p.items_per_cta * LP : 0));
+  int *s_item = reinterpret_cast<int *>(s_prob + (FUSED ? p.items_per_cta * LP : 0));   // s_prob: (max, 1/sum) per item (2 of the LP slots)
 
   for (int il = tid; il < nitems; il += kThreads) s_item[il] = p.order ? __ldg(p.order + chunk_begin + il) : chunk_begin + il;
   __syncthreads();
@@ -189,21 +189,45 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
     // phase 0: ONE thread per item: softmax over its L*P contiguous logits (OPS/modules/ms_deform_attn.py:103-104).  The row
     // (24 bytes at L*P = 12, bf16) is read twice from L1 (max, then exp) -- the first version used 4 threads + shuffles per
     // item and cost 13 % of the kernel's instructions (ncu source view, profiles/r2_msda.md); this form costs ~1.5 %.
+    // The row is fetched with 8-byte loads into registers (3 loads at L*P = 12, bf16): a 2-byte load per logit would cost one
+    // L1 wavefront per lane and logit -- the kernel is L1-wavefront bound -- and made the first one-thread version slower.
+    constexpr int EPV = 8 / int(sizeof(TP));                         // logits per 8-byte load
+    const bool vec_ok = (LP % EPV) == 0 && (reinterpret_cast<uintptr_t>(p.attn) & 7) == 0 && (p.attn_stride % EPV) == 0;
     for (int il = tid; il < nitems; il += kThreads) {
       const int item = s_item[il];
       const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
       const TP *lg = static_cast<const TP *>(p.attn) + ((size_t)n * p.Lq + q) * p.attn_stride + (size_t)m * LP;
-      float *pr = s_prob + il * LP;
-      float mx = -INFINITY;
-      for (int i = 0; i < LP; ++i) mx = fmaxf(mx, ldp<TP>(lg + i));
-      float sum = 0.f;
-      for (int i = 0; i < LP; ++i) {
-        const float e = __expf(ldp<TP>(lg + i) - mx);
-        pr[i] = e;
-        sum += e;
+      // only (max, 1 / sum) of the row go to shared memory; phase 1 recomputes exp(logit - max) for its own point (one L1-hit
+      // load + one MUFU) -- storing and re-reading L*P probabilities cost 4.5 shared-memory wavefronts per item with 4-way
+      // bank conflicts, on a kernel that is bound by L1 / shared-memory wavefronts (ncu: 91 % of the LSU data pipe)
+      float mx = -INFINITY, sum = 0.f;
+      if (vec_ok) {
+        const int nv = LP / EPV;
+        auto unpack = [](const uint2 u, float (&v)[EPV]) {
+          if constexpr (EPV == 4) {
+            v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+            v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+          } else {
+            v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y);
+          }
+        };
+        for (int i = 0; i < nv; ++i) {
+          float v[EPV];
+          unpack(__ldg(reinterpret_cast<const uint2 *>(lg) + i), v);
+#pragma unroll
+          for (int k = 0; k < EPV; ++k) mx = fmaxf(mx, v[k]);
+        }
+        for (int i = 0; i < nv; ++i) {                               // second read: L1 hit (the 40-register budget of the
+          float v[EPV];                                               // 6-CTA/SM gather loop does not hold 32 logits)
+          unpack(__ldg(reinterpret_cast<const uint2 *>(lg) + i), v);
+#pragma unroll
+          for (int k = 0; k < EPV; ++k) sum += __expf(v[k] - mx);
+        }
+      } else {
+        for (int i = 0; i < LP; ++i) mx = fmaxf(mx, ldp<TP>(lg + i));
+        for (int i = 0; i < LP; ++i) sum += __expf(ldp<TP>(lg + i) - mx);
       }
-      const float inv = 1.f / sum;
-      for (int i = 0; i < LP; ++i) pr[i] *= inv;
+      *reinterpret_cast<float2 *>(s_prob + 2 * il) = make_float2(mx, 1.f / sum);
     }
     __syncthreads();
   }
@@ -242,7 +266,10 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
           const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rf));
           rx = r4.x; ry = r4.y; sx = r4.z * (0.5f / float(P)); sy = r4.w * (0.5f / float(P));
         }
-        point_params<float>(fmaf(o.x, sx, rx), fmaf(o.y, sy, ry), s_prob[e], H, W, start, M, m, LPR, off, wt);
+        const float2 ms = *reinterpret_cast<const float2 *>(s_prob + 2 * il);      // (max, 1 / sum) of the item's logits
+        const TP *lgp = static_cast<const TP *>(p.attn) + nq * p.attn_stride + (size_t)m * LP + pt;
+        const float prob = __expf(ldp<TP>(lgp) - ms.x) * ms.y;
+        point_params<float>(fmaf(o.x, sx, rx), fmaf(o.y, sy, ry), prob, H, W, start, M, m, LPR, off, wt);
       } else {
         using TL = typename LocType<T>::type;   // plain op: loc / attn have the value's dtype
         const size_t i = (nq * M + m) * (size_t)LP + pt;
@@ -252,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
       }
       s_off[il * LPs + pt] = off;
       if constexpr (kMixed)
-        *reinterpret_cast<uint2 *>(&s_wt[il * LPs + pt]) = make_uint2(pack_bf16x2(wt.x, wt.y), pack_bf16x2(wt.z, wt.w));
+        reinterpret_cast<uint2 *>(s_wt)[il * LPs + pt] = make_uint2(pack_bf16x2(wt.x, wt.y), pack_bf16x2(wt.z, wt.w));   // dense 8-byte slots
       else
         s_wt[il * LPs + pt] = wt;
     }
@@ -269,11 +296,11 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
       const uint4 *so = reinterpret_cast<const uint4 *>(s_off) + il * LPs;
-      const float4 *sw = s_wt + il * LPs;
+      const uint2 *sw = reinterpret_cast<const uint2 *>(s_wt) + il * LPs;
 #pragma unroll UNROLL
       for (int pt = 0; pt < LP; ++pt) {
         const uint4 o = so[pt];
-        const uint2 w = *reinterpret_cast<const uint2 *>(&sw[pt]);
+        const uint2 w = sw[pt];
         const uint4 v00 = __ldg(reinterpret_cast<const uint4 *>(vb + o.x)), v01 = __ldg(reinterpret_cast<const uint4 *>(vb + o.y));
         const uint4 v10 = __ldg(reinterpret_cast<const uint4 *>(vb + o.z)), v11 = __ldg(reinterpret_cast<const uint4 *>(vb + o.w));
 #pragma unroll
@@ -476,6 +503,7 @@ extern "C" int dvis_msda_fused_forward(const void *value, int value_dtype, const
                                channels, num_levels, num_query, num_point))
     return rc;
   DVIS_REQUIRE(ref && (ref_dim == 2 || ref_dim == 4), "msda_fused: reference points must be 2-d or 4-d");
+  DVIS_REQUIRE(num_levels * num_point >= 2, "msda_fused: needs at least 2 sampling points per head (L*P = %d)", num_levels * num_point);
   DVIS_REQUIRE(aligned16(value) && aligned16(out), "msda_fused: value/out must be 16-byte aligned");
   DVIS_REQUIRE(aligned16(ref) && (reinterpret_cast<uintptr_t>(offsets) & 7) == 0 && offsets_stride % 2 == 0,
                "msda_fused: reference points must be 16-byte aligned, offsets 8-byte aligned with an even row stride");

@@ -123,14 +123,17 @@ def test_config5_daq_temporal_stage_device_matches_host_modules():
     for m in (pd, dec, cut, rf):
         m.cuda()
     cut._clear_memory()
+    cut.memory_seq_ids = []                       # the id generator avoids every id it has handed out before (daq.py:261-263)
     random.seed(1)
     n0 = _lib.launch_count
     with precision("fp32"):
         out = DAQOfflineRunner(pd, dec, cut, rf, K, segment=cached("cuda"), **kw)({k: v.cuda() for k, v in feats.items()})
     assert _lib.launch_count - n0 > 10
     assert {sid: (s.sT, len(s.embeds), s.dead) for sid, s in cut.video_ins_hub.items()} == hub_ref   # same instances, same life spans
-    assert out["pred_ids"].tolist() == ref["pred_ids"].tolist()
+    ids, ids_ref = out["pred_ids"][0].tolist(), ref["pred_ids"][0].tolist()
+    assert sorted(ids) == sorted(ids_ref)         # topk(sorted=False) orders the survivors differently on CPU and CUDA
+    perm = [ids.index(i) for i in ids_ref]
     for k in ("pred_logits", "pred_masks"):
-        a, b = out[k].float().cpu(), ref[k].float()
+        a, b = out[k].float().cpu()[:, perm], ref[k].float()
         assert a.shape == b.shape
         assert (a - b).abs().max() <= 3e-2 * b.abs().max().clamp_min(1.0), (k, float((a - b).abs().max()), float(b.abs().max()))
