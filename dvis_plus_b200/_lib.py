@@ -26,6 +26,7 @@ SIGNATURES = {
     "dvis_groupnorm_nhwc": [_vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp,
                             _vp, _i, _i64, _vp],
     "dvis_resize_bilinear_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
+    "dvis_level_tokens": [_vp, _i, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "dvis_attn_bias_from_logits": [_vp, _i64, _i, _vp, _i, _vp],
     "dvis_lap_chain": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "dvis_lap_rect": [_vp, _i, _i, _i, _vp, _vp],

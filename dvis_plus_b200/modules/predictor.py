@@ -178,8 +178,20 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
             xl = self.input_proj[l](x[l])   # empty nn.Sequential is the identity
             h, w = xl.shape[-2:]
             sizes.append((h, w))
-            tok = xl.permute(0, 2, 3, 1).reshape(B, h * w, C).float() + self.level_embed.weight[l]      # (B, hw, C)
             n_of = len(f["layers_of_level"][l])
+            cl = xl.stride(1) == 1 and xl.stride(3) == C and xl.stride(2) == w * C and xl.dtype in (torch.float32, torch.bfloat16)
+            if n_of and dt == torch.bfloat16 and cl and C % 4 == 0:
+                # src + level_embed and (src + level_embed) + pos, both straight to bf16, in one pass over the level
+                tok_lp, key_in = ops.level_tokens(xl, self.level_embed.weight[l].detach().float().contiguous(),
+                                                  self._pos(h, w, xl.device)[:, 0].contiguous())
+                k = F.linear(key_in, f["wk"][l], f["bk"][l]).view(B, h * w, n_of, H, dh)
+                v = F.linear(tok_lp, f["wv"][l], f["bv"][l]).view(B, h * w, n_of, H, dh)
+                k_all.append(k.permute(2, 0, 3, 1, 4))
+                v_all.append(v.permute(2, 0, 3, 1, 4))
+                kv_rows.append((k, v))
+                level_feats.append(ops.resize_bilinear_nhwc(mf_lp, (h, w)))
+                continue
+            tok = xl.permute(0, 2, 3, 1).reshape(B, h * w, C).float() + self.level_embed.weight[l]      # (B, hw, C)
             if n_of:
                 key_in = (tok + self._pos(h, w, tok.device)[:, 0][None]).to(dt)
                 k = F.linear(key_in, f["wk"][l], f["bk"][l]).view(B, h * w, n_of, H, dh)

@@ -318,6 +318,27 @@ def mask_attn_bias(mask_embed, level_features, dtype=torch.bfloat16):
     return bias
 
 
+def level_tokens(x, level_embed, pos=None):
+    """The decoder's memory of one attention level in one pass (dvis_level_tokens): x (B, C, h, w) f32|bf16 with
+    channels-last memory (any batch stride), level_embed (C,) f32, pos (h*w, C) f32 or None.
+    -> (tok (B, h*w, C) bf16 = x + level_embed,  key (B, h*w, C) bf16 = tok + pos  | None)."""
+    B, C, h, w = x.shape
+    if not x.is_cuda:
+        raise RuntimeError("level_tokens: CUDA tensors required (there is no CPU path)")
+    assert x.stride(1) == 1 and x.stride(3) == C and x.stride(2) == w * C, "channels-last rows expected"
+    assert x.dtype in (torch.float32, torch.bfloat16) and level_embed.dtype == torch.float32 and level_embed.is_contiguous()
+    tok = torch.empty((B, h * w, C), dtype=torch.bfloat16, device=x.device)
+    key = None
+    if pos is not None:
+        assert pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape == (h * w, C)
+        key = torch.empty((B, h * w, C), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dvis_level_tokens", x.data_ptr(), _DTYPE[x.dtype], x.stride(0), level_embed.data_ptr(),
+                  pos.data_ptr() if pos is not None else None, B, h * w, C, tok.data_ptr(), key.data_ptr() if key is not None else None,
+                  _stream())
+    return tok, key
+
+
 def mask_attn_bits(mask_embed, level_features):
     """The masked-attention decoder's attention mask as packed bits, straight from the tcgen05 mask GEMM
     (dvis_mask_attn_bits): mask_embed (B,Q,C); level_features (B,C,h,w) bf16 channels_last.

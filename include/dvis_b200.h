@@ -239,6 +239,11 @@ int dvis_mask_attn_bits(const void *emb, const void *feat, int B, int Q, int C, 
  *   sigmoid(logit) < 0.5 (py:370-371), 0 elsewhere; a row that would be -inf everywhere becomes all 0 (py:297).
  */
 int dvis_resize_bilinear_nhwc(const void *in, int N, int h, int w, int C, void *out, int H, int W, void *stream);
+/* The decoder's per-level memory in one pass (py:270-279: src = input_proj(x) + level_embed; keys see src + pos):
+ *   tok[b,p,:] = x[b,p,:] + level_embed[:]   and (key != NULL)   key[b,p,:] = tok[b,p,:] + pos[p,:],  both bf16 (B, HW, C).
+ * x: f32|bf16, pixel stride C, batch stride x_batch_stride elements (a slice of the encoder's token buffer); pos (HW, C) f32. */
+int dvis_level_tokens(const void *x, int x_dtype, int64_t x_batch_stride, const float *level_embed, const float *pos, int B, int HW,
+                      int C, void *tok, void *key, void *stream);
 int dvis_attn_bias_from_logits(const float *logits, int64_t rows, int hw, void *bias, int bias_dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -352,3 +352,28 @@ def test_refiner_fused_kernels_vs_reference_golden(golden, device):
     with precision("bf16"):
         o_lib = r(g["instance_embeds"], g["frame_embeds"], g["mask_features"])
     assert rel_err(o["pred_embds"].float(), o_lib["pred_embds"].float()) < 2e-2
+
+
+def test_predictor_level_tokens_kernel_path_equals_torch_path(device):
+    """channels-last level maps (what the pixel decoder hands over) take dvis_level_tokens (x + level_embed [+ pos] -> bf16 in
+    one pass); NCHW-contiguous maps take the torch ops: same values up to the order of the two fp32 additions"""
+    torch.manual_seed(1)
+    d = M.VideoMultiScaleMaskedTransformerDecoder_dvisPlus(
+        128, True, num_classes=7, hidden_dim=128, num_queries=12, nheads=4, dim_feedforward=256, dec_layers=3,
+        pre_norm=False, mask_dim=128, enforce_input_project=False, num_frames=1, num_reid_head_layers=3,
+        reid_hidden_dim=128).eval()
+    ms = [torch.randn(2, 128, 2, 3), torch.randn(2, 128, 4, 6), torch.randn(2, 128, 8, 12)]
+    mf = torch.randn(2, 128, 16, 24)
+    with precision("bf16"):
+        ref = d(ms, mf)
+        calls = _lib.launch_count
+        out = d([m.contiguous(memory_format=torch.channels_last) for m in ms], mf)
+        tok, key = __import__("dvis_plus_b200").ops.level_tokens(ms[1].contiguous(memory_format=torch.channels_last),
+                                                                 d.level_embed.weight[1].detach().float().contiguous(),
+                                                                 d._pos(4, 6, ms[1].device)[:, 0].contiguous())
+    assert _lib.launch_count - calls > 3
+    want = ms[1].permute(0, 2, 3, 1).reshape(2, 24, 128) + d.level_embed.weight[1]
+    assert torch.equal(tok, want.to(torch.bfloat16))
+    assert (key.float() - (want + d._pos(4, 6, ms[1].device)[:, 0])).abs().max() < 2e-2
+    for k in ("pred_logits", "pred_embds"):
+        assert rel_err(out[k].float(), ref[k].float()) < 2e-2, k
