@@ -54,6 +54,9 @@ struct LsParams {
   __nv_bfloat16 *y_bf16;
   int64_t ldy, y_batch;
   int M, N, K;
+  int splits;                                // split-K over gridDim.z (plain mode, batch == 1): K / splits per CTA, partial tiles
+  float *splitk_ws;                          // summed in split order by the LAST CTA of a tile (deterministic): (splits, M, N) f32
+  int *splitk_cnt;                           // one arrival counter per output tile, zero between launches (self-cleaning)
   int stages;                                // cp.async ring depth (2..8): bytes in flight cover the ~1 us L2 latency
   long long *prof;                           // debug (DVIS_LS_PROF=1): clock64 stamps of CTA (0,0,0): start, ring filled, first
 };                                           // chunk landed, k loop done, end
@@ -64,28 +67,47 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// one LayerNorm over a row held as NV float4 per lane (columns lane*4 + 128*i), two-pass like csrc/layernorm.cu;
-// gamma / beta are already in registers (loaded once per warp, in the same L2 round trip as the rows)
-template <int NV>
-__device__ __forceinline__ void ln_row(float4 (&v)[NV], int nv, int K, const float4 (&ga)[NV], const float4 (&be)[NV], float eps) {
-  float s = 0.f;
+// LayerNorm of RG rows at once, each held as NV float4 per lane (columns lane*4 + 128*i), two-pass like csrc/layernorm.cu.
+// The rows' shuffle chains are interleaved (RG independent shuffles per step): a warp that reduced its 4 rows one after the
+// other spent ~2 000 cycles in dependent shuffle latency.  gamma / beta are already in registers.
+template <int RG, int NV>
+__device__ __forceinline__ void ln_rows(float4 (&v)[RG][NV], int nv, int K, const float4 (&ga)[NV], const float4 (&be)[NV], float eps) {
+  float s[RG], q[RG];
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-    if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) / float(K);
-  float q = 0.f;
+  for (int j = 0; j < RG; ++j) {
+    s[j] = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-    if (i < nv) {
-      const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
-      q += (a * a + c * c) + (d * d + e * e);
-    }
-  const float rstd = rsqrtf(warp_sum(q) / float(K) + eps);
+    for (int i = 0; i < NV; ++i)
+      if (i < nv) s[j] += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+  }
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-    if (i < nv)
-      v[i] = make_float4((v[i].x - mean) * rstd * ga[i].x + be[i].x, (v[i].y - mean) * rstd * ga[i].y + be[i].y,
-                         (v[i].z - mean) * rstd * ga[i].z + be[i].z, (v[i].w - mean) * rstd * ga[i].w + be[i].w);
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < RG; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+#pragma unroll
+  for (int j = 0; j < RG; ++j) {
+    s[j] /= float(K);
+    q[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (i < nv) {
+        const float a = v[j][i].x - s[j], c = v[j][i].y - s[j], d = v[j][i].z - s[j], e = v[j][i].w - s[j];
+        q[j] += (a * a + c * c) + (d * d + e * e);
+      }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < RG; ++j) q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+#pragma unroll
+  for (int j = 0; j < RG; ++j) {
+    const float mean = s[j], rstd = rsqrtf(q[j] / float(K) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (i < nv)
+        v[j][i] = make_float4((v[j][i].x - mean) * rstd * ga[i].x + be[i].x, (v[j][i].y - mean) * rstd * ga[i].y + be[i].y,
+                              (v[j][i].z - mean) * rstd * ga[i].z + be[i].z, (v[j][i].w - mean) * rstd * ga[i].w + be[i].w);
+  }
 }
 
 __device__ __forceinline__ void cp_async_wait_dyn(int n) {   // cp.async.wait_group takes an immediate
@@ -100,29 +122,32 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {   // cp.async.wait_gr
   }
 }
 
-// 8 warps.  BM = 32: warps 2 x 4, warp tile 16 x 16;  BM = 64: warps 4 x 2, warp tile 16 x 32.
-// Every per-thread source pointer / shared address is computed once; a k-chunk costs each thread 3-4 cp.async, one wait, one
-// barrier, 8-12 ldmatrix and 8-16 mma.
-template <int BM, bool PRO>
+// 8 warps.  BM x BN = 32 x 64: warps 2 x 4, warp tile 16 x 16;  64 x 64: warps 4 x 2, warp tile 16 x 32;  32 x 32 (N <= 512:
+// twice the CTAs, 2/3 of the bytes per CTA -- the L2 -> SM fill is the floor of these kernels): warps 2 x 4, warp tile 16 x 8.
+// Every per-thread source pointer / shared address is computed once; a k-chunk costs each thread 2-4 cp.async, 4-12 ldmatrix
+// and 4-16 mma.
+template <int BM, bool PRO, int BN = kLsBN>
 __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams p) {
+  constexpr int kLsBN = BN;                                                        // shadows the default tile width below
   constexpr int WM = BM / 16, WN = 8 / WM, WCOLS = kLsBN / WN, NT = WCOLS / 8;
   constexpr int A_TILE = BM * kLsRS, W_TILE = kLsBN * kLsRS;
-  constexpr int AI = BM / 32;                                                      // A rows per thread and chunk (plain mode)
+  constexpr int AI = BM / 32, WI = BN / 32;                                        // A / W rows per thread and chunk
   extern __shared__ uint4 ls_smem[];
   __nv_bfloat16 *sw = reinterpret_cast<__nv_bfloat16 *>(ls_smem);                  // [stages][64][RS]
   __nv_bfloat16 *sa = sw + p.stages * W_TILE;                                      // plain: [stages][BM][RS]; PRO: [BM][K + 8]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int wm = warp / WN, wn = warp % WN;
-  const int n0 = blockIdx.x * kLsBN, m0 = blockIdx.y * BM, bz = blockIdx.z;
-  const int nk = p.K / kLsBK, S = p.stages;
+  const int n0 = blockIdx.x * kLsBN, m0 = blockIdx.y * BM;
+  const int bz = p.splits > 1 ? 0 : blockIdx.z, sz = p.splits > 1 ? blockIdx.z : 0;
+  const int nk = p.K / kLsBK / p.splits, kc0 = sz * nk, S = p.stages;          // this CTA's k-chunks: kc0 .. kc0 + nk
   const int ars = PRO ? p.K + 8 : kLsRS;                                           // A row stride in smem (elements)
 
   // ---- per-thread copy assignments: row (tid / 8) + 32 i, 16-byte piece (tid % 8) ----
   const int lr = tid >> 3, lc = (tid & 7) * 8;
-  const __nv_bfloat16 *w_src[2];
-  int w_bytes[2];
+  const __nv_bfloat16 *w_src[WI];
+  int w_bytes[WI];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < WI; ++i) {
     const int n = n0 + lr + 32 * i;
     w_bytes[i] = n < p.N ? 16 : 0;
     w_src[i] = p.w + (size_t)bz * p.w_batch + (size_t)(n < p.N ? n : 0) * p.K + lc;
@@ -143,10 +168,10 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
   }
   auto issue_w = [&](int kc, int slot) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) cp_async_16(w_dst + (slot * W_TILE + i * 32 * kLsRS) * 2, w_src[i] + kc * kLsBK, w_bytes[i]);
+    for (int i = 0; i < WI; ++i) cp_async_16(w_dst + (slot * W_TILE + i * 32 * kLsRS) * 2, w_src[i] + (kc0 + kc) * kLsBK, w_bytes[i]);
   };
   // chunks are issued in order 0, 1, 2, ...: the Conv1d tap / column of the next chunk is tracked incrementally (no division)
-  int a_col = 0, a_tap = 0;
+  int a_col = kc0 * kLsBK, a_tap = 0;          // (split-K is not combined with taps)
   auto issue_a = [&](int slot) {
     if constexpr (!PRO) {
       if (p.taps > 1 && a_col == 0) {                                              // first chunk of a tap: re-point the source rows
@@ -165,13 +190,17 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
 
   const bool prof = p.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (prof) p.prof[0] = clock64();
-  // weights first: they do not depend on the kernel before this one
-  for (int s = 0; s < S - 1; ++s)
-    if (s < nk) issue_w(s, s);
-  pdl_wait();
-  for (int s = 0; s < S - 1; ++s) {
-    if (s < nk) issue_a(s);
-    cp_async_commit();
+  if constexpr (!PRO) {
+    // weights first: they do not depend on the kernel before this one
+    for (int s = 0; s < S - 1; ++s)
+      if (s < nk) issue_w(s, s);
+    pdl_wait();
+    for (int s = 0; s < S - 1; ++s) {
+      if (s < nk) issue_a(s);
+      cp_async_commit();
+    }
+  } else {
+    pdl_wait();                                  // the LayerNorm sources are the critical path: their loads go out first
   }
 
   if constexpr (PRO) {
@@ -182,6 +211,9 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
     const int nv = p.K / 128;
     const int nseg = p.K / 64, gx = gridDim.x, my_seg = (int)blockIdx.x % min(gx, nseg);
     float4 g0[NV], b0[NV], g1[NV], b1[NV];
+    bool mine[NV];                               // does this CTA store side-output column segment (lane*4 + 128 i) / 64 ?
+#pragma unroll
+    for (int i = 0; i < NV; ++i) mine[i] = i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg;
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       if (i < nv) {
@@ -189,6 +221,7 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
         if (p.ln0_g) { g0[i] = *reinterpret_cast<const float4 *>(p.ln0_g + c); b0[i] = *reinterpret_cast<const float4 *>(p.ln0_b + c); }
         if (p.ln1_g) { g1[i] = *reinterpret_cast<const float4 *>(p.ln1_g + c); b1[i] = *reinterpret_cast<const float4 *>(p.ln1_b + c); }
       }
+    bool ring_issued = false;
     for (int r0 = warp; r0 < BM; r0 += 8 * RG) {
       float4 v[RG][NV], u[RG][NV];
 #pragma unroll
@@ -212,32 +245,42 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
           }
         }
       }
+      if (!ring_issued) {                        // the weight ring goes out behind the first group's row loads
+        ring_issued = true;
+        for (int s = 0; s < S - 1; ++s) {
+          if (s < nk) issue_w(s, s);
+          cp_async_commit();
+        }
+      }
+      // rows past M hold zeros: their LayerNorm is finite garbage that is never stored
+      if (p.ln0_g) ln_rows<RG, NV>(v, nv, p.K, g0, b0, p.eps);
+#pragma unroll
+      for (int j = 0; j < RG; ++j) {
+        const int m = m0 + r0 + 8 * j;
+        if (p.side0 && m < p.M) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (mine[i]) *reinterpret_cast<float4 *>(p.side0 + (size_t)m * p.K + lane * 4 + 128 * i) = v[j][i];
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { v[j][i].x += u[j][i].x; v[j][i].y += u[j][i].y; v[j][i].z += u[j][i].z; v[j][i].w += u[j][i].w; }
+      }
+      if (p.ln1_g) ln_rows<RG, NV>(v, nv, p.K, g1, b1, p.eps);
 #pragma unroll
       for (int j = 0; j < RG; ++j) {
         const int r = r0 + 8 * j, m = m0 + r;
-        if (m < p.M) {
-          if (p.ln0_g) ln_row<NV>(v[j], nv, p.K, g0, b0, p.eps);
-          if (p.side0) {
+        if (p.side1 && m < p.M) {
 #pragma unroll
-            for (int i = 0; i < NV; ++i)
-              if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg)
-                *reinterpret_cast<float4 *>(p.side0 + (size_t)m * p.K + lane * 4 + 128 * i) = v[j][i];
-          }
-#pragma unroll
-          for (int i = 0; i < NV; ++i) { v[j][i].x += u[j][i].x; v[j][i].y += u[j][i].y; v[j][i].z += u[j][i].z; v[j][i].w += u[j][i].w; }
-          if (p.ln1_g) ln_row<NV>(v[j], nv, p.K, g1, b1, p.eps);
-          if (p.side1) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i)
-              if (i < nv && ((lane * 4 + 128 * i) >> 6) % gx == my_seg)
-                *reinterpret_cast<float4 *>(p.side1 + (size_t)m * p.K + lane * 4 + 128 * i) = v[j][i];
-          }
+          for (int i = 0; i < NV; ++i)
+            if (mine[i]) *reinterpret_cast<float4 *>(p.side1 + (size_t)m * p.K + lane * 4 + 128 * i) = v[j][i];
         }
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-          if (i < nv)
+          if (i < nv) {
+            const bool live = m < p.M;            // rows past M feed zeros to the MMA
             *reinterpret_cast<uint2 *>(sa + r * ars + lane * 4 + 128 * i) =
-                make_uint2(pack_bf16x2(v[j][i].x, v[j][i].y), pack_bf16x2(v[j][i].z, v[j][i].w));
+                live ? make_uint2(pack_bf16x2(v[j][i].x, v[j][i].y), pack_bf16x2(v[j][i].z, v[j][i].w)) : make_uint2(0u, 0u);
+          }
       }
     }
   }
@@ -261,7 +304,8 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
   }
   // ldmatrix addresses of this lane inside a ring slot (A: 16 x 16 tile of the warp's rows; B: pairs of 8-column tiles)
   const saddr_t a_lds = saddr(sa) + ((wm * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * ars + (lane >> 4) * 8) * 2;
-  const saddr_t b_lds = saddr(sw) + ((wn * WCOLS + (lane >> 4) * 8 + (lane & 7)) * kLsRS + ((lane >> 3) & 1) * 8) * 2;
+  const saddr_t b_lds = NT == 1 ? saddr(sw) + ((wn * 8 + (lane & 7)) * kLsRS + (lane >> 3) * 8) * 2      // 4 k-pieces of one column tile
+                                : saddr(sw) + ((wn * WCOLS + (lane >> 4) * 8 + (lane & 7)) * kLsRS + ((lane >> 3) & 1) * 8) * 2;
 
   // resident: the ring holds ALL of K (S - 1 >= nk): everything is already in flight, one wait + one barrier, then a pure
   // ldmatrix / mma loop -- the per-chunk wait + barrier of the streaming form cost 550 cycles a chunk with 8 warps
@@ -284,16 +328,28 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
     }
     const saddr_t ca = PRO ? a_lds + kc * (kLsBK * 2) : a_lds + slot * (A_TILE * 2);
     const saddr_t cw = b_lds + slot * (W_TILE * 2);
+    if constexpr (NT == 1) {
 #pragma unroll
-    for (int ks = 0; ks < kLsBK / 16; ++ks) {
-      uint32_t af[4];
-      ldmatrix_x4(af, ca + ks * 32);
+      for (int k2 = 0; k2 < kLsBK / 32; ++k2) {
+        uint32_t a0[4], a1[4], bf[4];
+        ldmatrix_x4(a0, ca + k2 * 64);
+        ldmatrix_x4(a1, ca + k2 * 64 + 32);
+        ldmatrix_x4(bf, cw + k2 * 64);             // (8 columns) x (k .. k+31): b0, b1 of two consecutive k-steps
+        mma_bf16_16816(acc[0], a0, bf[0], bf[1]);
+        mma_bf16_16816(acc[0], a1, bf[2], bf[3]);
+      }
+    } else {
 #pragma unroll
-      for (int np = 0; np < NT / 2; ++np) {
-        uint32_t bf[4];
-        ldmatrix_x4(bf, cw + (np * 16 * kLsRS) * 2 + ks * 32);
-        mma_bf16_16816(acc[2 * np], af, bf[0], bf[1]);
-        mma_bf16_16816(acc[2 * np + 1], af, bf[2], bf[3]);
+      for (int ks = 0; ks < kLsBK / 16; ++ks) {
+        uint32_t af[4];
+        ldmatrix_x4(af, ca + ks * 32);
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+          uint32_t bf[4];
+          ldmatrix_x4(bf, cw + (np * 16 * kLsRS) * 2 + ks * 32);
+          mma_bf16_16816(acc[2 * np], af, bf[0], bf[1]);
+          mma_bf16_16816(acc[2 * np + 1], af, bf[2], bf[3]);
+        }
       }
     }
     slot = slot + 1 == S ? 0 : slot + 1;
@@ -301,6 +357,48 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
   }
   pdl_launch_dependents();
   if (prof) p.prof[3] = clock64();
+
+  if (p.splits > 1) {
+    // split-K: publish this CTA's partial tile; the LAST CTA to arrive adds the partials in split order (a fixed order: the
+    // result does not depend on which CTA was last) and runs the epilogue.  No float atomics -- run-to-run determinism is a
+    // property this library keeps (profiles/r2_determinism.md).
+    __shared__ int s_last;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m = m0 + wm * 16 + g + half * 8;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n = n0 + wn * WCOLS + nt * 8 + 2 * t;
+        if (m < p.M && n < p.N)
+          *reinterpret_cast<float2 *>(p.splitk_ws + ((size_t)sz * p.M + m) * p.N + n) = make_float2(acc[nt][half * 2], acc[nt][half * 2 + 1]);
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    int *cnt = p.splitk_cnt + blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) s_last = atomicAdd(cnt, 1) == p.splits - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) *cnt = 0;                       // ready for the next launch
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m = m0 + wm * 16 + g + half * 8;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n = n0 + wn * WCOLS + nt * 8 + 2 * t;
+        float2 sum = make_float2(0.f, 0.f);
+        if (m < p.M && n < p.N)
+          for (int z = 0; z < p.splits; ++z) {
+            const float *part = p.splitk_ws + ((size_t)z * p.M + m) * p.N + n;   // written by other CTAs: bypass L1 (ld.cg)
+            sum.x += __ldcg(part);
+            sum.y += __ldcg(part + 1);
+          }
+        acc[nt][half * 2] = sum.x;
+        acc[nt][half * 2 + 1] = sum.y;
+      }
+    }
+  }
 
   // ---- epilogue: bias, ReLU, residual, stores ----
 #pragma unroll
@@ -327,7 +425,7 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
 long long *g_ls_prof = nullptr;                // device buffer of 8 stamps when DVIS_LS_PROF is set (tests/perf only)
 #endif
 
-template <int BM, bool PRO>
+template <int BM, bool PRO, int BN = kLsBN>
 int launch_small_linear(LsParams p, int batch, cudaStream_t s) {
 #ifndef DVIS_SIMT_EMULATION
   static const bool want_prof = getenv("DVIS_LS_PROF") != nullptr;
@@ -335,13 +433,14 @@ int launch_small_linear(LsParams p, int batch, cudaStream_t s) {
   p.prof = g_ls_prof;
 #endif
   // K <= 512 (8 chunks; 6 for the 64-row tiles): the ring holds all of K (+1 slot: the loop's look-ahead index); else 6 deep
-  const int nk = p.K / kLsBK, cap = BM == 32 ? kLsMaxStages : 6;
+  const int nk = p.K / kLsBK / p.splits, cap = BM == 32 ? kLsMaxStages : 6;
   p.stages = nk <= cap ? nk + 1 : 6;
-  const size_t smem = (size_t)p.stages * kLsBN * kLsRS * 2 +
+  if (nk > cap) p.stages = BN == 32 ? kLsMaxStages : 6;     // streaming: as many bytes in flight as fit
+  const size_t smem = (size_t)p.stages * BN * kLsRS * 2 +
                       (PRO ? (size_t)BM * (p.K + 8) * 2 : (size_t)p.stages * BM * kLsRS * 2);
-  auto kern = small_linear_kernel<BM, PRO>;
+  auto kern = small_linear_kernel<BM, PRO, BN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  dim3 grid((p.N + kLsBN - 1) / kLsBN, (p.M + BM - 1) / BM, batch);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits > 1 ? p.splits : batch);
 #ifdef DVIS_SIMT_EMULATION
   kern<<<grid, kLsThreads, smem, s>>>(p);
 #else
@@ -370,7 +469,8 @@ extern "C" int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, in
                                  int src1_dtype, const float *ln1_gamma, const float *ln1_beta, float eps, float *side0,
                                  float *side1, const void *w, int64_t w_batch, const float *bias, int64_t bias_batch,
                                  const float *residual, int64_t ldr, int relu, float *y_f32, void *y_bf16, int64_t ldy,
-                                 int64_t y_batch, int batch, int M, int N, int K, void *stream) {
+                                 int64_t y_batch, int batch, int M, int N, int K, float *splitk_workspace, int *splitk_counters,
+                                 void *stream) {
   DVIS_REQUIRE(w && (y_f32 || y_bf16), "linear_small: null pointer argument");
   DVIS_REQUIRE((x != nullptr) != (src0 != nullptr), "linear_small: exactly one of x (bf16 operand) and src0 (prologue) must be given");
   DVIS_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0, "linear_small: sizes must be positive");
@@ -381,6 +481,7 @@ extern "C" int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, in
   p.w = static_cast<const __nv_bfloat16 *>(w); p.w_batch = w_batch; p.bias = bias; p.bias_batch = bias_batch;
   p.residual = residual; p.ldr = ldr; p.relu = relu; p.y_f32 = y_f32; p.y_bf16 = static_cast<__nv_bfloat16 *>(y_bf16);
   p.ldy = ldy; p.y_batch = y_batch; p.M = M; p.N = N; p.K = K;
+  p.splits = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool big = M > 512;                      // the refiner's T*Q rows: 64-row tiles halve the weight re-reads
   if (x) {
@@ -390,7 +491,19 @@ extern "C" int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, in
     DVIS_REQUIRE(aligned16(x) && ldx % 8 == 0 && x_batch % 8 == 0, "linear_small: x rows must be 16-byte aligned");
     p.x = static_cast<const __nv_bfloat16 *>(x); p.ldx = ldx; p.x_batch = x_batch;
     p.taps = taps; p.tap_pad = tap_pad; p.tap_period = tap_period; p.tap_len = tap_len;
-    return big ? launch_small_linear<64, false>(p, batch, s) : launch_small_linear<32, false>(p, batch, s);
+    if (big) return launch_small_linear<64, false>(p, batch, s);
+    // long reductions over a narrow output (FFN2: K = 2048 -> N = 512, 200 rows): 4-way split-K, every CTA's share of K fits
+    // the resident ring; needs the caller's workspace (4*M*N floats) and zeroed per-tile counters
+    if (splitk_workspace && splitk_counters && taps == 1 && batch == 1 && K >= 1024 && K % (4 * kLsBK) == 0 &&
+        (int64_t)((N + 31) / 32) * ((M + 31) / 32) <= 2 * kNumSMs) {
+      p.splits = 4;
+      p.splitk_ws = splitk_workspace;
+      p.splitk_cnt = splitk_counters;
+      return launch_small_linear<32, false, 32>(p, batch, s);
+    }
+    // narrow outputs (out-proj, FFN2: N = 512): 32-column tiles double the CTA count and cut the bytes each SM must pull
+    if ((int64_t)((N + 63) / 64) * ((M + 31) / 32) * batch < kNumSMs / 2) return launch_small_linear<32, false, 32>(p, batch, s);
+    return launch_small_linear<32, false>(p, batch, s);
   }
   DVIS_REQUIRE(batch == 1, "linear_small: the LayerNorm prologue is not batched");
   DVIS_REQUIRE(K <= kLsMaxProK && K % 128 == 0, "linear_small: prologue needs K <= 512 and K %% 128 == 0 (K=%d)", K);

@@ -141,6 +141,10 @@ int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, int64_t q_hea
  *              LN0(src0) and the final A rows (the next residual).
  * residual (optional): f32 (M, N), rows ldr apart, added after the activation.  Outputs: y_f32 and / or y_bf16 (M, N), rows
  * ldy apart.  K % 64 == 0, N % 8 == 0.
+ * splitk_workspace / splitk_counters (optional, NULL = never split): 4*M*N floats of scratch and ceil(M/32)*ceil(N/32) ints
+ * that are ZERO before the first call (the kernel leaves them zero): lets long reductions (K >= 1024) over a narrow output run
+ * as a 4-way split-K whose partial tiles are added in a fixed order by the last CTA to arrive (deterministic, no atomics on
+ * the data).
  * dvis_set_pdl(1) launches these kernels (and dvis_flash_attn) with programmatic dependent launch: weight tiles are
  * prefetched while the previous kernel of the stream drains.
  */
@@ -148,7 +152,8 @@ int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, int taps, int
                       const float *src0, const float *ln0_gamma, const float *ln0_beta, const void *src1, int src1_dtype,
                       const float *ln1_gamma, const float *ln1_beta, float eps, float *side0, float *side1, const void *w,
                       int64_t w_batch, const float *bias, int64_t bias_batch, const float *residual, int64_t ldr, int relu,
-                      float *y_f32, void *y_bf16, int64_t ldy, int64_t y_batch, int batch, int M, int N, int K, void *stream);
+                      float *y_f32, void *y_bf16, int64_t ldy, int64_t y_batch, int batch, int M, int N, int K,
+                      float *splitk_workspace, int *splitk_counters, void *stream);
 int dvis_set_pdl(int enabled);
 /* debug aid of tests/perf (DVIS_LS_PROF=1): clock64 stamps (8 values) of CTA 0 of the last dvis_linear_small launch */
 int dvis_debug_linear_small_stamps(long long *host_out);

@@ -81,8 +81,10 @@ inline float __low2float(__half2 h) { return float(h.x); }
 inline float __high2float(__half2 h) { return float(h.y); }
 #define __align__(n) alignas(n)
 inline long long clock64() { return 0; }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+template <typename T> inline T __ldcg(const T *p) { return *p; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 

@@ -172,3 +172,17 @@ def test_linear_small_rejects_bad_arguments():
     w = torch.zeros(64, 640, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="prologue needs"):
         simt.linear_small(w, None, src0=torch.zeros(4, 640))
+
+
+def test_linear_small_split_k_is_deterministic_and_exact():
+    """K >= 1024 over a narrow output: 4-way split-K, partial tiles added in split order by the last CTA (no float atomics)"""
+    torch.manual_seed(6)
+    M, N, K = 40, 64, 1024
+    x = torch.randn(M, K).to(torch.bfloat16)
+    w = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16)
+    b, res = torch.randn(N), torch.randn(M, N)
+    y32, _, _, _ = simt.linear_small(w, b, x=x, residual=res, out_f32=True, out_bf16=False)
+    ref = x.float() @ w.float().t() + b + res
+    assert (y32 - ref).abs().max() < 1e-4
+    again, _, _, _ = simt.linear_small(w, b, x=x, residual=res, out_f32=True, out_bf16=False)
+    assert torch.equal(again, y32)                                    # the counters were left at zero, the sum order is fixed
