@@ -37,6 +37,8 @@ SIGNATURES = {
                         _i, _i, _i, _i, _i, _f, _vp],
     "dvis_linear_small": [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _i64, _vp, _i64,
                           _vp, _i64, _i, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp],
+    "dvis_linear_small_ln": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp, _vp, _vp, _vp],
     "dvis_set_pdl": [_i],
     "dvis_debug_linear_small_stamps": [_vp],
     "dvis_class_scores": [_vp, _vp, _i, _i, _vp, _vp],

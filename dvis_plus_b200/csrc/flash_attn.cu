@@ -266,6 +266,7 @@ int launch_flash(const FlashParams &p, cudaStream_t s) {
   const int kb = SPLIT ? 32 : 64;
   const size_t ring = (size_t)(SPLIT ? kFaWarps : 1) * p.stages * 2 * kb * (DH + 8) * sizeof(__nv_bfloat16);
   cudaFuncSetAttribute(flash_attn_kernel<DH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring));
+  cudaFuncSetAttribute(flash_attn_kernel<DH, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // see small_linear.cu
   const int rows = SPLIT ? kFaRows : kFaRows * kFaWarps;
   dim3 grid((p.Lq + rows - 1) / rows, p.H, p.B);
 #ifdef DVIS_SIMT_EMULATION

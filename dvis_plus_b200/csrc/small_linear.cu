@@ -54,6 +54,14 @@ struct LsParams {
   __nv_bfloat16 *y_bf16;
   int64_t ldy, y_batch;
   int M, N, K;
+  // epilogue LayerNorm (plain mode, N <= 512 = one full row per row block): the LAST CTA of a row block to finish normalises
+  // the block's rows from y_f32:  e1 = LN_e1(y);  optionally  e2 = LN_e2(e1 + e_src1).  Outputs in f32 and bf16.
+  const float *e1_g, *e1_b, *e2_g, *e2_b;
+  const void *e_src1;
+  int e_src1_bf16;
+  float *e1_f32, *e2_f32;
+  __nv_bfloat16 *e1_bf16, *e2_bf16;
+  int *rowblk_cnt;                           // one arrival counter per row block, zero between launches
   int splits;                                // split-K over gridDim.z (plain mode, batch == 1): K / splits per CTA, partial tiles
   float *splitk_ws;                          // summed in split order by the LAST CTA of a tile (deterministic): (splits, M, N) f32
   int *splitk_cnt;                           // one arrival counter per output tile, zero between launches (self-cleaning)
@@ -418,6 +426,77 @@ __global__ void __launch_bounds__(kLsThreads) small_linear_kernel(const LsParams
       if (p.y_bf16) *reinterpret_cast<uint32_t *>(p.y_bf16 + o) = pack_bf16x2(v0, v1);
     }
   }
+  if constexpr (!PRO && BM == 32) {
+    if (p.e1_g) {
+      // ---- epilogue LayerNorm by the last CTA of the row block (the producer-side form of the post-norm blocks: consumers
+      // then are plain bf16 GEMMs; normalising in every consumer's prologue repeated the work N / 64 times) ----
+      __shared__ int s_last_row;
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_last_row = atomicAdd(p.rowblk_cnt + blockIdx.y, 1) == (int)gridDim.x - 1;
+      __syncthreads();
+      if (s_last_row) {
+        __threadfence();
+        if (tid == 0) p.rowblk_cnt[blockIdx.y] = 0;
+        constexpr int NV = kLsMaxProK / 128, RG = 4;
+        const int nv = p.N / 128;
+        float4 g1[NV], b1[NV], g2[NV], b2[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i < nv) {
+            const int c = lane * 4 + 128 * i;
+            g1[i] = *reinterpret_cast<const float4 *>(p.e1_g + c); b1[i] = *reinterpret_cast<const float4 *>(p.e1_b + c);
+            if (p.e2_g) { g2[i] = *reinterpret_cast<const float4 *>(p.e2_g + c); b2[i] = *reinterpret_cast<const float4 *>(p.e2_b + c); }
+          }
+        float4 v[RG][NV], u[RG][NV];
+#pragma unroll
+        for (int j = 0; j < RG; ++j) {
+          const int m = m0 + warp + 8 * j;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            v[j][i] = u[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < nv && m < p.M) {
+              v[j][i] = __ldcg(reinterpret_cast<const float4 *>(p.y_f32 + (size_t)m * p.ldy + lane * 4 + 128 * i));   // other CTAs' tiles: L2
+              if (p.e_src1) {
+                const size_t o = (size_t)m * p.N + lane * 4 + 128 * i;
+                if (p.e_src1_bf16) {
+                  const uint2 w2 = *reinterpret_cast<const uint2 *>(static_cast<const __nv_bfloat16 *>(p.e_src1) + o);
+                  u[j][i] = make_float4(__uint_as_float(w2.x << 16), __uint_as_float(w2.x & 0xffff0000u), __uint_as_float(w2.y << 16),
+                                        __uint_as_float(w2.y & 0xffff0000u));
+                } else {
+                  u[j][i] = *reinterpret_cast<const float4 *>(static_cast<const float *>(p.e_src1) + o);
+                }
+              }
+            }
+          }
+        }
+        ln_rows<RG, NV>(v, nv, p.N, g1, b1, p.eps);
+        auto store = [&](float *f32, __nv_bfloat16 *b16) {
+#pragma unroll
+          for (int j = 0; j < RG; ++j) {
+            const int m = m0 + warp + 8 * j;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+              if (i < nv) {
+                const size_t o = (size_t)m * p.N + lane * 4 + 128 * i;
+                if (f32) *reinterpret_cast<float4 *>(f32 + o) = v[j][i];
+                if (b16) *reinterpret_cast<uint2 *>(b16 + o) = make_uint2(pack_bf16x2(v[j][i].x, v[j][i].y), pack_bf16x2(v[j][i].z, v[j][i].w));
+              }
+          }
+        };
+        store(p.e1_f32, p.e1_bf16);
+        if (p.e2_g) {
+#pragma unroll
+          for (int j = 0; j < RG; ++j)
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { v[j][i].x += u[j][i].x; v[j][i].y += u[j][i].y; v[j][i].z += u[j][i].z; v[j][i].w += u[j][i].w; }
+          ln_rows<RG, NV>(v, nv, p.N, g2, b2, p.eps);
+          store(p.e2_f32, p.e2_bf16);
+        }
+      }
+    }
+  }
   if (prof) p.prof[4] = clock64();
 }
 
@@ -440,6 +519,9 @@ int launch_small_linear(LsParams p, int batch, cudaStream_t s) {
                       (PRO ? (size_t)BM * (p.K + 8) * 2 : (size_t)p.stages * BM * kLsRS * 2);
   auto kern = small_linear_kernel<BM, PRO, BN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  // one carve-out for every temporal-stage kernel: consecutive launches whose shared-memory needs fall into different L1 /
+  // shared splits make the SMs drain and reconfigure between them (~8 us per launch in a mixed chain, chain_probe.py)
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits > 1 ? p.splits : batch);
 #ifdef DVIS_SIMT_EMULATION
   kern<<<grid, kLsThreads, smem, s>>>(p);
@@ -453,6 +535,34 @@ int launch_small_linear(LsParams p, int batch, cudaStream_t s) {
 }  // namespace dvis
 
 using namespace dvis;
+
+extern "C" int dvis_linear_small_ln(const void *x, int64_t ldx, const void *w, const float *bias, const float *residual, int64_t ldr,
+                                    int relu, int M, int N, int K, float *y_f32, const float *ln_gamma, const float *ln_beta, float eps,
+                                    const void *src1, int src1_dtype, const float *ln2_gamma, const float *ln2_beta, float *ln_f32,
+                                    void *ln_bf16, float *ln2_f32, void *ln2_bf16, float *splitk_workspace, int *splitk_counters,
+                                    int *rowblock_counters, void *stream) {
+  DVIS_REQUIRE(x && w && y_f32 && ln_gamma && ln_beta && rowblock_counters && (ln_f32 || ln_bf16), "linear_small_ln: null pointer argument");
+  DVIS_REQUIRE(M > 0 && M <= 512 && N > 0 && N <= kLsMaxProK && N % 128 == 0 && K > 0 && K % kLsBK == 0,
+               "linear_small_ln: need M <= 512, N <= 512 with N %% 128 == 0, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  DVIS_REQUIRE(aligned16(x) && ldx % 8 == 0 && aligned16(w) && (!residual || ldr % 2 == 0), "linear_small_ln: operand alignment");
+  DVIS_REQUIRE(!ln2_gamma == !ln2_beta && (!ln2_gamma || ln2_f32 || ln2_bf16), "linear_small_ln: second LayerNorm needs gamma, beta and an output");
+  DVIS_REQUIRE(!src1 || src1_dtype == DVIS_F32 || src1_dtype == DVIS_BF16, "linear_small_ln: src1 must be f32 or bf16");
+  LsParams p{};
+  p.x = static_cast<const __nv_bfloat16 *>(x); p.ldx = ldx; p.taps = 1;
+  p.w = static_cast<const __nv_bfloat16 *>(w); p.bias = bias; p.residual = residual; p.ldr = ldr; p.relu = relu;
+  p.y_f32 = y_f32; p.ldy = N; p.M = M; p.N = N; p.K = K; p.eps = eps;
+  p.e1_g = ln_gamma; p.e1_b = ln_beta; p.e2_g = ln2_gamma; p.e2_b = ln2_beta; p.e_src1 = src1; p.e_src1_bf16 = src1_dtype == DVIS_BF16;
+  p.e1_f32 = ln_f32; p.e1_bf16 = static_cast<__nv_bfloat16 *>(ln_bf16); p.e2_f32 = ln2_f32; p.e2_bf16 = static_cast<__nv_bfloat16 *>(ln2_bf16);
+  p.rowblk_cnt = rowblock_counters;
+  p.splits = 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (splitk_workspace && splitk_counters && K >= 1024 && K % (4 * kLsBK) == 0) {
+    p.splits = 4;
+    p.splitk_ws = splitk_workspace;
+    p.splitk_cnt = splitk_counters;
+  }
+  return launch_small_linear<32, false, 32>(p, 1, s);
+}
 
 extern "C" int dvis_debug_linear_small_stamps(long long *host_out) {   // tests/perf: the stamps of the last profiled launch
 #ifndef DVIS_SIMT_EMULATION

@@ -360,15 +360,16 @@ class ReferringTracker_noiser(nn.Module):
         return self.use_fused_kernels and "k_layers" in f and C % 128 == 0 and C <= 512 and (C // self.num_heads) in (32, 64)
 
     def _frame_body_fused(self, f, prev, prev_is_pre, identity, kv, first):
-        """One frame of py:236-329 on libdvis_b200 kernels only -- 36 launches (3 + 1 + 1 + 1 + 6 x 5) for a frame after the
-        first, 66 for the first frame of a video (its referring query is re-derived per layer, py:244-251) -- and no
-        LayerNorm kernel: every producer writes the pre-norm sum and every consumer normalises its own rows in its prologue
-        (csrc/small_linear.cu).
-        prev (Q, C) fp32: the previous frame's last-layer output -- PRE-norm when `prev_is_pre` (then this frame's first
-        kernel also materialises the normalised output) -- or, for the first frame, the frame key; identity (Q, C) fp32;
-        kv (Q, L, 2, H, dh) bf16.
-        -> (pre (Q, C) fp32: this frame's last-layer PRE-norm output, prev_out: the previous frame's normalised last-layer
-        output (None unless prev_is_pre), reference (Q, C) fp32, inner: the L-1 inner layer outputs, fp32)."""
+        """One frame of py:236-329 on libdvis_b200 kernels only: 37 launches (3 + 1 + 1 + 1 + 1 + 6 x 5) for a frame after the
+        first, 67 for the first frame of a video (its referring query is re-derived per layer, py:244-251).  Every linear step
+        is a plain bf16 GEMM (csrc/small_linear.cu); the post-norm blocks' LayerNorms run in the PRODUCERS' epilogues
+        (dvis_linear_small_ln: the last CTA of a 32-row block normalises it), so no LayerNorm is a dependent step of its own
+        except the one that has no producer GEMM (layer 0's cross-attention residual).
+        prev (Q, C) fp32: the previous frame's NORMALISED last-layer output (or, for the first frame, the frame key);
+        identity (Q, C) fp32; kv (Q, L, 2, H, dh) bf16.  `prev_is_pre` is kept for the caller's bookkeeping and must be False.
+        -> (out (Q, C) fp32: this frame's normalised last-layer output, None, reference (Q, C) fp32, inner: the L-1 inner
+        layer outputs, fp32)."""
+        assert not prev_is_pre
         L, C, H = self.num_layers, f["C"], self.num_heads
         dh = C // H
         Q = identity.shape[0]
@@ -378,46 +379,48 @@ class ReferringTracker_noiser(nn.Module):
         (w1, b1), (w2, b2), (w3, b3) = f["k_ref"]
         kvl = kv.permute(1, 0, 2, 3, 4)                                                              # (L, Q, 2, H, dh) view
 
-        def ref_mlp(src, ln, want_side):
-            """ref_proj(LN(src)) -> (fp32, bf16, LN(src) | None)"""
-            _, h, _, side = ops.linear_small(w1, b1, src0=src, ln1=ln, eps=eps, want_side1=want_side, relu=True)
+        def ref_mlp(x16):
+            """ref_proj(x) -> (fp32, bf16)"""
+            _, h, _, _ = ops.linear_small(w1, b1, x=x16, relu=True)
             _, h, _, _ = ops.linear_small(w2, b2, x=h, relu=True)
             r32, r16, _, _ = ops.linear_small(w3, b3, x=h, out_f32=True)
-            return r32, r16, side
+            return r32, r16
 
-        prev_out = None
+        x16 = prev.to(torch.bfloat16)
         if not first:
             # reference = ref_proj(last_outputs[-1]) (py:278); the 6 layers' referring cross-attention shares it (py:293,313)
-            ref32, ref16, prev_out = ref_mlp(prev, lay[L - 1]["ln_ff"] if prev_is_pre else None, prev_is_pre)
+            ref32, ref16 = ref_mlp(x16)
             _, q_all, _, _ = ops.linear_small(f["k_wq"], f["k_bq"], x=ref16)                          # (Q, L*C)
             o = ops.flash_attn(q_all.view(Q, L, H, dh).permute(1, 0, 2, 3), kvl[:, :, 0], kvl[:, :, 1], scale)   # (L, Q, C)
             _, o_all, _, _ = ops.linear_small(f["k_wo"], f["k_bo"], x=o)                              # (L, Q, C) bf16
-        src, ln0 = identity, None
         inner = []
+        x32 = None                                                                                   # output of the previous layer
         for j in range(L):
             p = lay[j]
             if first:
                 # tgt = ref_proj(frame key) for layer 0, ref_proj(previous layer's output) afterwards (py:244-251)
-                r32, r16, _ = ref_mlp(prev if j == 0 else src, None if j == 0 else ln0, False)
+                r32, r16 = ref_mlp(x16)
                 if j == 0:
                     ref32 = r32
                 _, q, _, _ = ops.linear_small(f["k_wq"][j * C:(j + 1) * C], f["k_bq"][j * C:(j + 1) * C], x=r16)
                 o = ops.flash_attn(q.view(1, Q, H, dh), kvl[j:j + 1, :, 0], kvl[j:j + 1, :, 1], scale)[0]
                 _, o_j, _, _ = ops.linear_small(f["k_wo"][j], f["k_bo"][j], x=o)
-            else:
-                o_j = o_all[j]
-            # x1 = LN_ca(x + o_j) (tracker.py:47-48), x = identity or LN_ffn of the previous layer's pre-norm sum
-            _, qkv, x_prev, x1 = ops.linear_small(p["w_qkv"], p["b_qkv"], src0=src, ln0=ln0, src1=o_j, ln1=p["ln_ca"], eps=eps,
-                                                  want_side0=ln0 is not None, want_side1=True)
-            if x_prev is not None:
-                inner.append(x_prev)
-            qkv = qkv.view(1, Q, 3, H, dh)
+                # x1 = LN_ca(x + o_j) (tracker.py:47-48), x = identity or the previous layer's output
+                x1_32, x1_16, _ = ops.add_layernorm(o_j, identity if j == 0 else x32, *p["ln_ca"], eps, lp_dtype=torch.bfloat16)
+            elif j == 0:
+                x1_32, x1_16, _ = ops.add_layernorm(o_all[0], identity, *p["ln_ca"], eps, lp_dtype=torch.bfloat16)
+            # self-attention block: QKV, attention, out-proj + residual + LN_sa (epilogue)
+            qkv = ops.linear_small(p["w_qkv"], p["b_qkv"], x=x1_16)[1].view(1, Q, 3, H, dh)
             o = ops.flash_attn(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale)[0]
-            pre_sa, _, _, _ = ops.linear_small(p["w_o"], p["b_o"], x=o, residual=x1, out_f32=True, out_bf16=False)
-            _, hid, _, x2 = ops.linear_small(p["w_1"], p["b_1"], src0=pre_sa, ln1=p["ln_sa"], eps=eps, want_side1=True, relu=True)
-            pre_ff, _, _, _ = ops.linear_small(p["w_2"], p["b_2"], x=hid, residual=x2, out_f32=True, out_bf16=False)
-            src, ln0 = pre_ff, p["ln_ff"]
-        return src, prev_out, ref32, inner
+            x2_32, x2_16, _, _ = ops.linear_small_ln(p["w_o"], p["b_o"], o, x1_32, p["ln_sa"], eps=eps)
+            # FFN block: FFN1 + ReLU, FFN2 (split-K) + residual + LN_ffn (epilogue) [+ the next layer's LN_ca(x + o_all[j+1])]
+            hid = ops.linear_small(p["w_1"], p["b_1"], x=x2_16, relu=True)[1]
+            nxt = (not first) and j + 1 < L
+            x32, x16, x1_32, x1_16 = ops.linear_small_ln(p["w_2"], p["b_2"], hid, x2_32, p["ln_ff"], eps=eps,
+                                                          src1=o_all[j + 1] if nxt else None, ln2=lay[j + 1]["ln_ca"] if nxt else None)
+            if j + 1 < L:
+                inner.append(x32)
+        return x32, None, ref32, inner
 
     def _graph_step(self, f, first, Q, dev, prev_is_pre=False):
         """Capture one frame step (first / later frame; fused or library body) once per configuration; returns
@@ -482,16 +485,12 @@ class ReferringTracker_noiser(nn.Module):
         if self._fused_ok(f):
             # keys / values of all frames and layers: one launch (T*Q rows x L*2C columns)
             kv = ops.linear_small(f["wkv"], f["bkv"].float(), x=cur_nn.to(dt).view(T * Q, C))[1].view(T, Q, L, 2, H, C // H)
-            lasts, prev, is_pre = [], prev_last, False                                      # normalised last-layer outputs
+            lasts, prev = [], prev_last                                                     # normalised last-layer outputs
             for t in range(T):
                 first = prev is None
-                pre, prev_out, reference, inner = self._run_frame(f, cur_nn[t] if first else prev, is_pre, init[t], kv[t], first, True)
-                if prev_out is not None:
-                    lasts.append(prev_out)                                                  # frame t-1, materialised by frame t
+                prev, _, reference, inner = self._run_frame(f, cur_nn[t] if first else prev, False, init[t], kv[t], first, True)
+                lasts.append(prev)
                 refs.append(reference)
-                prev, is_pre = pre, True
-            n_last = self.transformer_ffn_layers[L - 1].norm
-            lasts.append(ops.add_layernorm(prev, None, n_last.weight, n_last.bias, n_last.eps)[0])
             last_stack = torch.stack([init[T - 1]] + inner + [lasts[-1]], 0)
             outputs = torch.stack(lasts, 0)[:, None, :, None, :]                            # (t, 1, q, b, c)  eval: last layer
         else:

@@ -447,6 +447,39 @@ def linear_small(w, bias=None, *, x=None, src0=None, ln0=None, src1=None, ln1=No
     return y32, y16, side0, side1
 
 
+def linear_small_ln(w, bias, x, residual, ln, *, src1=None, ln2=None, relu=False, eps=1e-5, want_f32=True):
+    """Linear step with the post-norm block's LayerNorm(s) in the producer's epilogue (dvis_linear_small_ln):
+        y = act(x @ w^T + bias) + residual;  e1 = LN(y; ln);  e2 = LN(e1 + src1; ln2)  (when ln2 is given)
+    x (M, K) bf16 (last dim contiguous), w (N, K) bf16, residual (M, N) f32 | None, ln / ln2 = (gamma, beta) f32.
+    -> (e1_f32 | None, e1_bf16, e2_f32 | None, e2_bf16 | None)."""
+    if not x.is_cuda:
+        raise RuntimeError("linear_small_ln: CUDA tensors required (there is no CPU path)")
+    assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.dim() == 2 and x.dtype == torch.bfloat16 and x.stride(-1) == 1
+    N, K = w.shape
+    M = x.shape[0]
+    dev = w.device
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(-1) == 1 and residual.shape == (M, N)
+    if src1 is not None:
+        assert src1.is_contiguous() and src1.shape == (M, N) and src1.dtype in (torch.float32, torch.bfloat16)
+    y = torch.empty((M, N), dtype=torch.float32, device=dev)
+    e1_32 = torch.empty((M, N), dtype=torch.float32, device=dev) if want_f32 else None
+    e1_16 = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    e2_32 = torch.empty((M, N), dtype=torch.float32, device=dev) if (ln2 is not None and want_f32) else None
+    e2_16 = torch.empty((M, N), dtype=torch.bfloat16, device=dev) if ln2 is not None else None
+    ws = torch.empty(4 * M * N, dtype=torch.float32, device=dev) if K >= 1024 else None
+    cnt = _splitk_counters(dev, 2 * (((M + 31) // 32) * ((N + 31) // 32) + (M + 31) // 32))
+    tiles = ((M + 31) // 32) * ((N + 31) // 32)
+    with torch.cuda.device(dev):
+        _lib.call("dvis_linear_small_ln", x.data_ptr(), x.stride(0), w.data_ptr(), ptr(bias), ptr(residual),
+                  residual.stride(0) if residual is not None else 0, int(relu), M, N, K, y.data_ptr(), ln[0].data_ptr(), ln[1].data_ptr(),
+                  float(eps), ptr(src1), _DTYPE[src1.dtype] if src1 is not None else DVIS_F32, ptr(ln2[0]) if ln2 else None,
+                  ptr(ln2[1]) if ln2 else None, ptr(e1_32), e1_16.data_ptr(), ptr(e2_32), ptr(e2_16), ptr(ws),
+                  cnt.data_ptr() if ws is not None else None, cnt.data_ptr() + 4 * tiles, _stream())
+    return e1_32, e1_16, e2_32, e2_16
+
+
 _SPLITK_CNT = {}
 
 

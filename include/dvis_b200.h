@@ -154,6 +154,17 @@ int dvis_linear_small(const void *x, int64_t ldx, int64_t x_batch, int taps, int
                       int64_t w_batch, const float *bias, int64_t bias_batch, const float *residual, int64_t ldr, int relu,
                       float *y_f32, void *y_bf16, int64_t ldy, int64_t y_batch, int batch, int M, int N, int K,
                       float *splitk_workspace, int *splitk_counters, void *stream);
+/* The same step with the post-norm block's LayerNorm in the producer's EPILOGUE (SelfAttentionLayer / FFNLayer.forward_post,
+ * P/mask2former_video/modeling/transformer_decoder/video_mask2former_transformer_decoder.py:40-50,160-164):
+ *     y = act(x @ W^T + bias) + residual;   e1 = LN(y; ln_gamma, ln_beta);   e2 = LN(e1 + src1; ln2_gamma, ln2_beta)  (optional)
+ * x bf16 (M, K) rows ldx apart, W (N, K) bf16, residual f32 (M, N) rows ldr apart, src1 (M, N) f32|bf16, M <= 512,
+ * N <= 512 with N % 128 == 0.  y_f32: (M, N) staging / pre-norm output.  The last CTA of a 32-row block to finish normalises
+ * the block (rowblock_counters: ceil(M/32) ints, zero before the first call and left zero).  Outputs ln_f32 / ln_bf16 and
+ * ln2_f32 / ln2_bf16, (M, N) contiguous, each optional.  splitk_* as in dvis_linear_small (K >= 1024). */
+int dvis_linear_small_ln(const void *x, int64_t ldx, const void *w, const float *bias, const float *residual, int64_t ldr, int relu,
+                         int M, int N, int K, float *y_f32, const float *ln_gamma, const float *ln_beta, float eps, const void *src1,
+                         int src1_dtype, const float *ln2_gamma, const float *ln2_beta, float *ln_f32, void *ln_bf16, float *ln2_f32,
+                         void *ln2_bf16, float *splitk_workspace, int *splitk_counters, int *rowblock_counters, void *stream);
 int dvis_set_pdl(int enabled);
 /* debug aid of tests/perf (DVIS_LS_PROF=1): clock64 stamps (8 values) of CTA 0 of the last dvis_linear_small launch */
 int dvis_debug_linear_small_stamps(long long *host_out);

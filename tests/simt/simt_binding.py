@@ -222,6 +222,13 @@ def linear_small(w, bias=None, **kw):
         return ops.linear_small(w, bias, **kw)
 
 
+def linear_small_ln(w, bias, x, residual, ln, **kw):
+    import emulated_device
+    from dvis_plus_b200 import ops
+    with emulated_device.emulated_b200():
+        return ops.linear_small_ln(w, bias, x, residual, ln, **kw)
+
+
 def lap_rect(cost):
     c = cost.float().contiguous()
     B = 1 if c.dim() == 2 else c.shape[0]

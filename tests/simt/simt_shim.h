@@ -91,7 +91,8 @@ inline int max(int a, int b) { return a > b ? a : b; }
 // ---- runtime API surface the entry points touch --------------------------------------------------------------------------
 typedef int cudaError_t;
 typedef void *cudaStream_t;
-enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9,
+       cudaSharedmemCarveoutMaxShared = 100 };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "simt"; }
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }

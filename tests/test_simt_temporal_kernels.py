@@ -186,3 +186,27 @@ def test_linear_small_split_k_is_deterministic_and_exact():
     assert (y32 - ref).abs().max() < 1e-4
     again, _, _, _ = simt.linear_small(w, b, x=x, residual=res, out_f32=True, out_bf16=False)
     assert torch.equal(again, y32)                                    # the counters were left at zero, the sum order is fixed
+
+
+@pytest.mark.parametrize("K", [128, 1024])
+def test_linear_small_ln_epilogue_by_last_cta(K):
+    """out-proj / FFN2 form: y = x W^T + b + residual; e1 = LN(y); e2 = LN(e1 + src1) -- normalised by the last CTA of each
+    32-row block (K = 1024 also goes through the 4-way split-K)"""
+    torch.manual_seed(K)
+    M, N = 45, 256
+    x = torch.randn(M, K).to(torch.bfloat16)
+    w = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16)
+    b, res = torch.randn(N), torch.randn(M, N)
+    g1, b1, g2, b2 = torch.rand(N) + 0.5, torch.randn(N) * 0.1, torch.rand(N) + 0.5, torch.randn(N) * 0.1
+    src1 = torch.randn(M, N).to(torch.bfloat16)
+    e1_32, e1_16, e2_32, e2_16 = simt.linear_small_ln(w, b, x, res, (g1, b1), src1=src1, ln2=(g2, b2))
+    y = x.float() @ w.float().t() + b + res
+    r1 = _ln(y, g1, b1)
+    r2 = _ln(r1 + src1.float(), g2, b2)
+    assert (e1_32 - r1).abs().max() < 1e-4 and (e2_32 - r2).abs().max() < 1e-4
+    assert torch.equal(e1_16, e1_32.to(torch.bfloat16)) and torch.equal(e2_16, e2_32.to(torch.bfloat16))
+    # single LayerNorm, ReLU, no residual; and the counters were left at zero (second call gives the same bits)
+    e1_32b, _, e2n, _ = simt.linear_small_ln(w, b, x, None, (g1, b1), relu=True)
+    assert e2n is None and (e1_32b - _ln(torch.relu(x.float() @ w.float().t() + b), g1, b1)).abs().max() < 1e-4
+    again = simt.linear_small_ln(w, b, x, res, (g1, b1), src1=src1, ln2=(g2, b2))
+    assert torch.equal(again[0], e1_32) and torch.equal(again[2], e2_32)
