@@ -208,3 +208,25 @@ def test_predictor_flash_attention_equals_library_attention(golden):
             outs[fused] = dec(ms, mf)
     for k in ("pred_logits", "pred_embds", "pred_masks"):
         assert rel_err(outs[True][k].float(), outs[False][k].float()) < 3e-2, (k, rel_err(outs[True][k].float(), outs[False][k].float()))
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 512, 512), (200, 512, 2048), (77, 256, 1024)])
+def test_linear_small_ln_epilogue(M, N, K):
+    """out-proj / FFN2 form at tracker sizes: LayerNorm(s) by the last CTA of each 32-row block (K >= 1024: 4-way split-K)"""
+    torch.manual_seed(K + M)
+    dev = "cuda"
+    x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+    b, res = torch.randn(N, device=dev), torch.randn(M, N, device=dev)
+    g1, b1, g2, b2 = (torch.rand(N, device=dev) + 0.5, torch.randn(N, device=dev) * 0.1, torch.rand(N, device=dev) + 0.5,
+                      torch.randn(N, device=dev) * 0.1)
+    src1 = torch.randn(M, N, device=dev).to(torch.bfloat16)
+    y = x.float() @ w.float().t() + b + res
+    r1 = _ln(y, g1, b1)
+    r2 = _ln(r1 + src1.float(), g2, b2)
+    outs = [ops.linear_small_ln(w, b, x, res, (g1, b1), src1=src1, ln2=(g2, b2)) for _ in range(3)]
+    e1_32, e1_16, e2_32, e2_16 = outs[0]
+    assert rel_err(e1_32, r1) < 1e-3 and rel_err(e2_32, r2) < 1e-3
+    assert torch.equal(e1_16, e1_32.to(torch.bfloat16)) and torch.equal(e2_16, e2_32.to(torch.bfloat16))
+    for o in outs[1:]:                                  # counters self-clean, sums in a fixed order: bit-identical repeats
+        assert torch.equal(o[0], e1_32) and torch.equal(o[2], e2_32)
