@@ -32,17 +32,21 @@ struct FlashParams {
 
 // SPLIT = true  (short key sequences): 16 query rows per CTA, the 8 warps split the keys in blocks of 32 (flash-decoding),
 //                warp-private cp.async ring, the 8 partial (max, sum, O) states merged through shared memory;
-// SPLIT = false (long key sequences, the predictor's 920 .. 14 720-pixel memories): 128 query rows per CTA, one m16 tile per
-//                warp, all warps walk every 64-key block through a CTA-wide 2-stage ring -- K / V are streamed 8x less often.
-template <int DH, bool SPLIT>
-__global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashParams p) {
+// SPLIT = false (long key sequences, the predictor's 920 .. 14 720-pixel memories): NW x 16 query rows per CTA, one m16 tile
+//                per warp, all warps walk every 64-key block through a CTA-wide 2-stage ring.  NW = 16 (256 rows) puts ALL
+//                200 queries of a (batch, head) in one CTA: K / V are streamed once per head and 16 frames x 8 heads = 128
+//                CTAs are a single wave on 148 SMs (NW = 8 needed 256 CTAs = 1.7 waves and streamed K / V twice).
+template <int DH, bool SPLIT, int NW = kFaWarps>
+__global__ void __launch_bounds__(NW * 32) flash_attn_kernel(const FlashParams p) {
+  constexpr int kFaWarps = NW;                     // warps of this instantiation (shadows the default)
   constexpr int KB = SPLIT ? 32 : 64;              // keys per block
   constexpr int RS = DH + 8;                       // padded row stride (bf16): 16-byte aligned, ldmatrix conflict-free
   constexpr int TILE = KB * RS;                    // elements of one K (or V) block
   constexpr int KSTEPS = DH / 16, DT = DH / 8, NKT = KB / 8;
   constexpr int CH = DH / 8;                       // 16-byte pieces per row
   constexpr int LDT = SPLIT ? 32 : kFaWarps * 32;  // threads copying one block
-  constexpr int RPP = LDT / CH, PASSES = KB / RPP; // rows per pass, passes per block
+  constexpr int RPP = LDT / CH;                    // rows copied per pass
+  constexpr int PASSES = (KB + RPP - 1) / RPP;     // passes per block (the last pass may be partial: 16 warps, 64 keys)
   extern __shared__ uint4 fa_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -60,6 +64,7 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
     const int key0 = blk * KB + lr;
 #pragma unroll
     for (int i = 0; i < PASSES; ++i) {
+      if (lr + i * RPP >= KB) break;               // more copying threads than 16-byte pieces in a block
       const int key = key0 + i * RPP;
       const bool ok = key < p.Lk;                  // rows past Lk are zero-filled so that 0-probability x V stays 0
       const size_t kr = ok ? (size_t)key : 0;
@@ -261,18 +266,19 @@ __global__ void __launch_bounds__(kFaWarps * 32) flash_attn_kernel(const FlashPa
   }
 }
 
-template <int DH, bool SPLIT>
+template <int DH, bool SPLIT, int NW = kFaWarps>
 int launch_flash(const FlashParams &p, cudaStream_t s) {
   const int kb = SPLIT ? 32 : 64;
-  const size_t ring = (size_t)(SPLIT ? kFaWarps : 1) * p.stages * 2 * kb * (DH + 8) * sizeof(__nv_bfloat16);
-  cudaFuncSetAttribute(flash_attn_kernel<DH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring));
-  cudaFuncSetAttribute(flash_attn_kernel<DH, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // see small_linear.cu
-  const int rows = SPLIT ? kFaRows : kFaRows * kFaWarps;
+  const size_t ring = (size_t)(SPLIT ? NW : 1) * p.stages * 2 * kb * (DH + 8) * sizeof(__nv_bfloat16);
+  auto kern = flash_attn_kernel<DH, SPLIT, NW>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring));
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // see small_linear.cu
+  const int rows = SPLIT ? kFaRows : kFaRows * NW;
   dim3 grid((p.Lq + rows - 1) / rows, p.H, p.B);
 #ifdef DVIS_SIMT_EMULATION
-  flash_attn_kernel<DH, SPLIT><<<grid, kFaWarps * 32, ring, s>>>(p);
+  kern<<<grid, NW * 32, ring, s>>>(p);
 #else
-  launch_pdl<FlashParams>(flash_attn_kernel<DH, SPLIT>, grid, dim3(kFaWarps * 32), ring, s, p);
+  launch_pdl<FlashParams>(kern, grid, dim3(NW * 32), ring, s, p);
 #endif
   return check_launch("flash_attn_kernel");
 }
@@ -312,6 +318,8 @@ extern "C" int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, in
   const int64_t split_ctas = (int64_t)((Lq + kFaRows - 1) / kFaRows) * H * B;
   if (Lk > 512 || (Lq > 64 && split_ctas > 2 * kNumSMs)) {
     p.stages = 2;
+    // (16 warps = all 200 queries of a head in one CTA, K / V streamed once, a single 128-CTA wave: measured SLOWER -- 500 us vs
+    //  465 us at 14 720 keys -- the 512-thread CTA barriers cost more than the second K / V stream; launch_flash<32, false, 16>)
     return Dh == 32 ? launch_flash<32, false>(p, s) : launch_flash<64, false>(p, s);
   }
   p.stages = (Lk + 31) / 32 > kFaWarps ? 2 : 1;    // a warp with more than one 32-key block prefetches the next one

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .blocks import (MLP, CrossAttentionLayer, FFNLayer, SelfAttentionLayer, _fast_path, add_norm, linear,
+from .blocks import (MLP, CrossAttentionLayer, FFNLayer, SelfAttentionLayer, _fast_path, add_norm, flash_attn_wins, linear,
                      sine_position_embedding)
 from .precision import gemm_dtype
 from .pixel_decoder import ConvNorm, _c2_xavier_fill, configurable
@@ -241,7 +241,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
             w, b = m._weights(dt)
             qk = F.linear(out_q, w[:2 * C], b[:2 * C]).view(B, Q, 2, H, dh)
             v = F.linear(out_lp, w[2 * C:], b[2 * C:]).view(B, Q, H, dh)
-            if own_attn:
+            if own_attn and flash_attn_wins(B, H, Q):
                 o = ops.flash_attn(qk[:, :, 0], qk[:, :, 1], v, scale)
             else:
                 o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2), scale=scale)

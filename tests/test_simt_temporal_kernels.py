@@ -33,7 +33,8 @@ def pack_bits(mask):
 
 
 @pytest.mark.parametrize("B,Lq,Lk,H,Dh", [(1, 20, 40, 2, 64), (2, 16, 7, 1, 32), (1, 33, 200, 1, 64), (1, 5, 330, 2, 32),
-                                          (1, 70, 530, 1, 32), (1, 9, 577, 1, 64)])      # Lk > 512: the 64-row variant
+                                          (1, 70, 530, 1, 32), (1, 9, 577, 1, 64),       # Lk > 512: the row-split variant
+                                          (1, 150, 530, 1, 32)])                         # two 128-row CTAs per head
 def test_flash_attn_matches_fp32_reference(B, Lq, Lk, H, Dh):
     torch.manual_seed(B * 1000 + Lq * 10 + Lk)
     scale = 1 / math.sqrt(Dh)
