@@ -430,11 +430,12 @@ def main():
     esz = 2 if args.precision == "bf16" else 4
     msda_bytes = t_local * (S * M_ * D_ * esz + S * M_ * L_ * P_ * 3 * esz + S * L_ * 2 * 4 + S * M_ * D_ * esz)
     roof = None
-    if kern and "dvis_msda_fused_forward" in kern:
-        n, tot = kern["dvis_msda_fused_forward"]
+    msda_entry = next((k for k in ("dvis_msda_fused_forward_hm", "dvis_msda_fused_forward") if kern and k in kern), None)
+    if msda_entry:
+        n, tot = kern[msda_entry]
         us = tot / n * 1e3
         ach = msda_bytes / us / 1e3
-        roof = {"kernel": "msda_fwd_staged_kernel (dvis_msda_fused_forward)", "bound": "hbm", "achieved": round(ach, 1),
+        roof = {"kernel": "msda_fwd_staged_kernel (%s)" % msda_entry, "bound": "hbm", "achieved": round(ach, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 # not measurable inside this run (needs ncu): imported from the committed ncu --set full capture, per launch,
                 # scaled by frames -- null for shapes that capture does not cover

@@ -20,8 +20,12 @@ SIGNATURES = {
     "dvis_msda_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "dvis_msda_fused_forward": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp,
                                 _vp, _i, _vp],
+    "dvis_msda_fused_forward_hm": [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "dvis_msda_pack_pairs": [_vp, _i, _i, _i, _i, _vp, _vp],
     "dvis_msda_pair_forward": [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "dvis_linear_tc": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp],
+    "dvis_linear_tc_heads": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "dvis_linear_tc_add_ln": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "dvis_mask_logits": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp],
     "dvis_groupnorm_nhwc": [_vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp,
                             _vp, _i, _i64, _vp],

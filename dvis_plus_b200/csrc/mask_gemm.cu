@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_emb,
                  const __grid_constant__ CUtensorMap tmap_out, const MaskGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by offset arithmetic on the __shared__ array (a uintptr_t round trip would turn the staging stores into generic ST)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_block_bytes = p.Qpad * 128;                       // one emb k-block
   uint8_t *sB = smem;
   uint8_t *sA = smem + p.KB * b_block_bytes;                    // 1024-aligned because Qpad % 8 == 0

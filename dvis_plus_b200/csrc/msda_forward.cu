@@ -112,6 +112,40 @@ __device__ __forceinline__ void point_params(A x, A y, A a, int H, int W, int st
   off.o11 = uint32_t(v11 ? o11 : safe) << 4;
 }
 
+// Head-major value layout (N, M, S, D) with D = 32 bf16 (64 bytes per pixel): the two x-adjacent corners of a sampling point are
+// 128 CONTIGUOUS bytes, one L1 line when the left pixel index is even.  A point is described by the byte offsets of its two
+// column PAIRS (row h0 and row h0 + 1; relative to the batch item's value base, head slab included) and the weights of the
+// (left, right) pixel of each pair.  At the borders the pair is shifted inside the row -- w0 == -1 reads columns (0, 1) with
+// the right weight 0, w0 == W - 1 reads (W - 2, W - 1) with the left weight 0 -- and a row outside the map is clamped to the
+// nearest valid row with weights 0, so every load is in bounds and a zero weight multiplies a finite value.
+//   rec.x / rec.y: byte offsets of the top / bottom pair      rec.z: bf16x2 (top, bottom) weight of the LEFT pixel
+//   rec.w: bf16x2 (top, bottom) weight of the RIGHT pixel
+__device__ __forceinline__ uint4 point_params_hm(float x, float y, float a, int H, int W, int start, int slab, int S) {
+  const float h_im = y * float(H) - 0.5f;
+  const float w_im = x * float(W) - 0.5f;
+  const bool inr = (h_im > -1.f) && (w_im > -1.f) && (h_im < float(H)) && (w_im < float(W));   // cuh:293
+  const float hf = floorf(h_im), wf = floorf(w_im);
+  const int h0 = inr ? int(hf) : 0, w0 = inr ? int(wf) : 0;
+  const float lh = h_im - hf, lw = w_im - wf;
+  const float hh = 1.f - lh, hw = 1.f - lw;
+  const bool top = inr && h0 >= 0, bot = inr && h0 + 1 <= H - 1;      // cuh:61-83 corner tests
+  const bool lef = w0 >= 0, rig = w0 + 1 <= W - 1;
+  const float w00 = (top && lef) ? hh * hw * a : 0.f, w01 = (top && rig) ? hh * lw * a : 0.f;
+  const float w10 = (bot && lef) ? lh * hw * a : 0.f, w11 = (bot && rig) ? lh * lw * a : 0.f;
+  int wb = w0;
+  float tl = w00, tr = w01, bl = w10, br = w11;
+  if (!lef) { wb = 0; tl = w01; tr = 0.f; bl = w11; br = 0.f; }                      // column 0 is the point's RIGHT corner
+  else if (!rig) { wb = max(W - 2, 0); tl = 0.f; tr = w00; bl = 0.f; br = w10; }     // column W-1 is the point's LEFT corner
+  const int r0 = max(h0, 0), r1 = min(h0 + 1, H - 1);
+  const int p0 = min(start + r0 * W + wb, S - 2), p1 = min(start + r1 * W + wb, S - 2);   // (W == 1 maps: stay inside the slab)
+  uint4 rec;
+  rec.x = uint32_t(slab + p0) << 6;
+  rec.y = uint32_t(slab + p1) << 6;
+  rec.z = pack_bf16x2(tl, bl);
+  rec.w = pack_bf16x2(tr, br);
+  return rec;
+}
+
 // Blackwell mixed-precision FMA (PTX fma.rn.f32.bf16 -> SASS FHFMA.BF16 with .H0 / .H1 operand selectors): fp32 accumulator +=
 // bf16 x bf16 straight from the halves of packed registers -- no bf16 -> fp32 conversion instructions (they were 32 of the
 // 54 instructions per sampling point of the bf16 gather loop).  a0 += lo(v) * w, a1 += hi(v) * w with w = the HI-th half of wp.
@@ -148,7 +182,8 @@ __device__ __forceinline__ float ldp<__nv_bfloat16>(const __nv_bfloat16 *p) {
 }
 
 // TP: dtype of the FUSED path's offsets / logits (float or bf16); unused for the plain op
-template <typename T, typename TO, int D, bool FUSED, typename TP = float, int MINB = 6, int UNROLL = 2>
+// HM: `value` is head-major (N, M, S, D) -- bf16 in / out, D = 32, FUSED only; see point_params_hm
+template <typename T, typename TO, int D, bool FUSED, typename TP = float, int MINB = 6, int UNROLL = 2, bool HM = false>
 __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const MsdaParams p) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;  // lanes per row
@@ -177,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
   // bf16 in AND out (the encoder's production path): the 4 corner weights are kept as packed bf16 and the gather loop runs on
   // FHFMA (fhfma2 above); every other combination keeps exact fp32 weights (the plain op's 2e-5 contract)
   constexpr bool kMixed = std::is_same<T, __nv_bfloat16>::value && std::is_same<TO, __nv_bfloat16>::value;
+  static_assert(!HM || (kMixed && FUSED && D == 32), "head-major value: bf16 in / out, 32 channels per head, fused parameters");
   PointOffsets *s_off = reinterpret_cast<PointOffsets *>(dyn_smem);
   float4 *s_wt = reinterpret_cast<float4 *>(dyn_smem + p.items_per_cta * LPs);   // kMixed: a dense uint2 array (2 x bf16x2) in the same region
   float *s_prob = reinterpret_cast<float *>(dyn_smem + 2 * p.items_per_cta * LPs);
@@ -269,6 +305,10 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
         const float2 ms = *reinterpret_cast<const float2 *>(s_prob + 2 * il);      // (max, 1 / sum) of the item's logits
         const TP *lgp = static_cast<const TP *>(p.attn) + nq * p.attn_stride + (size_t)m * LP + pt;
         const float prob = __expf(ldp<TP>(lgp) - ms.x) * ms.y;
+        if constexpr (HM) {
+          reinterpret_cast<uint4 *>(s_off)[il * LPs + pt] = point_params_hm(fmaf(o.x, sx, rx), fmaf(o.y, sy, ry), prob, H, W, start, m * p.S, p.S);
+          continue;
+        }
         point_params<float>(fmaf(o.x, sx, rx), fmaf(o.y, sy, ry), prob, H, W, start, M, m, LPR, off, wt);
       } else {
         using TL = typename LocType<T>::type;   // plain op: loc / attn have the value's dtype
@@ -287,6 +327,43 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
   __syncthreads();
 
   // phase 2: gather + accumulate
+  if constexpr (HM) {
+    // 8 lanes per item: lanes 0-3 read the 64 bytes of the LEFT pixel of a pair, lanes 4-7 the RIGHT pixel -- one 128-byte
+    // request per pair (one L1 wavefront when aligned, else two; the token-major layout always costs two), two pairs per point.
+    // Each half accumulates its own pixel's contribution for the same 8 channels; one xor-shuffle per channel joins them.
+    const int g8 = lane >> 3, j8 = lane & 7, half = j8 >> 2;
+    const char *vb8 = reinterpret_cast<const char *>(static_cast<const T *>(p.value) + (size_t)n * p.S * M * D) + j8 * 16;
+    const int rounds = (nitems + kWarps * 4 - 1) / (kWarps * 4);
+    for (int r = 0; r < rounds; ++r) {
+      const int il_raw = (r * kWarps + warp) * 4 + g8;
+      const bool live = il_raw < nitems;
+      const int il = live ? il_raw : nitems - 1;             // idle groups repeat the last item (all lanes reach the shuffles)
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      const uint4 *so = reinterpret_cast<const uint4 *>(s_off) + il * LPs;
+#pragma unroll UNROLL
+      for (int pt = 0; pt < LP; ++pt) {
+        const uint4 rec = so[pt];
+        const uint32_t w = half ? rec.w : rec.z;
+        const uint4 va = __ldg(reinterpret_cast<const uint4 *>(vb8 + rec.x)), vc = __ldg(reinterpret_cast<const uint4 *>(vb8 + rec.y));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          fhfma2<0>(acc[2 * k], acc[2 * k + 1], (&va.x)[k], w);
+          fhfma2<1>(acc[2 * k], acc[2 * k + 1], (&vc.x)[k], w);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 4);
+      if (live && half == 0) {
+        const int item = s_item[il];
+        const int q = p.m_shift >= 0 ? item >> p.m_shift : item / M, m = item - q * M;
+        TO *dst = static_cast<TO *>(p.out) + (((size_t)n * p.Lq + q) * M + m) * (size_t)D + j8 * 8;
+        store_vec<TO, float, 8>(dst, acc);
+      }
+    }
+    return;
+  }
   const int g = lane / LPR, j = lane % LPR;
   using V = decltype(Vec16<T>::v);
   const char *vb = reinterpret_cast<const char *>(static_cast<const T *>(p.value) + (size_t)n * p.S * M * D) + j * 16;
@@ -410,7 +487,7 @@ size_t staged_smem(int L, int P) {
   return (size_t)items * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
 }
 
-template <typename T, typename TO, int D, bool FUSED, typename TP = float>
+template <typename T, typename TO, int D, bool FUSED, typename TP = float, bool HM = false>
 int launch_staged(MsdaParams p, cudaStream_t stream) {
   constexpr int G = 32 / (D / Vec16<T>::N);
   const int per_batch = p.Lq * p.M, LP = p.L * p.P, LPs = LP | 1;
@@ -427,8 +504,8 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
   if (smem > kMaxStagedSmem)
     return fail(DVIS_ERR_UNSUPPORTED, "msda: %zu bytes of shared memory per CTA for D=%d, L*P=%d exceed the %d-byte opt-in limit", smem,
                 D, LP, int(kMaxStagedSmem));
-  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP>;
-  {  // occupancy / unroll variants (DVIS_MSDA_VARIANT), kept for the micro-benchmark.  Default: 6 CTAs/SM, unroll 2
+  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 2, HM>;
+  if constexpr (!HM) {  // occupancy / unroll variants (DVIS_MSDA_VARIANT), kept for the micro-benchmark.  Default: 6 CTAs/SM, unroll 2
      // (40 registers): measured 23 % faster than 3 CTAs/SM x unroll 4 (80 registers) -- the gather is latency bound.
     static const int variant = getenv("DVIS_MSDA_VARIANT") ? atoi(getenv("DVIS_MSDA_VARIANT")) : 0;
     if (variant == 1) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 3, 4>;
@@ -534,4 +611,33 @@ extern "C" int dvis_msda_fused_forward(const void *value, int value_dtype, const
   return fail(DVIS_ERR_UNSUPPORTED,
               "msda_fused: no kernel for value_dtype=%d out_dtype=%d channels=%d (built: f32/bf16 value and output, channels in {16,32,64})",
               value_dtype, out_dtype, channels);
+}
+
+// The same operator on a HEAD-MAJOR value tensor (N, M, S, D) -- what csrc/linear_tc.cu's value-projection epilogue writes --
+// for the production shape: bf16 value and output, 32 channels per head.  Everything else as dvis_msda_fused_forward.
+extern "C" int dvis_msda_fused_forward_hm(const void *value_hm, const int64_t *spatial_shapes, const int64_t *level_start,
+                                          const void *offsets, int64_t offsets_stride, const void *logits, int64_t logits_stride,
+                                          int param_dtype, const float *ref, int ref_dim, int batch, int spatial_size,
+                                          int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                          const int32_t *item_order, void *out, void *stream) {
+  if (int rc = validate_common(value_hm, spatial_shapes, level_start, offsets, logits, out, batch, spatial_size, num_heads,
+                               channels, num_levels, num_query, num_point))
+    return rc;
+  DVIS_REQUIRE(channels == 32, "msda_fused_hm: built for 32 channels per head (got %d)", channels);
+  DVIS_REQUIRE(spatial_size >= 2 && (long)spatial_size * num_heads < (1L << 26), "msda_fused_hm: spatial extent out of range");
+  DVIS_REQUIRE(ref && (ref_dim == 2 || ref_dim == 4), "msda_fused: reference points must be 2-d or 4-d");
+  DVIS_REQUIRE(num_levels * num_point >= 2 && num_levels * num_point <= kMaxStagedLP, "msda_fused_hm: L*P = %d outside [2, %d]",
+               num_levels * num_point, kMaxStagedLP);
+  DVIS_REQUIRE(aligned16(value_hm) && aligned16(out), "msda_fused_hm: value / out must be 16-byte aligned (128 for the value to get one-line pairs)");
+  DVIS_REQUIRE(aligned16(ref) && (reinterpret_cast<uintptr_t>(offsets) & 7) == 0 && offsets_stride % 2 == 0,
+               "msda_fused: reference points must be 16-byte aligned, offsets 8-byte aligned with an even row stride");
+  DVIS_REQUIRE(param_dtype == DVIS_F32 || param_dtype == DVIS_BF16, "msda_fused: offsets/logits must be f32 or bf16");
+  MsdaParams p{};
+  p.value = value_hm; p.shapes = spatial_shapes; p.level_start = level_start; p.loc = offsets; p.attn = logits;
+  p.ref = ref; p.ref_dim = ref_dim; p.loc_stride = offsets_stride; p.attn_stride = logits_stride;
+  p.order = item_order; p.out = out;
+  p.N = batch; p.S = spatial_size; p.M = num_heads; p.L = num_levels; p.Lq = num_query; p.P = num_point;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return param_dtype == DVIS_F32 ? launch_staged<__nv_bfloat16, __nv_bfloat16, 32, true, float, true>(p, s)
+                                 : launch_staged<__nv_bfloat16, __nv_bfloat16, 32, true, __nv_bfloat16, true>(p, s);
 }

@@ -66,6 +66,10 @@ class MSDeformAttn(nn.Module):
         self.output_proj = nn.Linear(d_model, d_model)
         self._reset_parameters()
         self._fused_cache = None
+        self.use_tc_linear = True      # bf16 inference: value_proj on csrc/linear_tc.cu (head-major epilogue) + head-major gather
+        # output_proj + residual + norm1 in one tcgen05 kernel (dvis_linear_tc_add_ln): correct and tested, but measured 226 us
+        # against 196 us for cuBLAS + add_layernorm at 16 x 19 320 tokens (profiles/r2_linear_tc.md) -- opt-in until it wins
+        self.fuse_output_norm = False
 
     def _reset_parameters(self):
         # py:66-80: zero offset weights, ring-shaped offset bias scaled by the point index, zero attention
@@ -101,25 +105,43 @@ class MSDeformAttn(nn.Module):
             self._fused_cache = (key, w, b, vw, vb, ow, ob)
         return self._fused_cache[1:]
 
-    def forward_fused(self, query, reference_points, input_flatten, host_spatial_shapes, spatial_shapes_dev,
-                      level_start_dev, input_padding_mask=None, out_dtype=None):
-        """Inference path: query / input_flatten (N, L, C) in the GEMM dtype; returns output_proj(...) in `out_dtype`."""
+    def tc_path_ok(self, dt, S):
+        """The tcgen05 projections + head-major gather are built for the production shape: bf16, 32 channels per head,
+        d_model <= 256 (csrc/linear_tc.cu, dvis_msda_fused_forward_hm)."""
+        return (self.use_tc_linear and dt == torch.bfloat16 and self.d_model // self.n_heads == 32 and self.d_model <= 256
+                and self.d_model % 64 == 0 and S >= 2 and 2 <= self.n_levels * self.n_points <= 32)
+
+    def forward_core(self, query, reference_points, input_flatten, host_spatial_shapes, spatial_shapes_dev, level_start_dev,
+                     input_padding_mask=None):
+        """Everything of the inference path up to (not including) output_proj: (N, Lq, C) in the GEMM dtype."""
         N, Lq, _ = query.shape
         S = input_flatten.shape[1]
         dt = query.dtype
         w, b, vw, vb, ow, ob = self._fused_weights(dt)
-        value = F.linear(input_flatten, vw, vb)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], 0.0)
-        value = value.view(N, S, self.n_heads, self.d_model // self.n_heads)
         ol = F.linear(query, w, b)                                   # (N, Lq, M*L*P*3): [offsets | logits]
         n_off = self.n_heads * self.n_levels * self.n_points * 2
         order = None
         if Lq == S and sum(h * w_ for h, w_ in host_spatial_shapes) == S:
             order = tiled_item_order(host_spatial_shapes, self.n_heads, query.device)
-        core = ops.msda_fused_forward(value, spatial_shapes_dev, level_start_dev, ol[..., :n_off], ol[..., n_off:],
-                                      reference_points.float().contiguous(), self.n_heads, self.n_levels,
-                                      self.n_points, item_order=order, out_dtype=dt)
+        ref = reference_points.float().contiguous()
+        if self.tc_path_ok(dt, S) and all(w_ >= 2 for _, w_ in host_spatial_shapes):
+            # value projection on tcgen05 with the head-major epilogue: (N, M, S, 32), x-adjacent corners in one line
+            value_hm = ops.linear_tc_heads(input_flatten, vw, self.value_proj.bias.detach().float(), row_mask=input_padding_mask)
+            return ops.msda_fused_forward_hm(value_hm, spatial_shapes_dev, level_start_dev, ol[..., :n_off], ol[..., n_off:], ref,
+                                             self.n_levels, self.n_points, item_order=order)
+        value = F.linear(input_flatten, vw, vb)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        value = value.view(N, S, self.n_heads, self.d_model // self.n_heads)
+        return ops.msda_fused_forward(value, spatial_shapes_dev, level_start_dev, ol[..., :n_off], ol[..., n_off:], ref,
+                                      self.n_heads, self.n_levels, self.n_points, item_order=order, out_dtype=dt)
+
+    def forward_fused(self, query, reference_points, input_flatten, host_spatial_shapes, spatial_shapes_dev,
+                      level_start_dev, input_padding_mask=None, out_dtype=None):
+        """Inference path: query / input_flatten (N, L, C) in the GEMM dtype; returns output_proj(...) in `out_dtype`."""
+        core = self.forward_core(query, reference_points, input_flatten, host_spatial_shapes, spatial_shapes_dev, level_start_dev,
+                                 input_padding_mask)
+        _, _, _, _, ow, ob = self._fused_weights(query.dtype)
         out = F.linear(core, ow, ob)
         return out if out_dtype is None else out.to(out_dtype)
 

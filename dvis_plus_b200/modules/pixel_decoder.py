@@ -110,8 +110,16 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         Returns (src32, src_lp, q_lp) for the next layer."""
         dt = src_lp.dtype
         w1, b1, w2, b2 = self._lp(dt)
-        a = self.self_attn.forward_fused(q_lp, ctx["ref"], src_lp, ctx["shapes"], ctx["shapes_dev"], ctx["lsi_dev"])
-        src32, src_lp, _ = ops.add_layernorm(a, src32, self.norm1.weight, self.norm1.bias, self.norm1.eps, lp_dtype=dt)
+        attn = self.self_attn
+        if attn.fuse_output_norm and attn.tc_path_ok(dt, src_lp.shape[1]):
+            # output_proj + residual + norm1 in ONE tcgen05 kernel (csrc/linear_tc.cu): the projection never reaches HBM
+            core = attn.forward_core(q_lp, ctx["ref"], src_lp, ctx["shapes"], ctx["shapes_dev"], ctx["lsi_dev"])
+            ow = attn._fused_weights(dt)[4]
+            src32, src_lp, _ = ops.linear_tc_add_layernorm(core, ow, attn.output_proj.bias.detach().float(), src32, self.norm1.weight,
+                                                           self.norm1.bias, self.norm1.eps)
+        else:
+            a = attn.forward_fused(q_lp, ctx["ref"], src_lp, ctx["shapes"], ctx["shapes_dev"], ctx["lsi_dev"])
+            src32, src_lp, _ = ops.add_layernorm(a, src32, self.norm1.weight, self.norm1.bias, self.norm1.eps, lp_dtype=dt)
         h = torch._addmm_activation(b1, src_lp.view(-1, src_lp.shape[-1]), w1.t())      # ReLU in the GEMM epilogue
         f = F.linear(h, w2, b2).view(src_lp.shape)
         return ops.add_layernorm(f, src32, self.norm2.weight, self.norm2.bias, self.norm2.eps, lp_dtype=dt,

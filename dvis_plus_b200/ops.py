@@ -91,6 +91,26 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     return out
 
 
+def msda_fused_forward_hm(value_hm, spatial_shapes, level_start_index, offsets, logits, reference_points, num_levels,
+                          num_points, item_order=None):
+    """msda_fused_forward on a head-major value tensor (N, M, S, 32) bf16 -> (N, Lq, M*32) bf16 (dvis_msda_fused_forward_hm)."""
+    N, M, S, D = value_hm.shape
+    Lq = offsets.shape[1]
+    assert value_hm.dtype == torch.bfloat16 and D == 32 and value_hm.is_contiguous() and reference_points.is_contiguous()
+    assert offsets.dtype == logits.dtype and offsets.dtype in (torch.float32, torch.bfloat16)
+    assert reference_points.dtype == torch.float32
+    assert offsets.stride(-1) == 1 and logits.stride(-1) == 1
+    assert offsets.stride(0) == offsets.stride(1) * Lq and logits.stride(0) == logits.stride(1) * Lq
+    out = torch.empty((N, Lq, M * D), dtype=torch.bfloat16, device=value_hm.device)
+    order_ptr = item_order.data_ptr() if item_order is not None else None
+    with torch.cuda.device(value_hm.device):
+        _lib.call("dvis_msda_fused_forward_hm", value_hm.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                  offsets.data_ptr(), offsets.stride(1), logits.data_ptr(), logits.stride(1), _DTYPE[offsets.dtype],
+                  reference_points.data_ptr(), reference_points.shape[-1], N, S, M, D, num_levels, Lq, num_points,
+                  order_ptr, out.data_ptr(), _stream())
+    return out
+
+
 def msda_pair_forward(value, spatial_shapes, level_start_index, offsets, logits, reference_points, num_heads,
                       num_levels, num_points, item_order=None):
     """Pair-packed bf16 fused forward: packs `value` (N,S,M,32) bf16 into x-adjacent corner pairs, then gathers 2 lines
@@ -209,6 +229,59 @@ def add_layernorm(x, residual, weight, bias, eps=1e-5, *, want_f32=True, lp_dtyp
                   _DTYPE[residual.dtype] if residual is not None else DVIS_F32, w.data_ptr(), b.data_ptr(), ptr(pos),
                   pos_rows, rows, C, float(eps), ptr(out_f32), ptr(out_lp), ptr(out_lp_pos),
                   _DTYPE[lp_dtype] if lp_dtype is not None else DVIS_F32, _stream())
+    return out_f32, out_lp, out_lp_pos
+
+
+def _check_linear_tc(x, w, bias):
+    K = x.shape[-1]
+    assert x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_contiguous() and w.is_contiguous()
+    assert w.shape[1] == K and (bias is None or (bias.dtype == torch.float32 and bias.numel() == w.shape[0]))
+    return x.numel() // K, w.shape[0], K
+
+
+def linear_tc(x, w, bias=None, relu=False):
+    """nn.Linear on the tcgen05 path (dvis_linear_tc): x (..., K) bf16, w (N, K) bf16, bias (N,) f32 -> (..., N) bf16."""
+    rows, N, K = _check_linear_tc(x, w, bias)
+    y = torch.empty(x.shape[:-1] + (N,), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dvis_linear_tc", x.data_ptr(), K, w.data_ptr(), bias.data_ptr() if bias is not None else None, int(relu),
+                  rows, N, K, y.data_ptr(), N, _stream())
+    return y
+
+
+def linear_tc_heads(x, w, bias=None, row_mask=None):
+    """MSDeformAttn.value_proj with a head-major result (dvis_linear_tc_heads): x (B, S, K) bf16 -> (B, N/32, S, 32) bf16."""
+    rows, N, K = _check_linear_tc(x, w, bias)
+    B, S = x.shape[0], x.shape[1]
+    assert x.dim() == 3
+    if row_mask is not None:
+        row_mask = row_mask.reshape(B * S).to(torch.uint8).contiguous()
+    out = torch.empty((B, N // 32, S, 32), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dvis_linear_tc_heads", x.data_ptr(), K, w.data_ptr(), bias.data_ptr() if bias is not None else None, B, S, N, K,
+                  row_mask.data_ptr() if row_mask is not None else None, out.data_ptr(), _stream())
+    return out
+
+
+def linear_tc_add_layernorm(x, w, bias, residual, gamma, beta, eps=1e-5, *, want_f32=True, want_lp=True, pos=None):
+    """LayerNorm(residual + x . w^T + bias) in one kernel (dvis_linear_tc_add_ln); outputs as add_layernorm:
+    (y_f32 | None, y_bf16 | None, (y + pos)_bf16 | None).  residual (..., N) f32; gamma / beta (N,) f32; pos (rows_p, N) f32."""
+    rows, N, K = _check_linear_tc(x, w, bias)
+    shape = x.shape[:-1] + (N,)
+    assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == shape
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    out_f32 = torch.empty(shape, dtype=torch.float32, device=x.device) if want_f32 else None
+    out_lp = torch.empty(shape, dtype=torch.bfloat16, device=x.device) if want_lp else None
+    out_lp_pos, pos_rows = None, 0
+    if pos is not None:
+        assert pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape[-1] == N
+        pos_rows = pos.numel() // N
+        assert rows % pos_rows == 0
+        out_lp_pos = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(x.device):
+        _lib.call("dvis_linear_tc_add_ln", x.data_ptr(), K, w.data_ptr(), ptr(bias), residual.data_ptr(), gamma.data_ptr(),
+                  beta.data_ptr(), float(eps), rows, N, K, ptr(pos), pos_rows, ptr(out_f32), ptr(out_lp), ptr(out_lp_pos), _stream())
     return out_f32, out_lp, out_lp_pos
 
 

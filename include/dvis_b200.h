@@ -82,6 +82,17 @@ int dvis_msda_fused_forward(const void *value, int value_dtype, const int64_t *s
                             int num_query, int num_point, const int32_t *item_order, void *out, int out_dtype,
                             void *stream);
 
+/* The fused forward on a HEAD-MAJOR value tensor (batch, num_heads, spatial_size, 32) bf16 -- the layout the value projection of
+ * dvis_linear_tc writes -- with bf16 output: the two x-adjacent corners of a sampling point are 128 contiguous bytes, so a point
+ * costs ~3 L1 lines instead of 4 (OPS/src/cuda/ms_deform_im2col_cuda.cuh:242-304 reads (batch, spatial, heads, channels)).
+ * channels must be 32; value_hm 16-byte aligned (128-byte for the one-line pairs); everything else as dvis_msda_fused_forward.
+ */
+int dvis_msda_fused_forward_hm(const void *value_hm, const int64_t *spatial_shapes, const int64_t *level_start,
+                               const void *offsets, int64_t offsets_stride, const void *logits, int64_t logits_stride,
+                               int param_dtype, const float *ref, int ref_dim, int batch, int spatial_size, int num_heads,
+                               int channels, int num_levels, int num_query, int num_point, const int32_t *item_order,
+                               void *out, void *stream);
+
 /* Pair-packed bf16 variant of the fused forward (same arithmetic as dvis_msda_fused_forward with bf16 value / output).
  * dvis_msda_pack_pairs re-lays `value` (batch, S, M, 32) bf16 out as pairs (batch, S+1, M, 2, 32) bf16 with
  * pairs[n, e, m] = [value[n, e-1, m], value[n, e, m]] (zeros outside [0, S)), so that the two x-adjacent bilinear
@@ -168,6 +179,27 @@ int dvis_linear_small_ln(const void *x, int64_t ldx, const void *w, const float 
 int dvis_set_pdl(int enabled);
 /* debug aid of tests/perf (DVIS_LS_PROF=1): clock64 stamps (8 values) of CTA 0 of the last dvis_linear_small launch */
 int dvis_debug_linear_small_stamps(long long *host_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Token-wise linear layers of the MSDeformAttn encoder on tcgen05 / TMEM, TMA-fed (csrc/linear_tc.cu):
+ *   y[r, :] = x[r, :] . W^T + bias,   x (rows, K) bf16 with row stride ldx, W (N, K) bf16 (nn.Linear.weight), bias (N,) f32 or NULL
+ *   N a multiple of 32, <= 256; K a multiple of 64, <= 512.
+ * dvis_linear_tc: y (rows, N) bf16, row stride ldy, optional ReLU -- nn.Linear.forward.
+ * dvis_linear_tc_heads: MSDeformAttn.value_proj (P/.../ops/modules/ms_deform_attn.py:98-101) with the output written
+ *   head-major, value_hm (batch, N/32, S, 32) bf16 -- what dvis_msda_fused_forward_hm reads -- rows = batch * S tokens,
+ *   row_mask (batch * S) bytes or NULL: 1 zeroes the token (input_padding_mask, py:99-100).
+ * dvis_linear_tc_add_ln: MSDeformAttn.output_proj followed by the encoder layer's post-norm residual block
+ *   (ms_deform_attn.py:118, msdeformattn.py:118-119): LayerNorm(residual + y) * gamma + beta over the N columns;
+ *   residual (rows, N) f32; outputs as dvis_add_layernorm: out_f32 (rows, N) f32, out_lp bf16, out_lp_pos bf16 = result +
+ *   pos[row % pos_rows] (pos (pos_rows, N) f32); each output optional (NULL).
+ */
+int dvis_linear_tc(const void *x, int64_t ldx, const void *w, const float *bias, int relu, int rows, int N, int K, void *y,
+                   int64_t ldy, void *stream);
+int dvis_linear_tc_heads(const void *x, int64_t ldx, const void *w, const float *bias, int batch, int S, int N, int K,
+                         const uint8_t *row_mask, void *value_hm, void *stream);
+int dvis_linear_tc_add_ln(const void *x, int64_t ldx, const void *w, const float *bias, const float *residual,
+                          const float *gamma, const float *beta, float eps, int rows, int N, int K, const float *pos,
+                          int pos_rows, float *out_f32, void *out_lp, void *out_lp_pos, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * y = LayerNorm(x + residual) * gamma + beta over the last dim C, one pass.

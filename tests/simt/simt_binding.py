@@ -121,7 +121,7 @@ def set_jitter(one_in):
 
 
 # ---- the remaining CUDA-core entry points (same argument order as dvis_plus_b200/ops.py) ------------------------------------
-ENTRY_POINTS += ("dvis_msda_forward", "dvis_msda_backward", "dvis_msda_fused_forward", "dvis_add_layernorm", "dvis_groupnorm_nhwc",
+ENTRY_POINTS += ("dvis_msda_forward", "dvis_msda_backward", "dvis_msda_fused_forward", "dvis_msda_fused_forward_hm", "dvis_add_layernorm", "dvis_groupnorm_nhwc",
                  "dvis_resize_bilinear_nhwc", "dvis_attn_bias_from_logits", "dvis_msda_pack_pairs",
                  "dvis_msda_pair_forward", "dvis_lap_rect")
 _DT[torch.float64] = 1
@@ -145,12 +145,17 @@ def msda_backward(value, shapes, lsi, loc, attn, grad_out):
     return gv, gl, ga
 
 
-def msda_fused_forward(value, shapes, lsi, offsets, logits, ref, L, P, item_order=None, out_dtype=None, pair=False):
+def msda_fused_forward(value, shapes, lsi, offsets, logits, ref, L, P, item_order=None, out_dtype=None, pair=False, head_major=False):
     """offsets (N, Lq, M*L*P*2), logits (N, Lq, M*L*P) -- possibly column slices of one tensor; ref (N, Lq, L, 2|4) f32."""
     N, S, M, D = value.shape
     Lq = offsets.shape[1]
     out_dtype = out_dtype or value.dtype
     out = torch.full((N, Lq, M * D), float("nan"), dtype=out_dtype)
+    if head_major:
+        hm_al = value.permute(0, 2, 1, 3).contiguous()
+        call("dvis_msda_fused_forward_hm", _p(hm_al), _p(shapes), _p(lsi), _p(offsets), offsets.stride(1), _p(logits), logits.stride(1),
+             _DT[offsets.dtype], _p(ref), ref.shape[-1], N, S, M, D, L, Lq, P, _p(item_order), _p(out), None)
+        return out
     if pair:
         pairs = torch.zeros((N, S + 1, M, 2, D), dtype=torch.bfloat16)
         call("dvis_msda_pack_pairs", _p(value), N, S, M, D, _p(pairs), None)

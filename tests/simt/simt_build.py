@@ -83,6 +83,58 @@ extern "C" int dvis_mask_attn_bits(const void *emb, const void *feat, int B, int
     }
   return 0;
 }
+// doubles of csrc/linear_tc.cu (tcgen05): plain loops with an fp32 accumulator
+namespace {
+void linear_row_double(const __nv_bfloat16 *x, const __nv_bfloat16 *w, const float *bias, int N, int K, float *y) {
+  for (int n = 0; n < N; ++n) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc += float(x[k]) * float(w[(int64_t)n * K + k]);
+    y[n] = acc + (bias ? bias[n] : 0.f);
+  }
+}
+}  // namespace
+extern "C" int dvis_linear_tc(const void *x, int64_t ldx, const void *w, const float *bias, int relu, int rows, int N, int K, void *y,
+                              int64_t ldy, void *) {
+  std::vector<float> row(N);
+  for (int64_t r = 0; r < rows; ++r) {
+    linear_row_double(static_cast<const __nv_bfloat16 *>(x) + r * ldx, static_cast<const __nv_bfloat16 *>(w), bias, N, K, row.data());
+    for (int n = 0; n < N; ++n) static_cast<__nv_bfloat16 *>(y)[r * ldy + n] = __nv_bfloat16(relu ? std::max(row[n], 0.f) : row[n]);
+  }
+  return 0;
+}
+extern "C" int dvis_linear_tc_heads(const void *x, int64_t ldx, const void *w, const float *bias, int batch, int S, int N, int K,
+                                    const uint8_t *row_mask, void *value_hm, void *) {
+  std::vector<float> row(N);
+  const int heads = N / 32;
+  for (int64_t r = 0; r < (int64_t)batch * S; ++r) {
+    linear_row_double(static_cast<const __nv_bfloat16 *>(x) + r * ldx, static_cast<const __nv_bfloat16 *>(w), bias, N, K, row.data());
+    const int64_t n = r / S, s = r % S;
+    for (int c = 0; c < N; ++c)
+      static_cast<__nv_bfloat16 *>(value_hm)[((n * heads + c / 32) * S + s) * 32 + c % 32] =
+          __nv_bfloat16((row_mask && row_mask[r]) ? 0.f : row[c]);
+  }
+  return 0;
+}
+extern "C" int dvis_linear_tc_add_ln(const void *x, int64_t ldx, const void *w, const float *bias, const float *residual,
+                                     const float *gamma, const float *beta, float eps, int rows, int N, int K, const float *pos,
+                                     int pos_rows, float *out_f32, void *out_lp, void *out_lp_pos, void *) {
+  std::vector<float> row(N);
+  for (int64_t r = 0; r < rows; ++r) {
+    linear_row_double(static_cast<const __nv_bfloat16 *>(x) + r * ldx, static_cast<const __nv_bfloat16 *>(w), bias, N, K, row.data());
+    float mean = 0.f, var = 0.f;
+    for (int n = 0; n < N; ++n) { row[n] += residual[r * N + n]; mean += row[n]; }
+    mean /= N;
+    for (int n = 0; n < N; ++n) var += (row[n] - mean) * (row[n] - mean);
+    const float rstd = 1.f / std::sqrt(var / N + eps);
+    for (int n = 0; n < N; ++n) {
+      const float y = (row[n] - mean) * rstd * gamma[n] + beta[n];
+      if (out_f32) out_f32[r * N + n] = y;
+      if (out_lp) static_cast<__nv_bfloat16 *>(out_lp)[r * N + n] = __nv_bfloat16(y);
+      if (out_lp_pos) static_cast<__nv_bfloat16 *>(out_lp_pos)[r * N + n] = __nv_bfloat16(y + pos[(r % pos_rows) * N + n]);
+    }
+  }
+  return 0;
+}
 extern "C" int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias, int bias_dtype, int *,
                                    void *) {
   const auto *e = static_cast<const __nv_bfloat16 *>(emb), *f = static_cast<const __nv_bfloat16 *>(feat);

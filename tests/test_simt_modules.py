@@ -84,6 +84,42 @@ def test_pixel_decoder_fused_path_vs_oracle(device):
             assert rel_err(a.float(), b) < tol
 
 
+def test_pixel_decoder_tensor_core_projections_vs_oracle(device):
+    """conv_dim = 256, 8 heads (32 channels per head, the production geometry): the encoder's value projection goes through
+    dvis_linear_tc_heads (test double here) into the HEAD-MAJOR gather dvis_msda_fused_forward_hm (emulated kernel), and
+    output_proj + residual + norm1 through dvis_linear_tc_add_ln; switching `use_tc_linear` off gives the library path."""
+    from oracle import torch_port as tp
+    torch.manual_seed(1)
+    chans = dict(res2=8, res3=16, res4=24, res5=32)
+    strides = dict(res2=4, res3=8, res4=16, res5=32)
+    pd = M.MSDeformAttnPixelDecoder({k: ShapeSpec(channels=chans[k], stride=strides[k]) for k in chans},
+                                    transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=128,
+                                    transformer_enc_layers=2, conv_dim=256, mask_dim=128, norm="GN",
+                                    transformer_in_features=["res3", "res4", "res5"], common_stride=4).eval()
+    for layer in pd.transformer.encoder.layers:
+        torch.nn.init.normal_(layer.self_attn.sampling_offsets.weight, std=0.02)
+        torch.nn.init.normal_(layer.self_attn.attention_weights.weight, std=0.1)
+        torch.nn.init.normal_(layer.self_attn.value_proj.bias, std=0.1)
+        torch.nn.init.normal_(layer.self_attn.output_proj.bias, std=0.1)
+    feats = {k: torch.randn(2, chans[k], 64 // strides[k], 96 // strides[k]) for k in chans}
+    sd = {k: v.detach() for k, v in pd.state_dict().items()}
+    ref_mf, ref_o0, ref_ms = tp.pixel_decoder_forward_features(sd, feats, num_layers=2)
+    outs = {}
+    for tc in (True, False):
+        for layer in pd.transformer.encoder.layers:
+            layer.self_attn.use_tc_linear = tc
+            layer.self_attn.fuse_output_norm = tc
+        calls = _lib.launch_count
+        with precision("bf16"):
+            mf, o0, ms = pd.forward_features(feats)
+        assert _lib.launch_count - calls == 2 * (4 if tc else 3) + 3 + 2, "the expected kernels did not run"
+        assert rel_err(mf.float(), ref_mf) < 3e-2 and rel_err(o0.float(), ref_o0) < 3e-2
+        for a, b in zip(ms, ref_ms):
+            assert rel_err(a.float(), b) < 3e-2
+        outs[tc] = mf.float()
+    assert rel_err(outs[True], outs[False]) < 2e-2
+
+
 @pytest.mark.parametrize("materialize", [True, False])
 def test_predictor_golden(golden, device, materialize):
     g = golden("predictor_small.pt")

@@ -106,6 +106,38 @@ def test_msda_fused_forward_kernel(vdt, odt, pdt, ref_dim):
         assert np.abs(pair.float().numpy() - ref).max() <= 1.5e-2 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("pdt,ref_dim,shapes,use_order", [(torch.bfloat16, 2, ((12, 20), (6, 10), (3, 5)), False),
+                                                           (torch.float32, 4, ((5, 7), (3, 2)), False),       # odd widths: unaligned pairs
+                                                           (torch.bfloat16, 2, ((9, 13), (4, 6), (2, 3)), True)])
+def test_msda_fused_forward_head_major_value(pdt, ref_dim, shapes, use_order):
+    """dvis_msda_fused_forward_hm: value laid out (N, M, S, 32); offsets scaled so that many points straddle every border."""
+    N, M, D, P = 2, 8, 32, 4
+    L = len(shapes)
+    sh = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(sh.prod(1).sum())
+    g = torch.Generator().manual_seed(23)
+    value = torch.randn(N, S, M, D, generator=g).bfloat16()
+    fused = (torch.randn(N, S, M * L * P * 3, generator=g) * torch.cat([torch.full((M * L * P * 2,), 4.0), torch.ones(M * L * P)])).to(pdt)
+    offsets, logits = fused[..., :M * L * P * 2], fused[..., M * L * P * 2:]
+    ref_pts = torch.rand(N, S, L, ref_dim, generator=g)
+    if ref_dim == 4:
+        ref_pts[..., 2:] *= 0.5
+    order = torch.randperm(S * M, generator=g).to(torch.int32) if use_order else None
+    out = simt.msda_fused_forward(value, sh, lsi_of(sh), offsets, logits, ref_pts, L, P, head_major=True, item_order=order)
+    off = offsets.float().view(N, S, M, L, P, 2)
+    aw = logits.float().view(N, S, M, L * P).softmax(-1).view(N, S, M, L, P)
+    if ref_dim == 2:
+        norm = torch.stack([sh[:, 1], sh[:, 0]], -1).float()
+        loc = ref_pts[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = ref_pts[:, :, None, :, None, :2] + off / P * ref_pts[:, :, None, :, None, 2:] * 0.5
+    ref = c_oracle.msda_forward(value.float().numpy(), sh.numpy(), lsi_of(sh).numpy(), loc.numpy(), aw.numpy())
+    assert torch.isfinite(out.float()).all()
+    assert np.abs(out.float().numpy() - ref).max() <= 1e-2 * max(1.0, np.abs(ref).max())
+    token_major = simt.msda_fused_forward(value, sh, lsi_of(sh), offsets, logits, ref_pts, L, P, item_order=order)
+    assert (out.float() - token_major.float()).abs().max() <= 1e-2 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("C", [128, 256, 512])
 def test_add_layernorm_kernel(C):
     g = torch.Generator().manual_seed(C)
