@@ -505,7 +505,14 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
     return fail(DVIS_ERR_UNSUPPORTED, "msda: %zu bytes of shared memory per CTA for D=%d, L*P=%d exceed the %d-byte opt-in limit", smem,
                 D, LP, int(kMaxStagedSmem));
   auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 2, HM>;
-  if constexpr (!HM) {  // occupancy / unroll variants (DVIS_MSDA_VARIANT), kept for the micro-benchmark.  Default: 6 CTAs/SM, unroll 2
+  if constexpr (HM) {   // the same experiment switch for the head-major gather (tests/perf/encoder_microbench.py)
+    static const int variant = getenv("DVIS_MSDA_HM_VARIANT") ? atoi(getenv("DVIS_MSDA_HM_VARIANT")) : 0;
+    if (variant == 1) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 4, HM>;
+    if (variant == 2) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 2, HM>;
+    if (variant == 3) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 4, HM>;
+    if (variant == 4) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 12, HM>;
+    if (variant == 5) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 4, 4, HM>;
+  } else {  // occupancy / unroll variants (DVIS_MSDA_VARIANT), kept for the micro-benchmark.  Default: 6 CTAs/SM, unroll 2
      // (40 registers): measured 23 % faster than 3 CTAs/SM x unroll 4 (80 registers) -- the gather is latency bound.
     static const int variant = getenv("DVIS_MSDA_VARIANT") ? atoi(getenv("DVIS_MSDA_VARIANT")) : 0;
     if (variant == 1) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 3, 4>;
