@@ -472,9 +472,9 @@ def main():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of msda_fwd_staged_kernel per 720p frame, bf16 fused variant, from the committed
-# `ncu --set full` capture (8 frames per launch: 172.9 + 62.0 MB); refreshed whenever the kernel changes
-MSDA_NCU_DRAM_BYTES_PER_FRAME = (172.886016e6 + 62.013440e6) / 8
-MSDA_NCU_SOURCE = "imported: profiles/r2_ncu_msda.txt (ncu --set full, 8 frames per launch), scaled to this launch"
+# `ncu --set full` capture of the head-major gather (8 frames per launch: 172.9 + 61.9 MB); refreshed whenever the kernel changes
+MSDA_NCU_DRAM_BYTES_PER_FRAME = (172.921344e6 + 61.916416e6) / 8
+MSDA_NCU_SOURCE = "imported: profiles/r2_ncu_msda.txt (ncu --set full of dvis_msda_fused_forward_hm, 8 frames per launch), scaled to this launch"
 
 
 if __name__ == "__main__":

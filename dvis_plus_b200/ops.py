@@ -567,3 +567,137 @@ def _splitk_counters(dev, n):
         c = torch.zeros(max(n, 4096), dtype=torch.int32, device=dev)
         _SPLITK_CNT[key] = c
     return c
+
+
+# ---- video post-processing (csrc/postproc.cu; P/dvis_Plus/meta_architecture.py:818-979) --------------------------------
+
+def _mask_view(pred_masks):
+    """(Q, T, h, w) f32|bf16 view with contiguous (h, w) planes -> (tensor, q_stride, t_stride); copies only if the
+    planes themselves are strided."""
+    if not pred_masks.is_cuda:
+        raise RuntimeError("post-processing: CUDA tensors required (there is no CPU path)")
+    if pred_masks.dim() != 4:
+        raise RuntimeError(f"post-processing: pred_masks must be (Q, T, h, w), got {tuple(pred_masks.shape)}")
+    if pred_masks.dtype not in (torch.float32, torch.bfloat16):
+        pred_masks = pred_masks.float()
+    if pred_masks.stride(3) != 1 or pred_masks.stride(2) != pred_masks.shape[3]:
+        pred_masks = pred_masks.contiguous()
+    return pred_masks, pred_masks.stride(0), pred_masks.stride(1)
+
+
+def _geom_args(pred_masks, first_resize_size, img_size, out_size):
+    h, w = pred_masks.shape[-2:]
+    return [int(v) for v in (h, w, first_resize_size[0], first_resize_size[1], img_size[0], img_size[1], out_size[0], out_size[1])]
+
+
+def class_scores(pred_cls, aux_pred_cls=None):
+    """(Q, K+1) logits -> (Q, K+1) f32 softmax scores, the K object columns max'ed with softmax(aux) (dvis_class_scores)."""
+    cls = pred_cls.float().contiguous()
+    aux = aux_pred_cls.float().contiguous() if aux_pred_cls is not None else None
+    if not cls.is_cuda:
+        raise RuntimeError("class_scores: CUDA tensors required (there is no CPU path)")
+    Q, K1 = cls.shape
+    scores = torch.empty_like(cls)
+    with torch.cuda.device(cls.device):
+        _lib.call("dvis_class_scores", cls.data_ptr(), aux.data_ptr() if aux is not None else None, Q, K1, scores.data_ptr(),
+                  _stream())
+    return scores
+
+
+def vis_topk(pred_cls, max_num, aux_pred_cls=None):
+    """Top-`max_num` (score, label, query) triples of softmax(pred_cls)[:, :-1] (max'ed with aux), score descending
+    (dvis_vis_topk).  -> (scores f32, labels i64, query indices i64), all (max_num,) on the device."""
+    cls = pred_cls.float().contiguous()
+    aux = aux_pred_cls.float().contiguous() if aux_pred_cls is not None else None
+    if not cls.is_cuda:
+        raise RuntimeError("vis_topk: CUDA tensors required (there is no CPU path)")
+    Q, K1 = cls.shape
+    ws = torch.empty((Q, K1), dtype=torch.float32, device=cls.device)
+    scores = torch.empty(max_num, dtype=torch.float32, device=cls.device)
+    labels = torch.empty(max_num, dtype=torch.int64, device=cls.device)
+    query = torch.empty(max_num, dtype=torch.int64, device=cls.device)
+    with torch.cuda.device(cls.device):
+        _lib.call("dvis_vis_topk", cls.data_ptr(), aux.data_ptr() if aux is not None else None, Q, K1, int(max_num),
+                  ws.data_ptr(), scores.data_ptr(), labels.data_ptr(), query.data_ptr(), _stream())
+    return scores, labels, query
+
+
+def vis_masks(pred_masks, sel, first_resize_size, img_size, out_size, out=None, packed=False):
+    """bool masks (n, T, Ho, Wo) = resize_chain(pred_masks[sel]) > 0 straight from the stride-4 logits (dvis_vis_masks).
+    pred_masks (Q, T, h, w) f32|bf16 view (any query / frame strides); sel (n,) int64 device tensor or None (all).
+    packed=True: one bit per pixel instead, uint8 (n, T, Ho, ceil(Wo/8)), little bit order (dvis_vis_masks_packed; see
+    unpack_masks) -- 8x less to write and to copy to the host."""
+    m, qs, ts = _mask_view(pred_masks)
+    n = m.shape[0] if sel is None else sel.numel()
+    T = m.shape[1]
+    Ho, Wo = int(out_size[0]), int(out_size[1])
+    row = (Wo + 7) // 8 if packed else Wo
+    if out is None:
+        out = torch.empty((n, T, Ho, row), dtype=torch.uint8 if packed else torch.bool, device=m.device)
+    assert out.dtype == (torch.uint8 if packed else torch.bool) and out.is_contiguous() and out.shape == (n, T, Ho, row)
+    if n == 0:
+        return out
+    if sel is not None:
+        assert sel.dtype == torch.int64 and sel.is_cuda
+        sel = sel.contiguous()
+    geom = _geom_args(m, first_resize_size, img_size, out_size)
+    per_call = max(1, 65535 // T)                     # grid.z limit: n_sel * frames <= 65535 per launch
+    entry = "dvis_vis_masks_packed" if packed else "dvis_vis_masks"
+    with torch.cuda.device(m.device):
+        for n0 in range(0, n, per_call):
+            n1 = min(n, n0 + per_call)
+            if sel is not None:
+                base, sel_ptr = m.data_ptr(), sel.data_ptr() + 8 * n0
+            else:
+                base, sel_ptr = m.data_ptr() + n0 * qs * m.element_size(), None
+            _lib.call(entry, base, _DTYPE[m.dtype], qs, ts, sel_ptr, n1 - n0, T, *geom, out.data_ptr() + n0 * T * Ho * row, _stream())
+    return out
+
+
+def unpack_masks(packed, width):
+    """Host side of vis_masks(packed=True): (..., Ho, ceil(Wo/8)) uint8 tensor -> (..., Ho, Wo) bool CPU tensor."""
+    import numpy as np
+    assert packed.dtype == torch.uint8
+    bits = np.unpackbits(packed.cpu().numpy(), axis=-1, bitorder="little")[..., :width]
+    return torch.from_numpy(bits).bool()
+
+
+def vps_argmax(pred_masks, keep_idx, keep_score, first_resize_size, img_size, out_size):
+    """Per-pixel arg-max of keep_score[k] * sigmoid(resize_chain(pred_masks[keep_idx[k]])) + the segment-filter counts
+    (dvis_vps_argmax).  -> win (T, Ho, Wo) int32 (k, or ~k if the winner's probability < 0.5), areas (3, n_keep) int64."""
+    m, qs, ts = _mask_view(pred_masks)
+    T = m.shape[1]
+    n = keep_idx.numel()
+    assert keep_idx.dtype == torch.int64 and keep_idx.is_cuda and keep_score.dtype == torch.float32 and keep_score.numel() == n
+    Ho, Wo = int(out_size[0]), int(out_size[1])
+    win = torch.empty((T, Ho, Wo), dtype=torch.int32, device=m.device)
+    areas = torch.empty((3, n), dtype=torch.int64, device=m.device)
+    with torch.cuda.device(m.device):
+        _lib.call("dvis_vps_argmax", m.data_ptr(), _DTYPE[m.dtype], qs, ts, keep_idx.contiguous().data_ptr(),
+                  keep_score.contiguous().data_ptr(), n, T, *_geom_args(m, first_resize_size, img_size, out_size),
+                  win.data_ptr(), areas.data_ptr(), _stream())
+    return win, areas
+
+
+def vps_paint(win, seg_of_k):
+    """panoptic = seg_of_k[win] where win >= 0 else 0 (dvis_vps_paint); seg_of_k (n_keep,) int32 on the device."""
+    assert win.dtype == torch.int32 and win.is_contiguous() and seg_of_k.dtype == torch.int32 and seg_of_k.is_cuda
+    out = torch.empty_like(win)
+    with torch.cuda.device(win.device):
+        _lib.call("dvis_vps_paint", win.data_ptr(), seg_of_k.contiguous().data_ptr(), win.numel(), out.data_ptr(), _stream())
+    return out
+
+
+def vss_argmax(pred_masks, mask_cls, first_resize_size, img_size, out_size):
+    """argmax_c sum_q mask_cls[q, c] * sigmoid(resize_chain(pred_masks[q])) -> (T, Ho, Wo) int64 (dvis_vss_argmax).
+    mask_cls (Q, K) f32 with unit column stride (e.g. class_scores(...)[:, :-1])."""
+    m, qs, ts = _mask_view(pred_masks)
+    Q, T = m.shape[:2]
+    assert mask_cls.dtype == torch.float32 and mask_cls.is_cuda and mask_cls.shape[0] == Q and mask_cls.stride(1) == 1
+    K = mask_cls.shape[1]
+    Ho, Wo = int(out_size[0]), int(out_size[1])
+    out = torch.empty((T, Ho, Wo), dtype=torch.int64, device=m.device)
+    with torch.cuda.device(m.device):
+        _lib.call("dvis_vss_argmax", m.data_ptr(), _DTYPE[m.dtype], qs, ts, mask_cls.data_ptr(), mask_cls.stride(0), Q, K, T,
+                  *_geom_args(m, first_resize_size, img_size, out_size), out.data_ptr(), _stream())
+    return out
