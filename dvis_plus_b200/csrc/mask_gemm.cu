@@ -70,7 +70,9 @@ __device__ __forceinline__ __nv_bfloat16 cvt_logit<__nv_bfloat16>(uint32_t bits)
 // a 16- or 32-bit bias: what csrc/flash_attn.cu consumes (16x fewer bytes than the bf16 bias, L2-resident; nothing else of the
 // 9 intermediate mask-head calls ever reaches HBM).  A warp's 32 lanes are 32 consecutive pixels, so one ballot per query
 // column is the packed word; lane i keeps column i's word and the 32 words of a chunk go out as 32 4-byte stores.
-template <typename TO, bool kTmaStore, bool kBias = false, bool kBits = false>
+// kTf32 = true: emb / feat are fp32 in memory and multiplied as TF32 (kind::tf32; a 128-byte swizzle row holds 32 elements): the
+// fp32-mode mask head (decoder.py:363 without autocast) at 1e-3 of the output scale instead of bf16's 1e-2.
+template <typename TO, bool kTmaStore, bool kBias = false, bool kBits = false, bool kTf32 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_emb,
                  const __grid_constant__ CUtensorMap tmap_out, const MaskGemmParams p) {
@@ -85,6 +87,7 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
   Barriers *bars = reinterpret_cast<Barriers *>(reinterpret_cast<uint8_t *>(sOut) + p.epi_bufs * kEpiCols * kTileM * sizeof(TO));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kBlkElems = kTf32 ? 32 : 64;                   // elements per 128-byte k-block row
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_feat);
@@ -115,14 +118,14 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
         if (b != cur_b) {
           if (n_bload > 0) mbar_wait(&bars->b_empty, (n_bload - 1) & 1);   // MMAs that read the old emb are done
           mbar_arrive_expect_tx(&bars->b_full, uint32_t(p.KB * b_block_bytes));
-          for (int kb = 0; kb < p.KB; ++kb) tma_load_3d(sB + kb * b_block_bytes, &tmap_emb, &bars->b_full, kb * kBlockK, 0, b);
+          for (int kb = 0; kb < p.KB; ++kb) tma_load_3d(sB + kb * b_block_bytes, &tmap_emb, &bars->b_full, kb * kBlkElems, 0, b);
           cur_b = b;
           ++n_bload;
         }
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
-          tma_load_3d(sA + stage * kStageBytes, &tmap_feat, &bars->full[stage], kb * kBlockK, tile * kTileM, b);
+          tma_load_3d(sA + stage * kStageBytes, &tmap_feat, &bars->full[stage], kb * kBlkElems, tile * kTileM, b);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -130,7 +133,7 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(kTileM, p.Qpad, /*BF16*/ 1);
+      const uint32_t idesc = make_idesc(kTileM, p.Qpad, kTf32 ? /*TF32*/ 2 : /*BF16*/ 1);
       int stage = 0, phase = 0, cur_b = -1, n_bload = 0, n_tile = 0;
       for (int t = tile_begin; t < tile_end; ++t, ++n_tile) {
         const int b = t / p.tiles_per_batch;
@@ -149,9 +152,12 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
           const uint32_t a_addr = smem_u32(sA + stage * kStageBytes);
           const uint32_t b_addr = smem_u32(sB + kb * b_block_bytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)                        // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
-            mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
-                        uint32_t(kb | k));
+          for (int k = 0; k < 4; ++k) {                                 // UMMA_K = 16 bf16 / 8 tf32 = 32 bytes inside the swizzle row
+            if constexpr (kTf32)
+              mma_tf32_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc, uint32_t(kb | k));
+            else
+              mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc, uint32_t(kb | k));
+          }
           mma_commit(&bars->empty[stage]);                               // frees the A stage when these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(128) reset_closed_bit_rows_kernel(const int *_
 }  // namespace
 int mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
                      int *row_open, void *stream, int64_t emb_batch = 0, int64_t out_batch = 0, int64_t bits_row = 0,
-                     int row_batch = 0);
+                     int row_batch = 0, bool tf32 = false);
 }  // namespace dvis
 
 extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out,
@@ -328,11 +334,45 @@ extern "C" int dvis_mask_attn_bits(const void *emb, const void *feat, int B, int
   return check_launch("reset_closed_bit_rows_kernel");
 }
 
+// fp32 operands multiplied as TF32.  emb (Q x C fp32 = 1 KB per query) stays resident in shared memory, so the queries are
+// processed in slices of <= 128 (feat is re-read once per slice: 2 passes at Q = 200).
+constexpr int kTf32QuerySlice = 128;
+extern "C" int dvis_mask_logits_tf32(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, void *stream) {
+  DVIS_REQUIRE(emb && feat && out && Q > 0, "mask_logits_tf32: null pointer argument");
+  for (int q0 = 0; q0 < Q; q0 += kTf32QuerySlice) {
+    const int nq = std::min(kTf32QuerySlice, Q - q0);
+    if (int rc = mask_gemm_launch(static_cast<const float *>(emb) + (size_t)q0 * C, feat, B, nq, C, HW,
+                                  static_cast<float *>(out) + (size_t)q0 * HW, DVIS_F32, nullptr, stream, (int64_t)Q * C,
+                                  (int64_t)Q * HW, 0, 0, true))
+      return rc;
+  }
+  return DVIS_OK;
+}
+
+extern "C" int dvis_mask_attn_bias_tf32(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias,
+                                        int *row_open_workspace, void *stream) {
+  DVIS_REQUIRE(emb && feat && bias && row_open_workspace && Q > 0, "mask_attn_bias_tf32: null pointer argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(row_open_workspace, 0, sizeof(int) * size_t(B) * Q, s);
+  for (int q0 = 0; q0 < Q; q0 += kTf32QuerySlice) {
+    const int nq = std::min(kTf32QuerySlice, Q - q0);
+    if (int rc = mask_gemm_launch(static_cast<const float *>(emb) + (size_t)q0 * C, feat, B, nq, C, HW,
+                                  static_cast<float *>(bias) + (size_t)q0 * HW, DVIS_F32, row_open_workspace + q0, stream,
+                                  (int64_t)Q * C, (int64_t)Q * HW, 0, Q, true))
+      return rc;
+  }
+  reset_closed_rows_kernel<float><<<B * Q, 256, 0, s>>>(row_open_workspace, static_cast<float *>(bias), HW);
+  return check_launch("reset_closed_rows_kernel");
+}
+
 int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
-                           int *row_open, void *stream, int64_t emb_batch, int64_t out_batch, int64_t bits_row, int row_batch) {
+                           int *row_open, void *stream, int64_t emb_batch, int64_t out_batch, int64_t bits_row, int row_batch,
+                           bool tf32) {
   DVIS_REQUIRE(emb && feat && out, "mask_logits: null pointer argument");
   DVIS_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_logits: sizes must be positive");
+  const int blk = tf32 ? 32 : kBlockK;                         // operand elements per 128-byte k-block row
   DVIS_REQUIRE(C % kBlockK == 0 && C <= 512, "mask_logits: C must be a multiple of 64 and <= 512 (got %d)", C);
+  DVIS_REQUIRE(!tf32 || (out_dtype == DVIS_F32 && !bits_row), "mask_logits: tf32 operands are built for f32 outputs");
   DVIS_REQUIRE(Q <= 256, "mask_logits: Q must be <= 256 (got %d); split the queries", Q);
   DVIS_REQUIRE(aligned16(emb) && aligned16(feat), "mask_logits: emb / feat must be 16-byte aligned");
   DVIS_REQUIRE(HW < (int64_t(1) << 31) && B < 65536, "mask_logits: extent too large");
@@ -340,7 +380,7 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
     return fail(DVIS_ERR_UNSUPPORTED, "mask_logits: out_dtype %d (f32 or bf16)", out_dtype);
 
   MaskGemmParams p{};
-  p.out = out; p.B = B; p.Q = Q; p.Qpad = (Q + 15) & ~15; p.KB = C / kBlockK; p.HW = HW;
+  p.out = out; p.B = B; p.Q = Q; p.Qpad = (Q + 15) & ~15; p.KB = C / blk; p.HW = HW;
   p.row_open = row_open;
   p.bits = bits_row ? static_cast<uint8_t *>(out) : nullptr;
   p.bits_row = bits_row;
@@ -363,9 +403,10 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
   const size_t smem = 1024 + b_bytes + size_t(p.stages) * kStageBytes + stage_out_bytes + sizeof(Barriers);
 
   CUtensorMap tm_feat, tm_emb, tm_out;
-  if (int rc = encode_map(&tm_feat, feat, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, HW, B, kBlockK, kTileM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  if (int rc = encode_map(&tm_emb, emb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, Q, B, kBlockK, p.Qpad, CU_TENSOR_MAP_SWIZZLE_128B,
-                          emb_batch)) return rc;
+  const CUtensorMapDataType in_dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const int in_es = tf32 ? 4 : 2;
+  if (int rc = encode_map(&tm_feat, feat, in_dt, in_es, C, HW, B, blk, kTileM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = encode_map(&tm_emb, emb, in_dt, in_es, C, Q, B, blk, p.Qpad, CU_TENSOR_MAP_SWIZZLE_128B, emb_batch)) return rc;
   if (tma_store) {
     if (int rc = encode_map(&tm_out, out, out_dtype == DVIS_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                             esize, HW, Q, B, kTileM, kEpiCols, CU_TENSOR_MAP_SWIZZLE_NONE, p.out_batch)) return rc;
@@ -385,10 +426,19 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
     if (row_open) { if (tma_store) DVIS_LAUNCH(TO, true, true); else DVIS_LAUNCH(TO, false, true); } \
     else { if (tma_store) DVIS_LAUNCH(TO, true, false); else DVIS_LAUNCH(TO, false, false); }        \
   } while (0)
-  if (bits_row) {
+#define DVIS_LAUNCH_TF32(TMA, BIAS)                                                                                              \
+  do {                                                                                                                         \
+    cudaFuncSetAttribute(mask_gemm_kernel<float, TMA, BIAS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
+    mask_gemm_kernel<float, TMA, BIAS, false, true><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);                   \
+  } while (0)
+  if (tf32) {
+    if (row_open) { if (tma_store) DVIS_LAUNCH_TF32(true, true); else DVIS_LAUNCH_TF32(false, true); }
+    else { if (tma_store) DVIS_LAUNCH_TF32(true, false); else DVIS_LAUNCH_TF32(false, false); }
+  } else if (bits_row) {
     cudaFuncSetAttribute(mask_gemm_kernel<float, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     mask_gemm_kernel<float, false, false, true><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);
   } else if (out_dtype == DVIS_F32) DVIS_LAUNCH_T(float); else DVIS_LAUNCH_T(__nv_bfloat16);
+#undef DVIS_LAUNCH_TF32
 #undef DVIS_LAUNCH_T
 #undef DVIS_LAUNCH
   return check_launch("mask_gemm_kernel");

@@ -1,8 +1,8 @@
 """Arithmetic policy of the module-level drop-ins.
 
 "fp32": every GEMM in fp32 on CUDA cores (tight parity with the reference's forced-fp32 pixel decoder,
-        P/mask2former/modeling/pixel_decoder/msdeformattn.py:314,320); mask logits still run on the bf16
-        tensor path (the reference evaluates that einsum in fp16 under autocast, P/train_net_video.py:259).
+        P/mask2former/modeling/pixel_decoder/msdeformattn.py:314,320); the mask-head GEMMs take fp32 operands and multiply
+        them as TF32 on the tensor cores (csrc/mask_gemm.cu kTf32: 1e-3 of the output scale).
 "bf16": GEMM / conv inputs rounded to bf16, fp32 accumulation, LayerNorm / softmax / residual stream in fp32.
 """
 import contextlib
@@ -15,6 +15,8 @@ _state = {"mode": "bf16"}
 def set_precision(mode: str):
     assert mode in ("fp32", "bf16"), mode
     _state["mode"] = mode
+    from .. import ops
+    ops.set_mask_operand_dtype(torch.float32 if mode == "fp32" else torch.bfloat16)
 
 
 def get_precision() -> str:
@@ -28,7 +30,7 @@ def precision(mode: str):
     try:
         yield
     finally:
-        _state["mode"] = old
+        set_precision(old)
 
 
 def gemm_dtype():

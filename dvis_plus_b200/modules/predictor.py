@@ -171,9 +171,15 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         B = x[0].shape[0]
         sizes, k_all, v_all, level_feats, kv_rows = [], [], [], [], []
         own_attn = self.use_fused_attention and dt == torch.bfloat16 and dh in (32, 64)
+        mask_dt = torch.bfloat16 if dt == torch.bfloat16 else torch.float32       # fp32 tier: TF32 operands for the mask head
         mf_lp = mask_features
-        if mf_lp.dtype != torch.bfloat16 or not mf_lp.is_contiguous(memory_format=torch.channels_last):
-            mf_lp = mf_lp.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        if mf_lp.dtype != mask_dt or not mf_lp.is_contiguous(memory_format=torch.channels_last):
+            mf_lp = mf_lp.to(dtype=mask_dt, memory_format=torch.channels_last)
+
+        def level_features(h, w):      # mask features resized once to a level's grid: interpolate(E @ F) == E @ interpolate(F)
+            if mask_dt == torch.bfloat16:
+                return ops.resize_bilinear_nhwc(mf_lp, (h, w))
+            return F.interpolate(mf_lp, size=(h, w), mode="bilinear", align_corners=False).contiguous(memory_format=torch.channels_last)
         for l in range(nl):
             xl = self.input_proj[l](x[l])   # empty nn.Sequential is the identity
             h, w = xl.shape[-2:]
@@ -189,7 +195,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
                 k_all.append(k.permute(2, 0, 3, 1, 4))
                 v_all.append(v.permute(2, 0, 3, 1, 4))
                 kv_rows.append((k, v))
-                level_feats.append(ops.resize_bilinear_nhwc(mf_lp, (h, w)))
+                level_feats.append(level_features(h, w))
                 continue
             tok = xl.permute(0, 2, 3, 1).reshape(B, h * w, C).float() + self.level_embed.weight[l]      # (B, hw, C)
             if n_of:
@@ -203,8 +209,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
                 k_all.append(None)
                 v_all.append(None)
                 kv_rows.append(None)
-            # mask features resized once to this level's grid: interpolate(E @ F) == E @ interpolate(F)
-            level_feats.append(ops.resize_bilinear_nhwc(mf_lp, (h, w)))
+            level_feats.append(level_features(h, w))
         query_embed = self.query_embed.weight.detach().float().contiguous()                            # (Q, C)
         Q = query_embed.shape[0]
         dn = self.decoder_norm
@@ -255,7 +260,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         output = out32
         normed = self.decoder_norm(output)
         cls = linear(self.class_embed, normed).float()                                                 # (B, Q, K+1)
-        masks = ops.mask_logits(self.mask_embed(normed), mask_features, torch.float32)                 # (B, Q, H, W)
+        masks = ops.mask_logits(self.mask_embed(normed), mf_lp, torch.float32, operand_dtype=mask_dt)   # (B, Q, H, W)
         reid = self.reid_embed(normed).float()
         b = B // self.num_frames if self.training else 1
         t = B // b
@@ -294,7 +299,7 @@ class VideoMultiScaleMaskedTransformerDecoder_dvisPlus(nn.Module):
         if fast:
             # mask features resized once to each level grid (3 small maps) for the attention masks
             level_feats = [F.interpolate(mask_features.float(), size=sz, mode="bilinear", align_corners=False)
-                           .to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for sz in size_list]
+                           .to(ops._MASK_OPERAND[0]).contiguous(memory_format=torch.channels_last) for sz in size_list]
             attn_mask = self._heads_lowres(output, level_feats[0])
         else:
             c, m, attn_mask = self.forward_prediction_heads(output, mask_features, size_list[0])

@@ -170,8 +170,22 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attn]
 
 
-def mask_logits(mask_embed, mask_features, out_dtype=torch.float32):
+_MASK_OPERAND = [torch.bfloat16]
+
+
+def set_mask_operand_dtype(dtype):
+    """Operand type of the mask-head GEMMs when the caller does not say: torch.bfloat16 (default: the reference evaluates this einsum
+    in half precision under autocast, P/train_net_video.py:259) or torch.float32 = TF32 tensor-core operands (the fp32 tier;
+    modules.precision.set_precision("fp32") selects it)."""
+    assert dtype in (torch.bfloat16, torch.float32)
+    _MASK_OPERAND[0] = dtype
+
+
+def mask_logits(mask_embed, mask_features, out_dtype=torch.float32, operand_dtype=None):
     """out[b,q,h,w] = sum_c mask_embed[b,q,c] * mask_features[b,c,h,w] on the tcgen05 tensor path (dvis_mask_logits).
+
+    operand_dtype=torch.float32: fp32 operands multiplied as TF32 (dvis_mask_logits_tf32; fp32 output only) -- the fp32 tier;
+    None: the process-wide setting of set_mask_operand_dtype (bf16 unless the fp32 tier is selected).
 
     mask_embed (B,Q,C) any float dtype (cast to bf16; Q*C elements -- negligible); mask_features (B,C,H,W) bf16 in
     torch.channels_last memory format (that is what the pixel decoder drop-in emits); any other layout / dtype is
@@ -185,6 +199,18 @@ def mask_logits(mask_embed, mask_features, out_dtype=torch.float32):
     if not mask_features.is_cuda:
         raise RuntimeError("mask_logits: CUDA tensors required (there is no CPU path)")
     feat = mask_features
+    if operand_dtype is None:
+        operand_dtype = _MASK_OPERAND[0] if out_dtype == torch.float32 else torch.bfloat16
+    if operand_dtype == torch.float32:
+        if out_dtype != torch.float32:
+            raise RuntimeError("mask_logits: TF32 operands produce fp32 logits")
+        if feat.dtype != torch.float32 or not feat.is_contiguous(memory_format=torch.channels_last):
+            feat = feat.to(dtype=torch.float32, memory_format=torch.channels_last)
+        emb = mask_embed.float().contiguous()
+        out = torch.empty((B, Q, H, W), dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(feat.device):
+            _lib.call("dvis_mask_logits_tf32", emb.data_ptr(), feat.data_ptr(), B, Q, C, H * W, out.data_ptr(), _stream())
+        return out
     if feat.dtype != torch.bfloat16 or not feat.is_contiguous(memory_format=torch.channels_last):
         feat = feat.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
     emb = mask_embed.to(torch.bfloat16).contiguous()
@@ -379,7 +405,17 @@ def mask_attn_bias(mask_embed, level_features, dtype=torch.bfloat16):
     -> (B, Q, h*w) `dtype`: -inf where sigmoid(E @ F) < 0.5, rows that would be fully masked reset to 0."""
     B, Q, C = mask_embed.shape
     _, _, h, w = level_features.shape
-    assert level_features.dtype == torch.bfloat16 and level_features.is_contiguous(memory_format=torch.channels_last)
+    assert level_features.is_contiguous(memory_format=torch.channels_last)
+    if level_features.dtype == torch.float32:                      # fp32 tier: TF32 operands, fp32 bias
+        assert dtype == torch.float32
+        emb = mask_embed.float().contiguous()
+        bias = torch.empty((B, Q, h * w), dtype=torch.float32, device=emb.device)
+        ws = torch.empty(B * Q, dtype=torch.int32, device=emb.device)
+        with torch.cuda.device(emb.device):
+            _lib.call("dvis_mask_attn_bias_tf32", emb.data_ptr(), level_features.data_ptr(), B, Q, C, h * w, bias.data_ptr(),
+                      ws.data_ptr(), _stream())
+        return bias
+    assert level_features.dtype == torch.bfloat16
     emb = mask_embed.to(torch.bfloat16).contiguous()
     if Q > 256:
         return attn_bias_from_logits(mask_logits(mask_embed, level_features, torch.float32).flatten(2), dtype)

@@ -262,6 +262,14 @@ int dvis_lap_rect(const float *cost, int B, int rows, int cols, int64_t *row_to_
 int dvis_mask_logits_strided(const void *emb, int64_t emb_batch_stride, const void *feat, int B, int Q, int C, int64_t HW,
                              void *out, int64_t out_batch_stride, int out_dtype, void *stream);
 
+/* The same two operators with fp32 operands multiplied as TF32 (tcgen05 kind::tf32) and fp32 results: the mask head of the
+ * reference when it runs without autocast (decoder.py:363), inside 1e-3 of the output scale.  emb (B, Q, C) f32, feat (B, HW, C)
+ * f32 (channels-last), out / bias (B, Q, HW) f32; any Q (query slices of 128 inside); row_open_workspace B*Q ints.
+ */
+int dvis_mask_logits_tf32(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, void *stream);
+int dvis_mask_attn_bias_tf32(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias,
+                             int *row_open_workspace, void *stream);
+
 /* Same GEMM with the masked-attention decoder's threshold fused into the epilogue
  * (P/dvis_Plus/video_mask2former_transformer_decoder.py:370-371 and :297): writes, instead of the logits, the additive
  * attention bias (B, Q, HW) in bias_dtype (DVIS_F32 | DVIS_BF16): -inf where sigmoid(logit) < 0.5, 0 elsewhere, rows that

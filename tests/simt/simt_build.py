@@ -36,8 +36,8 @@ extern "C" void simt_set_jitter(int one_in) { simt::g_jitter = one_in; }
 extern "C" int dvis_set_pdl(int) { return 0; }
 
 namespace {
-template <typename TO>
-void mask_gemm_double(const __nv_bfloat16 *emb, int64_t emb_batch, const __nv_bfloat16 *feat, int B, int Q, int C, int64_t HW,
+template <typename TO, typename TI = __nv_bfloat16>
+void mask_gemm_double(const TI *emb, int64_t emb_batch, const TI *feat, int B, int Q, int C, int64_t HW,
                       TO *out, int64_t out_batch, bool bias) {
   for (int b = 0; b < B; ++b)
     for (int q = 0; q < Q; ++q) {
@@ -81,6 +81,17 @@ extern "C" int dvis_mask_attn_bits(const void *emb, const void *feat, int B, int
       }
       if (!any_open) std::memset(row, 0, row_bytes);
     }
+  return 0;
+}
+// fp32-operand (TF32 on the device) variants: exact fp32 here
+extern "C" int dvis_mask_logits_tf32(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, void *) {
+  mask_gemm_double<float, float>(static_cast<const float *>(emb), (int64_t)Q * C, static_cast<const float *>(feat), B, Q, C, HW,
+                                 static_cast<float *>(out), (int64_t)Q * HW, false);
+  return 0;
+}
+extern "C" int dvis_mask_attn_bias_tf32(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias, int *, void *) {
+  mask_gemm_double<float, float>(static_cast<const float *>(emb), (int64_t)Q * C, static_cast<const float *>(feat), B, Q, C, HW,
+                                 static_cast<float *>(bias), (int64_t)Q * HW, true);
   return 0;
 }
 // doubles of csrc/linear_tc.cu (tcgen05): plain loops with an fp32 accumulator

@@ -3,6 +3,7 @@ P/dvis_Plus/video_mask2former_transformer_decoder.py:363).
 
 Inputs are rounded to bf16 on both sides (the kernel computes bf16 x bf16 -> fp32), so the only difference is the
 accumulation order: tolerance 1e-3 * scale for fp32 output, 1e-2 * scale for bf16 output (north star: 1e-2 bf16).
+The TF32 tests feed unrounded fp32 operands and hold the fp32 tier's 1e-3.
 """
 import pytest
 import torch
@@ -31,6 +32,43 @@ def test_mask_logits_vs_oracle(B, Q, C, H, W, out_dtype):
     tol = 1e-3 if out_dtype == torch.float32 else 1e-2
     err = (out.float().cpu() - ref).abs().max().item()
     assert err <= tol * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("B,Q,C,H,W", [(1, 12, 64, 16, 24), (2, 100, 256, 23, 40), (1, 200, 256, 46, 80), (2, 7, 64, 5, 8),
+                                      (1, 300, 256, 9, 13), (2, 129, 128, 12, 20), (2, 200, 256, 184, 320)])
+def test_mask_logits_tf32_operands_vs_oracle(B, Q, C, H, W):
+    """fp32-tier mask head: UNROUNDED fp32 operands multiplied as TF32 on the tensor cores against the double-accumulated oracle:
+    the north star's 1e-3 of the output scale (bf16 operands give ~4e-3).  Q > 128 exercises the query slices."""
+    from dvis_plus_b200 import ops
+    g = torch.Generator().manual_seed(Q + H)
+    emb, feat = torch.randn(B, Q, C, generator=g), torch.randn(B, C, H, W, generator=g)
+    out = ops.mask_logits(emb.cuda(), feat.cuda(), torch.float32, operand_dtype=torch.float32)
+    assert out.shape == (B, Q, H, W) and out.dtype == torch.float32
+    if H * W <= 4096:
+        ref = torch.from_numpy(c_oracle.mask_logits(emb.numpy(), feat.numpy()))
+        got = out.cpu()
+    else:                                           # full size: a strided pixel subset keeps the oracle in seconds
+        idx = torch.arange(0, H * W, 97)
+        sub = feat.flatten(2)[:, :, idx].reshape(B, C, -1, 1).contiguous()
+        ref = torch.from_numpy(c_oracle.mask_logits(emb.numpy(), sub.numpy()))
+        got = out.flatten(2)[:, :, idx.cuda()].reshape(B, Q, -1, 1).cpu()
+    assert (got - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+def test_mask_attn_bias_tf32_operands():
+    from dvis_plus_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, Q, C, h, w = 2, 200, 256, 23, 40
+    emb, feat = torch.randn(B, Q, C, generator=g), torch.randn(B, C, h, w, generator=g)
+    feat[0] = feat[0].abs()                           # a row that is masked everywhere must come back all zeros:
+    emb[0, 5] = -emb[0, 5].abs()                      # positive features x negative embedding
+    logits = torch.einsum("bqc,bchw->bqhw", emb.double(), feat.double()).flatten(2)
+    bias = ops.mask_attn_bias(emb.cuda(), feat.cuda().contiguous(memory_format=torch.channels_last), torch.float32).cpu()
+    ref = torch.where(logits < 0, float("-inf"), 0.0)
+    ref[(logits < 0).all(-1)] = 0.0
+    safe = logits.abs() > 1e-2 * logits.abs().max()   # pixels whose sign TF32 rounding cannot flip
+    assert (logits[0, 5] < 0).all() and (bias[0, 5] == 0).all()
+    assert torch.equal(bias[safe], ref.float()[safe])
 
 
 def test_mask_logits_golden_mask_head(golden):

@@ -121,11 +121,15 @@ def test_predictor_golden(golden, materialize):
     d.materialize_aux_masks = materialize
     with precision("fp32"):
         out = d(cuda(g["multi_scale"]), g["mask_features"].cuda())
-    # The boolean attention masks are thresholded mask logits (decoder.py:367-372).  Ours come from bf16 x bf16 -> fp32
-    # logits, the fixture from fp32 ones; with random-init weights many logits sit near 0, a few signs flip and the
-    # discrete change propagates through 3 layers.  5e-2 of the output scale bounds that; everything that does not
-    # go through a thresholded mask is held to 1e-2 / 1e-4 elsewhere in this file.
-    for k, tol in (("pred_logits", 5e-2), ("pred_masks", 5e-2), ("pred_embds", 5e-2), ("pred_embds_without_norm", 5e-2)):
+    # fp32 tier: every GEMM in fp32, the mask head on TF32 tensor-core operands (csrc/mask_gemm.cu kTf32).  The production
+    # formulation (materialize=False: attention masks from E @ resize(F) on each level's grid) reproduces the reference to
+    # fp32 round-off everywhere except the TF32 mask logits themselves (measured 4e-7 / 1.05e-3, tests/perf/fp32_tier_errors.py;
+    # round 1 with bf16 operands: 3e-2 .. 5e-2).  With materialize=True the attention masks are thresholded RESIZED full-size
+    # logits like the reference's (decoder.py:367-372): with random-init weights many of those sit near 0, TF32's 1e-3 flips a
+    # few signs and the discrete change propagates through 3 layers -- 5e-2 of the output scale bounds that.
+    tols = dict(pred_logits=1e-4, pred_masks=2e-3, pred_embds=1e-4, pred_embds_without_norm=1e-4) if not materialize else \
+        dict(pred_logits=5e-2, pred_masks=5e-2, pred_embds=5e-2, pred_embds_without_norm=5e-2)
+    for k, tol in tols.items():
         assert rel_err(out[k], g[k]) < tol, (k, rel_err(out[k], g[k]))
     if materialize:
         assert len(out["aux_outputs"]) == 3
