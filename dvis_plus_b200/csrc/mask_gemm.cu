@@ -13,7 +13,7 @@
 //     [32 queries][128 pixels] smem tile (conflict-free: lane = pixel) and written with one TMA store per chunk,
 //     double-buffered, so the (B, Q, HW) output is produced with full-line writes and no per-element predicates.
 //   * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
-//     warps 2..5 = epilogue (one per TMEM lane quarter).
+//     warps 2..9 = epilogue (two groups of four, one per accumulator stage; a warp per TMEM lane quarter).
 #include <algorithm>
 
 #include "common.cuh"
@@ -28,7 +28,12 @@ constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements per 128-byte swizzle row
 constexpr int kStageBytes = kTileM * 128;         // one A k-block: 128 rows x 128 B
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+// Epilogue groups of 4 warps, one per TMEM accumulator stage (round 2: a single epilogue warp per scheduler exposes every TMEM /
+// shared-memory latency).  Two groups for 2-byte outputs and the bit-mask epilogue (T = 16, Q = 200, bf16: 155.6 -> 148.4 us);
+// fp32 outputs keep one group: their 16 KB staging tiles would take the shared memory of the A pipeline (measured 219 -> 230 us).
+template <typename TO, bool kBits>
+constexpr int epi_groups() { return (kBits || sizeof(TO) == 2) ? 2 : 1; }
+constexpr int kThreads = 64 + 2 * 128;            // launch bound; a one-group kernel is launched with 192 threads
 constexpr int kAccCols = 256;                     // TMEM columns per accumulator stage
 constexpr int kEpiCols = 32;                      // queries per epilogue chunk (one tcgen05.ld.32x32b.x32)
 constexpr int kEpiThreads = 128;
@@ -76,6 +81,7 @@ template <typename TO, bool kTmaStore, bool kBias = false, bool kBits = false, b
 __global__ void __launch_bounds__(kThreads, 1)
 mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_emb,
                  const __grid_constant__ CUtensorMap tmap_out, const MaskGemmParams p) {
+  constexpr int kEpiGroups = epi_groups<TO, kBits>();
   extern __shared__ uint8_t smem_raw[];
   // aligned by offset arithmetic on the __shared__ array (a uintptr_t round trip would turn the staging stores into generic ST)
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -83,8 +89,9 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
   uint8_t *sB = smem;
   uint8_t *sA = smem + p.KB * b_block_bytes;                    // 1024-aligned because Qpad % 8 == 0
   // epi_bufs output staging tiles [kEpiCols queries][128 pixels] for the TMA store (row-major, no swizzle)
-  TO *sOut = reinterpret_cast<TO *>(sA + p.stages * kStageBytes);
-  Barriers *bars = reinterpret_cast<Barriers *>(reinterpret_cast<uint8_t *>(sOut) + p.epi_bufs * kEpiCols * kTileM * sizeof(TO));
+  TO *sOut = reinterpret_cast<TO *>(sA + p.stages * kStageBytes);      // kEpiGroups x epi_bufs staging tiles
+  Barriers *bars = reinterpret_cast<Barriers *>(reinterpret_cast<uint8_t *>(sOut) +
+                                                (kBits ? 0 : kEpiGroups * p.epi_bufs * kEpiCols * kTileM * sizeof(TO)));   // bits: no staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kBlkElems = kTf32 ? 32 : 64;                   // elements per 128-byte k-block row
@@ -172,10 +179,12 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
     // 32 lanes write 32 consecutive pixels of the staging row (conflict-free) and the TMA engine does the
     // (Q, HW)-strided global writes, clipping partial tiles in both pixel and query direction.
     const int quarter = warp & 3;                     // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
-    const bool issuer = (warp == 2 && lane == 0);
+    const int group = (warp - 2) >> 2;                // group g drains accumulator g: the tiles with n_tile % 2 == g
+    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
     const int px = quarter * 32 + lane;
-    int n_tile = 0, n_chunk = 0;
-    for (int t = tile_begin; t < tile_end; ++t, ++n_tile) {
+    TO *sOutG = sOut + group * p.epi_bufs * (kEpiCols * kTileM);
+    int n_chunk = 0;
+    for (int n_tile = group, t = tile_begin + group; t < tile_end; t += kEpiGroups, n_tile += kEpiGroups) {
       const int b = t / p.tiles_per_batch, tile = t - b * p.tiles_per_batch;
       const int acc = n_tile & 1;
       mbar_wait(&bars->acc_full[acc], (n_tile >> 1) & 1);
@@ -211,17 +220,18 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
           }
         }
         if constexpr (kTmaStore) {
-          TO *buf = sOut + (n_chunk % p.epi_bufs) * (kEpiCols * kTileM);
+          TO *buf = sOutG + (n_chunk % p.epi_bufs) * (kEpiCols * kTileM);
           if (issuer) {                                  // the store that last read this buffer (epi_bufs chunks ago) is done
             if (p.epi_bufs == 4) tma_store_wait_read<3>();
             else if (p.epi_bufs == 3) tma_store_wait_read<2>();
-            else tma_store_wait_read<1>();
+            else if (p.epi_bufs == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
           }
-          named_barrier_sync(1, kEpiThreads);
+          named_barrier_sync(1 + 2 * group, kEpiThreads);
 #pragma unroll
           for (int i = 0; i < kEpiCols; ++i) buf[i * kTileM + px] = cvt_logit<TO>(r[i]);
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
-          named_barrier_sync(2, kEpiThreads);
+          named_barrier_sync(2 + 2 * group, kEpiThreads);
           if (issuer) {
             tma_store_3d(&tmap_out, buf, tile * kTileM, c0, b);
             tma_store_commit();
@@ -391,12 +401,14 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
   const int b_bytes = p.KB * p.Qpad * 128;
   const int esize = out_dtype == DVIS_F32 ? 4 : 2;
   const bool tma_store = !bits_row && aligned16(out) && (HW * esize) % 16 == 0 && (p.out_batch * esize) % 16 == 0;   // TMA: 16-byte pitches
-  // deepest store pipeline (up to 4 staging tiles) that still leaves >= 4 A stages
+  // deepest store pipeline (up to 4 staging tiles per epilogue group) that still leaves >= 4 A stages
+  const int groups = (bits_row || esize == 2) ? 2 : 1;          // = epi_groups<TO, kBits>() of the kernel launched below
+  const int threads = 64 + 128 * groups;
   int stage_out_bytes = 0, budget = 0;
-  for (p.epi_bufs = 4; p.epi_bufs >= 2; --p.epi_bufs) {
-    stage_out_bytes = p.epi_bufs * kEpiCols * kTileM * esize;
+  for (p.epi_bufs = 4; p.epi_bufs >= 1; --p.epi_bufs) {
+    stage_out_bytes = bits_row ? 0 : groups * p.epi_bufs * kEpiCols * kTileM * esize;
     budget = 225 * 1024 - b_bytes - 1024 - stage_out_bytes - int(sizeof(Barriers));
-    if (budget / kStageBytes >= 4 || p.epi_bufs == 2) break;
+    if (budget / kStageBytes >= 4 || p.epi_bufs == 1) break;
   }
   p.stages = std::min(kMaxStages, budget / kStageBytes);
   if (p.stages < 2) return fail(DVIS_ERR_UNSUPPORTED, "mask_logits: Q=%d, C=%d do not fit in shared memory", Q, C);
@@ -419,7 +431,7 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
 #define DVIS_LAUNCH(TO, TMA, BIAS)                                                                                   \
   do {                                                                                                               \
     cudaFuncSetAttribute(mask_gemm_kernel<TO, TMA, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));    \
-    mask_gemm_kernel<TO, TMA, BIAS><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);                         \
+    mask_gemm_kernel<TO, TMA, BIAS><<<grid, threads, smem, s>>>(tm_feat, tm_emb, tm_out, p);                         \
   } while (0)
 #define DVIS_LAUNCH_T(TO)                                                                            \
   do {                                                                                               \
@@ -429,14 +441,14 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
 #define DVIS_LAUNCH_TF32(TMA, BIAS)                                                                                              \
   do {                                                                                                                         \
     cudaFuncSetAttribute(mask_gemm_kernel<float, TMA, BIAS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
-    mask_gemm_kernel<float, TMA, BIAS, false, true><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);                   \
+    mask_gemm_kernel<float, TMA, BIAS, false, true><<<grid, threads, smem, s>>>(tm_feat, tm_emb, tm_out, p);                   \
   } while (0)
   if (tf32) {
     if (row_open) { if (tma_store) DVIS_LAUNCH_TF32(true, true); else DVIS_LAUNCH_TF32(false, true); }
     else { if (tma_store) DVIS_LAUNCH_TF32(true, false); else DVIS_LAUNCH_TF32(false, false); }
   } else if (bits_row) {
     cudaFuncSetAttribute(mask_gemm_kernel<float, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    mask_gemm_kernel<float, false, false, true><<<grid, kThreads, smem, s>>>(tm_feat, tm_emb, tm_out, p);
+    mask_gemm_kernel<float, false, false, true><<<grid, threads, smem, s>>>(tm_feat, tm_emb, tm_out, p);
   } else if (out_dtype == DVIS_F32) DVIS_LAUNCH_T(float); else DVIS_LAUNCH_T(__nv_bfloat16);
 #undef DVIS_LAUNCH_TF32
 #undef DVIS_LAUNCH_T

@@ -23,9 +23,11 @@ def main():
         feat_nchw = feat.contiguous()
         feat32 = feat_nchw.float()
         emb32 = emb.float()
+        feat32_cl = feat32.contiguous(memory_format=torch.channels_last)
         variants = {
             "ours_tcgen05_out_bf16": (lambda: ops.mask_logits(emb, feat, torch.bfloat16), 2, 2),
-            "ours_tcgen05_out_f32": (lambda: ops.mask_logits(emb, feat, torch.float32), 2, 4),
+            "ours_tcgen05_out_f32": (lambda: ops.mask_logits(emb, feat, torch.float32, operand_dtype=torch.bfloat16), 2, 4),
+            "ours_tcgen05_tf32_operands_out_f32": (lambda: ops.mask_logits(emb32, feat32_cl, torch.float32, operand_dtype=torch.float32), 4, 4),
             "cublas_einsum_bf16_nchw": (lambda: torch.einsum("bqc,bchw->bqhw", emb, feat_nchw), 2, 2),
             "cublas_einsum_fp32_nchw": (lambda: torch.einsum("bqc,bchw->bqhw", emb32, feat32), 4, 4),
         }
