@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include <cstdarg>
@@ -38,6 +39,22 @@ inline int check_launch(const char *what) {
   do {                          \
     if (!(cond)) return ::dvis::fail(DVIS_ERR_INVALID, __VA_ARGS__); \
   } while (0)
+
+// Experiment switch DVIS_SMEM_CARVEOUT = 0..100 (unset: the driver's choice): preferred shared-memory carve-out applied to a kernel
+// before its launch.  Motivation (tests/perf/interference_probe.py): next to the per-frame stage's big kernels, a tiny kernel of
+// the temporal stage is nearly free when it needs no shared memory (0.01 - 0.2 us of the big stream lost per tiny kernel) and costs
+// 0.7 - 2 us when it needs a large shared-memory configuration the SM is not in.
+inline int smem_carveout_pct() {
+  static const int v = getenv("DVIS_SMEM_CARVEOUT") ? atoi(getenv("DVIS_SMEM_CARVEOUT")) : -1;
+  return v;
+}
+template <typename K>
+inline void prefer_carveout(K kern) {
+#ifndef DVIS_SIMT_EMULATION
+  const int v = smem_carveout_pct();
+  if (v >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+#endif
+}
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

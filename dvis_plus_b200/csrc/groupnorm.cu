@@ -194,6 +194,7 @@ extern "C" int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_s
   const int nchunks = (HW + kGnChunk - 1) / kGnChunk;
   double *partials = sums_workspace + (size_t)2 * N * G;      // workspace layout: [N*G*2 sums][N*nchunks*G*2 partials]
   dim3 grid(nchunks, N);
+  prefer_carveout(gn_partial_kernel<__nv_bfloat16>);
   if (x_dtype == DVIS_F32)
     gn_partial_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(x), x_batch_stride, HW, C, G, partials);
   else
@@ -206,6 +207,7 @@ extern "C" int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_s
   const int apply_pix = 64;                                     // 16 pixels per thread row at C = 256
   dim3 agrid((HW + apply_pix - 1) / apply_pix, N);
   using bf = __nv_bfloat16;
+  prefer_carveout(gn_apply_kernel<bf, bf>);
   if (x_dtype == DVIS_F32 && lp_dtype == DVIS_F32) gn_apply_kernel<float, float><<<agrid, 256, 0, s>>>(p, apply_pix);
   else if (x_dtype == DVIS_F32) gn_apply_kernel<float, bf><<<agrid, 256, 0, s>>>(p, apply_pix);
   else if (lp_dtype == DVIS_F32) gn_apply_kernel<bf, float><<<agrid, 256, 0, s>>>(p, apply_pix);

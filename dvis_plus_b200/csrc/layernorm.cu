@@ -111,7 +111,7 @@ int launch_ln(const LnParams &p, cudaStream_t s) {
   else if (vpl == 7) vpl = 8;
   else if (vpl > 8) vpl = 16;
   switch (vpl) {
-#define DVIS_LN(V) case V: add_layernorm_kernel<TX, TR, TL, V><<<grid, warps * 32, 0, s>>>(p); break;
+#define DVIS_LN(V) case V: prefer_carveout(add_layernorm_kernel<TX, TR, TL, V>); add_layernorm_kernel<TX, TR, TL, V><<<grid, warps * 32, 0, s>>>(p); break;
     DVIS_LN(1) DVIS_LN(2) DVIS_LN(3) DVIS_LN(4) DVIS_LN(6) DVIS_LN(8) DVIS_LN(16)
 #undef DVIS_LN
     default: return fail(DVIS_ERR_UNSUPPORTED, "add_layernorm: C=%d", p.C);

@@ -101,6 +101,7 @@ extern "C" int dvis_level_tokens(const void *x, int x_dtype, int64_t x_batch_str
   const int blocks = int(std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 32));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto *t = static_cast<__nv_bfloat16 *>(tok), *k = static_cast<__nv_bfloat16 *>(key);
+  prefer_carveout(level_tokens_kernel<__nv_bfloat16>);
   if (x_dtype == DVIS_F32)
     level_tokens_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float *>(x), x_batch_stride, level_embed, pos, t, k, B, HW, C);
   else if (x_dtype == DVIS_BF16)
@@ -114,6 +115,7 @@ extern "C" int dvis_resize_bilinear_nhwc(const void *in, int N, int h, int w, in
   DVIS_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "resize_bilinear_nhwc: bad sizes (C %% 4 == 0)");
   const int64_t total = (int64_t)N * H * W * (C / 4);
   const int blocks = int(std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 32));
+  prefer_carveout(resize_bilinear_nhwc_kernel);
   resize_bilinear_nhwc_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16 *>(in), static_cast<__nv_bfloat16 *>(out), N, h, w, H, W, C);
   return check_launch("resize_bilinear_nhwc_kernel");

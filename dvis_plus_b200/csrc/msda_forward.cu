@@ -522,6 +522,7 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 48 * 1024))) != cudaSuccess)
     return check_launch("msda_fwd_staged_kernel (shared-memory opt-in)");
   dim3 grid((per_batch + p.items_per_cta - 1) / p.items_per_cta, p.N);
+  if (getenv("DVIS_SMEM_CARVEOUT_MSDA")) prefer_carveout(kern);   // the gather lives on its L1 hits: excluded from the experiment by default
   kern<<<grid, kThreads, smem, stream>>>(p);
   return check_launch("msda_fwd_staged_kernel");
 }

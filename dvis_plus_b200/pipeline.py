@@ -405,7 +405,8 @@ class GraphedClipRunner:
     overlaps stage A of clip i+1 (bandwidth / tensor bound) on a second stream.
     """
 
-    def __init__(self, runner: OfflineClipRunner, example_features, depth=2, vis=None, d2h_stream=False):
+    def __init__(self, runner: OfflineClipRunner, example_features, depth=2, vis=None, d2h_stream=False, eager_b=False,
+                 stream_a=None, stream_b=None):
         """d2h_stream: copy the results to the host on a stream of their own instead of the temporal stage's stream, so a
         clip's device->host copy no longer delays the NEXT clip's temporal stage (opt-in until timed on a B200).
         vis: None -> stage B ends with all Q mask logits (temporal_from_block); or a dict(post=VideoPostProcessor,
@@ -414,9 +415,14 @@ class GraphedClipRunner:
         self.r = runner
         self.depth = depth
         self.vis = vis
+        # eager_b: stage B is not one big captured graph but is issued from the host on its stream (the tracker then replays
+        # its own small per-frame graphs): measured with tests/perf/stage_overlap_probe.py
+        self.eager_b = eager_b
         self.slots = []
-        self.stream_a = torch.cuda.Stream()
-        self.stream_b = torch.cuda.Stream(priority=-1)           # latency-bound stage: its tiny kernels go first
+        # stream_a / stream_b: optional externally created streams (e.g. streams of two green contexts = disjoint SM partitions,
+        # dvis_plus_b200.partition.sm_partition_streams)
+        self.stream_a = stream_a if stream_a is not None else torch.cuda.Stream()
+        self.stream_b = stream_b if stream_b is not None else torch.cuda.Stream(priority=-1)   # latency-bound stage: its tiny kernels go first
         self.stream_c = torch.cuda.Stream()                      # host -> device copies of the next clip's inputs
         self.stream_d = torch.cuda.Stream() if d2h_stream else None   # device -> host copies of the results
         self.n = 0
@@ -484,7 +490,14 @@ class GraphedClipRunner:
                 dist.all_gather_into_tensor(slot["gathered"], slot["block"], group=self.r.group)
             else:
                 slot["gathered"].copy_(slot["block"])
-            slot["gb"].replay()
+            if self.eager_b:
+                with torch.no_grad():
+                    slot["out"] = self._stage_b(slot["gathered"], slot["mf"], self._C(slot["block"]))
+                if self.stream_d is not None:
+                    for v in slot["out"].values():
+                        v.record_stream(self.stream_d)
+            else:
+                slot["gb"].replay()
             if d2h is not None and self.stream_d is None:
                 for k, v in d2h.items():
                     v.copy_(slot["out"][k], non_blocking=True)

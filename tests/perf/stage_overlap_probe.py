@@ -51,12 +51,35 @@ def measure(fused):
     out["stage_a_graph_alone_ms"] = round(loop_ms(a_only), 3)
     out["stage_b_graph_alone_ms"] = round(loop_ms(b_only), 3)
 
-    def piped():
-        g.submit()
-    t = loop_ms(lambda: (piped(), None)[1], n=15, warm=6)
-    g.wait_all()
-    torch.cuda.synchronize()
-    out["pipelined_ms_per_clip"] = round(t, 3)
+    def pipelined(runner_g, n=15, warm=6):
+        for _ in range(warm):
+            runner_g.submit()
+        runner_g.wait_all()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            runner_g.submit()
+        runner_g.wait_all()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    out["pipelined_ms_per_clip"] = round(pipelined(g), 3)
+    g2 = GraphedClipRunner(runner, feats, depth=3, d2h_stream=True, eager_b=True)
+    out["pipelined_ms_per_clip_stage_b_issued_eagerly"] = round(pipelined(g2), 3)
+    del g2
+    if not fused:
+        from dvis_plus_b200.partition import sm_partition_streams
+        for n_small in (8, 16, 24, 32, 48):
+            try:
+                sa, sb, info = sm_partition_streams(n_small)
+                g3 = GraphedClipRunner(runner, feats, depth=3, d2h_stream=True, stream_a=sa, stream_b=sb)
+                out[f"pipelined_ms_per_clip_sm_partition_{info['sms_big']}+{info['sms_small']}"] = round(pipelined(g3), 3)
+                print(n_small, info["sms_big"], info["sms_small"], out[f"pipelined_ms_per_clip_sm_partition_{info['sms_big']}+{info['sms_small']}"], flush=True)
+                del g3
+            except Exception as e:   # noqa: BLE001
+                out[f"sm_partition_{n_small}_error"] = repr(e)[:300]
+                print("partition", n_small, "failed:", repr(e)[:300], flush=True)
     # stage-B wall duration inside the pipelined loop: events recorded on the temporal stream around the graph replay
     starts, ends = [], []
     orig = [s["gb"] for s in g.slots]

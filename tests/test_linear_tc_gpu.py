@@ -143,3 +143,22 @@ def test_pixel_decoder_tensor_core_path_matches_library_path():
     for a, b in zip(outs[True], outs[False]):
         assert torch.isfinite(a).all()
         assert _rel(a, b) < 2e-2
+
+
+def test_sm_partition_streams_run_kernels_on_disjoint_sm_sets():
+    """dvis_plus_b200.partition: two green-context streams (driver API through cuda-python); kernels launched on either give the
+    same results as on the default stream, and the partition sizes add up to the device."""
+    from dvis_plus_b200 import ops
+    from dvis_plus_b200.partition import sm_partition_streams
+    big, small, info = sm_partition_streams(16)
+    assert info["sms_small"] >= 16 and info["sms_big"] + info["sms_small"] <= torch.cuda.get_device_properties(0).multi_processor_count
+    x, w, b = _case((1000,), 256, 256, 7)
+    ref = ops.linear_tc(x, w, b)
+    torch.cuda.synchronize()
+    outs = []
+    for st in (big, small):
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            outs.append(ops.linear_tc(x, w, b))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
