@@ -279,6 +279,8 @@ def main():
     set_precision(args.precision)
     _lib.lib()
     runner = build_models(dev, queries=Q, backbone=backbone)
+    if os.environ.get("DVIS_BENCH_TRACKER_LIBRARY_ATTENTION"):       # experiment switch (profiles/r2_stage_overlap_probe.json)
+        runner.tracker.use_custom_attention = False
     t_local = T // world
     host = synthetic_features(T, backbone, pin=False)
     host = {k: v[rank * t_local:(rank + 1) * t_local].contiguous(memory_format=torch.channels_last).pin_memory() for k, v in host.items()}

@@ -23,6 +23,7 @@ SIGNATURES = {
     "dvis_msda_fused_forward_hm": [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "dvis_msda_pack_pairs": [_vp, _i, _i, _i, _i, _vp, _vp],
     "dvis_msda_pair_forward": [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "dvis_mask_logits_clip": [_vp, _vp, _i, _i, _i, _i64, _vp, _i, _vp],
     "dvis_mask_logits_tf32": [_vp, _vp, _i, _i, _i, _i64, _vp, _vp],
     "dvis_mask_attn_bias_tf32": [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp],
     "dvis_linear_tc": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp],

@@ -45,6 +45,7 @@ struct MaskGemmParams {
   int tiles_per_batch, total_tiles, stages;
   int *row_open;        // kBias epilogue: row_open[b*Q + q] = 1 if some pixel of the row has logit >= 0
   int64_t out_batch;    // elements between batch items of `out` (Q*HW when dense; larger for a query slice)
+  int64_t out_row;      // elements between query rows of `out` (HW when dense; B*HW for the query-major clip layout (Q, B, HW))
   int epi_bufs;         // output staging tiles in flight (2..4): depth of the TMA-store pipeline
   uint8_t *bits;        // kBits epilogue: (B*Q) rows of bits_row bytes, bit (p % 8) of byte (p / 8) set <=> logit[p] < 0
   int64_t bits_row;
@@ -239,9 +240,9 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
         } else {
           const int64_t pix = (int64_t)tile * kTileM + px;
           if (pix < p.HW) {
-            TO *dst = static_cast<TO *>(p.out) + (int64_t)b * p.out_batch + (int64_t)c0 * p.HW + pix;
+            TO *dst = static_cast<TO *>(p.out) + (int64_t)b * p.out_batch + (int64_t)c0 * p.out_row + pix;
             const int nq = min(kEpiCols, p.Q - c0);
-            for (int i = 0; i < nq; ++i) dst[(int64_t)i * p.HW] = cvt_logit<TO>(r[i]);
+            for (int i = 0; i < nq; ++i) dst[(int64_t)i * p.out_row] = cvt_logit<TO>(r[i]);
           }
         }
       }
@@ -259,11 +260,12 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
 
 // 3-D map over a dense (batch, rows, inner) tensor; box = (box_inner, box_rows, 1)
 int encode_map(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int esize, uint64_t inner, uint64_t rows,
-               uint64_t batch, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz, uint64_t batch_stride = 0) {
+               uint64_t batch, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz, uint64_t batch_stride = 0,
+               uint64_t row_stride = 0) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(DVIS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[3] = {inner, rows, batch};
-  const cuuint64_t strides[2] = {inner * esize, (batch_stride ? batch_stride : inner * rows) * esize};   // bytes, dims 1..2
+  const cuuint64_t strides[2] = {(row_stride ? row_stride : inner) * esize, (batch_stride ? batch_stride : inner * rows) * esize};   // bytes, dims 1..2
   const cuuint32_t box[3] = {box_inner, box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr,
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(128) reset_closed_bit_rows_kernel(const int *_
 }  // namespace
 int mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
                      int *row_open, void *stream, int64_t emb_batch = 0, int64_t out_batch = 0, int64_t bits_row = 0,
-                     int row_batch = 0, bool tf32 = false);
+                     int row_batch = 0, bool tf32 = false, int64_t out_row = 0);
 }  // namespace dvis
 
 extern "C" int dvis_mask_logits(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out,
@@ -311,6 +313,15 @@ extern "C" int dvis_mask_logits_strided(const void *emb, int64_t emb_batch_strid
   DVIS_REQUIRE(emb_batch_stride >= (int64_t)Q * C && out_batch_stride >= (int64_t)Q * HW, "mask_logits_strided: batch strides too small");
   DVIS_REQUIRE(emb_batch_stride % 8 == 0, "mask_logits_strided: emb batch stride must be a multiple of 8 elements (16 bytes)");
   return mask_gemm_launch(emb, feat, B, Q, C, HW, out, out_dtype, nullptr, stream, emb_batch_stride, out_batch_stride);
+}
+
+// The mask logits of a CLIP in the layout the meta-architecture keeps them in, (Q, T, H, W) = "b q t h w" with b = 1
+// (P/dvis_Plus/refiner.py:185-189 "lbtqc,btchw->lbqthw"): frame t is a batch item of the GEMM whose rows are written T*HW apart --
+// no transposition pass over the (T, Q, HW) result (377 MB at T = 16, Q = 200, 720p, bf16).
+extern "C" int dvis_mask_logits_clip(const void *emb, const void *feat, int T, int Q, int C, int64_t HW, void *out, int out_dtype,
+                                     void *stream) {
+  DVIS_REQUIRE(Q <= 256, "mask_logits_clip: Q must be <= 256 (got %d)", Q);
+  return mask_gemm_launch(emb, feat, T, Q, C, HW, out, out_dtype, nullptr, stream, 0, HW, 0, 0, false, (int64_t)T * HW);
 }
 
 extern "C" int dvis_mask_attn_bias(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *bias,
@@ -377,7 +388,7 @@ extern "C" int dvis_mask_attn_bias_tf32(const void *emb, const void *feat, int B
 
 int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, int out_dtype,
                            int *row_open, void *stream, int64_t emb_batch, int64_t out_batch, int64_t bits_row, int row_batch,
-                           bool tf32) {
+                           bool tf32, int64_t out_row) {
   DVIS_REQUIRE(emb && feat && out, "mask_logits: null pointer argument");
   DVIS_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_logits: sizes must be positive");
   const int blk = tf32 ? 32 : kBlockK;                         // operand elements per 128-byte k-block row
@@ -396,11 +407,12 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
   p.bits_row = bits_row;
   p.row_batch = row_batch ? row_batch : Q;
   p.out_batch = out_batch ? out_batch : (int64_t)Q * HW;
+  p.out_row = out_row ? out_row : HW;
   p.tiles_per_batch = int((HW + kTileM - 1) / kTileM);
   p.total_tiles = p.tiles_per_batch * B;
   const int b_bytes = p.KB * p.Qpad * 128;
   const int esize = out_dtype == DVIS_F32 ? 4 : 2;
-  const bool tma_store = !bits_row && aligned16(out) && (HW * esize) % 16 == 0 && (p.out_batch * esize) % 16 == 0;   // TMA: 16-byte pitches
+  const bool tma_store = !bits_row && aligned16(out) && (p.out_row * esize) % 16 == 0 && (p.out_batch * esize) % 16 == 0;   // TMA: 16-byte pitches
   // deepest store pipeline (up to 4 staging tiles per epilogue group) that still leaves >= 4 A stages
   const int groups = (bits_row || esize == 2) ? 2 : 1;          // = epi_groups<TO, kBits>() of the kernel launched below
   const int threads = 64 + 128 * groups;
@@ -421,7 +433,7 @@ int dvis::mask_gemm_launch(const void *emb, const void *feat, int B, int Q, int 
   if (int rc = encode_map(&tm_emb, emb, in_dt, in_es, C, Q, B, blk, p.Qpad, CU_TENSOR_MAP_SWIZZLE_128B, emb_batch)) return rc;
   if (tma_store) {
     if (int rc = encode_map(&tm_out, out, out_dtype == DVIS_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                            esize, HW, Q, B, kTileM, kEpiCols, CU_TENSOR_MAP_SWIZZLE_NONE, p.out_batch)) return rc;
+                            esize, HW, Q, B, kTileM, kEpiCols, CU_TENSOR_MAP_SWIZZLE_NONE, p.out_batch, p.out_row)) return rc;
   } else {
     tm_out = tm_emb;   // unused by the direct-store variant; any valid map
   }

@@ -49,6 +49,24 @@ class TemporalRefiner(nn.Module):
         y = F.conv1d(rep(F.relu(y), 1), c3.weight.to(dt), c3.bias.to(dt))
         return y
 
+    def _short_conv_rows(self, i, xt):
+        """The same two convolutions over time as GEMMs on rows (bq, t): xt (bq, t, c) in the GEMM dtype -> (bq, t, c).
+        A[(q, t), (k, ci)] = x[q, clamp(t + k - pad), ci] is one gather per convolution (replicate padding = clamped indices)
+        and the convolution one cuBLAS GEMM with the ReLU in its epilogue -- instead of cat (padding) + cuDNN's NCHW <-> NHWC
+        conversion kernels around each Conv1d (15 -> 7 launches per layer; py:44-52,116-119)."""
+        c5, c3 = self.conv_short_aggregate_layers[i][0], self.conv_short_aggregate_layers[i][2]
+        dt, T = xt.dtype, xt.shape[1]
+        key = (dt, c5.weight._version, c3.weight._version, c5.weight.data_ptr(), str(xt.device), T)
+        cache = self.__dict__.setdefault("_conv_rows_cache", {})
+        if cache.get(i, (None,))[0] != key:
+            rows = lambda conv: conv.weight.detach().permute(0, 2, 1).reshape(conv.out_channels, -1).to(dt).contiguous()   # (co, k*ci)
+            idx = lambda k: (torch.arange(T, device=xt.device)[:, None] + torch.arange(k, device=xt.device)[None] - k // 2).clamp_(0, T - 1)
+            cache[i] = (key, rows(c5), c5.bias.detach().to(dt), rows(c3), c3.bias.detach().to(dt), idx(5), idx(3))
+        _, w5, b5, w3, b3, i5, i3 = cache[i]
+        bq, _, C = xt.shape
+        h = torch._addmm_activation(b5, xt[:, i5].reshape(bq * T, 5 * C), w5.t())            # ReLU in the GEMM epilogue
+        return torch.addmm(b3, h.view(bq, T, -1)[:, i3].reshape(bq * T, 3 * h.shape[-1]), w3.t()).view(bq, T, -1)
+
     # opt-in (bf16 mode, batch 1): the layers run on csrc/small_linear.cu + csrc/flash_attn.cu only (14 launches each).
     # Parity-green but slower than the library GEMMs at T*Q = 3 200 rows (4.7 ms vs 1.8 ms per clip): off by default
     use_fused_kernels = False
@@ -146,10 +164,16 @@ class TemporalRefiner(nn.Module):
         for i in range(self.num_layers):
             output = output.permute(2, 0, 3, 1).flatten(1, 2)                        # (t, bq, c)
             output = self.transformer_time_self_attention_layers[i](output, tgt_mask=None, tgt_key_padding_mask=None, query_pos=None)
-            output = output.permute(1, 2, 0)                                         # (bq, c, t)
-            y = self._short_conv(i, output)
-            output = add_norm(self.conv_norms[i], y.transpose(1, 2).contiguous(), output.transpose(1, 2).contiguous()).transpose(1, 2)
-            output = output.reshape(n_batch, n_instance, n_channel, n_frames).permute(1, 0, 3, 2).flatten(1, 2)   # (q, bt, c)
+            if _fast_path(output) and not self.training:
+                xt = output.permute(1, 0, 2).contiguous()                            # (bq, t, c): rows for the conv GEMMs and the residual
+                y = self._short_conv_rows(i, xt.to(gemm_dtype()))
+                output = add_norm(self.conv_norms[i], y, xt)                         # (bq, t, c)
+                output = output.reshape(n_batch, n_instance, n_frames, n_channel).permute(1, 0, 2, 3).flatten(1, 2)   # (q, bt, c)
+            else:
+                output = output.permute(1, 2, 0)                                     # (bq, c, t)
+                y = self._short_conv(i, output)
+                output = add_norm(self.conv_norms[i], y.transpose(1, 2).contiguous(), output.transpose(1, 2).contiguous()).transpose(1, 2)
+                output = output.reshape(n_batch, n_instance, n_channel, n_frames).permute(1, 0, 3, 2).flatten(1, 2)   # (q, bt, c)
             output = self.transformer_obj_self_attention_layers[i](output, tgt_mask=None, tgt_key_padding_mask=None, query_pos=None)
             output = self.transformer_cross_attention_layers[i](output, frame_embeds, memory_mask=None,
                                                                 memory_key_padding_mask=None, pos=None, query_pos=None)
@@ -189,6 +213,11 @@ class TemporalRefiner(nn.Module):
         """einsum "lbtqc,btchw->lbqthw" (py:185-189,223)."""
         if _fast_path(mask_features):
             l, b, t, q, c = mask_embed.shape
+            if b == 1 and q <= 256 and gemm_dtype() == torch.bfloat16:
+                # one clip: the GEMM writes "q t h w" directly (no transposition of the (t, q, h, w) result)
+                return torch.stack([ops.mask_logits_clip(mask_embed[li, 0], mask_features[0], self.mask_dtype)[None]
+                                    for li in range(l)], 0) if l > 1 else \
+                    ops.mask_logits_clip(mask_embed[0, 0], mask_features[0], self.mask_dtype)[None, None]
             feats = mask_features.flatten(0, 1)
             out = [ops.mask_logits(mask_embed[li].flatten(0, 1), feats, self.mask_dtype)
                    .reshape(b, t, q, *mask_features.shape[-2:]).permute(0, 2, 1, 3, 4) for li in range(l)]

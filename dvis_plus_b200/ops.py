@@ -229,6 +229,22 @@ def mask_logits(mask_embed, mask_features, out_dtype=torch.float32, operand_dtyp
     return out
 
 
+def mask_logits_clip(mask_embed, mask_features, out_dtype=torch.float32):
+    """Mask logits of a clip, written query-major (dvis_mask_logits_clip): mask_embed (T, Q, C), mask_features (T, C, H, W) bf16
+    channels_last -> (Q, T, H, W): the "q t h w" layout the meta-architecture keeps, without a transposition pass."""
+    T, Q, C = mask_embed.shape
+    Tf, Cf, H, W = mask_features.shape
+    assert Tf == T and Cf == C and Q <= 256 and mask_features.is_cuda
+    feat = mask_features
+    if feat.dtype != torch.bfloat16 or not feat.is_contiguous(memory_format=torch.channels_last):
+        feat = feat.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    emb = mask_embed.to(torch.bfloat16).contiguous()
+    out = torch.empty((Q, T, H, W), dtype=out_dtype, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.call("dvis_mask_logits_clip", emb.data_ptr(), feat.data_ptr(), T, Q, C, H * W, out.data_ptr(), _DTYPE[out_dtype], _stream())
+    return out
+
+
 def add_layernorm(x, residual, weight, bias, eps=1e-5, *, want_f32=True, lp_dtype=None, pos=None):
     """LayerNorm(x + residual) in one pass (dvis_add_layernorm).
 

@@ -262,6 +262,11 @@ int dvis_lap_rect(const float *cost, int B, int rows, int cols, int64_t *row_to_
 int dvis_mask_logits_strided(const void *emb, int64_t emb_batch_stride, const void *feat, int B, int Q, int C, int64_t HW,
                              void *out, int64_t out_batch_stride, int out_dtype, void *stream);
 
+/* dvis_mask_logits for the T frames of a clip, written query-major: out (Q, T, HW) -- the "b q t h w" layout (b = 1) of
+ * P/dvis_Plus/refiner.py:185-189 / tracker.py:379 -- instead of (T, Q, HW); emb (T, Q, C) bf16, feat (T, HW, C) bf16, Q <= 256. */
+int dvis_mask_logits_clip(const void *emb, const void *feat, int T, int Q, int C, int64_t HW, void *out, int out_dtype,
+                          void *stream);
+
 /* The same two operators with fp32 operands multiplied as TF32 (tcgen05 kind::tf32) and fp32 results: the mask head of the
  * reference when it runs without autocast (decoder.py:363), inside 1e-3 of the output scale.  emb (B, Q, C) f32, feat (B, HW, C)
  * f32 (channels-last), out / bias (B, Q, HW) f32; any Q (query slices of 128 inside); row_open_workspace B*Q ints.

@@ -83,6 +83,18 @@ extern "C" int dvis_mask_attn_bits(const void *emb, const void *feat, int B, int
     }
   return 0;
 }
+extern "C" int dvis_mask_logits_clip(const void *emb, const void *feat, int T, int Q, int C, int64_t HW, void *out, int out_dtype, void *) {
+  const auto *e = static_cast<const __nv_bfloat16 *>(emb), *f = static_cast<const __nv_bfloat16 *>(feat);
+  for (int t = 0; t < T; ++t)
+    for (int q = 0; q < Q; ++q)
+      for (int64_t p = 0; p < HW; ++p) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc += float(e[((int64_t)t * Q + q) * C + c]) * float(f[((int64_t)t * HW + p) * C + c]);
+        const int64_t o = ((int64_t)q * T + t) * HW + p;
+        if (out_dtype == DVIS_F32) static_cast<float *>(out)[o] = acc; else static_cast<__nv_bfloat16 *>(out)[o] = __nv_bfloat16(acc);
+      }
+  return 0;
+}
 // fp32-operand (TF32 on the device) variants: exact fp32 here
 extern "C" int dvis_mask_logits_tf32(const void *emb, const void *feat, int B, int Q, int C, int64_t HW, void *out, void *) {
   mask_gemm_double<float, float>(static_cast<const float *>(emb), (int64_t)Q * C, static_cast<const float *>(feat), B, Q, C, HW,

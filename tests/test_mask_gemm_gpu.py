@@ -71,6 +71,19 @@ def test_mask_attn_bias_tf32_operands():
     assert torch.equal(bias[safe], ref.float()[safe])
 
 
+@pytest.mark.parametrize("T,Q,H,W,dt", [(16, 200, 46, 80, torch.bfloat16), (3, 100, 23, 40, torch.float32), (5, 7, 5, 7, torch.bfloat16),
+                                        (2, 256, 16, 24, torch.float32)])
+def test_mask_logits_clip_layout(T, Q, H, W, dt):
+    """dvis_mask_logits_clip writes "q t h w" (refiner.py:185-189) directly: bit-identical to the (t, q, h, w) GEMM transposed."""
+    from dvis_plus_b200 import ops
+    emb, feat = _case(T, Q, 256, H, W, seed=T)
+    feat_cl = feat.cuda().to(torch.bfloat16, memory_format=torch.channels_last)
+    ref = ops.mask_logits(emb.cuda(), feat_cl, dt, operand_dtype=torch.bfloat16).permute(1, 0, 2, 3)
+    out = ops.mask_logits_clip(emb.cuda(), feat_cl, dt)
+    assert out.shape == (Q, T, H, W) and out.is_contiguous() and out.dtype == dt
+    assert torch.equal(out, ref)
+
+
 def test_mask_logits_golden_mask_head(golden):
     """The mask head's einsum on the reference's own fixture (mask_embed recomputed by the oracle port)."""
     from dvis_plus_b200 import ops
