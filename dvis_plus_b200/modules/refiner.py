@@ -151,9 +151,84 @@ class TemporalRefiner(nn.Module):
         outs.append(ops.add_layernorm(src, None, *pending, eps)[0])
         return torch.stack(outs, 0).view(L, T, Q, 1, C).permute(1, 0, 2, 3, 4)                     # (t, l, q, b, c)
 
+    def _attend(self, q, k, v, scale, out=None):
+        """(B, Lq, H, dh) x (B, Lk, H, dh) views -> (B, Lq, H*dh) bf16 (written into the view `out` when given): csrc/flash_attn.cu
+        where it measured faster than cuDNN's SDPA (blocks.flash_attn_wins), else SDPA on the same strided views."""
+        from .blocks import flash_attn_wins
+        B, Lq, H, dh = q.shape
+        if flash_attn_wins(B, H, Lq):
+            return ops.flash_attn(q, k, v, scale, out=out)
+        o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), scale=scale)   # (B, H, Lq, dh)
+        o = o.transpose(1, 2).reshape(B, Lq, H * dh)
+        if out is not None:
+            out.copy_(o)
+            return out
+        return o
+
+    def _refine_rows(self, instance_embeds, frame_embeds):
+        """py:104-145 for batch 1 (bf16 inference) with the tokens kept as (t, q, c) rows throughout: the same cuBLAS GEMMs as the
+        module path, but no (t, bq, c) <-> (q, bt, c) <-> (b, c, t, q) permutation copies between the blocks, attention on strided
+        views of the packed QKV projections, the residual + LayerNorm kernel after every block, the convolutions over time as
+        one row gather + one GEMM each (replicate padding = clamped frame index): 21 launches per layer."""
+        f = self._stacked()
+        L, C, H = self.num_layers, f["C"], self.num_heads
+        dh = C // H
+        _, _, T, Q = instance_embeds.shape
+        scale = 1.0 / (dh ** 0.5)
+        eps = self.decoder_norm.eps
+        bf = torch.bfloat16
+        dev = instance_embeds.device
+        if "b16" not in f:                                            # bf16 copies of the biases for cuBLAS's epilogue
+            f["b16"] = [{k: p[k][1].to(bf) for k in ("t_qkv", "t_o", "c5", "c3", "o_qkv", "o_o", "x_q", "x_o", "f1", "f2")} for p in f["layers"]]
+            f["b_kv16"] = f["b_kv"].to(bf)
+            f["taps"] = {}
+        if (T, Q, str(dev)) not in f["taps"]:
+            def rows(k):   # source row of (row (t, q), tap j): clamp(t + j - k // 2) * Q + q
+                t = (torch.arange(T, device=dev)[:, None] + torch.arange(k, device=dev)[None] - k // 2).clamp_(0, T - 1)   # (T, k)
+                return (t[:, None, :] * Q + torch.arange(Q, device=dev)[None, :, None]).reshape(T * Q, k)
+            f["taps"][(T, Q, str(dev))] = (rows(5), rows(3))
+        r5, r3 = f["taps"][(T, Q, str(dev))]
+
+        def lin(i, name, x, relu=False):
+            w, b = f["layers"][i][name][0], f["b16"][i][name]
+            return torch._addmm_activation(b, x, w.t()) if relu else torch.addmm(b, x, w.t())
+        ln = lambda y, res, g: ops.add_layernorm(y, res, g[0], g[1], eps, lp_dtype=bf)[:2]
+        x32 = instance_embeds[0].permute(1, 2, 0).float().contiguous().view(T * Q, C)              # rows t*Q + q, fp32 stream
+        x16 = x32.to(bf)
+        mem = frame_embeds[0].permute(1, 2, 0).to(bf).contiguous().view(T * Q, C)
+        kv = torch.addmm(f["b_kv16"], mem, f["w_kv"].t()).view(T, Q, L, 2, H, dh)                  # all layers' cross-attention K / V
+        outs = []
+        for i in range(L):
+            p = f["layers"][i]
+            # time self-attention: every query attends over its own T frames (py:105-113)
+            qkv = lin(i, "t_qkv", x16).view(T, Q, 3, H, dh).permute(1, 0, 2, 3, 4)                 # (q, t, 3, H, dh) view
+            o = torch.empty((T, Q, C), dtype=bf, device=dev)
+            self._attend(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, out=o.permute(1, 0, 2))  # written as (t, q, c) rows
+            x32, x16 = ln(lin(i, "t_o", o.view(T * Q, C)), x32, p["ln_t"])
+            # short-term convolution over time (py:116-119)
+            h = lin(i, "c5", x16[r5].view(T * Q, 5 * C), relu=True)
+            x32, x16 = ln(lin(i, "c3", h[r3].view(T * Q, 3 * C)), x32, p["ln_c"])
+            # object self-attention within each frame (py:125-129)
+            qkv = lin(i, "o_qkv", x16).view(T, Q, 3, H, dh)
+            o = self._attend(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale)
+            x32, x16 = ln(lin(i, "o_o", o.reshape(T * Q, C)), x32, p["ln_o"])
+            # cross-attention to the same frame's segmenter queries (py:132-137)
+            q = lin(i, "x_q", x16).view(T, Q, H, dh)
+            o = self._attend(q, kv[:, :, i, 0], kv[:, :, i, 1], scale)
+            x32, x16 = ln(lin(i, "x_o", o.reshape(T * Q, C)), x32, p["ln_x"])
+            # FFN (py:140-142)
+            x32, x16 = ln(lin(i, "f2", lin(i, "f1", x16, relu=True)), x32, p["ln_f"])
+            outs.append(x32)
+        return torch.stack(outs, 0).view(L, T, Q, 1, C).permute(1, 0, 2, 3, 4)                     # (t, l, q, b, c)
+
+    use_row_layout = True     # bf16 inference, batch 1: _refine_rows (library GEMMs on (t, q, c) rows)
+
     def refine(self, instance_embeds, frame_embeds):
         """The 6 refinement layers (py:104-145).  (b, c, t, q) x2 -> stacked per-layer outputs (t, l, q, b, c), fp32."""
         n_batch, n_channel, n_frames, n_instance = instance_embeds.size()
+        if (self.use_row_layout and not self.use_fused_kernels and not self.training and _fast_path(instance_embeds) and n_batch == 1
+                and gemm_dtype() == torch.bfloat16 and n_channel // self.num_heads in (32, 64) and n_channel % 4 == 0):
+            return self._refine_rows(instance_embeds, frame_embeds)
         if (self.use_fused_kernels and not self.training and _fast_path(instance_embeds) and n_batch == 1
                 and gemm_dtype() == torch.bfloat16 and n_channel % 128 == 0 and n_channel <= 512
                 and n_channel // self.num_heads in (32, 64)):

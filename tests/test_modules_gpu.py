@@ -186,6 +186,21 @@ def test_refiner_golden(golden, mode, tol):
 
 
 @torch.no_grad()
+@torch.no_grad()
+def test_refiner_row_layout_equals_module_path(golden):
+    """TemporalRefiner._refine_rows (default on the bf16 inference path) against the module-by-module path on the device."""
+    g = golden("refiner_small.pt")
+    r = build_refiner(g).cuda()
+    outs = {}
+    for rows in (True, False):
+        r.use_row_layout = rows
+        with precision("bf16"):
+            outs[rows] = r(g["instance_embeds"].cuda(), g["frame_embeds"].cuda(), g["mask_features"].cuda())
+    for k in ("pred_embds", "pred_logits", "pred_masks"):
+        assert rel_err(outs[True][k], outs[False][k].float().cpu()) < 2e-2, k
+        assert rel_err(outs[True][k], g[k]) < 3e-2, k
+
+
 def test_add_layernorm_kernel():
     from dvis_plus_b200 import ops
     torch.manual_seed(0)

@@ -161,6 +161,23 @@ def test_refiner_golden(golden, device):
         assert rel_err(o[k].float(), g[k]) < 3e-2, k
 
 
+def test_refiner_row_layout_equals_module_path(golden, device):
+    """bf16 inference, batch 1: TemporalRefiner._refine_rows (tokens as (t, q, c) rows, no permutation copies, convolutions over
+    time as gather + GEMM) against the module-by-module path of the same class; the former is what the default path runs."""
+    g = golden("refiner_small.pt")
+    r = build_refiner(g)
+    outs = {}
+    for rows in (True, False):
+        r.use_row_layout = rows
+        calls = _lib.launch_count
+        with precision("bf16"):
+            outs[rows] = r(g["instance_embeds"], g["frame_embeds"], g["mask_features"])
+        outs[rows]["launches"] = _lib.launch_count - calls
+    for k in ("pred_embds", "pred_logits", "pred_masks"):
+        assert rel_err(outs[True][k].float(), outs[False][k].float()) < 2e-2, k
+        assert rel_err(outs[True][k].float(), g[k]) < 3e-2, k
+
+
 def test_postprocessor_with_emulated_kernels_vs_reference_golden(golden, device):
     g = golden("postprocess_vis.pt")
     for name, c in g["cases"].items():
