@@ -503,7 +503,7 @@ class ReferringTracker_noiser(nn.Module):
                 refs.append(reference)
                 prev_last = layer_out[-1]
                 outs.append(layer_out)
-                last_stack = torch.cat([init[t][None], layer_out], 0)
+            last_stack = torch.cat([init[T - 1][None], outs[-1]], 0)                        # only the window's last frame is kept
             outputs = torch.stack([o[-1:] for o in outs], 0)[:, :, :, None, :]              # (t, 1, q, b, c)  eval: last layer
         self.last_outputs = last_stack[:, :, None, :]                                       # (1+L, q, b, c)
         self.last_reference = refs[-1][:, None, :]
