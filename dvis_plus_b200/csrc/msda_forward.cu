@@ -81,7 +81,12 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16, float, 4>(__nv_bfloat16
 // marks a corner outside the map (or a whole point outside (-1, size)); its offset is redirected to a valid row.
 struct PointOffsets { uint32_t o00, o01, o10, o11; };   // BYTE offsets (unsigned: one IADD3 + IADD3.X per address)
 
-template <typename A>
+constexpr uint32_t kNoCorner = 0xffffffffu;   // offset of a corner outside the map when kSkip is set: phase 2 does not load it
+
+// kSkip = false: corners outside the map keep weight 0 and are redirected to a valid row (unconditional loads: the inference
+// kernels).  kSkip = true (the plain op = the reference's own contract): their offset is kNoCorner and phase 2 SKIPS the load like
+// the reference does (cuh:61-83), so a NaN / Inf anywhere in `value` reaches exactly the outputs it reaches in the reference.
+template <typename A, bool kSkip = false>
 __device__ __forceinline__ void point_params(A x, A y, A a, int H, int W, int start, int M, int m, int lpr,
                                              PointOffsets &off, float4 &wt) {
   // un-fused multiply / subtract like the reference (cuh:290-291) so that floor() sees the same value
@@ -105,6 +110,13 @@ __device__ __forceinline__ void point_params(A x, A y, A a, int H, int W, int st
   // Phase 2 loads all four corners unconditionally; a corner outside the map (weight 0) is pointed at a valid
   // corner of the same point (or at pixel 0 of this head when the whole point is out of range), so the load is
   // always in bounds and contributes 0 * finite = 0.
+  if constexpr (kSkip) {
+    off.o00 = v00 ? uint32_t(o00) << 4 : kNoCorner;
+    off.o01 = v01 ? uint32_t(o01) << 4 : kNoCorner;
+    off.o10 = v10 ? uint32_t(o10) << 4 : kNoCorner;
+    off.o11 = v11 ? uint32_t(o11) << 4 : kNoCorner;
+    return;
+  }
   const int safe = v00 ? o00 : v01 ? o01 : v10 ? o10 : v11 ? o11 : m * lpr;
   off.o00 = uint32_t(v00 ? o00 : safe) << 4;
   off.o01 = uint32_t(v01 ? o01 : safe) << 4;
@@ -314,8 +326,8 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
         using TL = typename LocType<T>::type;   // plain op: loc / attn have the value's dtype
         const size_t i = (nq * M + m) * (size_t)LP + pt;
         const TL *lc = static_cast<const TL *>(p.loc) + 2 * i;
-        point_params<TL>(__ldg(lc), __ldg(lc + 1), __ldg(static_cast<const TL *>(p.attn) + i), H, W, start, M, m, LPR,
-                         off, wt);
+        point_params<TL, true>(__ldg(lc), __ldg(lc + 1), __ldg(static_cast<const TL *>(p.attn) + i), H, W, start, M, m, LPR,
+                               off, wt);
       }
       s_off[il * LPs + pt] = off;
       if constexpr (kMixed)
@@ -405,10 +417,18 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
       const uint4 o = so[pt];
       const float4 w = sw[pt];
       Vec16<T> v00, v01, v10, v11;
-      v00.v = __ldg(reinterpret_cast<const V *>(vb + o.x));
-      v01.v = __ldg(reinterpret_cast<const V *>(vb + o.y));
-      v10.v = __ldg(reinterpret_cast<const V *>(vb + o.z));
-      v11.v = __ldg(reinterpret_cast<const V *>(vb + o.w));
+      if constexpr (!FUSED) {          // the plain op: corners outside the map are not loaded at all (reference semantics)
+        v00.v = V{}; v01.v = V{}; v10.v = V{}; v11.v = V{};
+        if (o.x != kNoCorner) v00.v = __ldg(reinterpret_cast<const V *>(vb + o.x));
+        if (o.y != kNoCorner) v01.v = __ldg(reinterpret_cast<const V *>(vb + o.y));
+        if (o.z != kNoCorner) v10.v = __ldg(reinterpret_cast<const V *>(vb + o.z));
+        if (o.w != kNoCorner) v11.v = __ldg(reinterpret_cast<const V *>(vb + o.w));
+      } else {
+        v00.v = __ldg(reinterpret_cast<const V *>(vb + o.x));
+        v01.v = __ldg(reinterpret_cast<const V *>(vb + o.y));
+        v10.v = __ldg(reinterpret_cast<const V *>(vb + o.z));
+        v11.v = __ldg(reinterpret_cast<const V *>(vb + o.w));
+      }
       const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y), wz = make_float2(w.z, w.z), ww = make_float2(w.w, w.w);
 #pragma unroll
       for (int k = 0; k < VEC / 2; ++k) {

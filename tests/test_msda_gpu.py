@@ -234,3 +234,27 @@ def test_vit_adapter_call_site_shapes(kind):
     ref = _oracle(value, shapes, loc, attn)
     assert out.shape == (2, Lq, M * D)
     assert (out - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max())
+
+
+def test_plain_op_propagates_nonfinite_values_like_the_reference():
+    """Corners outside the map are skipped, not multiplied by 0 (ms_deform_im2col_cuda.cuh:61-83): NaN / Inf in `value` --
+    including pixel 0 of a head -- reach exactly the outputs they reach in the reference (oracle = its conditionals)."""
+    import numpy as np
+    from dvis_plus_b200 import ops
+    from oracle import c_oracle
+    g = torch.Generator().manual_seed(4)
+    sh = torch.tensor([(23, 40), (12, 20), (6, 10)])
+    lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    S = int(sh.prod(1).sum())
+    value = torch.randn(2, S, 8, 32, generator=g)
+    value[:, 0] = float("nan")
+    value[0, 500, 1, 3] = float("inf")
+    value[1, 1100, 2] = float("nan")
+    loc = torch.rand(2, 300, 8, 3, 4, 2, generator=g) * 1.6 - 0.3
+    attn = torch.rand(2, 300, 8, 3, 4, generator=g)
+    out = ops.ms_deform_attn_forward(value.cuda(), sh.cuda(), lsi.cuda(), loc.cuda(), attn.cuda(), 128).cpu().numpy()
+    ref = c_oracle.msda_forward(value.numpy(), sh.numpy(), lsi.numpy(), loc.numpy(), attn.numpy())
+    assert np.array_equal(np.isnan(out), np.isnan(ref)) and np.array_equal(np.isinf(out), np.isinf(ref))
+    assert np.isnan(ref).any() and (~np.isnan(ref)).any()
+    fin = np.isfinite(ref)
+    assert np.abs(out[fin] - ref[fin]).max() <= 2e-5 * max(1.0, np.abs(ref[fin]).max())

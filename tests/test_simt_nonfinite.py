@@ -63,3 +63,26 @@ def test_nonfinite_inputs_never_leave_the_buffers():
         assert int(s.min()) >= 0 and int(s.max()) < 9 and all(len(set(row.tolist())) == 9 for row in s)
         r = simt.lap_rect(torch.where(torch.rand(5, 8, generator=g) < 0.3, torch.tensor(bad), torch.rand(5, 8, generator=g)))
         assert int(r.max()) < 8 and len(set(r.tolist())) == 5
+
+
+def test_msda_plain_op_propagates_nonfinite_values_like_the_reference():
+    """The plain op skips corners outside the map (ms_deform_im2col_cuda.cuh:61-83) instead of multiplying a redirected row by 0:
+    a NaN / Inf in `value` -- also at pixel 0 of a head, where round 1's kernel leaked it into every fully-outside point --
+    reaches exactly the outputs it reaches in the reference (oracle/msda_oracle.c restates the reference's conditionals)."""
+    import numpy as np
+    from oracle import c_oracle
+    g = torch.Generator().manual_seed(4)
+    sh, lsi, S = torch.tensor([(6, 9), (3, 5)]), torch.tensor([0, 54]), 69
+    for D in (32, 8):
+        value = torch.randn(2, S, 4, D, generator=g)
+        value[:, 0] = float("nan")                    # pixel 0 of every head (the redirect target of round 1's kernel)
+        value[0, 17, 1, 3] = float("inf")
+        value[1, 60, 2] = float("nan")
+        loc = torch.rand(2, 23, 4, 2, 4, 2, generator=g) * 1.6 - 0.3        # many points partly or fully outside the maps
+        attn = torch.rand(2, 23, 4, 2, 4, generator=g)
+        out = simt.msda_forward(value, sh, lsi, loc, attn).numpy()
+        ref = c_oracle.msda_forward(value.numpy(), sh.numpy(), lsi.numpy(), loc.numpy(), attn.numpy())
+        assert np.array_equal(np.isnan(out), np.isnan(ref)) and np.array_equal(np.isinf(out), np.isinf(ref))
+        assert np.isnan(ref).any() and (~np.isnan(ref)).any()
+        fin = np.isfinite(ref)
+        assert np.abs(out[fin] - ref[fin]).max() <= 2e-5 * max(1.0, np.abs(ref[fin]).max())
