@@ -313,14 +313,32 @@ extern "C" int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, in
                 o_batch, static_cast<const uint8_t *>(mask_bits), mask_row_bytes, mask_batch_bytes, B, Lq, Lk, H,
                 scale * 1.4426950408889634f, 1};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // 128-row tiles (every warp walks every key block) for long memories, and for big batches of 200-query problems, where
-  // 16-row CTAs would re-stream K / V 13x per head (refiner: 1 664 CTAs, 30 us; cuDNN 8 us)
+  // Row-split tiles (every warp of a CTA walks every key block; K / V streamed once per CTA) for long memories and for big
+  // batches of 200-query problems, where 16-row key-split CTAs would re-stream K / V 13x per head (refiner: 1 664 CTAs, 30 us;
+  // cuDNN 8 us).  With few (batch, head) pairs -- the predictor's masked cross-attention at 2 frames per rank (8 GPUs) -- 128-row
+  // tiles leave most SMs idle (32 CTAs: 1.24 ms of a 3.6 ms stage A): fall back to 64-row tiles, then to the key-split variant,
+  // until the grid covers the machine.
   const int64_t split_ctas = (int64_t)((Lq + kFaRows - 1) / kFaRows) * H * B;
-  if (Lk > 512 || (Lq > 64 && split_ctas > 2 * kNumSMs)) {
+  const int64_t bh = (int64_t)H * B;
+  const int64_t row_ctas8 = (int64_t)((Lq + 8 * kFaRows - 1) / (8 * kFaRows)) * bh, row_ctas4 = (int64_t)((Lq + 4 * kFaRows - 1) / (4 * kFaRows)) * bh;
+  constexpr int64_t kEnough = (kNumSMs * 2) / 3;                 // CTAs that keep the 148 SMs reasonably busy
+  const bool long_mem = Lk > 512;
+  const char *force = getenv("DVIS_FLASH_VARIANT");              // tests / experiments: 1 = 128-row tiles, 2 = 64-row tiles, 3 = key split
+  const int forced = force ? atoi(force) : 0;
+  if (forced == 2) {
+    p.stages = 2;
+    return Dh == 32 ? launch_flash<32, false, 4>(p, s) : launch_flash<64, false, 4>(p, s);
+  }
+  if (forced == 1 || (forced == 0 && ((long_mem && (row_ctas8 >= kEnough || split_ctas > 4 * kNumSMs)) ||
+                                      (!long_mem && Lq > 64 && split_ctas > 2 * kNumSMs)))) {
     p.stages = 2;
     // (16 warps = all 200 queries of a head in one CTA, K / V streamed once, a single 128-CTA wave: measured SLOWER -- 500 us vs
     //  465 us at 14 720 keys -- the 512-thread CTA barriers cost more than the second K / V stream; launch_flash<32, false, 16>)
     return Dh == 32 ? launch_flash<32, false>(p, s) : launch_flash<64, false>(p, s);
+  }
+  if (forced == 0 && long_mem && row_ctas4 >= kEnough) {
+    p.stages = 2;
+    return Dh == 32 ? launch_flash<32, false, 4>(p, s) : launch_flash<64, false, 4>(p, s);
   }
   p.stages = (Lk + 31) / 32 > kFaWarps ? 2 : 1;    // a warp with more than one 32-key block prefetches the next one
   return Dh == 32 ? launch_flash<32, true>(p, s) : launch_flash<64, true>(p, s);

@@ -48,6 +48,25 @@ def test_flash_attn_matches_fp32_reference(B, Lq, Lk, H, Dh):
     assert (out.float() - ref).abs().max() < 2e-2 * ref.abs().max()          # bf16 P and bf16 output rounding
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])      # 128-row tiles, 64-row tiles, key split inside the CTA (DVIS_FLASH_VARIANT)
+@pytest.mark.parametrize("B,Lq,Lk,H,Dh,masked", [(1, 70, 530, 1, 32, True), (1, 150, 577, 1, 64, False), (2, 37, 130, 2, 32, True)])
+def test_flash_attn_every_variant_on_the_same_problem(variant, B, Lq, Lk, H, Dh, masked, monkeypatch):
+    """The dispatch picks the tiling from the problem size (long memory, few (batch, head) pairs -> smaller row tiles -> key split);
+    every variant must give the same result on any problem, with and without the bit mask."""
+    monkeypatch.setenv("DVIS_FLASH_VARIANT", str(variant))
+    torch.manual_seed(variant * 7 + Lq)
+    q = torch.randn(B, Lq, H, Dh).to(torch.bfloat16)
+    k = torch.randn(B, Lk, H, Dh).to(torch.bfloat16)
+    v = torch.randn(B, Lk, H, Dh).to(torch.bfloat16)
+    mask = None
+    if masked:
+        mask = torch.rand(B, Lq, Lk) < 0.6
+        mask[:, :, 5] = False
+    out = simt.flash_attn(q, k, v, 0.25, pack_bits(mask) if masked else None)
+    ref = ref_attention(q, k, v, 0.25, mask)
+    assert (out.float() - ref).abs().max() < 2e-2 * ref.abs().max()
+
+
 def test_flash_attn_two_stage_ring_and_bit_mask():
     """Lk > 4 blocks -> 2-stage cp.async ring; random mask with at least one open key per row."""
     torch.manual_seed(5)

@@ -60,6 +60,23 @@ def test_flash_attn_bit_mask_predictor_levels(Lk):
     assert rel_err(out.float(), ref) < 1e-2
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])   # auto, 128-row tiles, 64-row tiles, key split (DVIS_FLASH_VARIANT)
+@pytest.mark.parametrize("B,Lk", [(2, 3680), (4, 920), (16, 920), (1, 14720)])
+def test_flash_attn_variants_agree_on_predictor_shapes(variant, B, Lk, monkeypatch):
+    """Masked cross-attention of the predictor at the frames-per-rank of 8 / 4 / 1 GPUs: whichever tiling the dispatch picks (or is
+    forced to), the result is the fp32 reference's."""
+    monkeypatch.setenv("DVIS_FLASH_VARIANT", str(variant))
+    g = torch.Generator().manual_seed(B + Lk)
+    q = torch.randn(B, 200, 8, 32, generator=g).bfloat16()
+    k = torch.randn(B, Lk, 8, 32, generator=g).bfloat16()
+    v = torch.randn(B, Lk, 8, 32, generator=g).bfloat16()
+    mask = torch.rand(B, 200, Lk, generator=g) < 0.7
+    mask[:, :, 11] = False
+    out = ops.flash_attn(q.cuda(), k.cuda(), v.cuda(), 32 ** -0.5, mask_bits=pack_bits(mask).cuda()).float().cpu()
+    ref = ref_attention(q, k, v, 32 ** -0.5, mask)
+    assert (out - ref).abs().max() < 2e-2 * ref.abs().max()
+
+
 def test_flash_attn_rejects_cpu_tensors():
     q = torch.zeros(1, 4, 1, 64, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="no CPU path"):
