@@ -64,11 +64,21 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const T *__restrict__ x
   if (pl < prow) {
     const float K = gn_pivot<T>(x, batch_stride, n, g, cpg);
     const T *xn = x + (size_t)n * batch_stride + cq * 4;
-    for (int p = p0 + pl; p < p1; p += prow) {
-      const float4 v = ld4<T>(xn + (size_t)p * C);
-      const float a = v.x - K, b = v.y - K, c = v.z - K, d = v.w - K;
-      s += (a + b) + (c + d);
-      q += (a * a + b * b) + (c * c + d * d);
+    // 8 loads in flight per thread (the sums stay in pixel order): one load per iteration left the SM with ~16 KB in flight,
+    // a third of what the HBM latency needs
+    for (int pb = p0 + pl; pb < p1; pb += 8 * prow) {
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int p = pb + k * prow;
+        v[k] = p < p1 ? ld4<T>(xn + (size_t)p * C) : make_float4(K, K, K, K);       // K - K = 0: contributes nothing
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float a = v[k].x - K, b = v[k].y - K, c = v[k].z - K, d = v[k].w - K;
+        s += (a + b) + (c + d);
+        q += (a * a + b * b) + (c * c + d * d);
+      }
     }
   }
   s_s[threadIdx.x] = s;
@@ -89,18 +99,28 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const T *__restrict__ x
   }
 }
 
-__global__ void gn_finalize_kernel(const double *__restrict__ partials, int nchunks, int G, int total, double *__restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (n, g)
-  if (i >= total) return;
+// one WARP per (sample, group): lane l adds chunks l, l + 32, ... in order, then the 32 lane sums are added in lane order by a
+// fixed shuffle tree -- a fixed order (deterministic), 32 loads in flight instead of a 230-long dependent chain per thread
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const double *__restrict__ partials, int nchunks, int G, int total,
+                                                          double *__restrict__ sums) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;   // (n, g)
+  if (i >= total) return;                                                                  // whole warps leave together
   const int n = i / G, g = i - n * G;
   double ts = 0.0, tq = 0.0;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = lane; c < nchunks; c += 32) {
     const double *src = partials + (((size_t)n * nchunks + c) * G + g) * 2;
     ts += src[0];
     tq += src[1];
   }
-  sums[(size_t)i * 2] = ts;
-  sums[(size_t)i * 2 + 1] = tq;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ts += __shfl_down_sync(0xffffffffu, ts, o);
+    tq += __shfl_down_sync(0xffffffffu, tq, o);
+  }
+  if (lane == 0) {
+    sums[(size_t)i * 2] = ts;
+    sums[(size_t)i * 2 + 1] = tq;
+  }
 }
 
 struct GnApplyParams {
@@ -122,7 +142,7 @@ struct GnApplyParams {
 
 // grid (pixel chunks, N); a thread owns 4 fixed channels (its group's mean / rstd and gamma / beta stay in registers) and
 // walks pixels with stride blockDim / (C/4)
-template <typename T, typename TL>
+template <typename T, typename TL, bool kUp>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, int pix_per_cta) {
   const int quads = p.C / 4;
   const int cq = threadIdx.x % quads, pl = threadIdx.x / quads, prow = blockDim.x / quads;
@@ -137,36 +157,56 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, in
   const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
   const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
   const T *xn = static_cast<const T *>(p.x) + (size_t)n * p.x_batch_stride + c;
-  const float *u = p.up ? p.up + (size_t)n * p.up_batch_stride + c : nullptr;
+  const float *u = kUp ? p.up + (size_t)n * p.up_batch_stride + c : nullptr;
   const float ry = float(p.uh) / float(max(p.H, 1)), rx = float(p.uw) / float(max(p.W, 1));
   const int p0 = blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, p.HW);
-  for (int pix = p0 + pl; pix < p1; pix += prow) {
-    const float4 v = ld4<T>(xn + (size_t)pix * p.C);
-    float4 y = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
-    if (u) {
-      // F.interpolate(mode="bilinear", align_corners=False): src = (dst + 0.5) * in/out - 0.5, clamped at 0
-      const int oy = pix / p.W, ox = pix - oy * p.W;
-      const float fy = fmaxf((oy + 0.5f) * ry - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * rx - 0.5f, 0.f);
-      const int y0 = min(int(fy), p.uh - 1), x0 = min(int(fx), p.uw - 1);
-      const int y1 = min(y0 + 1, p.uh - 1), x1 = min(x0 + 1, p.uw - 1);
-      const float ly = fy - y0, lx = fx - x0;
-      const float4 a = *reinterpret_cast<const float4 *>(u + ((size_t)y0 * p.uw + x0) * p.C);
-      const float4 b = *reinterpret_cast<const float4 *>(u + ((size_t)y0 * p.uw + x1) * p.C);
-      const float4 cc = *reinterpret_cast<const float4 *>(u + ((size_t)y1 * p.uw + x0) * p.C);
-      const float4 d = *reinterpret_cast<const float4 *>(u + ((size_t)y1 * p.uw + x1) * p.C);
-      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-      y.x += w00 * a.x + w01 * b.x + w10 * cc.x + w11 * d.x;
-      y.y += w00 * a.y + w01 * b.y + w10 * cc.y + w11 * d.y;
-      y.z += w00 * a.z + w01 * b.z + w10 * cc.z + w11 * d.z;
-      y.w += w00 * a.w + w01 * b.w + w10 * cc.w + w11 * d.w;
+  // 4 pixels per iteration; ALL their loads -- the map itself and, for the FPN's top-down add, the 4 bilinear taps of the low-res
+  // map -- are issued before any of them is used: with one dependent load chain per pixel an SM kept ~16 KB in flight and the
+  // kernel ran at 48 % of the HBM roofline (the taps are L2 round trips of ~1 us each)
+  constexpr int KP = 4;
+  for (int pb = p0 + pl; pb < p1; pb += KP * prow) {
+    float4 vv[KP], ta[KP], tb[KP], tc[KP], td[KP];
+    float wy[KP], wx[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int pix = min(pb + k * prow, p1 - 1);                 // tail: repeat the last pixel (not stored)
+      vv[k] = ld4<T>(xn + (size_t)pix * p.C);
+      if constexpr (kUp) {
+        // F.interpolate(mode="bilinear", align_corners=False): src = (dst + 0.5) * in/out - 0.5, clamped at 0
+        const int oy = pix / p.W, ox = pix - oy * p.W;
+        const float fy = fmaxf((oy + 0.5f) * ry - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * rx - 0.5f, 0.f);
+        const int y0 = min(int(fy), p.uh - 1), x0 = min(int(fx), p.uw - 1);
+        const int y1 = min(y0 + 1, p.uh - 1), x1 = min(x0 + 1, p.uw - 1);
+        wy[k] = fy - y0; wx[k] = fx - x0;
+        ta[k] = *reinterpret_cast<const float4 *>(u + ((size_t)y0 * p.uw + x0) * p.C);
+        tb[k] = *reinterpret_cast<const float4 *>(u + ((size_t)y0 * p.uw + x1) * p.C);
+        tc[k] = *reinterpret_cast<const float4 *>(u + ((size_t)y1 * p.uw + x0) * p.C);
+        td[k] = *reinterpret_cast<const float4 *>(u + ((size_t)y1 * p.uw + x1) * p.C);
+      }
     }
-    if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-    const size_t o = (size_t)n * p.out_batch_stride + (size_t)pix * p.C + c;
-    if (p.out_f32) st4<float>(p.out_f32 + o, y);
-    if (p.out_lp) st4<TL>(static_cast<TL *>(p.out_lp) + o, y);
-    if (p.out_lp_pos) {
-      const float4 q = *reinterpret_cast<const float4 *>(p.pos + (size_t)pix * p.C + c);
-      st4<TL>(static_cast<TL *>(p.out_lp_pos) + o, make_float4(y.x + q.x, y.y + q.y, y.z + q.z, y.w + q.w));
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int pix = pb + k * prow;
+      if (pix >= p1) break;
+      const float4 v = vv[k];
+      float4 y = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+      if constexpr (kUp) {
+        const float ly = wy[k], lx = wx[k];
+        const float4 a = ta[k], b = tb[k], cc = tc[k], d = td[k];
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        y.x += w00 * a.x + w01 * b.x + w10 * cc.x + w11 * d.x;
+        y.y += w00 * a.y + w01 * b.y + w10 * cc.y + w11 * d.y;
+        y.z += w00 * a.z + w01 * b.z + w10 * cc.z + w11 * d.z;
+        y.w += w00 * a.w + w01 * b.w + w10 * cc.w + w11 * d.w;
+      }
+      if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      const size_t o = (size_t)n * p.out_batch_stride + (size_t)pix * p.C + c;
+      if (p.out_f32) st4<float>(p.out_f32 + o, y);
+      if (p.out_lp) st4<TL>(static_cast<TL *>(p.out_lp) + o, y);
+      if (p.out_lp_pos) {
+        const float4 q = *reinterpret_cast<const float4 *>(p.pos + (size_t)pix * p.C + c);
+        st4<TL>(static_cast<TL *>(p.out_lp_pos) + o, make_float4(y.x + q.x, y.y + q.y, y.z + q.z, y.w + q.w));
+      }
     }
   }
 }
@@ -200,17 +240,23 @@ extern "C" int dvis_groupnorm_nhwc(const void *x, int x_dtype, int64_t x_batch_s
   else
     gn_partial_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(x), x_batch_stride, HW, C, G, partials);
   if (int rc = check_launch("gn_partial_kernel")) return rc;
-  gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partials, nchunks, G, N * G, sums_workspace);
+  gn_finalize_kernel<<<(N * G + 3) / 4, 128, 0, s>>>(partials, nchunks, G, N * G, sums_workspace);   // 4 warps = 4 (sample, group) pairs per CTA
   if (int rc = check_launch("gn_finalize_kernel")) return rc;
   GnApplyParams p{x, x_batch_stride, sums_workspace, gamma, beta, N, HW, C, G, eps, relu, up, up_batch_stride, up_h, up_w,
                   H, W, pos, out_f32, out_lp, out_lp_pos, out_batch_stride};
   const int apply_pix = 64;                                     // 16 pixels per thread row at C = 256
   dim3 agrid((HW + apply_pix - 1) / apply_pix, N);
   using bf = __nv_bfloat16;
-  prefer_carveout(gn_apply_kernel<bf, bf>);
-  if (x_dtype == DVIS_F32 && lp_dtype == DVIS_F32) gn_apply_kernel<float, float><<<agrid, 256, 0, s>>>(p, apply_pix);
-  else if (x_dtype == DVIS_F32) gn_apply_kernel<float, bf><<<agrid, 256, 0, s>>>(p, apply_pix);
-  else if (lp_dtype == DVIS_F32) gn_apply_kernel<bf, float><<<agrid, 256, 0, s>>>(p, apply_pix);
-  else gn_apply_kernel<bf, bf><<<agrid, 256, 0, s>>>(p, apply_pix);
+#define DVIS_GN_APPLY(TX, TLP)                                                               \
+  do {                                                                                       \
+    if (up) gn_apply_kernel<TX, TLP, true><<<agrid, 256, 0, s>>>(p, apply_pix);              \
+    else gn_apply_kernel<TX, TLP, false><<<agrid, 256, 0, s>>>(p, apply_pix);                \
+  } while (0)
+  prefer_carveout(gn_apply_kernel<bf, bf, false>);
+  if (x_dtype == DVIS_F32 && lp_dtype == DVIS_F32) DVIS_GN_APPLY(float, float);
+  else if (x_dtype == DVIS_F32) DVIS_GN_APPLY(float, bf);
+  else if (lp_dtype == DVIS_F32) DVIS_GN_APPLY(bf, float);
+  else DVIS_GN_APPLY(bf, bf);
+#undef DVIS_GN_APPLY
   return check_launch("gn_apply_kernel");
 }
