@@ -4,8 +4,9 @@ weights.  The oracle needs a few seconds per case on the 
   config 2: R50 MSDeformAttnPixelDecoder, 720p single frame, + the Q=100 predictor (10 mask-head calls)
   config 3: T=5 clip, Q=200, ReferringTracker (hidden 512) -- the online model's final masks come from the tracker
   config 4: T=16, Q=200 TemporalRefiner (hidden 512), via the frame-sharded pipeline's temporal stage
-Tolerances: bf16 GEMM operands vs the fp32 oracle -> 3e-2 of the output scale (north star: 1e-2 per bf16 op; these are
-6..9 stacked layers); anything downstream of thresholded attention masks 8e-2 (see tests/test_modules_gpu.py).
+Tolerances: bf16 GEMM operands vs the fp32 oracle -> 2e-2 of the output scale everywhere (north star: 1e-2 per bf16 op; these
+are 6..9 stacked layers).  Measured on the B200 (profiles/r2_test_errors.json, tests/perf/report_test_errors.py): 7e-3 .. 1.2e-2;
+round 1 allowed 3e-2, and 8e-2 downstream of the thresholded attention masks (then a dense bf16 bias, now bits from fp32 logits).
 """
 import pytest
 import torch
@@ -39,16 +40,16 @@ def test_config2_r50_pixel_decoder_and_predictor_720p():
     with precision("bf16"):
         mf, o0, ms = pd.forward_features({k: v.cuda() for k, v in feats.items()})
         assert mf.shape == (1, 256, 184, 320) and mf.dtype == torch.bfloat16
-        assert rel_err(mf.float(), ref_mf) < 3e-2
-        assert rel_err(o0.float(), ref_o0) < 3e-2
+        assert rel_err(mf.float(), ref_mf) < 2e-2
+        assert rel_err(o0.float(), ref_o0) < 2e-2
         for a, b in zip(ms, ref_ms):
-            assert rel_err(a.float(), b) < 3e-2
+            assert rel_err(a.float(), b) < 2e-2
         # predictor on the ORACLE's pixel-decoder outputs so that only the predictor's own error is measured
         seg = dec([m.cuda() for m in ref_ms], ref_mf.cuda())
     assert _lib.launch_count - n0 > 20, "libdvis_b200 kernels did not run"
     assert seg["pred_masks"].shape == (1, 100, 1, 184, 320)
     for k in ("pred_logits", "pred_masks", "pred_embds"):
-        assert rel_err(seg[k].float(), ref_seg[k]) < 8e-2, (k, rel_err(seg[k].float(), ref_seg[k]))
+        assert rel_err(seg[k].float(), ref_seg[k]) < 2e-2, (k, rel_err(seg[k].float(), ref_seg[k]))
 
 
 @torch.no_grad()
@@ -68,9 +69,9 @@ def test_config3_online_tracker_T5_Q200():
         out, idx = trk(fe.cuda(), mfeat.cuda(), resume=False, return_indices=True, frame_embeds_no_norm=fn.cuda())
     for a, b in zip(idx, ref["indices"]):
         assert (torch.as_tensor(a) == torch.as_tensor(b)).all(), "GPU Hungarian differs from SciPy"
-    assert rel_err(out["pred_embds"].float(), ref["pred_embds"]) < 3e-2
-    assert rel_err(out["pred_logits"].float(), ref["pred_logits"]) < 3e-2
-    assert rel_err(out["pred_masks"].float(), ref["pred_masks"]) < 3e-2
+    assert rel_err(out["pred_embds"].float(), ref["pred_embds"]) < 2e-2
+    assert rel_err(out["pred_logits"].float(), ref["pred_logits"]) < 2e-2
+    assert rel_err(out["pred_masks"].float(), ref["pred_masks"]) < 2e-2
 
 
 @torch.no_grad()
@@ -90,6 +91,6 @@ def test_config4_offline_temporal_stage_T16_Q200():
     with precision("bf16"):
         out = r.temporal_stage({k: v.cuda() for k, v in seg.items()}, mfeat.cuda().to(torch.bfloat16, memory_format=torch.channels_last))
     assert out["pred_masks"].shape == (1, Q, T, 46, 80)
-    assert rel_err(out["pred_embds"].float(), ref["pred_embds"]) < 3e-2
-    assert rel_err(out["pred_logits"].float(), ref["pred_logits"]) < 3e-2
-    assert rel_err(out["pred_masks"].float(), ref["pred_masks"]) < 3e-2
+    assert rel_err(out["pred_embds"].float(), ref["pred_embds"]) < 2e-2
+    assert rel_err(out["pred_logits"].float(), ref["pred_logits"]) < 2e-2
+    assert rel_err(out["pred_masks"].float(), ref["pred_masks"]) < 2e-2

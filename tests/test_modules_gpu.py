@@ -1,7 +1,9 @@
 """GPU parity of the module-level drop-ins against golden outputs of the unmodified reference modules.
 
-Tolerances (relative to the output scale): "fp32" mode 1e-3 (north star fp32 bound; mask logits always run on the
-bf16 tensor path, so anything downstream of a mask GEMM uses 1e-2); "bf16" mode 1e-2 ... 3e-2 after stacked layers.
+Tolerances (relative to the output scale): "fp32" mode 1e-3 (north star fp32 bound; mask logits run on TF32 tensor-core
+operands there, 2e-3 downstream of a mask GEMM); "bf16" mode 1e-2 for one op, 1.5e-2 .. 2e-2 after 6..9 stacked layers (3e-2
+where thresholded attention masks feed later layers).  The errors the B200 actually measures are in profiles/r2_test_errors.json
+(tests/perf/report_test_errors.py): every asserted bound is ~2x the measured value; round 1 asserted 3e-2 .. 8e-2.
 """
 import numpy as np
 import pytest
@@ -88,7 +90,7 @@ def test_pixel_decoder_production_width():
     sd = {k: v.detach() for k, v in pd.state_dict().items()}
     ref_mf, ref_o0, ref_ms = tp.pixel_decoder_forward_features(sd, feats, num_layers=3)
     pd = pd.cuda()
-    for mode, tol in (("fp32", 1e-3), ("bf16", 3e-2)):
+    for mode, tol in (("fp32", 1e-3), ("bf16", 2e-2)):
         calls = _lib.launch_count
         with precision(mode):
             mf, o0, ms = pd.forward_features(cuda(feats))
@@ -155,7 +157,7 @@ def test_mask_head_golden_and_lowres_equivalence(golden):
     assert not bad.any()
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 1e-2), ("bf16", 3e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 1.5e-2)])
 @torch.no_grad()
 def test_tracker_golden(golden, mode, tol):
     g = golden("tracker_small.pt")
@@ -172,7 +174,7 @@ def test_tracker_golden(golden, mode, tol):
     assert rel_err(torch.cat([o1["pred_masks"], o2["pred_masks"]], 2), g["pred_masks"]) < tol   # folded conv + bf16 GEMM
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 1e-2), ("bf16", 3e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 1.5e-2)])
 @torch.no_grad()
 def test_refiner_golden(golden, mode, tol):
     g = golden("refiner_small.pt")
@@ -198,7 +200,7 @@ def test_refiner_row_layout_equals_module_path(golden):
             outs[rows] = r(g["instance_embeds"].cuda(), g["frame_embeds"].cuda(), g["mask_features"].cuda())
     for k in ("pred_embds", "pred_logits", "pred_masks"):
         assert rel_err(outs[True][k], outs[False][k].float().cpu()) < 2e-2, k
-        assert rel_err(outs[True][k], g[k]) < 3e-2, k
+        assert rel_err(outs[True][k], g[k]) < 1.5e-2, k
 
 
 def test_add_layernorm_kernel():
@@ -265,7 +267,7 @@ def test_predictor_prenorm_variant_golden(golden):
         out = d(cuda(base["multi_scale"]), base["mask_features"].cuda())
     assert _lib.launch_count > calls
     for k in ("pred_logits", "pred_masks", "pred_embds", "pred_embds_without_norm"):
-        assert rel_err(out[k], g[k]) < 5e-2, (k, rel_err(out[k], g[k]))     # thresholded bf16 logits, see above
+        assert rel_err(out[k], g[k]) < 3e-2, (k, rel_err(out[k], g[k]))     # thresholded bf16 logits, see above
 
 
 @torch.no_grad()
@@ -287,11 +289,11 @@ def test_predictor_fast_path_production_width():
         out = d(cuda(ms), mf.cuda())
     assert _lib.launch_count > calls
     for k in ("pred_logits", "pred_masks", "pred_embds", "pred_embds_without_norm"):
-        assert rel_err(out[k], ref[k]) < 5e-2, (k, rel_err(out[k], ref[k]))     # thresholded bf16 logits, see above
+        assert rel_err(out[k], ref[k]) < 3e-2, (k, rel_err(out[k], ref[k]))     # thresholded bf16 logits, see above
     with precision("bf16"):
         out = d(cuda(ms), mf.cuda())
     for k in ("pred_logits", "pred_masks", "pred_embds"):
-        assert rel_err(out[k], ref[k]) < 8e-2, (k, rel_err(out[k], ref[k]))
+        assert rel_err(out[k], ref[k]) < 3e-2, (k, rel_err(out[k], ref[k]))
 
 
 def test_lap_chain_matches_scipy():
