@@ -65,6 +65,15 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+def _check_item_order(item_order, n_items, device):
+    """item_order: optional int32 CUDA permutation of the Lq*M (query, head) items (locality.tiled_item_order)."""
+    if item_order is None:
+        return None
+    assert item_order.dtype == torch.int32 and item_order.is_cuda and item_order.device == device and item_order.is_contiguous()
+    assert item_order.numel() == n_items, f"item_order has {item_order.numel()} entries, expected Lq*M = {n_items}"
+    return item_order.data_ptr()
+
+
 def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits, reference_points, num_heads,
                        num_levels, num_points, item_order=None, out_dtype=None):
     """Fused softmax + location arithmetic + gather (dvis_msda_fused_forward).
@@ -81,7 +90,7 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     assert offsets.stride(0) == offsets.stride(1) * Lq and logits.stride(0) == logits.stride(1) * Lq
     out_dtype = out_dtype or value.dtype
     out = torch.empty((N, Lq, M * D), dtype=out_dtype, device=value.device)
-    order_ptr = item_order.data_ptr() if item_order is not None else None
+    order_ptr = _check_item_order(item_order, Lq * M, value.device)
     with torch.cuda.device(value.device):
         _lib.call("dvis_msda_fused_forward", value.data_ptr(), _DTYPE[value.dtype], spatial_shapes.data_ptr(),
                   level_start_index.data_ptr(), offsets.data_ptr(), offsets.stride(1), logits.data_ptr(),
@@ -102,7 +111,7 @@ def msda_fused_forward_hm(value_hm, spatial_shapes, level_start_index, offsets, 
     assert offsets.stride(-1) == 1 and logits.stride(-1) == 1
     assert offsets.stride(0) == offsets.stride(1) * Lq and logits.stride(0) == logits.stride(1) * Lq
     out = torch.empty((N, Lq, M * D), dtype=torch.bfloat16, device=value_hm.device)
-    order_ptr = item_order.data_ptr() if item_order is not None else None
+    order_ptr = _check_item_order(item_order, Lq * M, value_hm.device)
     with torch.cuda.device(value_hm.device):
         _lib.call("dvis_msda_fused_forward_hm", value_hm.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                   offsets.data_ptr(), offsets.stride(1), logits.data_ptr(), logits.stride(1), _DTYPE[offsets.dtype],
@@ -118,9 +127,11 @@ def msda_pair_forward(value, spatial_shapes, level_start_index, offsets, logits,
     N, S, M, D = value.shape
     Lq = offsets.shape[1]
     assert value.dtype == torch.bfloat16 and D == 32 and value.is_contiguous() and reference_points.is_contiguous()
+    assert reference_points.dtype == torch.float32, "reference points are read as float32"
     assert offsets.dtype == logits.dtype and offsets.dtype in (torch.float32, torch.bfloat16)
     assert offsets.stride(-1) == 1 and logits.stride(-1) == 1
     assert offsets.stride(0) == offsets.stride(1) * Lq and logits.stride(0) == logits.stride(1) * Lq
+    _check_item_order(item_order, Lq * M, value.device)
     pairs = torch.empty((N, S + 1, M, 2, D), dtype=torch.bfloat16, device=value.device)
     out = torch.empty((N, Lq, M * D), dtype=torch.bfloat16, device=value.device)
     order_ptr = item_order.data_ptr() if item_order is not None else None
