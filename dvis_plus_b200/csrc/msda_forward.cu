@@ -227,8 +227,10 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_staged_kernel(const M
   static_assert(!HM || (kMixed && FUSED && D == 32), "head-major value: bf16 in / out, 32 channels per head, fused parameters");
   PointOffsets *s_off = reinterpret_cast<PointOffsets *>(dyn_smem);
   float4 *s_wt = reinterpret_cast<float4 *>(dyn_smem + p.items_per_cta * LPs);   // kMixed: a dense uint2 array (2 x bf16x2) in the same region
-  float *s_prob = reinterpret_cast<float *>(dyn_smem + 2 * p.items_per_cta * LPs);
-  int *s_item = reinterpret_cast<int *>(s_prob + (FUSED ? p.items_per_cta * LP : 0));   // s_prob: (max, 1/sum) per item (2 of the LP slots)
+  // head-major: ONE 16-byte record per point (no separate weight array) and 2 floats per item of softmax state: 14 KB per CTA
+  // instead of 30 KB, i.e. ~100 KB more L1 for the gather at 6 CTAs per SM
+  float *s_prob = reinterpret_cast<float *>(dyn_smem + (HM ? 1 : 2) * p.items_per_cta * LPs);
+  int *s_item = reinterpret_cast<int *>(s_prob + (FUSED ? p.items_per_cta * (HM ? 2 : LP) : 0));   // s_prob: (max, 1/sum) per item
 
   for (int il = tid; il < nitems; il += kThreads) s_item[il] = p.order ? __ldg(p.order + chunk_begin + il) : chunk_begin + il;
   __syncthreads();
@@ -520,17 +522,18 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
   while (lpc < LP) { lpc <<= 1; ++sh; }
   p.lpc_shift = sh;
   p.lp_magic = ((1u << 20) + LP - 1) / LP;
-  const size_t smem = (size_t)p.items_per_cta * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
+  const size_t smem = HM ? (size_t)p.items_per_cta * (LPs * 16 + 2 * 4 + 4)
+                         : (size_t)p.items_per_cta * (2 * LPs * 16 + (FUSED ? LP * 4 : 0) + 4);
   if (smem > kMaxStagedSmem)
     return fail(DVIS_ERR_UNSUPPORTED, "msda: %zu bytes of shared memory per CTA for D=%d, L*P=%d exceed the %d-byte opt-in limit", smem,
                 D, LP, int(kMaxStagedSmem));
-  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 2, HM>;
+  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, HM ? 12 : 2, HM>;   // head-major: the 12-point loop fully unrolled (556.6 vs 565.0 us)
   if constexpr (HM) {   // the same experiment switch for the head-major gather (tests/perf/encoder_microbench.py)
     static const int variant = getenv("DVIS_MSDA_HM_VARIANT") ? atoi(getenv("DVIS_MSDA_HM_VARIANT")) : 0;
     if (variant == 1) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 4, HM>;
     if (variant == 2) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 2, HM>;
     if (variant == 3) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 4, HM>;
-    if (variant == 4) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 12, HM>;
+    if (variant == 4) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 2, HM>;
     if (variant == 5) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 4, 4, HM>;
   } else {  // occupancy / unroll variants (DVIS_MSDA_VARIANT), kept for the micro-benchmark.  Default: 6 CTAs/SM, unroll 2
      // (40 registers): measured 23 % faster than 3 CTAs/SM x unroll 4 (80 registers) -- the gather is latency bound.
