@@ -527,7 +527,9 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
   if (smem > kMaxStagedSmem)
     return fail(DVIS_ERR_UNSUPPORTED, "msda: %zu bytes of shared memory per CTA for D=%d, L*P=%d exceed the %d-byte opt-in limit", smem,
                 D, LP, int(kMaxStagedSmem));
-  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, HM ? 12 : 2, HM>;   // head-major: the 12-point loop fully unrolled (556.6 vs 565.0 us)
+  // head-major: 8 CTAs per SM (32 registers, 14 KB of shared memory each) with the 12-point loop fully unrolled: 541 us isolated
+  // at T = 16 vs 557 us for 6 CTAs per SM (profiles/r2_msda_hm_variants.log)
+  auto kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, HM ? 8 : 6, HM ? 12 : 2, HM>;
   if constexpr (HM) {   // the same experiment switch for the head-major gather (tests/perf/encoder_microbench.py)
     static const int variant = getenv("DVIS_MSDA_HM_VARIANT") ? atoi(getenv("DVIS_MSDA_HM_VARIANT")) : 0;
     if (variant == 1) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 4, HM>;
@@ -535,6 +537,12 @@ int launch_staged(MsdaParams p, cudaStream_t stream) {
     if (variant == 3) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 4, HM>;
     if (variant == 4) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 2, HM>;
     if (variant == 5) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 4, 4, HM>;
+    if (variant == 6) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 7, 12, HM>;
+    if (variant == 7) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 7, 3, HM>;
+    if (variant == 8) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 5, 12, HM>;
+    if (variant == 9) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 6, HM>;
+    if (variant == 10) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 6, 12, HM>;
+    if (variant == 11) kern = msda_fwd_staged_kernel<T, TO, D, FUSED, TP, 8, 3, HM>;
   } else {  // occupancy / unroll variants (DVIS_MSDA_VARIANT), kept for the micro-benchmark.  Default: 6 CTAs/SM, unroll 2
      // (40 registers): measured 23 % faster than 3 CTAs/SM x unroll 4 (80 registers) -- the gather is latency bound.
     static const int variant = getenv("DVIS_MSDA_VARIANT") ? atoi(getenv("DVIS_MSDA_VARIANT")) : 0;

@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_linear_tc_gpu.py tests/test_configs_gpu.py -q -x -p no:cacheprovider 2>&1 | tail -2
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2c46_bench_n1.json 2> gpurun_out/r2c46_n1.err
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2c47_bench_n1.json 2> gpurun_out/r2c47_n1.err
 python - <<'P'
 import json
-l=json.load(open('gpurun_out/r2c46_bench_n1.json')); r=l['roofline']
+l=json.load(open('gpurun_out/r2c47_bench_n1.json')); r=l['roofline']
 print('n1', l['value'], l['ms_per_step'], 'lat', l['latency_ms_per_clip'], 'e2e', l['e2e']['value'], 'parity', l['parity_check']['bit_identical'], 'msda us', r['us_per_launch'], 'frac', r['frac'])
 P
