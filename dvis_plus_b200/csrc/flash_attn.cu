@@ -313,32 +313,32 @@ extern "C" int dvis_flash_attn(const void *q, int64_t q_row, int64_t q_batch, in
                 o_batch, static_cast<const uint8_t *>(mask_bits), mask_row_bytes, mask_batch_bytes, B, Lq, Lk, H,
                 scale * 1.4426950408889634f, 1};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // Row-split tiles (every warp of a CTA walks every key block; K / V streamed once per CTA) for long memories and for big
-  // batches of 200-query problems, where 16-row key-split CTAs would re-stream K / V 13x per head (refiner: 1 664 CTAs, 30 us;
-  // cuDNN 8 us).  With few (batch, head) pairs -- the predictor's masked cross-attention at 2 frames per rank (8 GPUs) -- 128-row
-  // tiles leave most SMs idle (32 CTAs: 1.24 ms of a 3.6 ms stage A): fall back to 64-row tiles, then to the key-split variant,
-  // until the grid covers the machine.
+  // Tiling, from measurements on the B200 (tests/perf/flash_long_memory_probe.py, flash_variant_probe.py;
+  // profiles/r2_flash_long_memory_probe.json):
+  //  * long memories (the predictor's masked cross-attention over 920 / 3 680 / 14 720 pixels): 64-ROW tiles (4 warps, every warp
+  //    walks every key block, K / V streamed once per CTA) from 48 (batch, head) pairs on -- 425 us at 16 frames x 14 720 keys vs
+  //    469 us for 128-row tiles (2 CTAs per head: 256 CTAs leave the 148 SMs unevenly loaded) and 430 us for cuDNN with a dense
+  //    bias; below that (4 and 2 frames per rank: 4 / 8 GPUs) the KEY-SPLIT variant (16-row CTAs, the 8 warps split the keys):
+  //    141 vs 182 us at 4 frames, 93 vs 182 us at 2;
+  //  * short memories: key split, except big batches of 200-query problems, where 16-row CTAs would re-stream K / V 13x per head
+  //    (refiner: 1 664 CTAs, 30 us; cuDNN 8 us): 128-row tiles.
   const int64_t split_ctas = (int64_t)((Lq + kFaRows - 1) / kFaRows) * H * B;
   const int64_t bh = (int64_t)H * B;
-  const int64_t row_ctas8 = (int64_t)((Lq + 8 * kFaRows - 1) / (8 * kFaRows)) * bh, row_ctas4 = (int64_t)((Lq + 4 * kFaRows - 1) / (4 * kFaRows)) * bh;
-  constexpr int64_t kEnough = (kNumSMs * 2) / 3;                 // CTAs that keep the 148 SMs reasonably busy
   const bool long_mem = Lk > 512;
-  const char *force = getenv("DVIS_FLASH_VARIANT");              // tests / experiments: 1 = 128-row tiles, 2 = 64-row tiles, 3 = key split
+  const char *force = getenv("DVIS_FLASH_VARIANT");   // tests / experiments: 1 = 128-row, 2 = 64-row, 4 = 32-row tiles, 3 = key split
   const int forced = force ? atoi(force) : 0;
-  if (forced == 2) {
+  if (forced == 2 || (forced == 0 && long_mem && bh >= 48)) {
     p.stages = 2;
     return Dh == 32 ? launch_flash<32, false, 4>(p, s) : launch_flash<64, false, 4>(p, s);
   }
-  if (forced == 1 || (forced == 0 && ((long_mem && (row_ctas8 >= kEnough || split_ctas > 4 * kNumSMs)) ||
-                                      (!long_mem && Lq > 64 && split_ctas > 2 * kNumSMs)))) {
+  if (forced == 4) {
     p.stages = 2;
-    // (16 warps = all 200 queries of a head in one CTA, K / V streamed once, a single 128-CTA wave: measured SLOWER -- 500 us vs
-    //  465 us at 14 720 keys -- the 512-thread CTA barriers cost more than the second K / V stream; launch_flash<32, false, 16>)
+    return Dh == 32 ? launch_flash<32, false, 2>(p, s) : launch_flash<64, false, 2>(p, s);
+  }
+  if (forced == 1 || (forced == 0 && !long_mem && Lq > 64 && split_ctas > 2 * kNumSMs)) {
+    p.stages = 2;
+    // (16 warps = all 200 queries of a head in one CTA, K / V streamed once: measured SLOWER -- 500 us vs 465 us at 14 720 keys)
     return Dh == 32 ? launch_flash<32, false>(p, s) : launch_flash<64, false>(p, s);
-  }
-  if (forced == 0 && long_mem && row_ctas4 >= kEnough) {
-    p.stages = 2;
-    return Dh == 32 ? launch_flash<32, false, 4>(p, s) : launch_flash<64, false, 4>(p, s);
   }
   p.stages = (Lk + 31) / 32 > kFaWarps ? 2 : 1;    // a warp with more than one 32-key block prefetches the next one
   return Dh == 32 ? launch_flash<32, true>(p, s) : launch_flash<64, true>(p, s);

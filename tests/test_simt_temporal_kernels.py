@@ -48,7 +48,7 @@ def test_flash_attn_matches_fp32_reference(B, Lq, Lk, H, Dh):
     assert (out.float() - ref).abs().max() < 2e-2 * ref.abs().max()          # bf16 P and bf16 output rounding
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])      # 128-row tiles, 64-row tiles, key split inside the CTA (DVIS_FLASH_VARIANT)
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])   # 128-row, 64-row tiles, key split inside the CTA, 32-row tiles (DVIS_FLASH_VARIANT)
 @pytest.mark.parametrize("B,Lq,Lk,H,Dh,masked", [(1, 70, 530, 1, 32, True), (1, 150, 577, 1, 64, False), (2, 37, 130, 2, 32, True)])
 def test_flash_attn_every_variant_on_the_same_problem(variant, B, Lq, Lk, H, Dh, masked, monkeypatch):
     """The dispatch picks the tiling from the problem size (long memory, few (batch, head) pairs -> smaller row tiles -> key split);

@@ -60,7 +60,7 @@ def test_flash_attn_bit_mask_predictor_levels(Lk):
     assert rel_err(out.float(), ref) < 1e-2
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])   # auto, 128-row tiles, 64-row tiles, key split (DVIS_FLASH_VARIANT)
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])   # auto, 128-row, 64-row tiles, key split, 32-row tiles (DVIS_FLASH_VARIANT)
 @pytest.mark.parametrize("B,Lk", [(2, 3680), (4, 920), (16, 920), (1, 14720)])
 def test_flash_attn_variants_agree_on_predictor_shapes(variant, B, Lk, monkeypatch):
     """Masked cross-attention of the predictor at the frames-per-rank of 8 / 4 / 1 GPUs: whichever tiling the dispatch picks (or is
